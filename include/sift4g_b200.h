@@ -1,0 +1,142 @@
+/*
+ * sift4g_b200 -- C ABI of the B200-native SIFT4G database-search hot path.
+ *
+ * This is the drop-in boundary: plain C types, caller-allocated outputs, 0 = OK / negative = error,
+ * no exceptions and no exit() across it.  The C++ host shims in sift4g_b200/host/ keep the
+ * reference's own C++ seams (searchDatabase / alignDatabase) and call only these entry points.
+ *
+ * Reference interfaces replaced (paths relative to the rvaser/sift4g tree, "sw/" =
+ * vendor/swsharp/swsharp/src/):
+ *   s4g_prefilter      <- searchDatabase()            sift4g/src/database_search.hpp:17-19
+ *                         (threadSearchDatabase        sift4g/src/database_search.cpp:185-253,
+ *                          Hash / createKmerVector     sift4g/src/hash.cpp:21-90)
+ *   s4g_sw_score       <- scoreDatabasesGpu()         sw/gpu_module.h:280-291  (the reference's own
+ *                         GPU plug-in seam, a stub in CPU builds: sw/gpu_module.cu:22-95) and
+ *                         scoreDatabaseCpu()           sw/cpu_module.h:143-144
+ *   s4g_sw_align       <- alignScoredPair()           sw/align.h (sw/align.c:235-255) ->
+ *                         alignScoredPairCpu()         sw/cpu_module.h:67-68
+ *   s4g_db_* / s4g_queries_*  <- chainDatabaseGpuCreate/Delete()  sw/gpu_module.h:210-240
+ *   s4g_db_open_fasta  <- readFastaChainsPart()       sw/pre_proc.h:76-81 (reader quirks kept)
+ *
+ * Pointer arguments marked [io] live on the host when `where == S4G_HOST` (the call copies in and
+ * out and returns when results are on the host) or on the device of the context when
+ * `where == S4G_DEVICE` (the call only enqueues work on the context's stream; use s4g_sync()).
+ *
+ * Residue codes are the reference's: 'A'..'Z' -> 0..25, case folded, everything else dropped
+ * (sw/scorer.c:45-72).  Sequence ids are FASTA-order indices (id_base + local index).
+ * Threading: one in-flight call per s4g_ctx.
+ */
+#ifndef SIFT4G_B200_H
+#define SIFT4G_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S4G_OK 0
+#define S4G_ERR_CUDA (-1)
+#define S4G_ERR_ARG (-2)
+#define S4G_ERR_NOMEM (-3)
+#define S4G_ERR_IO (-4)
+#define S4G_ERR_CAPACITY (-5)
+#define S4G_ERR_INTERNAL (-6)
+
+#define S4G_HOST 0
+#define S4G_DEVICE 1
+
+typedef struct s4g_ctx s4g_ctx;
+typedef struct s4g_db s4g_db;
+typedef struct s4g_queries s4g_queries;
+
+/* ---- context ---------------------------------------------------------------------------- */
+int s4g_version(void);
+int s4g_init(int device, s4g_ctx** out);
+void s4g_shutdown(s4g_ctx* ctx);
+/* last error text of this context (or of the calling thread when ctx == NULL) */
+const char* s4g_last_error(const s4g_ctx* ctx);
+/* run all later work of this context on an existing cudaStream_t (e.g. torch's current stream) */
+int s4g_set_stream(s4g_ctx* ctx, void* cuda_stream);
+int s4g_sync(s4g_ctx* ctx);
+/* kernels launched by this context since creation / last reset (bench.py's gpu_launches) */
+int64_t s4g_launch_count(const s4g_ctx* ctx);
+void s4g_launch_count_reset(s4g_ctx* ctx);
+
+/* ---- database shard (resident in HBM) ---------------------------------------------------- */
+/* codes: concatenated residue codes; offsets[n_seqs+1]; id_base = FASTA index of sequence 0 of
+ * this shard (multi-GPU: one resident shard per GPU). */
+int s4g_db_create(s4g_ctx* ctx, const uint8_t* codes, const int64_t* offsets, int64_t n_seqs,
+                  uint32_t id_base, int where, s4g_db** out);
+/* Parse a FASTA file like the reference reader (sw/pre_proc.c:437-538) and keep shard
+ * `shard` of `n_shards` (contiguous ranges of FASTA order).  Names are kept on the host. */
+int s4g_db_open_fasta(s4g_ctx* ctx, const char* path, int shard, int n_shards, s4g_db** out);
+void s4g_db_close(s4g_db* db);
+int64_t s4g_db_num_seqs(const s4g_db* db);
+uint64_t s4g_db_num_residues(const s4g_db* db);   /* = `cells` returned by searchDatabase() */
+uint32_t s4g_db_id_base(const s4g_db* db);
+/* host-side metadata (valid until s4g_db_close) */
+const int64_t* s4g_db_host_offsets(const s4g_db* db);
+const uint8_t* s4g_db_host_codes(const s4g_db* db);      /* NULL for device-created shards */
+const char* s4g_db_name(const s4g_db* db, int64_t local_index); /* NULL unless opened from FASTA */
+
+/* ---- query batch -------------------------------------------------------------------------- */
+int s4g_queries_create(s4g_ctx* ctx, const uint8_t* codes, const int64_t* offsets, int32_t n_queries,
+                       int where, s4g_queries** out);
+void s4g_queries_free(s4g_queries* q);
+
+/* ---- stage 1: k-mer candidate prefilter ---------------------------------------------------- */
+/* For every query: the max_candidates sequences of this shard with the largest
+ * LIS(k-mer hit positions)/len score (float32), ties broken by ascending id (the deterministic
+ * member of the reference's tie family).  out_ids / out_scores: n_queries x max_candidates, row q
+ * holds out_counts[q] entries.  `sorted_by_id` != 0: rows ordered by ascending id (what
+ * searchDatabase() returns); 0: rows ordered best-first (what the multi-GPU merge consumes). */
+int s4g_prefilter(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int kmer_length, int max_candidates,
+                  int sorted_by_id, uint32_t* out_ids /*[io]*/, float* out_scores /*[io], may be NULL*/,
+                  uint32_t* out_counts /*[io]*/, int where);
+
+/* Multi-GPU merge step: given per-rank best-first candidate rows gathered from n_ranks shards
+ * (gathered_ids/scores: n_ranks x n_queries x max_candidates, gathered_counts: n_ranks x n_queries)
+ * select the global top max_candidates per query by (score desc, id asc) and write them sorted by
+ * ascending id.  Device pointers only (it runs right after the NCCL all-gather). */
+int s4g_merge_candidates(s4g_ctx* ctx, int n_ranks, int n_queries, int max_candidates,
+                         const uint32_t* gathered_ids, const float* gathered_scores,
+                         const uint32_t* gathered_counts, uint32_t* out_ids, float* out_scores,
+                         uint32_t* out_counts);
+
+/* ---- stage 2: Smith-Waterman affine-gap scores ------------------------------------------------ */
+/* cand_ids: concatenated per-query candidate ids (global ids inside this shard's range),
+ * cand_offsets[n_queries+1].  matrix: 26x26 int32 row-major (sw/scorer.c:206-208).
+ * A gap of length L costs gap_open + (L-1)*gap_extend.  out_scores[i] = exact integer score of
+ * cand_ids[i] against its query (sw/swimd/Swimd.cpp:241-275 semantics). */
+int s4g_sw_score(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, const uint32_t* cand_ids /*[io]*/,
+                 const int64_t* cand_offsets /*[io]*/, int64_t n_pairs, const int32_t* matrix /*host*/,
+                 int gap_open, int gap_extend, int32_t* out_scores /*[io]*/, int where);
+
+/* ---- stage 3: traceback of kept hits ---------------------------------------------------------- */
+/* For pair i: query pair_q[i], target id pair_t[i], known score pair_score[i].
+ * out_coords[4*i..] = {qstart,qend,tstart,tend} (0-based inclusive);
+ * path bytes 1=DIAG 2=LEFT 3=UP (sw/alignment.h:43-65) are written to
+ * out_paths[out_path_offsets[i] .. out_path_offsets[i+1]).  Rules: SSW's for score <= 32767
+ * (sw/ssw/ssw.c:549-856), swAlign's otherwise (sw/cpu_module.c:1185-1413).
+ * path_capacity: bytes available in out_paths; S4G_ERR_CAPACITY if too small (a safe bound is
+ * sum(qlen+tlen)). */
+int s4g_sw_align(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_pairs, const uint32_t* pair_q,
+                 const uint32_t* pair_t, const int32_t* pair_score, const int32_t* matrix /*host*/,
+                 int gap_open, int gap_extend, int32_t* out_coords, uint8_t* out_paths,
+                 int64_t path_capacity, int64_t* out_path_offsets, int where);
+
+/* ---- measurement helpers ------------------------------------------------------------------------ */
+/* Sustained issue rate of the DPX / integer ALU pipe (lane-operations per second of
+ * VIADDMNMX.S16x2), measured for ~`millis` ms on the context's device: the denominator of the SW
+ * roofline (BASELINE.md "Algorithmic work definitions"). */
+int s4g_measure_dpx_peak(s4g_ctx* ctx, int millis, double* lane_ops_per_s);
+/* device time (ms) spent in the dominant kernel of the most recent s4g_sw_score call, measured with
+ * CUDA events on the context's stream (valid after s4g_sync), and the number of DP cells it covered
+ * including padding (algorithmic cells are computed by the caller from lengths). */
+int s4g_last_sw_kernel_ms(s4g_ctx* ctx, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

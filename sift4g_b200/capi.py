@@ -1,0 +1,242 @@
+"""ctypes binding of the C ABI (include/sift4g_b200.h -> sift4g_b200/libsift4g_b200.so).
+
+This is the only way Python reaches the CUDA path: there is no Python/CPU fallback.  Loading fails
+loudly when the shared library is missing or was not built.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsift4g_b200.so")
+
+S4G_HOST, S4G_DEVICE = 0, 1
+
+_u8p, _i32p, _i64p, _u32p, _f32p, _f64p = (C.POINTER(t) for t in (C.c_uint8, C.c_int32, C.c_int64, C.c_uint32, C.c_float, C.c_double))
+_vp = C.c_void_p
+
+# name -> (restype, argtypes); must list every symbol include/sift4g_b200.h declares
+SIGNATURES = {
+    "s4g_version": (C.c_int, []),
+    "s4g_init": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "s4g_shutdown": (None, [_vp]),
+    "s4g_last_error": (C.c_char_p, [_vp]),
+    "s4g_set_stream": (C.c_int, [_vp, _vp]),
+    "s4g_sync": (C.c_int, [_vp]),
+    "s4g_launch_count": (C.c_int64, [_vp]),
+    "s4g_launch_count_reset": (None, [_vp]),
+    "s4g_db_create": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_uint32, C.c_int, C.POINTER(_vp)]),
+    "s4g_db_open_fasta": (C.c_int, [_vp, C.c_char_p, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "s4g_db_close": (None, [_vp]),
+    "s4g_db_num_seqs": (C.c_int64, [_vp]),
+    "s4g_db_num_residues": (C.c_uint64, [_vp]),
+    "s4g_db_id_base": (C.c_uint32, [_vp]),
+    "s4g_db_host_offsets": (_i64p, [_vp]),
+    "s4g_db_host_codes": (_u8p, [_vp]),
+    "s4g_db_name": (C.c_char_p, [_vp, C.c_int64]),
+    "s4g_queries_create": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int, C.POINTER(_vp)]),
+    "s4g_queries_free": (None, [_vp]),
+    "s4g_prefilter": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int]),
+    "s4g_merge_candidates": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "s4g_sw_score": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int64, _vp, C.c_int, C.c_int, _vp, C.c_int]),
+    "s4g_sw_align": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int64, _vp, C.c_int]),
+    "s4g_measure_dpx_peak": (C.c_int, [_vp, C.c_int, _f64p]),
+    "s4g_last_sw_kernel_ms": (C.c_int, [_vp, _f32p]),
+}
+
+_LIB = None
+
+
+def load():
+    """Load the shared library (raises if it has not been built: no fallback)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("sift4g_b200: %s is missing -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback)" % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = lib
+    return _LIB
+
+
+class S4GError(RuntimeError):
+    pass
+
+
+def _ptr(a):
+    """host numpy array / torch tensor / int / None -> void pointer value"""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data
+    return a.data_ptr()      # torch tensor
+
+
+class Context:
+    def __init__(self, device=0):
+        self.lib = load()
+        h = _vp()
+        rc = self.lib.s4g_init(device, C.byref(h))
+        if rc != 0:
+            raise S4GError("s4g_init failed (%d): %s" % (rc, self.lib.s4g_last_error(None).decode()))
+        self.h = h
+        self.device = device
+
+    def check(self, rc):
+        if rc != 0:
+            raise S4GError("sift4g_b200 error %d: %s" % (rc, self.lib.s4g_last_error(self.h).decode()))
+
+    def set_stream(self, stream_ptr):
+        self.check(self.lib.s4g_set_stream(self.h, stream_ptr))
+
+    def sync(self):
+        self.check(self.lib.s4g_sync(self.h))
+
+    def launch_count(self):
+        return int(self.lib.s4g_launch_count(self.h))
+
+    def reset_launch_count(self):
+        self.lib.s4g_launch_count_reset(self.h)
+
+    def dpx_peak(self, millis=50):
+        v = C.c_double(0)
+        self.check(self.lib.s4g_measure_dpx_peak(self.h, millis, C.byref(v)))
+        return v.value
+
+    def last_sw_kernel_ms(self):
+        v = C.c_float(0)
+        self.check(self.lib.s4g_last_sw_kernel_ms(self.h, C.byref(v)))
+        return v.value
+
+    def close(self):
+        if self.h:
+            self.lib.s4g_shutdown(self.h)
+            self.h = None
+
+    # ---- objects -----------------------------------------------------------------------------
+    def database(self, codes, offsets, id_base=0, where=S4G_HOST):
+        return Database(self, codes, offsets, id_base, where)
+
+    def database_from_fasta(self, path, shard=0, n_shards=1):
+        db = Database.__new__(Database)
+        db.ctx = self
+        h = _vp()
+        self.check(self.lib.s4g_db_open_fasta(self.h, path.encode(), shard, n_shards, C.byref(h)))
+        db.h = h
+        return db
+
+    def queries(self, codes, offsets, where=S4G_HOST):
+        return Queries(self, codes, offsets, where)
+
+
+class Database:
+    def __init__(self, ctx, codes, offsets, id_base=0, where=S4G_HOST):
+        self.ctx = ctx
+        if where == S4G_HOST:
+            codes = np.ascontiguousarray(codes, dtype=np.uint8)
+            offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = (len(offsets) if where == S4G_HOST else offsets.numel()) - 1
+        h = _vp()
+        ctx.check(ctx.lib.s4g_db_create(ctx.h, _ptr(codes), _ptr(offsets), n, id_base, where, C.byref(h)))
+        self.h = h
+
+    @property
+    def n_seqs(self):
+        return int(self.ctx.lib.s4g_db_num_seqs(self.h))
+
+    @property
+    def n_residues(self):
+        return int(self.ctx.lib.s4g_db_num_residues(self.h))
+
+    @property
+    def id_base(self):
+        return int(self.ctx.lib.s4g_db_id_base(self.h))
+
+    def host_offsets(self):
+        p = self.ctx.lib.s4g_db_host_offsets(self.h)
+        return np.ctypeslib.as_array(p, shape=(self.n_seqs + 1,)).copy()
+
+    def host_codes(self):
+        p = self.ctx.lib.s4g_db_host_codes(self.h)
+        if not p:
+            return None
+        return np.ctypeslib.as_array(p, shape=(self.n_residues,)).copy()
+
+    def name(self, i):
+        s = self.ctx.lib.s4g_db_name(self.h, i)
+        return s.decode() if s is not None else None
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.s4g_db_close(self.h)
+            self.h = None
+
+
+class Queries:
+    def __init__(self, ctx, codes, offsets, where=S4G_HOST):
+        self.ctx = ctx
+        if where == S4G_HOST:
+            codes = np.ascontiguousarray(codes, dtype=np.uint8)
+            offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        self.n = (len(offsets) if where == S4G_HOST else offsets.numel()) - 1
+        h = _vp()
+        ctx.check(ctx.lib.s4g_queries_create(ctx.h, _ptr(codes), _ptr(offsets), self.n, where, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.s4g_queries_free(self.h)
+            self.h = None
+
+
+# ---- stage calls (host numpy in / out: the e2e path; device tensors: pass where=S4G_DEVICE) ----------
+
+def prefilter(ctx, db, q, k=5, max_candidates=5000, sorted_by_id=True, out=None, where=S4G_HOST):
+    """-> (ids [nq, max_candidates] uint32, scores float32, counts uint32)"""
+    if out is None:
+        ids = np.zeros((q.n, max_candidates), dtype=np.uint32)
+        sc = np.zeros((q.n, max_candidates), dtype=np.float32)
+        cnt = np.zeros(q.n, dtype=np.uint32)
+    else:
+        ids, sc, cnt = out
+    ctx.check(ctx.lib.s4g_prefilter(ctx.h, db.h, q.h, k, max_candidates, 1 if sorted_by_id else 0, _ptr(ids), _ptr(sc), _ptr(cnt), where))
+    return ids, sc, cnt
+
+
+def sw_score(ctx, db, q, cand_ids, cand_offsets, matrix, gap_open=10, gap_extend=1, out=None, where=S4G_HOST):
+    matrix = np.ascontiguousarray(matrix, dtype=np.int32)
+    if where == S4G_HOST:
+        cand_ids = np.ascontiguousarray(cand_ids, dtype=np.uint32)
+        cand_offsets = np.ascontiguousarray(cand_offsets, dtype=np.int64)
+        n = len(cand_ids)
+        if out is None:
+            out = np.zeros(n, dtype=np.int32)
+    else:
+        n = cand_ids.numel()
+    ctx.check(ctx.lib.s4g_sw_score(ctx.h, db.h, q.h, _ptr(cand_ids), _ptr(cand_offsets), n, _ptr(matrix), gap_open, gap_extend, _ptr(out), where))
+    return out
+
+
+def sw_align(ctx, db, q, pair_q, pair_t, pair_score, matrix, gap_open=10, gap_extend=1, path_capacity=None, q_lens=None, t_lens=None):
+    """host path: -> (coords [n,4] int32, list of path arrays)"""
+    matrix = np.ascontiguousarray(matrix, dtype=np.int32)
+    pair_q = np.ascontiguousarray(pair_q, dtype=np.uint32)
+    pair_t = np.ascontiguousarray(pair_t, dtype=np.uint32)
+    pair_score = np.ascontiguousarray(pair_score, dtype=np.int32)
+    n = len(pair_q)
+    if path_capacity is None:
+        path_capacity = int(np.sum(q_lens[pair_q]) + np.sum(t_lens[pair_t - db.id_base])) + 16
+    coords = np.zeros((n, 4), dtype=np.int32)
+    paths = np.zeros(path_capacity, dtype=np.uint8)
+    off = np.zeros(n + 1, dtype=np.int64)
+    ctx.check(ctx.lib.s4g_sw_align(ctx.h, db.h, q.h, n, _ptr(pair_q), _ptr(pair_t), _ptr(pair_score), _ptr(matrix), gap_open, gap_extend,
+                                   _ptr(coords), _ptr(paths), path_capacity, _ptr(off), S4G_HOST))
+    return coords, [paths[off[i]:off[i + 1]].copy() for i in range(n)]

@@ -1,0 +1,351 @@
+// C ABI entry points: context, database shard, query batch, host<->device marshalling.
+// The stage kernels live in sw_score.cu / prefilter.cu / align.cu.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cctype>
+
+#include "common.cuh"
+
+static thread_local std::string g_tls_error;
+
+void s4g_set_error(s4g_ctx* ctx, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_tls_error = buf;
+    if (ctx) ctx->err = buf;
+}
+
+void* s4g_scratch(s4g_ctx* ctx, int slot, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    if (ctx->slot_bytes[slot] >= bytes) return ctx->slot_ptr[slot];
+    if (ctx->slot_ptr[slot]) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(ctx->slot_ptr[slot]);
+        ctx->slot_ptr[slot] = nullptr;
+        ctx->slot_bytes[slot] = 0;
+    }
+    size_t want = bytes + bytes / 4 + 256;   // grow with slack so repeated calls settle
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        s4g_set_error(ctx, "cudaMalloc(%zu bytes, scratch slot %d): %s", want, slot, cudaGetErrorString(e));
+        return nullptr;
+    }
+    ctx->slot_ptr[slot] = p;
+    ctx->slot_bytes[slot] = want;
+    return p;
+}
+
+void* s4g_pinned(s4g_ctx* ctx, int slot, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    if (ctx->pin_bytes[slot] >= bytes) return ctx->pin_ptr[slot];
+    if (ctx->pin_ptr[slot]) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFreeHost(ctx->pin_ptr[slot]);
+        ctx->pin_ptr[slot] = nullptr;
+        ctx->pin_bytes[slot] = 0;
+    }
+    size_t want = bytes + bytes / 4 + 256;
+    void* p = nullptr;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e != cudaSuccess) {
+        s4g_set_error(ctx, "cudaMallocHost(%zu bytes): %s", want, cudaGetErrorString(e));
+        return nullptr;
+    }
+    ctx->pin_ptr[slot] = p;
+    ctx->pin_bytes[slot] = want;
+    return p;
+}
+
+extern "C" {
+
+int s4g_version(void) { return 100; }
+
+const char* s4g_last_error(const s4g_ctx* ctx) { return ctx ? ctx->err.c_str() : g_tls_error.c_str(); }
+
+int s4g_init(int device, s4g_ctx** out) {
+    if (!out) return S4G_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        s4g_set_error(nullptr, "no CUDA device available (%s); sift4g_b200 has no CPU fallback",
+                      e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return S4G_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) { s4g_set_error(nullptr, "device %d out of range (0..%d)", device, n - 1); return S4G_ERR_ARG; }
+    s4g_ctx* ctx = new s4g_ctx();
+    ctx->device = device;
+    S4G_CUDA(ctx, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    S4G_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        s4g_set_error(nullptr, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        delete ctx;
+        return S4G_ERR_CUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    S4G_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    S4G_CUDA(ctx, cudaEventCreate(&ctx->ev_sw0));
+    S4G_CUDA(ctx, cudaEventCreate(&ctx->ev_sw1));
+    *out = ctx;
+    return S4G_OK;
+}
+
+void s4g_shutdown(s4g_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < s4g_ctx::kSlots; ++i) if (ctx->slot_ptr[i]) cudaFree(ctx->slot_ptr[i]);
+    for (int i = 0; i < 8; ++i) if (ctx->pin_ptr[i]) cudaFreeHost(ctx->pin_ptr[i]);
+    if (ctx->ev_sw0) cudaEventDestroy(ctx->ev_sw0);
+    if (ctx->ev_sw1) cudaEventDestroy(ctx->ev_sw1);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int s4g_set_stream(s4g_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return S4G_ERR_ARG;
+    S4G_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
+    return S4G_OK;
+}
+
+int s4g_sync(s4g_ctx* ctx) {
+    if (!ctx) return S4G_ERR_ARG;
+    S4G_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return S4G_OK;
+}
+
+int64_t s4g_launch_count(const s4g_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void s4g_launch_count_reset(s4g_ctx* ctx) { if (ctx) ctx->launches = 0; }
+
+// ---- database -------------------------------------------------------------------------------------
+
+static int db_finish(s4g_ctx* ctx, s4g_db* db, const uint8_t* codes, const int64_t* offsets, int where) {
+    const int64_t n = db->n;
+    // offsets are needed on the host in every case (metadata for the shims and for tiling)
+    db->h_off.resize(n + 1);
+    if (where == S4G_HOST) memcpy(db->h_off.data(), offsets, sizeof(int64_t) * (n + 1));
+    else S4G_CUDA(ctx, cudaMemcpy(db->h_off.data(), offsets, sizeof(int64_t) * (n + 1), cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < n; ++i) {
+        int64_t len = db->h_off[i + 1] - db->h_off[i];
+        if (len <= 0 || len > 0x7fffff00) { s4g_set_error(ctx, "sequence %lld has invalid length %lld", (long long)i, (long long)len); return S4G_ERR_ARG; }
+        if (len > db->max_len) db->max_len = (int32_t)len;
+    }
+    if (n > 0 && db->h_off[0] != 0) { s4g_set_error(ctx, "offsets[0] must be 0"); return S4G_ERR_ARG; }
+    db->residues = n > 0 ? (uint64_t)db->h_off[n] : 0;
+    S4G_CUDA(ctx, cudaMalloc(&db->d_codes, db->residues + S4G_DB_TAIL_PAD));
+    S4G_CUDA(ctx, cudaMalloc(&db->d_off, sizeof(int64_t) * (n + 1)));
+    cudaMemcpyKind kind = where == S4G_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    if (db->residues) S4G_CUDA(ctx, cudaMemcpyAsync(db->d_codes, codes, db->residues, kind, ctx->stream));
+    S4G_CUDA(ctx, cudaMemsetAsync(db->d_codes + db->residues, S4G_PAD_CODE, S4G_DB_TAIL_PAD, ctx->stream));
+    S4G_CUDA(ctx, cudaMemcpyAsync(db->d_off, db->h_off.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, ctx->stream));
+    S4G_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return S4G_OK;
+}
+
+int s4g_db_create(s4g_ctx* ctx, const uint8_t* codes, const int64_t* offsets, int64_t n_seqs, uint32_t id_base,
+                  int where, s4g_db** out) {
+    if (!ctx || !out || n_seqs < 0 || (n_seqs > 0 && (!codes || !offsets))) return S4G_ERR_ARG;
+    *out = nullptr;
+    S4G_CUDA(ctx, cudaSetDevice(ctx->device));
+    s4g_db* db = new s4g_db();
+    db->ctx = ctx; db->n = n_seqs; db->id_base = id_base;
+    int64_t zero = 0;
+    int rc = db_finish(ctx, db, codes, n_seqs ? offsets : &zero, n_seqs ? where : S4G_HOST);
+    if (rc != S4G_OK) { s4g_db_close(db); return rc; }
+    if (where == S4G_HOST && db->residues) db->h_codes.assign(codes, codes + db->residues);
+    *out = db;
+    return S4G_OK;
+}
+
+// FASTA reader with the observable behaviour of sw/pre_proc.c:437-538 + sw/chain.c:59-105:
+//  * a record ends at the next '>' that follows a sequence line, or at the LAST BYTE of the file
+//    (that byte is consumed as a terminator, so a file without trailing newline loses it);
+//  * name = header line without leading '>'/whitespace, without '\r', without trailing whitespace;
+//  * residues: letters only, case folded to 0..25; everything else is dropped;
+//  * a record that encodes to zero residues is an error (the reference aborts).
+int s4g_db_open_fasta(s4g_ctx* ctx, const char* path, int shard, int n_shards, s4g_db** out) {
+    if (!ctx || !path || !out || n_shards < 1 || shard < 0 || shard >= n_shards) return S4G_ERR_ARG;
+    *out = nullptr;
+    FILE* f = fopen(path, "rb");
+    if (!f) { s4g_set_error(ctx, "cannot open '%s'", path); return S4G_ERR_IO; }
+    std::vector<uint8_t> codes;
+    std::vector<int64_t> off(1, 0);
+    std::vector<std::string> names;
+    std::string name;
+    bool in_name = true;
+    int64_t cur_len = 0;
+    std::vector<char> buf(1 << 20);
+    // total size to detect the final byte
+    fseek(f, 0, SEEK_END);
+    long long total = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    long long pos = 0;
+    int rc = S4G_OK;
+    auto close_record = [&]() -> bool {
+        while (!name.empty() && isspace((unsigned char)name.back())) name.pop_back();
+        if (name.empty() || cur_len == 0) return false;
+        names.push_back(name);
+        off.push_back((int64_t)codes.size());
+        name.clear();
+        cur_len = 0;
+        return true;
+    };
+    while (rc == S4G_OK) {
+        size_t got = fread(buf.data(), 1, buf.size(), f);
+        if (got == 0) break;
+        for (size_t i = 0; i < got && rc == S4G_OK; ++i, ++pos) {
+            char c = buf[i];
+            // the reference only sees "end of file" on a short fread (1 MiB buffer): a file whose size is an
+            // exact multiple of 1 MiB never closes its last record (sw/pre_proc.c:465-488)
+            bool last_byte = (pos == total - 1) && (total % (1 << 20) != 0);
+            if (!in_name && (c == '>' || last_byte)) {
+                if (!close_record()) { s4g_set_error(ctx, "'%s': empty record near byte %lld", path, pos); rc = S4G_ERR_IO; break; }
+                in_name = true;
+            }
+            if (in_name) {
+                if (c == '\n') in_name = false;
+                else if (!(name.empty() && (c == '>' || isspace((unsigned char)c))) && c != '\r') name.push_back(c);
+            } else {
+                unsigned char u = (unsigned char)c;
+                if (u >= 'A' && u <= 'Z') { codes.push_back((uint8_t)(u - 'A')); ++cur_len; }
+                else if (u >= 'a' && u <= 'z') { codes.push_back((uint8_t)(u - 'a')); ++cur_len; }
+            }
+        }
+    }
+    fclose(f);
+    if (rc != S4G_OK) return rc;
+    int64_t n_all = (int64_t)names.size();
+    int64_t lo = n_all * shard / n_shards, hi = n_all * (shard + 1) / n_shards;
+    std::vector<int64_t> soff(hi - lo + 1);
+    for (int64_t i = lo; i <= hi; ++i) soff[i - lo] = off[i] - off[lo];
+    rc = s4g_db_create(ctx, codes.data() + off[lo], soff.data(), hi - lo, (uint32_t)lo, S4G_HOST, out);
+    if (rc == S4G_OK) (*out)->names.assign(names.begin() + lo, names.begin() + hi);
+    return rc;
+}
+
+void s4g_db_close(s4g_db* db) {
+    if (!db) return;
+    cudaSetDevice(db->ctx->device);
+    cudaStreamSynchronize(db->ctx->stream);
+    if (db->d_codes) cudaFree(db->d_codes);
+    if (db->d_off) cudaFree(db->d_off);
+    delete db;
+}
+
+int64_t s4g_db_num_seqs(const s4g_db* db) { return db ? db->n : 0; }
+uint64_t s4g_db_num_residues(const s4g_db* db) { return db ? db->residues : 0; }
+uint32_t s4g_db_id_base(const s4g_db* db) { return db ? db->id_base : 0; }
+const int64_t* s4g_db_host_offsets(const s4g_db* db) { return db ? db->h_off.data() : nullptr; }
+const uint8_t* s4g_db_host_codes(const s4g_db* db) { return (db && !db->h_codes.empty()) ? db->h_codes.data() : nullptr; }
+const char* s4g_db_name(const s4g_db* db, int64_t i) {
+    if (!db || i < 0 || i >= (int64_t)db->names.size()) return nullptr;
+    return db->names[i].c_str();
+}
+
+// ---- queries ---------------------------------------------------------------------------------------
+
+int s4g_queries_create(s4g_ctx* ctx, const uint8_t* codes, const int64_t* offsets, int32_t nq, int where,
+                       s4g_queries** out) {
+    if (!ctx || !out || nq <= 0 || !codes || !offsets) return S4G_ERR_ARG;
+    *out = nullptr;
+    S4G_CUDA(ctx, cudaSetDevice(ctx->device));
+    s4g_queries* q = new s4g_queries();
+    q->ctx = ctx; q->n = nq;
+    q->h_off.resize(nq + 1);
+    if (where == S4G_HOST) memcpy(q->h_off.data(), offsets, sizeof(int64_t) * (nq + 1));
+    else cudaMemcpy(q->h_off.data(), offsets, sizeof(int64_t) * (nq + 1), cudaMemcpyDeviceToHost);
+    for (int32_t i = 0; i < nq; ++i) {
+        int64_t len = q->h_off[i + 1] - q->h_off[i];
+        if (len <= 0 || len > (1 << 24)) { s4g_set_error(ctx, "query %d has invalid length %lld", i, (long long)len); delete q; return S4G_ERR_ARG; }
+        if (len > q->max_len) q->max_len = (int32_t)len;
+    }
+    int64_t total = q->h_off[nq];
+    q->h_codes.resize(total);
+    if (where == S4G_HOST) memcpy(q->h_codes.data(), codes, total);
+    else cudaMemcpy(q->h_codes.data(), codes, total, cudaMemcpyDeviceToHost);
+    for (int64_t i = 0; i < total; ++i) if (q->h_codes[i] >= S4G_NLET) { s4g_set_error(ctx, "query code %d out of range", q->h_codes[i]); delete q; return S4G_ERR_ARG; }
+    if (cudaMalloc(&q->d_codes, total + S4G_DB_TAIL_PAD) != cudaSuccess || cudaMalloc(&q->d_off, sizeof(int64_t) * (nq + 1)) != cudaSuccess) {
+        s4g_set_error(ctx, "cudaMalloc failed for the query batch");
+        s4g_queries_free(q);
+        return S4G_ERR_NOMEM;
+    }
+    cudaMemcpyAsync(q->d_codes, q->h_codes.data(), total, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemsetAsync(q->d_codes + total, S4G_PAD_CODE, S4G_DB_TAIL_PAD, ctx->stream);
+    cudaMemcpyAsync(q->d_off, q->h_off.data(), sizeof(int64_t) * (nq + 1), cudaMemcpyHostToDevice, ctx->stream);
+    S4G_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = q;
+    return S4G_OK;
+}
+
+void s4g_queries_free(s4g_queries* q) {
+    if (!q) return;
+    cudaSetDevice(q->ctx->device);
+    cudaStreamSynchronize(q->ctx->stream);
+    if (q->d_codes) cudaFree(q->d_codes);
+    if (q->d_off) cudaFree(q->d_off);
+    delete q;
+}
+
+// ---- stage wrappers: host <-> device marshalling -----------------------------------------------------
+
+int s4g_sw_score(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, const uint32_t* cand_ids, const int64_t* cand_offsets,
+                 int64_t n_pairs, const int32_t* matrix, int gap_open, int gap_extend, int32_t* out_scores, int where) {
+    if (!ctx || !db || !q || !cand_offsets || !matrix || n_pairs < 0 || (n_pairs > 0 && (!cand_ids || !out_scores))) return S4G_ERR_ARG;
+    if (gap_open < 0 || gap_extend < 0 || gap_open > 4096 || gap_extend > 4096) { s4g_set_error(ctx, "gap penalties out of range"); return S4G_ERR_ARG; }
+    S4G_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n_pairs == 0) return S4G_OK;
+    if (where == S4G_DEVICE)
+        return s4g_sw_score_device(ctx, db, q, cand_ids, cand_offsets, n_pairs, matrix, gap_open, gap_extend, out_scores);
+    uint32_t* d_ids = (uint32_t*)s4g_scratch(ctx, SLOT_IO_A, sizeof(uint32_t) * n_pairs);
+    int64_t* d_off = (int64_t*)s4g_scratch(ctx, SLOT_IO_B, sizeof(int64_t) * (q->n + 1));
+    int32_t* d_out = (int32_t*)s4g_scratch(ctx, SLOT_IO_C, sizeof(int32_t) * n_pairs);
+    if (!d_ids || !d_off || !d_out) return S4G_ERR_NOMEM;
+    S4G_CUDA(ctx, cudaMemcpyAsync(d_ids, cand_ids, sizeof(uint32_t) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
+    S4G_CUDA(ctx, cudaMemcpyAsync(d_off, cand_offsets, sizeof(int64_t) * (q->n + 1), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = s4g_sw_score_device(ctx, db, q, d_ids, d_off, n_pairs, matrix, gap_open, gap_extend, d_out);
+    if (rc != S4G_OK) return rc;
+    S4G_CUDA(ctx, cudaMemcpyAsync(out_scores, d_out, sizeof(int32_t) * n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+    S4G_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return S4G_OK;
+}
+
+int s4g_prefilter(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int max_candidates, int sorted_by_id,
+                  uint32_t* out_ids, float* out_scores, uint32_t* out_counts, int where) {
+    if (!ctx || !db || !q || !out_ids || !out_counts) return S4G_ERR_ARG;
+    if (k < 3 || k > 5) { s4g_set_error(ctx, "kmer_length possible values = 3,4,5"); return S4G_ERR_ARG; }
+    if (max_candidates <= 0) { s4g_set_error(ctx, "invalid max candidates number"); return S4G_ERR_ARG; }
+    S4G_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (where == S4G_DEVICE)
+        return s4g_prefilter_device(ctx, db, q, k, max_candidates, sorted_by_id, out_ids, out_scores, out_counts);
+    size_t cells = (size_t)q->n * (size_t)max_candidates;
+    uint32_t* d_ids = (uint32_t*)s4g_scratch(ctx, SLOT_IO_A, sizeof(uint32_t) * cells);
+    float* d_sc = (float*)s4g_scratch(ctx, SLOT_IO_B, sizeof(float) * cells);
+    uint32_t* d_cnt = (uint32_t*)s4g_scratch(ctx, SLOT_IO_C, sizeof(uint32_t) * q->n);
+    if (!d_ids || !d_sc || !d_cnt) return S4G_ERR_NOMEM;
+    int rc = s4g_prefilter_device(ctx, db, q, k, max_candidates, sorted_by_id, d_ids, d_sc, d_cnt);
+    if (rc != S4G_OK) return rc;
+    S4G_CUDA(ctx, cudaMemcpyAsync(out_ids, d_ids, sizeof(uint32_t) * cells, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_scores) S4G_CUDA(ctx, cudaMemcpyAsync(out_scores, d_sc, sizeof(float) * cells, cudaMemcpyDeviceToHost, ctx->stream));
+    S4G_CUDA(ctx, cudaMemcpyAsync(out_counts, d_cnt, sizeof(uint32_t) * q->n, cudaMemcpyDeviceToHost, ctx->stream));
+    S4G_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return S4G_OK;
+}
+
+int s4g_last_sw_kernel_ms(s4g_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return S4G_ERR_ARG;
+    if (!ctx->sw_timed) { s4g_set_error(ctx, "no s4g_sw_score call has been timed yet"); return S4G_ERR_ARG; }
+    S4G_CUDA(ctx, cudaEventSynchronize(ctx->ev_sw1));
+    S4G_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev_sw0, ctx->ev_sw1));
+    return S4G_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,101 @@
+// Shared declarations of the sift4g_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/sift4g_b200.h"
+
+#define S4G_NLET 26          // reference alphabet: 'A'..'Z' (sw/scorer.c:45-72)
+#define S4G_PAD_CODE 26      // extra profile row used beyond sequence ends
+#define S4G_DB_TAIL_PAD 256  // readable slack after the last residue (vector loads never fault)
+
+struct s4g_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    std::string err;
+    int64_t launches = 0;
+    cudaEvent_t ev_sw0 = nullptr, ev_sw1 = nullptr;
+    bool sw_timed = false;
+    // grow-only scratch arena, one buffer per slot (device memory)
+    static const int kSlots = 32;
+    void* slot_ptr[kSlots] = {nullptr};
+    size_t slot_bytes[kSlots] = {0};
+    // pinned host staging, grow-only
+    void* pin_ptr[8] = {nullptr};
+    size_t pin_bytes[8] = {0};
+};
+
+struct s4g_db {
+    s4g_ctx* ctx = nullptr;
+    uint8_t* d_codes = nullptr;     // concatenated codes, FASTA order, + S4G_DB_TAIL_PAD
+    int64_t* d_off = nullptr;       // n+1
+    int64_t n = 0;
+    uint64_t residues = 0;
+    uint32_t id_base = 0;
+    int32_t max_len = 0;
+    std::vector<int64_t> h_off;     // always kept (metadata for the host shims)
+    std::vector<uint8_t> h_codes;   // kept when created from host memory
+    std::vector<std::string> names; // kept when opened from FASTA
+};
+
+struct s4g_queries {
+    s4g_ctx* ctx = nullptr;
+    uint8_t* d_codes = nullptr;
+    int64_t* d_off = nullptr;
+    int32_t n = 0;
+    int32_t max_len = 0;
+    std::vector<int64_t> h_off;
+    std::vector<uint8_t> h_codes;
+};
+
+// ---- error plumbing ---------------------------------------------------------------------------
+void s4g_set_error(s4g_ctx* ctx, const char* fmt, ...);
+
+#define S4G_CUDA(ctx, call)                                                                   \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            s4g_set_error((ctx), "%s:%d: %s -> %s", __FILE__, __LINE__, #call,                \
+                          cudaGetErrorString(e_));                                            \
+            return S4G_ERR_CUDA;                                                              \
+        }                                                                                     \
+    } while (0)
+
+#define S4G_CHECK_LAUNCH(ctx)                                                                 \
+    do {                                                                                      \
+        (ctx)->launches++;                                                                    \
+        S4G_CUDA((ctx), cudaGetLastError());                                                  \
+    } while (0)
+
+// grow-only device scratch; returns nullptr (and sets the error) on failure
+void* s4g_scratch(s4g_ctx* ctx, int slot, size_t bytes);
+void* s4g_pinned(s4g_ctx* ctx, int slot, size_t bytes);
+
+// scratch slot ids
+enum {
+    SLOT_IO_A = 0, SLOT_IO_B, SLOT_IO_C, SLOT_IO_D, SLOT_IO_E, SLOT_IO_F,
+    SLOT_SW_KEYS, SLOT_SW_KEYS2, SLOT_SW_VALS, SLOT_SW_VALS2, SLOT_SW_CUB, SLOT_SW_TILES,
+    SLOT_SW_MISC, SLOT_SW_OVF, SLOT_SW_BOUND, SLOT_SW_MAT,
+    SLOT_PF_INDEX, SLOT_PF_BITMAP, SLOT_PF_RANK, SLOT_PF_BUCKET, SLOT_PF_HITS, SLOT_PF_CAND,
+    SLOT_PF_COUNT, SLOT_PF_THR, SLOT_PF_CUB, SLOT_PF_TMP, SLOT_PF_TMP2, SLOT_PF_SPILL,
+    SLOT_AL_WORK, SLOT_AL_DIR, SLOT_AL_MISC, SLOT_AL_OUT
+};
+
+// ---- stage launchers (device pointers, enqueue on ctx->stream) ----------------------------------
+int s4g_sw_score_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, const uint32_t* d_cand_ids,
+                        const int64_t* d_cand_off, int64_t n_pairs, const int32_t* h_matrix, int gap_open,
+                        int gap_extend, int32_t* d_out);
+
+int s4g_prefilter_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int max_candidates,
+                         int sorted_by_id, uint32_t* d_ids, float* d_scores, uint32_t* d_counts);
+
+int s4g_sw_align_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_pairs, const uint32_t* d_pair_q,
+                        const uint32_t* d_pair_t, const int32_t* d_pair_score, const int32_t* h_matrix,
+                        int gap_open, int gap_extend, int32_t* d_coords, uint8_t* d_paths, int64_t path_capacity,
+                        int64_t* d_path_off, const int64_t* h_path_off);

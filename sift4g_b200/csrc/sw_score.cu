@@ -1,0 +1,491 @@
+// Stage 2: Smith-Waterman affine-gap SCORES of every query against its candidates (sm_100a).
+//
+// Replaces the swimd scorer behind scoreDatabaseCpu (vendor/swsharp/swsharp/src/cpu_module.c:179-192,
+// swimd/Swimd.cpp:139-449) and the legacy CUDA scorers behind scoreDatabasesGpu
+// (src/gpu_module.h:280-291).  Result = exact integer max over all cells of
+//   E[i][j] = max(E[i][j-1] - R, H[i][j-1] - Q)
+//   F[i][j] = max(F[i-1][j] - R, H[i-1][j] - Q)
+//   H[i][j] = max(0, H[i-1][j-1] + S[q_i][t_j], E[i][j], F[i][j])        (Q = gap open, R = gap extend)
+//
+// Kernel design (inter-sequence, one warp per PAIR of candidates of the same query):
+//   * the two targets of a pair ride in the two 16-bit halves of every register (s16x2), and all
+//     recurrences are Blackwell DPX instructions: VIADDMNMX.S16x2(.RELU), VIMNMX.S16x2, VIMNMX3.S16x2,
+//     plus VIADD.16x2 for H-Q (which issues on a different pipe than the DPX/ALU ops -- measured,
+//     tools/dpx_microbench.cu);
+//   * query rows are striped over the 32 lanes, K consecutive rows per lane held in registers
+//     (H and E, 2*K registers); lane L works on target column (step - L), so the anti-diagonal
+//     dependency is carried by two warp shuffles per step (H and F of the lane's last row);
+//   * the query profile (int8, [27 letters][K/4 words][32 lanes]) sits in shared memory in a layout that
+//     makes every lane's load bank-conflict free whatever letter each lane is looking at; one PRMT with
+//     sign replication builds the packed s16x2 substitution word for both targets;
+//   * target residues are staged per warp through a small shared-memory ring as pre-multiplied profile
+//     row offsets (2 x LDS.U16 per step, zero ALU work);
+//   * pairs whose 16-bit score could have wrapped (best > 32767 - max(S)) and queries longer than
+//     32*32 rows are re-run by the 32-bit multi-pass kernel (exact, any length).
+//
+// Work decomposition: candidates of each query are sorted by length (device radix sort) and paired
+// neighbour-wise; a persistent grid of CTAs pulls (query, block of pairs) tiles from an atomic counter,
+// builds the query profile once per tile and lets its warps pull pairs from the tile.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kWarps = 8;                 // warps per CTA
+constexpr int kTilePairs = 64;            // pairs per (query, tile)
+constexpr int kRing = 64;                 // ring refill granularity (columns), >= 32
+constexpr int kMaxK = 32;                 // rows per lane in the packed kernel -> queries up to 1024
+constexpr int kGenK = 8;                  // rows per lane in the 32-bit kernel (256 rows per pass)
+
+__device__ __forceinline__ unsigned prmt(unsigned a, unsigned b, unsigned sel) {
+    unsigned d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+struct ScoreParams {
+    const uint8_t* db_codes;
+    const int64_t* db_off;
+    uint32_t id_base;
+    const uint8_t* q_codes;
+    const int64_t* q_off;
+    int32_t nq;
+    const uint32_t* cand_ids;       // original order
+    const int64_t* cand_off;        // nq+1
+    const uint32_t* sorted_idx;     // positions into cand_ids, grouped by query, longest target first
+    const int64_t* tile_start;      // nq+1: exclusive scan of packed-kernel tiles per query
+    const int8_t* mat8;             // 27 x 32 int8 (row = target letter incl. pad, col = query letter)
+    int32_t* out;                   // scores, original order
+    unsigned long long* counters;   // [0] tile counter, [1] overflow count, [2] generic work counter
+    uint32_t* overflow;             // list of cand positions to re-run in 32 bit
+    int32_t* bound;                 // generic kernel: per-warp boundary rows
+    int64_t bound_stride;           // ints per warp
+    int32_t gap_open, gap_extend;
+    int32_t ovf_limit;              // 32767 - max(matrix)
+};
+
+// ------------------------------------------------------------------------------------------------------
+// packed s16x2 kernel body for one pair, K rows per lane
+
+template <int K>
+__device__ __forceinline__ unsigned score_pair_packed(const unsigned* __restrict__ prof_lane,   // smem, + lane
+                                                      unsigned short* ring1, unsigned short* ring2,
+                                                      const uint8_t* __restrict__ t1, int len1,
+                                                      const uint8_t* __restrict__ t2, int len2,
+                                                      unsigned negQ, unsigned negR, int lane) {
+    constexpr int KW = (K + 3) / 4;
+    constexpr unsigned kRowBytes = KW * 128;             // bytes per profile letter row
+    constexpr unsigned kPadOff = S4G_PAD_CODE * kRowBytes;
+    constexpr int kRingMask = 2 * kRing - 1;
+    const unsigned FULL = 0xffffffffu;
+
+    unsigned H[K], E[K];
+#pragma unroll
+    for (int r = 0; r < K; ++r) { H[r] = 0; E[r] = 0; }
+    unsigned best = 0, h_last = 0, f_out = 0, diag_in = 0;
+
+    const int maxlen = len1 > len2 ? len1 : len2;
+    const int nsteps = maxlen + 31;
+
+    // columns -kRing..-1 read as padding
+    for (int c = lane; c < kRing; c += 32) { ring1[kRing + c] = kPadOff; ring2[kRing + c] = kPadOff; }
+
+    const char* prof_bytes = reinterpret_cast<const char*>(prof_lane);
+
+    for (int s0 = 0; s0 < nsteps; s0 += kRing) {
+        // refill: columns s0 .. s0+kRing-1 into ring slot (s0/kRing)&1
+        {
+            const int base = s0 & kRingMask;
+#pragma unroll
+            for (int c = 0; c < kRing; c += 32) {
+                int j = s0 + c + lane;
+                unsigned o1 = j < len1 ? (unsigned)t1[j] * kRowBytes : kPadOff;
+                unsigned o2 = j < len2 ? (unsigned)t2[j] * kRowBytes : kPadOff;
+                ring1[base + c + lane] = (unsigned short)o1;
+                ring2[base + c + lane] = (unsigned short)o2;
+            }
+        }
+        __syncwarp();
+        const int send = (nsteps - s0) < kRing ? (nsteps - s0) : kRing;
+#pragma unroll 1
+        for (int ss = 0; ss < send; ++ss) {
+            const int j = (s0 + ss - lane) & kRingMask;
+            const unsigned o1 = ring1[j];
+            const unsigned o2 = ring2[j];
+            unsigned w1[KW], w2[KW];
+#pragma unroll
+            for (int m = 0; m < KW; ++m) {
+                w1[m] = *reinterpret_cast<const unsigned*>(prof_bytes + o1 + m * 128);
+                w2[m] = *reinterpret_cast<const unsigned*>(prof_bytes + o2 + m * 128);
+            }
+            unsigned h_up = __shfl_up_sync(FULL, h_last, 1);
+            unsigned f = __shfl_up_sync(FULL, f_out, 1);
+            if (lane == 0) { h_up = 0; f = 0; }
+            unsigned hd = diag_in;
+            diag_in = h_up;
+#pragma unroll
+            for (int r = 0; r < K; ++r) {
+                const unsigned sel = (r & 3) == 0 ? 0xC480u : (r & 3) == 1 ? 0xD591u : (r & 3) == 2 ? 0xE6A2u : 0xF7B3u;
+                const unsigned sc = prmt(w1[r >> 2], w2[r >> 2], sel);
+                const unsigned m = __viaddmax_s16x2_relu(hd, sc, E[r]);   // max(Hdiag + S, E, 0)
+                const unsigned h = __vmaxs2(m, f);                         // H
+                hd = H[r];
+                H[r] = h;
+                const unsigned hq = __vadd2(h, negQ);                      // H - Q
+                E[r] = __viaddmax_s16x2(E[r], negR, hq);                   // E of the next column
+                f = __viaddmax_s16x2(f, negR, hq);                         // F of the next row
+                if (r & 1) best = __vimax3_s16x2(best, H[r - 1], h);
+                else if (r == K - 1) best = __vmaxs2(best, h);
+            }
+            h_last = H[K - 1];
+            f_out = f;
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = __vmaxs2(best, __shfl_xor_sync(FULL, best, o));
+    return best;
+}
+
+// Build the int8 profile of one query into shared memory: prof[letter][m][lane] words, byte b of word
+// (m, lane) = S[q[lane*K + 4m + b]][letter]; rows beyond the query read 0; pad letter row reads mat8 row 26.
+template <int K>
+__device__ void build_profile(unsigned* prof, const int8_t* smat, const uint8_t* q, int qlen) {
+    constexpr int KW = (K + 3) / 4;
+    for (int w = threadIdx.x; w < (S4G_PAD_CODE + 1) * KW * 32; w += blockDim.x) {
+        const int lane = w & 31, m = (w >> 5) % KW, letter = w / (KW * 32);
+        unsigned word = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int rr = 4 * m + b;
+            const int row = lane * K + rr;
+            int v = 0;
+            if (rr < K && row < qlen) v = smat[letter * 32 + q[row]];
+            word |= (unsigned)(v & 0xff) << (8 * b);
+        }
+        prof[w] = word;
+    }
+}
+
+template <int K>
+__device__ void run_tile(const ScoreParams& P, unsigned* prof, const int8_t* smat, unsigned short* rings,
+                         int* s_next, int q, int pair_begin, int pair_end) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t qo = P.q_off[q];
+    const int qlen = (int)(P.q_off[q + 1] - qo);
+    build_profile<K>(prof, smat, P.q_codes + qo, qlen);
+    if (threadIdx.x == 0) *s_next = pair_begin;
+    __syncthreads();
+    const int64_t cbeg = P.cand_off[q], cend = P.cand_off[q + 1];
+    unsigned short* ring1 = rings + warp * (4 * kRing);
+    unsigned short* ring2 = ring1 + 2 * kRing;
+    const unsigned negQ = ((unsigned)(-P.gap_open) & 0xffffu) * 0x10001u;
+    const unsigned negR = ((unsigned)(-P.gap_extend) & 0xffffu) * 0x10001u;
+    while (true) {
+        int p = 0;
+        if (lane == 0) p = atomicAdd(s_next, 1);
+        p = __shfl_sync(0xffffffffu, p, 0);
+        if (p >= pair_end) break;
+        const int64_t i1 = cbeg + 2 * (int64_t)p, i2 = i1 + 1;
+        const uint32_t c1 = P.sorted_idx[i1];
+        const bool has2 = i2 < cend;
+        const uint32_t c2 = has2 ? P.sorted_idx[i2] : c1;
+        const int64_t a1 = P.db_off[P.cand_ids[c1] - P.id_base], b1 = P.db_off[P.cand_ids[c1] - P.id_base + 1];
+        const int64_t a2 = P.db_off[P.cand_ids[c2] - P.id_base], b2 = P.db_off[P.cand_ids[c2] - P.id_base + 1];
+        const unsigned best = score_pair_packed<K>(prof + lane, ring1, ring2, P.db_codes + a1, (int)(b1 - a1),
+                                                   P.db_codes + a2, has2 ? (int)(b2 - a2) : 0, negQ, negR, lane);
+        if (lane == 0) {
+            const int s1 = (int)(best & 0xffffu), s2 = (int)(best >> 16);
+            if (s1 > P.ovf_limit) P.overflow[atomicAdd(&P.counters[1], 1ull)] = c1; else P.out[c1] = s1;
+            if (has2) { if (s2 > P.ovf_limit) P.overflow[atomicAdd(&P.counters[1], 1ull)] = c2; else P.out[c2] = s2; }
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kWarps * 32, 2) sw_score_packed_kernel(ScoreParams P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned* prof = reinterpret_cast<unsigned*>(smem);                                   // 27*8*32 words max
+    int8_t* smat = reinterpret_cast<int8_t*>(smem + (S4G_PAD_CODE + 1) * 8 * 32 * 4);      // 27*32
+    unsigned short* rings = reinterpret_cast<unsigned short*>(smat + (S4G_PAD_CODE + 1) * 32);
+    __shared__ int s_next;
+    __shared__ long long s_tile;
+    for (int i = threadIdx.x; i < (S4G_PAD_CODE + 1) * 32; i += blockDim.x) smat[i] = P.mat8[i];
+    const long long total = P.tile_start[P.nq];
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = (long long)atomicAdd(&P.counters[0], 1ull);
+        __syncthreads();
+        const long long tile = s_tile;
+        if (tile >= total) break;
+        // query of this tile: last q with tile_start[q] <= tile
+        int lo = 0, hi = P.nq;
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (P.tile_start[mid] <= tile) lo = mid; else hi = mid; }
+        const int q = lo;
+        const int qlen = (int)(P.q_off[q + 1] - P.q_off[q]);
+        const long long n_c = P.cand_off[q + 1] - P.cand_off[q];
+        const int n_pairs = (int)((n_c + 1) >> 1);
+        const int pb = (int)(tile - P.tile_start[q]) * kTilePairs;
+        const int pe = pb + kTilePairs < n_pairs ? pb + kTilePairs : n_pairs;
+        const int K = (qlen + 31) >> 5;
+        switch ((K + 1) >> 1) {
+            case 0: case 1: run_tile<2>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 2: run_tile<4>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 3: run_tile<6>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 4: run_tile<8>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 5: run_tile<10>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 6: run_tile<12>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 7: run_tile<14>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 8: run_tile<16>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 9: run_tile<18>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 10: run_tile<20>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 11: run_tile<22>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 12: run_tile<24>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 13: run_tile<26>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 14: run_tile<28>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 15: run_tile<30>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            default: run_tile<32>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// exact 32-bit kernel: one warp per (query, target), any query length (256-row passes, the boundary row
+// H/F travels through a per-warp global scratch that stays in L2).  Used for 16-bit overflow re-runs and
+// for queries longer than 32*kMaxK rows.
+
+struct GenericWork {
+    const uint32_t* list;         // cand positions (overflow list) or nullptr = "all candidates of long queries"
+    const unsigned long long* n_list;   // device count for `list`
+    const uint32_t* long_idx;     // for the long-query path: sorted positions
+    long long n_long;
+};
+
+__device__ __forceinline__ int find_query(const int64_t* cand_off, int nq, int64_t pos) {
+    int lo = 0, hi = nq;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (cand_off[mid] <= pos) lo = mid; else hi = mid; }
+    return lo;
+}
+
+__global__ void __launch_bounds__(kWarps * 32) sw_score_generic_kernel(ScoreParams P, GenericWork W) {
+    __shared__ int8_t smat[(S4G_PAD_CODE + 1) * 32];
+    for (int i = threadIdx.x; i < (S4G_PAD_CODE + 1) * 32; i += blockDim.x) smat[i] = P.mat8[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int gwarp = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    int32_t* bH = P.bound + (int64_t)gwarp * P.bound_stride;
+    int32_t* bF = bH + P.bound_stride / 2;
+    const unsigned FULL = 0xffffffffu;
+    const long long n_work = W.list ? (long long)*W.n_list : W.n_long;
+    const int Q = P.gap_open, R = P.gap_extend;
+    while (true) {
+        unsigned long long w = 0;
+        if (lane == 0) w = atomicAdd(&P.counters[2], 1ull);
+        w = __shfl_sync(FULL, w, 0);
+        if ((long long)w >= n_work) break;
+        const uint32_t c = W.list ? W.list[w] : W.long_idx[w];
+        const int q = find_query(P.cand_off, P.nq, (int64_t)c);
+        const uint8_t* qs = P.q_codes + P.q_off[q];
+        const int qlen = (int)(P.q_off[q + 1] - P.q_off[q]);
+        const uint32_t tid = P.cand_ids[c] - P.id_base;
+        const uint8_t* ts = P.db_codes + P.db_off[tid];
+        const int tlen = (int)(P.db_off[tid + 1] - P.db_off[tid]);
+        const int npass = (qlen + 32 * kGenK - 1) / (32 * kGenK);
+        int best = 0;
+        for (int pass = 0; pass < npass; ++pass) {
+            const int row0 = pass * 32 * kGenK + lane * kGenK;
+            int ql[kGenK];
+#pragma unroll
+            for (int r = 0; r < kGenK; ++r) ql[r] = row0 + r < qlen ? qs[row0 + r] : -1;
+            int H[kGenK], E[kGenK];
+#pragma unroll
+            for (int r = 0; r < kGenK; ++r) { H[r] = 0; E[r] = 0; }
+            int h_last = 0, f_out = 0, diag_in = 0;
+            const bool first = pass == 0, last = pass == npass - 1;
+            for (int s = 0; s < tlen + 31; ++s) {
+                const int j = s - lane;
+                int h_up = __shfl_up_sync(FULL, h_last, 1);
+                int f = __shfl_up_sync(FULL, f_out, 1);
+                if (lane == 0) {
+                    if (first || j >= tlen) { h_up = 0; f = 0; }
+                    else { h_up = __ldcg(bH + j); f = __ldcg(bF + j); }
+                }
+                int hd = diag_in;
+                diag_in = h_up;
+                const bool live = j >= 0 && j < tlen;
+                const int8_t* srow = smat + (live ? ts[j] : S4G_PAD_CODE) * 32;
+#pragma unroll
+                for (int r = 0; r < kGenK; ++r) {
+                    const int sc = ql[r] >= 0 ? (int)srow[ql[r]] : 0;
+                    int h = __vimax3_s32_relu(hd + sc, E[r], f);
+                    if (!live) h = 0;
+                    hd = H[r];
+                    H[r] = h;
+                    const int hq = h - Q;
+                    E[r] = __viaddmax_s32(E[r], -R, hq);
+                    f = __viaddmax_s32(f, -R, hq);
+                    if (!live) { E[r] = 0; f = 0; }
+                    best = max(best, h);
+                }
+                h_last = H[kGenK - 1];
+                f_out = f;
+                if (lane == 31 && !last && live) { __stcg(bH + j, h_last); __stcg(bF + j, f_out); }
+            }
+            __syncwarp();
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(FULL, best, o));
+        if (lane == 0) P.out[c] = best;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// preparation kernels
+
+__global__ void make_keys_kernel(ScoreParams P, int64_t n_pairs, unsigned long long* keys, uint32_t* vals) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pairs) return;
+    const int q = find_query(P.cand_off, P.nq, i);
+    const uint32_t t = P.cand_ids[i] - P.id_base;
+    const unsigned len = (unsigned)(P.db_off[t + 1] - P.db_off[t]);
+    keys[i] = ((unsigned long long)q << 32) | (unsigned long long)(0xffffffffu - len);
+    vals[i] = (uint32_t)i;
+}
+
+// tiles per query for the packed kernel (0 for long queries), and the number of long-query candidates
+__global__ void count_tiles_kernel(ScoreParams P, int64_t* tiles, int64_t* long_cands) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q > P.nq) return;
+    int64_t t = 0, l = 0;
+    if (q < P.nq) {
+        const int64_t n_c = P.cand_off[q + 1] - P.cand_off[q];
+        const int qlen = (int)(P.q_off[q + 1] - P.q_off[q]);
+        if (qlen <= 32 * kMaxK) t = ((n_c + 1) / 2 + kTilePairs - 1) / kTilePairs;
+        else l = n_c;
+    }
+    tiles[q] = t;
+    long_cands[q] = l;
+}
+
+// positions (in sorted order) of the candidates of long queries
+__global__ void gather_long_kernel(ScoreParams P, const int64_t* long_start, const uint32_t* sorted_idx, uint32_t* long_idx) {
+    const int q = blockIdx.x;
+    const int qlen = (int)(P.q_off[q + 1] - P.q_off[q]);
+    if (qlen <= 32 * kMaxK) return;
+    const int64_t b = P.cand_off[q], e = P.cand_off[q + 1];
+    for (int64_t i = b + threadIdx.x; i < e; i += blockDim.x) long_idx[long_start[q] + (i - b)] = sorted_idx[i];
+}
+
+}  // namespace
+
+int s4g_sw_score_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, const uint32_t* d_cand_ids,
+                        const int64_t* d_cand_off, int64_t n_pairs, const int32_t* h_matrix, int gap_open,
+                        int gap_extend, int32_t* d_out) {
+    cudaStream_t st = ctx->stream;
+    const int nq = q->n;
+    // int8 matrix, rows = target letter (27, row 26 = pad), cols = query letter (32)
+    int8_t h_mat8[(S4G_PAD_CODE + 1) * 32];
+    int max_s = 0, min_s = 0;
+    memset(h_mat8, 0, sizeof(h_mat8));
+    for (int a = 0; a < S4G_NLET; ++a)
+        for (int b = 0; b < S4G_NLET; ++b) {
+            int v = h_matrix[b * S4G_NLET + a];   // S[query=b][target=a]
+            if (v > 127 || v < -127) { s4g_set_error(ctx, "matrix entry %d outside int8 range", v); return S4G_ERR_ARG; }
+            h_mat8[a * 32 + b] = (int8_t)v;
+            if (v > max_s) max_s = v;
+            if (v < min_s) min_s = v;
+        }
+    for (int b = 0; b < 32; ++b) h_mat8[S4G_PAD_CODE * 32 + b] = (int8_t)(min_s < -1 ? min_s : -1);
+    if (gap_open + max_s >= 16000 || gap_extend >= 16000) { s4g_set_error(ctx, "gap penalties too large for the 16-bit kernel"); return S4G_ERR_ARG; }
+
+    int8_t* d_mat8 = (int8_t*)s4g_scratch(ctx, SLOT_SW_MAT, sizeof(h_mat8));
+    unsigned long long* d_keys = (unsigned long long*)s4g_scratch(ctx, SLOT_SW_KEYS, sizeof(unsigned long long) * n_pairs);
+    unsigned long long* d_keys2 = (unsigned long long*)s4g_scratch(ctx, SLOT_SW_KEYS2, sizeof(unsigned long long) * n_pairs);
+    uint32_t* d_vals = (uint32_t*)s4g_scratch(ctx, SLOT_SW_VALS, sizeof(uint32_t) * n_pairs);
+    uint32_t* d_vals2 = (uint32_t*)s4g_scratch(ctx, SLOT_SW_VALS2, sizeof(uint32_t) * n_pairs);
+    int64_t* d_tiles = (int64_t*)s4g_scratch(ctx, SLOT_SW_TILES, sizeof(int64_t) * 4 * (nq + 1));
+    unsigned long long* d_counters = (unsigned long long*)s4g_scratch(ctx, SLOT_SW_MISC, 64);
+    uint32_t* d_ovf = (uint32_t*)s4g_scratch(ctx, SLOT_SW_OVF, sizeof(uint32_t) * 2 * n_pairs);
+    if (!d_mat8 || !d_keys || !d_keys2 || !d_vals || !d_vals2 || !d_tiles || !d_counters || !d_ovf) return S4G_ERR_NOMEM;
+    uint32_t* d_long_idx = d_ovf + n_pairs;
+    int64_t* d_tile_cnt = d_tiles, *d_tile_start = d_tiles + (nq + 1), *d_long_cnt = d_tiles + 2 * (nq + 1), *d_long_start = d_tiles + 3 * (nq + 1);
+
+    const int gen_blocks = ctx->sm_count * 2;
+    const int64_t bound_stride = 2 * ((int64_t)db->max_len + 64);
+    int32_t* d_bound = (int32_t*)s4g_scratch(ctx, SLOT_SW_BOUND, sizeof(int32_t) * bound_stride * gen_blocks * kWarps);
+    if (!d_bound) return S4G_ERR_NOMEM;
+
+    S4G_CUDA(ctx, cudaMemcpyAsync(d_mat8, h_mat8, sizeof(h_mat8), cudaMemcpyHostToDevice, st));
+    S4G_CUDA(ctx, cudaMemsetAsync(d_counters, 0, 64, st));
+
+    ScoreParams P;
+    P.db_codes = db->d_codes; P.db_off = db->d_off; P.id_base = db->id_base;
+    P.q_codes = q->d_codes; P.q_off = q->d_off; P.nq = nq;
+    P.cand_ids = d_cand_ids; P.cand_off = d_cand_off;
+    P.sorted_idx = d_vals2; P.tile_start = d_tile_start; P.mat8 = d_mat8; P.out = d_out;
+    P.counters = d_counters; P.overflow = d_ovf; P.bound = d_bound; P.bound_stride = bound_stride;
+    P.gap_open = gap_open; P.gap_extend = gap_extend; P.ovf_limit = 32767 - max_s;
+
+    // 1. sort candidates of each query by target length (longest first)
+    {
+        const int threads = 256;
+        const int blocks = (int)((n_pairs + threads - 1) / threads);
+        make_keys_kernel<<<blocks, threads, 0, st>>>(P, n_pairs, d_keys, d_vals);
+        S4G_CHECK_LAUNCH(ctx);
+        int qbits = 1;
+        while ((1ll << qbits) < nq) ++qbits;
+        size_t tmp_bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, (int)n_pairs, 0, 32 + qbits, st);
+        void* d_tmp = s4g_scratch(ctx, SLOT_SW_CUB, tmp_bytes);
+        if (!d_tmp) return S4G_ERR_NOMEM;
+        S4G_CUDA(ctx, cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, (int)n_pairs, 0, 32 + qbits, st));
+        ctx->launches += 4;
+    }
+    // 2. tile table
+    {
+        count_tiles_kernel<<<(nq + 1 + 255) / 256, 256, 0, st>>>(P, d_tile_cnt, d_long_cnt);
+        S4G_CHECK_LAUNCH(ctx);
+        size_t tmp_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_tile_cnt, d_tile_start, nq + 1, st);
+        void* d_tmp = s4g_scratch(ctx, SLOT_SW_CUB, tmp_bytes);
+        if (!d_tmp) return S4G_ERR_NOMEM;
+        S4G_CUDA(ctx, cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_tile_cnt, d_tile_start, nq + 1, st));
+        S4G_CUDA(ctx, cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_long_cnt, d_long_start, nq + 1, st));
+        ctx->launches += 2;
+    }
+    // 3. packed kernel (persistent grid)
+    {
+        const size_t smem = (S4G_PAD_CODE + 1) * 8 * 32 * 4 + (S4G_PAD_CODE + 1) * 32 + kWarps * 4 * kRing * sizeof(unsigned short);
+        S4G_CUDA(ctx, cudaFuncSetAttribute(sw_score_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        S4G_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw_score_packed_kernel, kWarps * 32, smem));
+        if (per_sm < 1) per_sm = 1;
+        S4G_CUDA(ctx, cudaEventRecord(ctx->ev_sw0, st));
+        sw_score_packed_kernel<<<ctx->sm_count * per_sm, kWarps * 32, smem, st>>>(P);
+        S4G_CHECK_LAUNCH(ctx);
+        S4G_CUDA(ctx, cudaEventRecord(ctx->ev_sw1, st));
+        ctx->sw_timed = true;
+    }
+    // 4. long queries (all their candidates) and 16-bit overflow re-runs, exact 32-bit kernel
+    {
+        bool any_long = q->max_len > 32 * kMaxK;
+        if (any_long) {
+            // number of long-query candidates is data dependent but bounded by n_pairs; the kernel reads
+            // the true count from d_long_start[nq]
+            gather_long_kernel<<<nq, 128, 0, st>>>(P, d_long_start, d_vals2, d_long_idx);
+            S4G_CHECK_LAUNCH(ctx);
+            int64_t h_long = 0;
+            S4G_CUDA(ctx, cudaMemcpyAsync(&h_long, d_long_start + nq, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+            S4G_CUDA(ctx, cudaStreamSynchronize(st));
+            GenericWork W; W.list = nullptr; W.n_list = nullptr; W.long_idx = d_long_idx; W.n_long = h_long;
+            sw_score_generic_kernel<<<gen_blocks, kWarps * 32, 0, st>>>(P, W);
+            S4G_CHECK_LAUNCH(ctx);
+            S4G_CUDA(ctx, cudaMemsetAsync(d_counters + 2, 0, 8, st));
+        }
+        GenericWork W; W.list = d_ovf; W.n_list = d_counters + 1; W.long_idx = nullptr; W.n_long = 0;
+        sw_score_generic_kernel<<<gen_blocks, kWarps * 32, 0, st>>>(P, W);
+        S4G_CHECK_LAUNCH(ctx);
+    }
+    return S4G_OK;
+}
