@@ -1,9 +1,638 @@
+// Stage 1: k-mer candidate prefilter (sm_100a).
+//
+// Replaces searchDatabase / threadSearchDatabase (sift4g/src/database_search.cpp:66-253), the query k-mer
+// index (sift4g/src/hash.cpp:21-90) and longestIncreasingSubsequence (database_search.cpp:255-280):
+//   for every database sequence d and every query q sharing at least one k-mer with it,
+//       score(q,d) = LIS_strict(query positions of the shared k-mers, in database order) / (float) len(d)
+//   and every query keeps its max_candidates best sequences.  Ties at the cut-off are broken by ascending
+//   sequence id (a deterministic member of the reference's thread-count dependent tie family).
+//
+// Device data structures (all L2 resident for the configurations of BASELINE.json):
+//   bitrank[2^(5k)/32] = {32 presence bits, number of present k-mers before this word}   (one 8 B load)
+//   bucket_start[D+1]  = first entry of each present k-mer in `hits`
+//   hits[]             = (query << 32 | position) sorted by (k-mer, query, position)        (hash.cpp:80-84)
+// The database streams from HBM exactly once per call: one warp per sequence, 32 k-mer positions per step.
+// Hits of a sequence are gathered in the reference's emission order into a per-warp shared-memory buffer,
+// bitonic-sorted by (query, emission order), and each query's run is reduced with an in-place patience LIS.
+// Sequences with more hits than the buffer holds are deferred to a global-memory path (radix sort + one
+// thread per run).  Scored pairs that beat the query's current cut-off are appended to that query's
+// candidate buffer; buffers are compacted (segmented sort, keep the best N, raise the cut-off) whenever
+// they could overflow during the next chunk of sequences.
+#include <cub/cub.cuh>
+
 #include "common.cuh"
-int s4g_prefilter_device(s4g_ctx* ctx, s4g_db*, s4g_queries*, int, int, int, uint32_t*, float*, uint32_t*) {
-    s4g_set_error(ctx, "prefilter not built yet");
-    return S4G_ERR_INTERNAL;
+
+namespace {
+
+constexpr int kWarps = 8;
+constexpr int kSCap = 1024;            // hits per sequence handled in shared memory
+constexpr int kSeqBatch = 4;           // sequences claimed per atomic
+constexpr unsigned long long kNoThr = ~0ull;
+
+struct PfParams {
+    const uint8_t* db_codes;
+    const int64_t* db_off;
+    uint32_t id_base;
+    int64_t seq_begin, seq_end;
+    int k;
+    uint32_t mask;
+    const uint2* bitrank;
+    const uint32_t* bucket_start;
+    const unsigned long long* hits;
+    int nq;
+    unsigned long long* thr;
+    uint32_t* count;
+    unsigned long long* cand;
+    uint32_t cap;
+    unsigned long long* counters;     // [0] sequence cursor [1] deferred sequences [2] pool cursor [3] error flags
+    uint32_t* def_seq;                // deferred: local sequence index
+    unsigned long long* def_off;      // deferred: offset into the pool
+    uint32_t max_deferred;
+    unsigned long long* pool_keys;    // (slot << 50 | q << 30 | order)
+    uint32_t* pool_vals;              // query position
+    unsigned long long pool_cap;
+};
+
+__device__ __forceinline__ unsigned long long cand_key(float score, uint32_t id) {
+    return ((unsigned long long)(~__float_as_uint(score)) << 32) | id;   // ascending = (score desc, id asc)
 }
-extern "C" int s4g_merge_candidates(s4g_ctx* ctx, int, int, int, const uint32_t*, const float*, const uint32_t*, uint32_t*, float*, uint32_t*) {
-    s4g_set_error(ctx, "merge not built yet");
-    return S4G_ERR_INTERNAL;
+
+__device__ __forceinline__ void emit(const PfParams& P, uint32_t q, int lis, int len, uint32_t id) {
+    const float score = __fdiv_rn((float)lis, (float)len);               // database_search.cpp:228-229
+    const unsigned long long key = cand_key(score, id);
+    if (key < __ldcg(P.thr + q)) {
+        const uint32_t slot = atomicAdd(P.count + q, 1u);
+        if (slot < P.cap) P.cand[(size_t)q * P.cap + slot] = key;
+        else atomicOr(P.counters + 3, 1ull);
+    }
+}
+
+// k-mer at position j (needs j + k <= len)
+__device__ __forceinline__ uint32_t kmer_at(const uint8_t* s, int j, int k) {
+    uint32_t v = 0;
+    for (int i = 0; i < k; ++i) v = (v << 5) | s[j + i];
+    return v;
+}
+
+__device__ __forceinline__ void lookup(const PfParams& P, uint32_t kmer, uint32_t& b, uint32_t& c) {
+    const uint2 br = __ldg(P.bitrank + (kmer >> 5));
+    const uint32_t bit = kmer & 31u;
+    c = 0; b = 0;
+    if ((br.x >> bit) & 1u) {
+        const uint32_t r = br.y + __popc(br.x & ((1u << bit) - 1u));
+        b = __ldg(P.bucket_start + r);
+        c = __ldg(P.bucket_start + r + 1) - b;
+    }
+}
+
+__device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane, uint32_t& total) {
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    total = __shfl_sync(0xffffffffu, x, 31);
+    return x - v;
+}
+
+// in-place patience LIS over the positions of entries [a, a+n): strictly increasing
+__device__ int lis_inplace(unsigned long long* buf, int a, int n) {
+    uint32_t* tails = reinterpret_cast<uint32_t*>(buf + a);
+    int len = 0;
+    for (int i = 0; i < n; ++i) {
+        const uint32_t x = (uint32_t)(buf[a + i] & 0x3fffffu);
+        int lo = 0, hi = len;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (tails[mid] < x) lo = mid + 1; else hi = mid; }
+        tails[lo] = x;
+        if (lo == len) ++len;
+    }
+    return len;
+}
+
+__global__ void __launch_bounds__(kWarps * 32) pf_scan_kernel(PfParams P) {
+    extern __shared__ unsigned long long sbuf[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long* buf = sbuf + warp * kSCap;
+    const unsigned FULL = 0xffffffffu;
+    const int k = P.k;
+    while (true) {
+        long long s0 = 0;
+        if (lane == 0) s0 = (long long)atomicAdd(P.counters + 0, (unsigned long long)kSeqBatch);
+        s0 = __shfl_sync(FULL, s0, 0) + P.seq_begin;
+        if (s0 >= P.seq_end) break;
+        for (long long s = s0; s < s0 + kSeqBatch && s < P.seq_end; ++s) {
+            const int64_t a = P.db_off[s];
+            const int len = (int)(P.db_off[s + 1] - a);
+            if (len < k) continue;
+            const uint8_t* seq = P.db_codes + a;
+            const int npos = len - k + 1;
+            uint32_t T = 0, carry = 0xffffffffu;
+            bool overflow = false;
+            for (int base = 0; base < npos; base += 32) {
+                const int j = base + lane;
+                const bool valid = j < npos;
+                const uint32_t kmer = valid ? kmer_at(seq, j, k) : 0xfffffffeu;
+                uint32_t prevk = __shfl_up_sync(FULL, kmer, 1);
+                if (lane == 0) prevk = carry;
+                carry = __shfl_sync(FULL, kmer, 31);
+                uint32_t b = 0, c = 0;
+                if (valid && !(j > 0 && kmer == prevk)) lookup(P, kmer, b, c);      // database_search.cpp:212-214
+                uint32_t total;
+                const uint32_t excl = warp_excl_scan(c, lane, total);
+                if (!overflow && T + total <= (uint32_t)kSCap) {
+                    for (uint32_t t = 0; t < c; ++t) {
+                        const unsigned long long h = __ldg(P.hits + b + t);
+                        const uint32_t ord = T + excl + t;
+                        buf[ord] = ((h >> 32) << 44) | ((unsigned long long)ord << 22) | (h & 0x3fffffu);
+                    }
+                } else if (total) overflow = true;
+                T += total;
+            }
+            if (T == 0) continue;
+            if (overflow) {
+                if (lane == 0) {
+                    const unsigned long long slot = atomicAdd(P.counters + 1, 1ull);
+                    const unsigned long long off = atomicAdd(P.counters + 2, (unsigned long long)T);
+                    if (slot < P.max_deferred && off + T <= P.pool_cap) { P.def_seq[slot] = (uint32_t)(s - P.seq_begin); P.def_off[slot] = off; }
+                    else atomicOr(P.counters + 3, 2ull);
+                }
+                continue;
+            }
+            // bitonic sort of buf[0..P2) by (query, emission order)
+            int P2 = 32;
+            while (P2 < (int)T) P2 <<= 1;
+            for (int i = T + lane; i < P2; i += 32) buf[i] = ~0ull;
+            __syncwarp();
+            for (int size = 2; size <= P2; size <<= 1) {
+                for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                    for (int t = lane; t < (P2 >> 1); t += 32) {
+                        const int lo = ((t / stride) * stride * 2) + (t % stride);
+                        const int hi = lo + stride;
+                        const bool up = ((lo & size) == 0);
+                        const unsigned long long x = buf[lo], y = buf[hi];
+                        if ((x > y) == up) { buf[lo] = y; buf[hi] = x; }
+                    }
+                    __syncwarp();
+                }
+            }
+            // run starts, one ballot word per 32 entries, kept by lane (i / 32)
+            uint32_t my_starts = 0;
+            for (int base = 0; base < (int)T; base += 32) {
+                const int i = base + lane;
+                const bool st = i < (int)T && (i == 0 || (buf[i] >> 44) != (buf[i - 1] >> 44));
+                const uint32_t bal = __ballot_sync(FULL, st);
+                if (lane == (base >> 5)) my_starts = bal;
+            }
+            __syncwarp();
+            const uint32_t id = P.id_base + (uint32_t)s;
+            for (int base = 0; base < (int)T; base += 32) {
+                const uint32_t bal = __shfl_sync(FULL, my_starts, base >> 5);
+                if ((bal >> lane) & 1u) {
+                    const int i = base + lane;
+                    const uint32_t q = (uint32_t)(buf[i] >> 44);
+                    int e = i + 1;
+                    while (e < (int)T && (uint32_t)(buf[e] >> 44) == q) ++e;
+                    const int n = e - i;
+                    const int lis = n == 1 ? 1 : lis_inplace(buf, i, n);
+                    emit(P, q, lis, len, id);
+                }
+                __syncwarp();
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// deferred path, step 1: re-walk the sequence and write its hits into the pool
+__global__ void __launch_bounds__(kWarps * 32) pf_fill_deferred_kernel(PfParams P, uint32_t n_def) {
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    const int k = P.k;
+    for (uint32_t slot = blockIdx.x * kWarps + (threadIdx.x >> 5); slot < n_def; slot += gridDim.x * kWarps) {
+        const long long s = P.seq_begin + P.def_seq[slot];
+        const int64_t a = P.db_off[s];
+        const int len = (int)(P.db_off[s + 1] - a);
+        const uint8_t* seq = P.db_codes + a;
+        const int npos = len - k + 1;
+        unsigned long long* keys = P.pool_keys + P.def_off[slot];
+        uint32_t* vals = P.pool_vals + P.def_off[slot];
+        uint32_t T = 0, carry = 0xffffffffu;
+        for (int base = 0; base < npos; base += 32) {
+            const int j = base + lane;
+            const bool valid = j < npos;
+            const uint32_t kmer = valid ? kmer_at(seq, j, k) : 0xfffffffeu;
+            uint32_t prevk = __shfl_up_sync(FULL, kmer, 1);
+            if (lane == 0) prevk = carry;
+            carry = __shfl_sync(FULL, kmer, 31);
+            uint32_t b = 0, c = 0;
+            if (valid && !(j > 0 && kmer == prevk)) lookup(P, kmer, b, c);
+            uint32_t total;
+            const uint32_t excl = warp_excl_scan(c, lane, total);
+            for (uint32_t t = 0; t < c; ++t) {
+                const unsigned long long h = __ldg(P.hits + b + t);
+                const uint32_t ord = T + excl + t;
+                keys[ord] = ((unsigned long long)slot << 50) | ((h >> 32) << 30) | (unsigned long long)(ord & 0x3fffffffu);
+                vals[ord] = (uint32_t)h;
+            }
+            T += total;
+        }
+    }
+}
+
+// deferred path, step 2 (after a radix sort of the pool): one thread per run of equal (slot, query)
+__global__ void pf_lis_deferred_kernel(PfParams P, const unsigned long long* keys, const uint32_t* vals, uint32_t* tails,
+                                       unsigned long long n) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long g = keys[i] >> 30;
+    if (i > 0 && (keys[i - 1] >> 30) == g) return;
+    unsigned long long e = i + 1;
+    int len = 0;
+    uint32_t* tl = tails + i;
+    for (unsigned long long x = i; x < n && (keys[x] >> 30) == g; ++x) {
+        const uint32_t v = vals[x];
+        int lo = 0, hi = len;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (tl[mid] < v) lo = mid + 1; else hi = mid; }
+        tl[lo] = v;
+        if (lo == len) ++len;
+        e = x + 1;
+    }
+    (void)e;
+    const uint32_t slot = (uint32_t)(g >> 20), q = (uint32_t)(g & 0xfffffu);
+    const long long s = P.seq_begin + P.def_seq[slot];
+    const int slen = (int)(P.db_off[s + 1] - P.db_off[s]);
+    emit(P, q, len, slen, P.id_base + (uint32_t)s);
+}
+
+// ---- index build -----------------------------------------------------------------------------------------
+
+__global__ void ix_kmers_kernel(const uint8_t* q_codes, const int64_t* q_off, int nq, int k, uint32_t mask,
+                                const int64_t* hit_start, uint32_t* keys, unsigned long long* vals, uint32_t* bits) {
+    const int q = blockIdx.x;
+    const int64_t a = q_off[q];
+    const int len = (int)(q_off[q + 1] - a);
+    const int npos = len - k + 1;
+    for (int j = threadIdx.x; j < npos; j += blockDim.x) {
+        uint32_t v = 0;
+        for (int i = 0; i < k; ++i) v = (v << 5) | q_codes[a + j + i];
+        keys[hit_start[q] + j] = v;
+        vals[hit_start[q] + j] = ((unsigned long long)q << 32) | (unsigned)j;
+        atomicOr(bits + (v >> 5), 1u << (v & 31u));
+    }
+}
+
+__global__ void ix_count_kernel(const int64_t* q_off, int nq, int k, int64_t* cnt) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q > nq) return;
+    int64_t c = 0;
+    if (q < nq) { const int64_t len = q_off[q + 1] - q_off[q]; c = len >= k ? len - k + 1 : 0; }
+    cnt[q] = c;
+}
+
+__global__ void ix_popc_kernel(const uint32_t* bits, uint32_t n_words, uint32_t* pc) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_words) pc[i] = __popc(bits[i]);
+}
+
+__global__ void ix_bitrank_kernel(const uint32_t* bits, const uint32_t* prefix, uint32_t n_words, uint2* bitrank) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_words) bitrank[i] = make_uint2(bits[i], prefix[i]);
+}
+
+__global__ void ix_bucket_kernel(const uint32_t* sorted_keys, int64_t n, const uint2* bitrank, uint32_t* bucket_start, uint32_t n_distinct) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) bucket_start[n_distinct] = (uint32_t)n;
+    if (i >= n) return;
+    const uint32_t kmer = sorted_keys[i];
+    if (i == 0 || sorted_keys[i - 1] != kmer) {
+        const uint2 br = bitrank[kmer >> 5];
+        const uint32_t r = br.y + __popc(br.x & ((1u << (kmer & 31u)) - 1u));
+        bucket_start[r] = (uint32_t)i;
+    }
+}
+
+// ---- candidate buffers -------------------------------------------------------------------------------------
+
+__global__ void cb_init_kernel(unsigned long long* thr, uint32_t* count, int nq) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq) { thr[q] = kNoThr; count[q] = 0; }
+}
+
+// list the queries whose buffer could overflow during the next chunk (or all non-empty ones when `all`)
+__global__ void cb_select_kernel(const uint32_t* count, int nq, uint32_t cap, uint32_t limit, int all, int64_t* seg_begin,
+                                 int64_t* seg_end, uint32_t* seg_q, unsigned long long* n_seg) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const uint32_t c = count[q] < cap ? count[q] : cap;
+    if ((all && c > 0) || c > limit) {
+        const unsigned long long s = atomicAdd(n_seg, 1ull);
+        seg_begin[s] = (int64_t)q * cap;
+        seg_end[s] = (int64_t)q * cap + c;
+        seg_q[s] = (uint32_t)q;
+    }
+}
+
+// one CTA per compacted query: copy the best min(count, N) keys back from the sort output, set count and cut-off
+__global__ void cb_truncate_kernel(unsigned long long* cand, const unsigned long long* sorted, uint32_t* count, unsigned long long* thr,
+                                   uint32_t cap, uint32_t N, const uint32_t* seg_q) {
+    const uint32_t q = seg_q[blockIdx.x];
+    uint32_t c = count[q] < cap ? count[q] : cap;
+    if (c > N) c = N;
+    for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) cand[(size_t)q * cap + i] = sorted[(size_t)q * cap + i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (c >= N && N != 0xffffffffu) thr[q] = sorted[(size_t)q * cap + N - 1];
+        count[q] = c;
+    }
+}
+
+// final: sorted candidate keys -> (ids, scores) rows; optionally re-ordered by ascending id
+__global__ void cb_output_kernel(const unsigned long long* cand, const uint32_t* count, uint32_t cap, uint32_t N, int nq,
+                                 uint32_t* out_ids, float* out_scores, uint32_t* out_counts) {
+    const int q = blockIdx.x;
+    const uint32_t c = count[q] < N ? count[q] : N;
+    if (threadIdx.x == 0) out_counts[q] = c;
+    for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) {
+        const unsigned long long key = cand[(size_t)q * cap + i];
+        out_ids[(size_t)q * N + i] = (uint32_t)key;
+        if (out_scores) out_scores[(size_t)q * N + i] = __uint_as_float(~(uint32_t)(key >> 32));
+    }
+}
+
+// keys for the id-order pass: (id << 32 | score bits), sorted ascending per query
+__global__ void cb_idkeys_kernel(unsigned long long* cand, const uint32_t* count, uint32_t cap, uint32_t N, int nq) {
+    const int q = blockIdx.x;
+    const uint32_t c = count[q] < N ? count[q] : N;
+    for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) {
+        const unsigned long long key = cand[(size_t)q * cap + i];
+        cand[(size_t)q * cap + i] = (key << 32) | (key >> 32);
+    }
+}
+
+__global__ void cb_output_byid_kernel(const unsigned long long* cand, const uint32_t* count, uint32_t cap, uint32_t N, int nq,
+                                      uint32_t* out_ids, float* out_scores, uint32_t* out_counts) {
+    const int q = blockIdx.x;
+    const uint32_t c = count[q] < N ? count[q] : N;
+    if (threadIdx.x == 0) out_counts[q] = c;
+    for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) {
+        const unsigned long long key = cand[(size_t)q * cap + i];
+        out_ids[(size_t)q * N + i] = (uint32_t)(key >> 32);
+        if (out_scores) out_scores[(size_t)q * N + i] = __uint_as_float(~(uint32_t)key);
+    }
+}
+
+__global__ void mg_keys_kernel(int n_ranks, int nq, uint32_t N, const uint32_t* ids, const float* scores, const uint32_t* counts,
+                               unsigned long long* cand, uint32_t* count, uint32_t cap) {
+    const int q = blockIdx.x;
+    uint32_t base = 0;
+    for (int r = 0; r < n_ranks; ++r) {
+        const uint32_t c = counts[(size_t)r * nq + q];
+        for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) {
+            const size_t src = ((size_t)r * nq + q) * N + i;
+            cand[(size_t)q * cap + base + i] = cand_key(scores[src], ids[src]);
+        }
+        base += c;
+    }
+    if (threadIdx.x == 0) count[q] = base;
+}
+
+int segmented_sort(s4g_ctx* ctx, const unsigned long long* keys_in, unsigned long long* keys_out, int64_t n_items_bound, int n_seg,
+                   const int64_t* d_begin, const int64_t* d_end) {
+    size_t tmp = 0;
+    cub::DeviceSegmentedSort::SortKeys(nullptr, tmp, keys_in, keys_out, n_items_bound, (int64_t)n_seg, d_begin, d_end, ctx->stream);
+    void* d_tmp = s4g_scratch(ctx, SLOT_PF_CUB, tmp);
+    if (!d_tmp) return S4G_ERR_NOMEM;
+    S4G_CUDA(ctx, cub::DeviceSegmentedSort::SortKeys(d_tmp, tmp, keys_in, keys_out, n_items_bound, (int64_t)n_seg, d_begin, d_end, ctx->stream));
+    ctx->launches += 3;
+    return S4G_OK;
+}
+
+}  // namespace
+
+// Compact (sort + keep best N) the listed queries.  `all` = every non-empty query (final pass).
+static int compact(s4g_ctx* ctx, int nq, uint32_t cap, uint32_t N, uint32_t limit, int all, unsigned long long* d_cand,
+                   unsigned long long* d_cand_alt, uint32_t* d_count, unsigned long long* d_thr, int64_t* d_seg, uint32_t* d_seg_q,
+                   unsigned long long* d_nseg, bool* did) {
+    cudaStream_t st = ctx->stream;
+    S4G_CUDA(ctx, cudaMemsetAsync(d_nseg, 0, 8, st));
+    cb_select_kernel<<<(nq + 255) / 256, 256, 0, st>>>(d_count, nq, cap, limit, all, d_seg, d_seg + nq, d_seg_q, d_nseg);
+    S4G_CHECK_LAUNCH(ctx);
+    unsigned long long h_nseg = 0;
+    S4G_CUDA(ctx, cudaMemcpyAsync(&h_nseg, d_nseg, 8, cudaMemcpyDeviceToHost, st));
+    S4G_CUDA(ctx, cudaStreamSynchronize(st));
+    if (did) *did = h_nseg > 0;
+    if (h_nseg == 0) return S4G_OK;
+    int rc = segmented_sort(ctx, d_cand, d_cand_alt, (int64_t)nq * cap, (int)h_nseg, d_seg, d_seg + nq);
+    if (rc != S4G_OK) return rc;
+    cb_truncate_kernel<<<(unsigned)h_nseg, 256, 0, st>>>(d_cand, d_cand_alt, d_count, d_thr, cap, N, d_seg_q);
+    S4G_CHECK_LAUNCH(ctx);
+    return S4G_OK;
+}
+
+int s4g_prefilter_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int max_candidates, int sorted_by_id,
+                         uint32_t* d_ids, float* d_scores, uint32_t* d_counts) {
+    cudaStream_t st = ctx->stream;
+    const int nq = q->n;
+    const uint32_t N = (uint32_t)max_candidates;
+    if (nq >= (1 << 20)) { s4g_set_error(ctx, "at most 2^20-1 queries per batch"); return S4G_ERR_ARG; }
+    if (q->max_len >= (1 << 22)) { s4g_set_error(ctx, "query longer than 2^22"); return S4G_ERR_ARG; }
+
+    // ---- index over all queries ----
+    int64_t n_hits = 0;
+    for (int i = 0; i < nq; ++i) { int64_t len = q->h_off[i + 1] - q->h_off[i]; if (len >= k) n_hits += len - k + 1; }
+    const uint32_t n_kmer_space = 1u << (5 * k);
+    const uint32_t n_words = n_kmer_space / 32;
+    const uint32_t mask = n_kmer_space - 1;
+
+    size_t ix_bytes = sizeof(int64_t) * 2 * (nq + 1) + sizeof(uint32_t) * 2 * (size_t)(n_hits + 1) + sizeof(unsigned long long) * 2 * (size_t)(n_hits + 1) + 64;
+    char* ix = (char*)s4g_scratch(ctx, SLOT_PF_INDEX, ix_bytes);
+    uint32_t* d_bits = (uint32_t*)s4g_scratch(ctx, SLOT_PF_BITMAP, sizeof(uint32_t) * 3 * (size_t)n_words);
+    uint2* d_bitrank = (uint2*)s4g_scratch(ctx, SLOT_PF_RANK, sizeof(uint2) * (size_t)n_words);
+    uint32_t* d_bucket = (uint32_t*)s4g_scratch(ctx, SLOT_PF_BUCKET, sizeof(uint32_t) * (size_t)(n_hits + 2));
+    if (!ix || !d_bits || !d_bitrank || !d_bucket) return S4G_ERR_NOMEM;
+    int64_t* d_cnt = (int64_t*)ix;
+    int64_t* d_start = d_cnt + (nq + 1);
+    unsigned long long* d_vals = (unsigned long long*)(d_start + (nq + 1));
+    unsigned long long* d_vals2 = d_vals + (n_hits + 1);
+    uint32_t* d_keys = (uint32_t*)(d_vals2 + (n_hits + 1));
+    uint32_t* d_keys2 = d_keys + (n_hits + 1);
+    uint32_t* d_pc = d_bits + n_words;
+    uint32_t* d_prefix = d_pc + n_words;
+
+    S4G_CUDA(ctx, cudaMemsetAsync(d_bits, 0, sizeof(uint32_t) * n_words, st));
+    ix_count_kernel<<<(nq + 1 + 255) / 256, 256, 0, st>>>(q->d_off, nq, k, d_cnt);
+    S4G_CHECK_LAUNCH(ctx);
+    {
+        size_t tmp = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_cnt, d_start, nq + 1, st);
+        void* d_tmp = s4g_scratch(ctx, SLOT_PF_CUB, tmp);
+        if (!d_tmp) return S4G_ERR_NOMEM;
+        S4G_CUDA(ctx, cub::DeviceScan::ExclusiveSum(d_tmp, tmp, d_cnt, d_start, nq + 1, st));
+        ctx->launches += 1;
+    }
+    uint32_t n_distinct = 0;
+    if (n_hits > 0) {
+        ix_kmers_kernel<<<nq, 128, 0, st>>>(q->d_codes, q->d_off, nq, k, mask, d_start, d_keys, d_vals, d_bits);
+        S4G_CHECK_LAUNCH(ctx);
+        size_t tmp = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp, d_keys, d_keys2, d_vals, d_vals2, (int)n_hits, 0, 5 * k, st);
+        void* d_tmp = s4g_scratch(ctx, SLOT_PF_CUB, tmp);
+        if (!d_tmp) return S4G_ERR_NOMEM;
+        S4G_CUDA(ctx, cub::DeviceRadixSort::SortPairs(d_tmp, tmp, d_keys, d_keys2, d_vals, d_vals2, (int)n_hits, 0, 5 * k, st));
+        ctx->launches += 3;
+    }
+    ix_popc_kernel<<<(n_words + 255) / 256, 256, 0, st>>>(d_bits, n_words, d_pc);
+    S4G_CHECK_LAUNCH(ctx);
+    {
+        size_t tmp = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_pc, d_prefix, (int)n_words, st);
+        void* d_tmp = s4g_scratch(ctx, SLOT_PF_CUB, tmp);
+        if (!d_tmp) return S4G_ERR_NOMEM;
+        S4G_CUDA(ctx, cub::DeviceScan::ExclusiveSum(d_tmp, tmp, d_pc, d_prefix, (int)n_words, st));
+        ctx->launches += 1;
+    }
+    ix_bitrank_kernel<<<(n_words + 255) / 256, 256, 0, st>>>(d_bits, d_prefix, n_words, d_bitrank);
+    S4G_CHECK_LAUNCH(ctx);
+    {
+        uint32_t last_pc = 0, last_prefix = 0;
+        S4G_CUDA(ctx, cudaMemcpyAsync(&last_pc, d_pc + n_words - 1, 4, cudaMemcpyDeviceToHost, st));
+        S4G_CUDA(ctx, cudaMemcpyAsync(&last_prefix, d_prefix + n_words - 1, 4, cudaMemcpyDeviceToHost, st));
+        S4G_CUDA(ctx, cudaStreamSynchronize(st));
+        n_distinct = last_pc + last_prefix;
+    }
+    if (n_hits > 0) {
+        ix_bucket_kernel<<<(unsigned)((n_hits + 255) / 256), 256, 0, st>>>(d_keys2, n_hits, d_bitrank, d_bucket, n_distinct);
+        S4G_CHECK_LAUNCH(ctx);
+    }
+
+    // ---- candidate buffers ----
+    // chunk of sequences per scan launch; every buffer can take a whole chunk on top of N + slack
+    const uint32_t slack = N / 4 > 256 ? N / 4 : 256;
+    int64_t chunk = 131072;
+    const size_t budget = (size_t)6 << 30;   // bytes for both candidate buffers
+    while (chunk > 4096 && (size_t)nq * (size_t)(N + slack + chunk) * 16 > budget) chunk >>= 1;
+    if (chunk > db->n) chunk = db->n > 0 ? db->n : 1;
+    const uint32_t cap = (uint32_t)(N + slack + chunk);
+    unsigned long long* d_cand = (unsigned long long*)s4g_scratch(ctx, SLOT_PF_CAND, sizeof(unsigned long long) * (size_t)nq * cap);
+    unsigned long long* d_cand_alt = (unsigned long long*)s4g_scratch(ctx, SLOT_PF_TMP, sizeof(unsigned long long) * (size_t)nq * cap);
+    uint32_t* d_count = (uint32_t*)s4g_scratch(ctx, SLOT_PF_COUNT, sizeof(uint32_t) * nq);
+    unsigned long long* d_thr = (unsigned long long*)s4g_scratch(ctx, SLOT_PF_THR, sizeof(unsigned long long) * nq + 64);
+    const uint32_t max_deferred = 1u << 14;
+    const unsigned long long pool_cap = 1ull << 26;   // 64 M hits per chunk through the deferred path
+    char* spill = (char*)s4g_scratch(ctx, SLOT_PF_SPILL, 64 + sizeof(int64_t) * 2 * nq + sizeof(uint32_t) * nq + (sizeof(uint32_t) + sizeof(unsigned long long)) * max_deferred);
+    if (!d_cand || !d_cand_alt || !d_count || !d_thr || !spill) return S4G_ERR_NOMEM;
+    unsigned long long* d_counters = (unsigned long long*)spill;          // 8 counters
+    int64_t* d_seg = (int64_t*)(spill + 64);
+    unsigned long long* d_def_off = (unsigned long long*)(d_seg + 2 * nq);
+    uint32_t* d_seg_q = (uint32_t*)(d_def_off + max_deferred);
+    uint32_t* d_def_seq = d_seg_q + nq;
+    unsigned long long* d_nseg = d_counters + 4;
+
+    cb_init_kernel<<<(nq + 255) / 256, 256, 0, st>>>(d_thr, d_count, nq);
+    S4G_CHECK_LAUNCH(ctx);
+
+    PfParams P;
+    P.db_codes = db->d_codes; P.db_off = db->d_off; P.id_base = db->id_base;
+    P.k = k; P.mask = mask; P.bitrank = d_bitrank; P.bucket_start = d_bucket; P.hits = d_vals2; P.nq = nq;
+    P.thr = d_thr; P.count = d_count; P.cand = d_cand; P.cap = cap; P.counters = d_counters;
+    P.def_seq = d_def_seq; P.def_off = d_def_off; P.max_deferred = max_deferred;
+    P.pool_keys = nullptr; P.pool_vals = nullptr; P.pool_cap = pool_cap;
+
+    int per_sm = 0;
+    const size_t scan_smem = sizeof(unsigned long long) * kWarps * kSCap;
+    S4G_CUDA(ctx, cudaFuncSetAttribute(pf_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
+    S4G_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pf_scan_kernel, kWarps * 32, scan_smem));
+    if (per_sm < 1) per_sm = 1;
+    const int grid = ctx->sm_count * per_sm;
+
+    for (int64_t s0 = 0; s0 < db->n && n_hits > 0; s0 += chunk) {
+        P.seq_begin = s0;
+        P.seq_end = s0 + chunk < db->n ? s0 + chunk : db->n;
+        S4G_CUDA(ctx, cudaMemsetAsync(d_counters, 0, 32, st));
+        // the pool is only allocated once a chunk needs it (first pass counts; see below)
+        P.pool_keys = (unsigned long long*)ctx->slot_ptr[SLOT_PF_HITS];
+        pf_scan_kernel<<<grid, kWarps * 32, scan_smem, st>>>(P);
+        S4G_CHECK_LAUNCH(ctx);
+        unsigned long long h_c[4];
+        S4G_CUDA(ctx, cudaMemcpyAsync(h_c, d_counters, 32, cudaMemcpyDeviceToHost, st));
+        S4G_CUDA(ctx, cudaStreamSynchronize(st));
+        if (h_c[3] & 1ull) { s4g_set_error(ctx, "prefilter: candidate buffer overflow (internal)"); return S4G_ERR_INTERNAL; }
+        if (h_c[3] & 2ull) { s4g_set_error(ctx, "prefilter: more than %u deferred sequences or %llu deferred hits in one chunk", max_deferred, pool_cap); return S4G_ERR_CAPACITY; }
+        if (h_c[1] > 0) {
+            const unsigned long long n_pool = h_c[2];
+            const uint32_t n_def = (uint32_t)h_c[1];
+            char* pool = (char*)s4g_scratch(ctx, SLOT_PF_HITS, (sizeof(unsigned long long) * 2 + sizeof(uint32_t) * 3) * (size_t)n_pool + 256);
+            if (!pool) return S4G_ERR_NOMEM;
+            unsigned long long* pk = (unsigned long long*)pool;
+            unsigned long long* pk2 = pk + n_pool;
+            uint32_t* pv = (uint32_t*)(pk2 + n_pool);
+            uint32_t* pv2 = pv + n_pool;
+            uint32_t* tails = pv2 + n_pool;
+            P.pool_keys = pk; P.pool_vals = pv;
+            pf_fill_deferred_kernel<<<ctx->sm_count * 2, kWarps * 32, 0, st>>>(P, n_def);
+            S4G_CHECK_LAUNCH(ctx);
+            size_t tmp = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, tmp, pk, pk2, pv, pv2, (int64_t)n_pool, 0, 64, st);
+            void* d_tmp = s4g_scratch(ctx, SLOT_PF_TMP2, tmp);
+            if (!d_tmp) return S4G_ERR_NOMEM;
+            S4G_CUDA(ctx, cub::DeviceRadixSort::SortPairs(d_tmp, tmp, pk, pk2, pv, pv2, (int64_t)n_pool, 0, 64, st));
+            ctx->launches += 8;
+            pf_lis_deferred_kernel<<<(unsigned)((n_pool + 127) / 128), 128, 0, st>>>(P, pk2, pv2, tails, n_pool);
+            S4G_CHECK_LAUNCH(ctx);
+        }
+        // compact buffers that could overflow in the next chunk
+        const bool last = P.seq_end >= db->n;
+        if (!last) {
+            int rc = compact(ctx, nq, cap, N, N + slack, 0, d_cand, d_cand_alt, d_count, d_thr, d_seg, d_seg_q, d_nseg, nullptr);
+            if (rc != S4G_OK) return rc;
+        }
+    }
+    // ---- final top-N, output ----
+    {
+        int rc = compact(ctx, nq, cap, N, 0, 1, d_cand, d_cand_alt, d_count, d_thr, d_seg, d_seg_q, d_nseg, nullptr);
+        if (rc != S4G_OK) return rc;
+    }
+    if (!sorted_by_id) {
+        cb_output_kernel<<<nq, 128, 0, st>>>(d_cand, d_count, cap, N, nq, d_ids, d_scores, d_counts);
+        S4G_CHECK_LAUNCH(ctx);
+    } else {
+        cb_idkeys_kernel<<<nq, 128, 0, st>>>(d_cand, d_count, cap, N, nq);
+        S4G_CHECK_LAUNCH(ctx);
+        bool did = false;
+        // sort every non-empty query by the swapped key (id major)
+        int rc = compact(ctx, nq, cap, 0xffffffffu, 0, 1, d_cand, d_cand_alt, d_count, d_thr, d_seg, d_seg_q, d_nseg, &did);
+        if (rc != S4G_OK) return rc;
+        cb_output_byid_kernel<<<nq, 128, 0, st>>>(d_cand, d_count, cap, N, nq, d_ids, d_scores, d_counts);
+        S4G_CHECK_LAUNCH(ctx);
+    }
+    return S4G_OK;
+}
+
+extern "C" int s4g_merge_candidates(s4g_ctx* ctx, int n_ranks, int n_queries, int max_candidates, const uint32_t* gathered_ids,
+                                    const float* gathered_scores, const uint32_t* gathered_counts, uint32_t* out_ids,
+                                    float* out_scores, uint32_t* out_counts) {
+    if (!ctx || n_ranks < 1 || n_queries < 1 || max_candidates < 1 || !gathered_ids || !gathered_scores || !gathered_counts || !out_ids || !out_counts)
+        return S4G_ERR_ARG;
+    S4G_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int nq = n_queries;
+    const uint32_t N = (uint32_t)max_candidates, cap = N * (uint32_t)n_ranks;
+    unsigned long long* d_cand = (unsigned long long*)s4g_scratch(ctx, SLOT_PF_CAND, sizeof(unsigned long long) * (size_t)nq * cap);
+    unsigned long long* d_cand_alt = (unsigned long long*)s4g_scratch(ctx, SLOT_PF_TMP, sizeof(unsigned long long) * (size_t)nq * cap);
+    uint32_t* d_count = (uint32_t*)s4g_scratch(ctx, SLOT_PF_COUNT, sizeof(uint32_t) * nq);
+    unsigned long long* d_thr = (unsigned long long*)s4g_scratch(ctx, SLOT_PF_THR, sizeof(unsigned long long) * nq + 64);
+    char* spill = (char*)s4g_scratch(ctx, SLOT_PF_SPILL, 64 + sizeof(int64_t) * 2 * nq + sizeof(uint32_t) * nq);
+    if (!d_cand || !d_cand_alt || !d_count || !d_thr || !spill) return S4G_ERR_NOMEM;
+    unsigned long long* d_nseg = (unsigned long long*)spill;
+    int64_t* d_seg = (int64_t*)(spill + 64);
+    uint32_t* d_seg_q = (uint32_t*)(d_seg + 2 * nq);
+    mg_keys_kernel<<<nq, 128, 0, st>>>(n_ranks, nq, N, gathered_ids, gathered_scores, gathered_counts, d_cand, d_count, cap);
+    S4G_CHECK_LAUNCH(ctx);
+    int rc = compact(ctx, nq, cap, N, 0, 1, d_cand, d_cand_alt, d_count, d_thr, d_seg, d_seg_q, d_nseg, nullptr);
+    if (rc != S4G_OK) return rc;
+    cb_idkeys_kernel<<<nq, 128, 0, st>>>(d_cand, d_count, cap, N, nq);
+    S4G_CHECK_LAUNCH(ctx);
+    rc = compact(ctx, nq, cap, 0xffffffffu, 0, 1, d_cand, d_cand_alt, d_count, d_thr, d_seg, d_seg_q, d_nseg, nullptr);
+    if (rc != S4G_OK) return rc;
+    cb_output_byid_kernel<<<nq, 128, 0, st>>>(d_cand, d_count, cap, N, nq, out_ids, out_scores, out_counts);
+    S4G_CHECK_LAUNCH(ctx);
+    return S4G_OK;
 }
