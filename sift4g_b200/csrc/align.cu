@@ -1,6 +1,466 @@
+// Stage 3: traceback (alignment paths) of the kept hits (sm_100a).
+//
+// Replaces alignScoredPair -> alignScoredPairCpu -> SSW (vendor/swsharp/swsharp/src/align.c:235-255,
+// cpu_module.c:111-142, sse_module.c:62-122,178-265, ssw/ssw.c:771-856) for score <= 32767.  The result
+// must be the reference's, not just "an" optimal alignment, so the three SSW steps are reproduced rule
+// for rule:
+//   1. end cell   : among cells with H == score the smallest target column, then the smallest query row
+//                   (ssw.c:283-308,491-512);
+//   2. begin cell : the same sweep over the reversed query prefix / target prefix scanned right to left;
+//                   first column holding `score`, smallest reversed row (ssw.c:296,500,827-838);
+//   3. path       : banded_sw on the sub-rectangle, band |dt - dq| + 1 doubled until the banded maximum
+//                   reaches the score; direction rules and band-edge behaviour of ssw.c:549-727.
+// Steps 1+2: one warp per hit, 32-bit systolic sweep (lanes own 8 query rows each, the anti-diagonal moves
+// by shuffles, any query length through 256-row passes).  Step 3: one thread per hit with its three band
+// rows in shared memory and one packed direction byte per band cell in HBM; hits are batched by band width.
+// The host only sequences the band-doubling rounds (it needs the end/begin cells anyway to size buffers).
+#include <algorithm>
+#include <cub/cub.cuh>
+
 #include "common.cuh"
-extern "C" int s4g_sw_align(s4g_ctx* ctx, s4g_db*, s4g_queries*, int64_t, const uint32_t*, const uint32_t*, const int32_t*,
-                            const int32_t*, int, int, int32_t*, uint8_t*, int64_t, int64_t*, int) {
-    s4g_set_error(ctx, "align not built yet");
-    return S4G_ERR_INTERNAL;
+
+namespace {
+
+constexpr int kWarps = 8;
+constexpr int kRows = 8;     // query rows per lane in the endpoint sweep
+
+struct AlParams {
+    const uint8_t* db_codes;
+    const int64_t* db_off;
+    uint32_t id_base;
+    const uint8_t* q_codes;
+    const int64_t* q_off;
+    const uint32_t* pair_q;
+    const uint32_t* pair_t;
+    const int32_t* pair_score;
+    int64_t n_pairs;
+    const int8_t* mat8;          // [target letter 27][query letter 32]
+    int32_t go, ge;
+    int32_t* coords;             // 4 per pair
+    unsigned long long* counters;   // [0] work cursor, [1] error flags
+    int32_t* bound;              // per-warp boundary rows for multi-pass sweeps
+    int64_t bound_stride;
+};
+
+// Sweep: Gotoh local alignment of q[0..qlen) (index i -> q[qbase + i*qstep]) against t (j -> t[tbase + j*tstep]);
+// returns the lexicographically smallest (column, row) whose H equals `score` (packed col << 32 | row), or ~0.
+__device__ unsigned long long sweep_first_cell(const uint8_t* q, int qstep, int qlen, const uint8_t* t, int tstep, int tlen,
+                                               int score, const int8_t* smat, int Q, int R, int32_t* bH, int32_t* bF, int lane) {
+    const unsigned FULL = 0xffffffffu;
+    unsigned long long found = ~0ull;
+    const int npass = (qlen + 32 * kRows - 1) / (32 * kRows);
+    for (int pass = 0; pass < npass; ++pass) {
+        const int row0 = pass * 32 * kRows + lane * kRows;
+        int ql[kRows];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) ql[r] = row0 + r < qlen ? (int)q[(long long)(row0 + r) * qstep] : -1;
+        int H[kRows], E[kRows];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) { H[r] = 0; E[r] = 0; }
+        int h_last = 0, f_out = 0, diag_in = 0;
+        const bool first = pass == 0, last = pass == npass - 1;
+        for (int s = 0; s < tlen + 31; ++s) {
+            const int j = s - lane;
+            int h_up = __shfl_up_sync(FULL, h_last, 1);
+            int f = __shfl_up_sync(FULL, f_out, 1);
+            const bool live = j >= 0 && j < tlen;
+            if (lane == 0) {
+                if (first || !live) { h_up = 0; f = 0; }
+                else { h_up = __ldcg(bH + j); f = __ldcg(bF + j); }
+            }
+            int hd = diag_in;
+            diag_in = h_up;
+            const int8_t* srow = smat + (live ? (int)t[(long long)j * tstep] : S4G_PAD_CODE) * 32;
+            int colmax = 0;
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) {
+                const int sc = ql[r] >= 0 ? (int)srow[ql[r]] : -1;
+                int h = __vimax3_s32_relu(hd + sc, E[r], f);
+                if (!live || ql[r] < 0) h = 0;
+                hd = H[r];
+                H[r] = h;
+                const int hq = h - Q;
+                E[r] = __viaddmax_s32_relu(E[r], -R, hq);      // SSW keeps E, F >= 0 (saturating subtract)
+                f = __viaddmax_s32_relu(f, -R, hq);
+                colmax = max(colmax, h);
+            }
+            h_last = H[kRows - 1];
+            f_out = f;
+            if (lane == 31 && !last && live) { __stcg(bH + j, h_last); __stcg(bF + j, f_out); }
+            if (colmax == score && live) {
+                int rr = 0;
+#pragma unroll
+                for (int r = kRows - 1; r >= 0; --r) if (H[r] == score) rr = r;
+                const unsigned long long cand = ((unsigned long long)(unsigned)j << 32) | (unsigned)(row0 + rr);
+                if (cand < found) found = cand;
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(FULL, found, o);
+        if (other < found) found = other;
+    }
+    return found;
+}
+
+__global__ void __launch_bounds__(kWarps * 32) al_endpoints_kernel(AlParams P) {
+    __shared__ int8_t smat[(S4G_PAD_CODE + 1) * 32];
+    for (int i = threadIdx.x; i < (S4G_PAD_CODE + 1) * 32; i += blockDim.x) smat[i] = P.mat8[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int gwarp = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    int32_t* bH = P.bound + (int64_t)gwarp * P.bound_stride;
+    int32_t* bF = bH + P.bound_stride / 2;
+    const unsigned FULL = 0xffffffffu;
+    while (true) {
+        unsigned long long w = 0;
+        if (lane == 0) w = atomicAdd(P.counters + 0, 1ull);
+        w = __shfl_sync(FULL, w, 0);
+        if ((long long)w >= P.n_pairs) break;
+        const uint32_t qi = P.pair_q[w], ti = P.pair_t[w] - P.id_base;
+        const uint8_t* q = P.q_codes + P.q_off[qi];
+        const int qlen = (int)(P.q_off[qi + 1] - P.q_off[qi]);
+        const uint8_t* t = P.db_codes + P.db_off[ti];
+        const int tlen = (int)(P.db_off[ti + 1] - P.db_off[ti]);
+        const int score = P.pair_score[w];
+        int c0 = -1, c1 = -1, c2 = -1, c3 = -1;
+        if (score > 0) {
+            const unsigned long long e = sweep_first_cell(q, 1, qlen, t, 1, tlen, score, smat, P.go, P.ge, bH, bF, lane);
+            if (e != ~0ull) {
+                const int t_end = (int)(e >> 32), q_end = (int)(e & 0xffffffffu);
+                const unsigned long long b = sweep_first_cell(q + q_end, -1, q_end + 1, t + t_end, -1, t_end + 1, score, smat, P.go,
+                                                              P.ge, bH, bF, lane);
+                if (b != ~0ull) {
+                    c1 = q_end; c3 = t_end;
+                    c0 = q_end - (int)(b & 0xffffffffu);
+                    c2 = t_end - (int)(b >> 32);
+                }
+            }
+        }
+        if (lane == 0) {
+            if (c0 < 0) atomicOr(P.counters + 1, 1ull);
+            P.coords[4 * w + 0] = c0; P.coords[4 * w + 1] = c1; P.coords[4 * w + 2] = c2; P.coords[4 * w + 3] = c3;
+        }
+    }
+}
+
+// ---- banded traceback ---------------------------------------------------------------------------------------
+
+struct BandWork {
+    uint32_t pair;       // index into the pair arrays
+    int32_t w;           // band half-width of this round
+    int64_t dir_off;     // offset of this hit's direction bytes
+};
+
+struct BandParams {
+    const BandWork* work;
+    int32_t n_work;
+    int32_t stride;              // ints per band row in shared memory (odd, >= 2*w_max + 4)
+    uint8_t* dir;
+    uint8_t* rev_paths;          // per pair slot: reversed path ops
+    const int64_t* slot_off;     // n_pairs + 1
+    int32_t* path_len;           // per pair, -1 while pending
+    int32_t* status;             // per work item: 1 done, 0 needs a wider band, <0 error
+};
+
+__device__ __forceinline__ int slot_of(int w, int i, int j) { int x = i - w; if (x < 0) x = 0; return j - x + 1; }
+
+__global__ void al_band_kernel(AlParams P, BandParams B) {
+    extern __shared__ int32_t rows[];
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= B.n_work) return;
+    const BandWork wk = B.work[tid];
+    int32_t* hb = rows + (size_t)threadIdx.x * 3 * B.stride;
+    int32_t* eb = hb + B.stride;
+    int32_t* hc = eb + B.stride;
+    const uint32_t p = wk.pair;
+    const int q0 = P.coords[4 * p + 0], q1 = P.coords[4 * p + 1], t0 = P.coords[4 * p + 2], t1 = P.coords[4 * p + 3];
+    const uint8_t* read = P.q_codes + P.q_off[P.pair_q[p]] + q0;
+    const uint8_t* ref = P.db_codes + P.db_off[P.pair_t[p] - P.id_base] + t0;
+    const int readLen = q1 - q0 + 1, refLen = t1 - t0 + 1;
+    const int score = P.pair_score[p];
+    const int w = wk.w, width = 2 * w + 3, width_d = 2 * w + 1;
+    const int go = P.go, ge = P.ge;
+    uint8_t* dir = B.dir + wk.dir_off;
+    for (int j = 0; j < width + 1; ++j) { hb[j] = 0; eb[j] = 0; hc[j] = 0; }
+    int best = 0;
+    for (int i = 0; i < readLen; ++i) {
+        const int beg = i - w > 0 ? i - w : 0;
+        const int end = i + w < refLen - 1 ? i + w : refLen - 1;
+        const int edge = end + 1 < width - 1 ? end + 1 : width - 1;
+        int f = 0, u = 0;
+        hb[0] = 0; eb[0] = 0; hb[edge] = 0; eb[edge] = 0; hc[0] = 0;
+        uint8_t* line = dir + (size_t)width_d * i;
+        const int8_t* mrow = P.mat8 + read[i];          // mat8[target*32 + query]
+        const int xi = beg, xp = (i - 1 - w > 0) ? i - 1 - w : 0;
+        for (int j = beg; j <= end; ++j) {
+            u = j - xi + 1;
+            const int up = j - xp + 1, dg = up - 1;
+            int open = i == 0 ? -go : hb[up] - go;
+            int ext = i == 0 ? -ge : eb[up] - ge;
+            const int e = open > ext ? open : ext;
+            const unsigned de_open = open > ext ? 1u : 0u;
+            eb[u] = e;
+            open = hc[u - 1] - go;
+            ext = f - ge;
+            const unsigned df_open = open > ext ? 1u : 0u;
+            f = open > ext ? open : ext;
+            const int e1 = e > 0 ? e : 0, f1 = f > 0 ? f : 0;
+            const int gap = e1 > f1 ? e1 : f1;
+            const int dsc = hb[dg] + (int)__ldg(mrow + (int)ref[j] * 32);
+            const int h = gap > dsc ? gap : dsc;
+            hc[u] = h;
+            if (h > best) best = h;
+            const unsigned sel = gap <= dsc ? 0u : (e1 > f1 ? 1u : 2u);
+            line[j - xi] = (uint8_t)(de_open | (df_open << 1) | (sel << 2));
+        }
+        for (int j = 1; j <= u; ++j) hb[j] = hc[j];
+    }
+    if (best < score) { B.status[tid] = 0; return; }
+    // traceback from the bottom-right corner in state H until row 0 is reached (ssw.c:634-706)
+    uint8_t* out = B.rev_paths + B.slot_off[p];
+    const int cap = (int)(B.slot_off[p + 1] - B.slot_off[p]);
+    int i = readLen - 1, j = refLen - 1, state = 2, n = 0, rc = 1;
+    while (i > 0) {
+        const int x = i - w > 0 ? i - w : 0;
+        const int hi = i + w < refLen - 1 ? i + w : refLen - 1;
+        if (j < x || j > hi || n >= cap - 1) { rc = -2; break; }
+        const unsigned d = dir[(size_t)width_d * i + (j - x)];
+        unsigned code;
+        if (state == 0) code = (d & 1u) ? 3u : 2u;
+        else if (state == 1) code = (d & 2u) ? 5u : 4u;
+        else { const unsigned sel = d >> 2; code = sel == 0 ? 1u : sel == 1 ? ((d & 1u) ? 3u : 2u) : ((d & 2u) ? 5u : 4u); }
+        switch (code) {
+            case 1: --i; --j; state = 2; out[n++] = 1; break;
+            case 2: --i; state = 0; out[n++] = 3; break;
+            case 3: --i; state = 2; out[n++] = 3; break;
+            case 4: --j; state = 1; out[n++] = 2; break;
+            default: --j; state = 2; out[n++] = 2; break;
+        }
+    }
+    if (rc == 1) { out[n++] = 1; B.path_len[p] = n; }
+    B.status[tid] = rc;
+}
+
+__global__ void al_slot_sizes_kernel(AlParams P, int64_t* sizes) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > P.n_pairs) return;
+    int64_t s = 0;
+    if (i < P.n_pairs && P.coords[4 * i] >= 0) s = (P.coords[4 * i + 1] - P.coords[4 * i] + 1) + (P.coords[4 * i + 3] - P.coords[4 * i + 2] + 1) + 2;
+    sizes[i] = s;
+}
+
+__global__ void al_len64_kernel(const int32_t* path_len, int64_t n, int64_t* len64) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    len64[i] = (i < n && path_len[i] > 0) ? path_len[i] : 0;
+}
+
+// forward-order copy of each reversed path into the packed output
+__global__ void al_pack_paths_kernel(const uint8_t* rev, const int64_t* slot_off, const int32_t* path_len, const int64_t* out_off,
+                                     int64_t n, uint8_t* out, int64_t cap) {
+    const int64_t p = blockIdx.x;
+    if (p >= n) return;
+    const int len = path_len[p] > 0 ? path_len[p] : 0;
+    const uint8_t* src = rev + slot_off[p];
+    uint8_t* dst = out + out_off[p];
+    if (out_off[p] + len > cap) return;
+    for (int i = threadIdx.x; i < len; i += blockDim.x) dst[i] = src[len - 1 - i];
+}
+
+}  // namespace
+
+extern "C" int s4g_sw_align(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_pairs, const uint32_t* pair_q,
+                            const uint32_t* pair_t, const int32_t* pair_score, const int32_t* matrix, int gap_open,
+                            int gap_extend, int32_t* out_coords, uint8_t* out_paths, int64_t path_capacity,
+                            int64_t* out_path_offsets, int where) {
+    if (!ctx || !db || !q || n_pairs < 0 || !matrix || !out_path_offsets) return S4G_ERR_ARG;
+    if (n_pairs > 0 && (!pair_q || !pair_t || !pair_score || !out_coords || !out_paths)) return S4G_ERR_ARG;
+    S4G_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    if (n_pairs == 0) {
+        int64_t zero = 0;
+        if (where == S4G_HOST) out_path_offsets[0] = 0;
+        else S4G_CUDA(ctx, cudaMemcpyAsync(out_path_offsets, &zero, 8, cudaMemcpyHostToDevice, st));
+        return S4G_OK;
+    }
+    if (abs(gap_open) > 127 || abs(gap_extend) > 127) { s4g_set_error(ctx, "gap penalties above 127 take the reference's swAlign path, which this build does not provide yet"); return S4G_ERR_ARG; }
+
+    // host copies of the pair arrays (the band rounds are sequenced on the host)
+    std::vector<uint32_t> h_q(n_pairs), h_t(n_pairs);
+    std::vector<int32_t> h_s(n_pairs);
+    const uint32_t *d_pq, *d_pt; const int32_t* d_ps;
+    if (where == S4G_HOST) {
+        memcpy(h_q.data(), pair_q, 4 * n_pairs); memcpy(h_t.data(), pair_t, 4 * n_pairs); memcpy(h_s.data(), pair_score, 4 * n_pairs);
+        uint32_t* a = (uint32_t*)s4g_scratch(ctx, SLOT_IO_A, 4 * n_pairs);
+        uint32_t* b = (uint32_t*)s4g_scratch(ctx, SLOT_IO_B, 4 * n_pairs);
+        int32_t* c = (int32_t*)s4g_scratch(ctx, SLOT_IO_C, 4 * n_pairs);
+        if (!a || !b || !c) return S4G_ERR_NOMEM;
+        S4G_CUDA(ctx, cudaMemcpyAsync(a, pair_q, 4 * n_pairs, cudaMemcpyHostToDevice, st));
+        S4G_CUDA(ctx, cudaMemcpyAsync(b, pair_t, 4 * n_pairs, cudaMemcpyHostToDevice, st));
+        S4G_CUDA(ctx, cudaMemcpyAsync(c, pair_score, 4 * n_pairs, cudaMemcpyHostToDevice, st));
+        d_pq = a; d_pt = b; d_ps = c;
+    } else {
+        S4G_CUDA(ctx, cudaMemcpyAsync(h_q.data(), pair_q, 4 * n_pairs, cudaMemcpyDeviceToHost, st));
+        S4G_CUDA(ctx, cudaMemcpyAsync(h_t.data(), pair_t, 4 * n_pairs, cudaMemcpyDeviceToHost, st));
+        S4G_CUDA(ctx, cudaMemcpyAsync(h_s.data(), pair_score, 4 * n_pairs, cudaMemcpyDeviceToHost, st));
+        S4G_CUDA(ctx, cudaStreamSynchronize(st));
+        d_pq = pair_q; d_pt = pair_t; d_ps = pair_score;
+    }
+    for (int64_t i = 0; i < n_pairs; ++i) {
+        if (h_q[i] >= (uint32_t)q->n || h_t[i] < db->id_base || h_t[i] - db->id_base >= (uint64_t)db->n) { s4g_set_error(ctx, "pair %lld references an unknown query or target", (long long)i); return S4G_ERR_ARG; }
+        if (h_s[i] > 32767) { s4g_set_error(ctx, "pair %lld: score %d > 32767 takes the reference's swAlign path (sw/cpu_module.c:1185), which this build does not provide yet", (long long)i, h_s[i]); return S4G_ERR_ARG; }
+    }
+
+    int8_t h_mat8[(S4G_PAD_CODE + 1) * 32];
+    memset(h_mat8, 0, sizeof(h_mat8));
+    int min_s = 0;
+    for (int a = 0; a < S4G_NLET; ++a)
+        for (int b = 0; b < S4G_NLET; ++b) {
+            int v = matrix[b * S4G_NLET + a];
+            if (v > 127 || v < -127) { s4g_set_error(ctx, "matrix entry %d outside int8 range", v); return S4G_ERR_ARG; }
+            h_mat8[a * 32 + b] = (int8_t)v;
+            if (v < min_s) min_s = v;
+        }
+    for (int b = 0; b < 32; ++b) h_mat8[S4G_PAD_CODE * 32 + b] = (int8_t)(min_s < -1 ? min_s : -1);
+
+    const int ep_blocks = ctx->sm_count * 4;
+    const int64_t bound_stride = 2 * ((int64_t)db->max_len + 64);
+    char* misc = (char*)s4g_scratch(ctx, SLOT_AL_MISC, 256 + sizeof(h_mat8) + sizeof(int64_t) * 4 * (n_pairs + 1) + sizeof(int32_t) * 6 * n_pairs);
+    int32_t* d_bound = (int32_t*)s4g_scratch(ctx, SLOT_SW_BOUND, sizeof(int32_t) * bound_stride * ep_blocks * kWarps);
+    if (!misc || !d_bound) return S4G_ERR_NOMEM;
+    unsigned long long* d_counters = (unsigned long long*)misc;
+    int8_t* d_mat8 = (int8_t*)(misc + 64);
+    int64_t* d_sizes = (int64_t*)(misc + 64 + ((sizeof(h_mat8) + 63) / 64) * 64);
+    int64_t* d_slot_off = d_sizes + (n_pairs + 1);
+    int64_t* d_len64 = d_slot_off + (n_pairs + 1);
+    int64_t* d_out_off = d_len64 + (n_pairs + 1);
+    int32_t* d_coords_own = (int32_t*)(d_out_off + (n_pairs + 1));
+    int32_t* d_path_len = d_coords_own + 4 * n_pairs;
+    int32_t* d_coords = where == S4G_DEVICE ? out_coords : d_coords_own;
+
+    S4G_CUDA(ctx, cudaMemsetAsync(d_counters, 0, 64, st));
+    S4G_CUDA(ctx, cudaMemcpyAsync(d_mat8, h_mat8, sizeof(h_mat8), cudaMemcpyHostToDevice, st));
+    S4G_CUDA(ctx, cudaMemsetAsync(d_path_len, 0xff, sizeof(int32_t) * n_pairs, st));
+
+    AlParams P;
+    P.db_codes = db->d_codes; P.db_off = db->d_off; P.id_base = db->id_base;
+    P.q_codes = q->d_codes; P.q_off = q->d_off;
+    P.pair_q = d_pq; P.pair_t = d_pt; P.pair_score = d_ps; P.n_pairs = n_pairs;
+    P.mat8 = d_mat8; P.go = gap_open; P.ge = gap_extend; P.coords = d_coords; P.counters = d_counters;
+    P.bound = d_bound; P.bound_stride = bound_stride;
+
+    // 1+2: end and begin cells
+    al_endpoints_kernel<<<ep_blocks, kWarps * 32, 0, st>>>(P);
+    S4G_CHECK_LAUNCH(ctx);
+    std::vector<int32_t> h_coords(4 * n_pairs);
+    unsigned long long h_counters[2];
+    S4G_CUDA(ctx, cudaMemcpyAsync(h_coords.data(), d_coords, sizeof(int32_t) * 4 * n_pairs, cudaMemcpyDeviceToHost, st));
+    S4G_CUDA(ctx, cudaMemcpyAsync(h_counters, d_counters, 16, cudaMemcpyDeviceToHost, st));
+    // slots for the reversed paths
+    al_slot_sizes_kernel<<<(unsigned)((n_pairs + 1 + 255) / 256), 256, 0, st>>>(P, d_sizes);
+    S4G_CHECK_LAUNCH(ctx);
+    {
+        size_t tmp = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_sizes, d_slot_off, (int)(n_pairs + 1), st);
+        void* d_tmp = s4g_scratch(ctx, SLOT_SW_CUB, tmp);
+        if (!d_tmp) return S4G_ERR_NOMEM;
+        S4G_CUDA(ctx, cub::DeviceScan::ExclusiveSum(d_tmp, tmp, d_sizes, d_slot_off, (int)(n_pairs + 1), st));
+        ctx->launches += 1;
+    }
+    S4G_CUDA(ctx, cudaStreamSynchronize(st));
+    if (h_counters[1] & 1ull) { s4g_set_error(ctx, "s4g_sw_align: a pair's score is not attained by any cell (score does not belong to the pair)"); return S4G_ERR_ARG; }
+    int64_t total_slots = 0;
+    for (int64_t i = 0; i < n_pairs; ++i) total_slots += (h_coords[4 * i + 1] - h_coords[4 * i] + 1) + (h_coords[4 * i + 3] - h_coords[4 * i + 2] + 1) + 2;
+    uint8_t* d_rev = (uint8_t*)s4g_scratch(ctx, SLOT_AL_OUT, (size_t)total_slots + 64);
+    if (!d_rev) return S4G_ERR_NOMEM;
+
+    // 3: banded traceback, rounds of band doubling sequenced here
+    struct Pending { uint32_t pair; int32_t w, readLen, refLen; };
+    std::vector<Pending> pending(n_pairs);
+    for (int64_t i = 0; i < n_pairs; ++i) {
+        const int readLen = h_coords[4 * i + 1] - h_coords[4 * i] + 1, refLen = h_coords[4 * i + 3] - h_coords[4 * i + 2] + 1;
+        pending[i] = {(uint32_t)i, abs(refLen - readLen) + 1, readLen, refLen};
+    }
+    const size_t dir_budget = (size_t)4 << 30;
+    const int threads = 64;
+    const size_t smem_limit = 200 * 1024;
+    int round = 0;
+    while (!pending.empty()) {
+        if (++round > 40) { s4g_set_error(ctx, "s4g_sw_align: band doubling did not converge"); return S4G_ERR_INTERNAL; }
+        std::sort(pending.begin(), pending.end(), [](const Pending& a, const Pending& b) { return a.w < b.w; });
+        std::vector<Pending> next;
+        size_t pos = 0;
+        while (pos < pending.size()) {
+            // batch: hits of similar band width whose direction bytes fit the budget
+            size_t end = pos, dir_bytes = 0;
+            const int w_lo = pending[pos].w;
+            std::vector<BandWork> work;
+            int w_max = w_lo;
+            while (end < pending.size() && pending[end].w <= 2 * w_lo + 2) {
+                const size_t need = (size_t)(2 * pending[end].w + 1) * pending[end].readLen;
+                if (!work.empty() && dir_bytes + need > dir_budget) break;
+                work.push_back({pending[end].pair, pending[end].w, (int64_t)dir_bytes});
+                dir_bytes += need;
+                w_max = std::max(w_max, pending[end].w);
+                ++end;
+            }
+            int stride = (2 * w_max + 5) | 1;
+            int tpb = threads;
+            while (tpb > 1 && (size_t)tpb * 3 * stride * 4 > smem_limit) tpb >>= 1;
+            if ((size_t)tpb * 3 * stride * 4 > smem_limit) { s4g_set_error(ctx, "s4g_sw_align: band %d too wide for this build", w_max); return S4G_ERR_CAPACITY; }
+            const size_t smem = (size_t)tpb * 3 * stride * 4;
+            BandWork* d_work = (BandWork*)s4g_scratch(ctx, SLOT_AL_WORK, sizeof(BandWork) * work.size() + sizeof(int32_t) * work.size() + 64);
+            uint8_t* d_dir = (uint8_t*)s4g_scratch(ctx, SLOT_AL_DIR, dir_bytes + 64);
+            if (!d_work || !d_dir) return S4G_ERR_NOMEM;
+            int32_t* d_status = (int32_t*)(d_work + work.size());
+            S4G_CUDA(ctx, cudaMemcpyAsync(d_work, work.data(), sizeof(BandWork) * work.size(), cudaMemcpyHostToDevice, st));
+            BandParams B;
+            B.work = d_work; B.n_work = (int32_t)work.size(); B.stride = stride; B.dir = d_dir; B.rev_paths = d_rev;
+            B.slot_off = d_slot_off; B.path_len = d_path_len; B.status = d_status;
+            S4G_CUDA(ctx, cudaFuncSetAttribute(al_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
+            al_band_kernel<<<(unsigned)((work.size() + tpb - 1) / tpb), tpb, smem, st>>>(P, B);
+            S4G_CHECK_LAUNCH(ctx);
+            std::vector<int32_t> h_status(work.size());
+            S4G_CUDA(ctx, cudaMemcpyAsync(h_status.data(), d_status, sizeof(int32_t) * work.size(), cudaMemcpyDeviceToHost, st));
+            S4G_CUDA(ctx, cudaStreamSynchronize(st));
+            for (size_t i = 0; i < work.size(); ++i) {
+                if (h_status[i] == 0) { Pending p2 = pending[pos + i]; p2.w *= 2; next.push_back(p2); }
+                else if (h_status[i] < 0) { s4g_set_error(ctx, "s4g_sw_align: traceback left the band for pair %u (the reference's behaviour is undefined there)", work[i].pair); return S4G_ERR_INTERNAL; }
+            }
+            pos = end;
+        }
+        pending.swap(next);
+    }
+
+    // pack: path offsets = exclusive scan of the lengths, then forward-order copy
+    al_len64_kernel<<<(unsigned)((n_pairs + 1 + 255) / 256), 256, 0, st>>>(d_path_len, n_pairs, d_len64);
+    S4G_CHECK_LAUNCH(ctx);
+    {
+        size_t tmp = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_len64, d_out_off, (int)(n_pairs + 1), st);
+        void* d_tmp = s4g_scratch(ctx, SLOT_SW_CUB, tmp);
+        if (!d_tmp) return S4G_ERR_NOMEM;
+        S4G_CUDA(ctx, cub::DeviceScan::ExclusiveSum(d_tmp, tmp, d_len64, d_out_off, (int)(n_pairs + 1), st));
+        ctx->launches += 1;
+    }
+    int64_t h_total = 0;
+    S4G_CUDA(ctx, cudaMemcpyAsync(&h_total, d_out_off + n_pairs, 8, cudaMemcpyDeviceToHost, st));
+    S4G_CUDA(ctx, cudaStreamSynchronize(st));
+    if (h_total > path_capacity) { s4g_set_error(ctx, "s4g_sw_align: paths need %lld bytes, capacity %lld", (long long)h_total, (long long)path_capacity); return S4G_ERR_CAPACITY; }
+    uint8_t* d_paths = where == S4G_DEVICE ? out_paths : (uint8_t*)s4g_scratch(ctx, SLOT_IO_D, (size_t)h_total + 64);
+    if (!d_paths) return S4G_ERR_NOMEM;
+    al_pack_paths_kernel<<<(unsigned)n_pairs, 64, 0, st>>>(d_rev, d_slot_off, d_path_len, d_out_off, n_pairs, d_paths, h_total);
+    S4G_CHECK_LAUNCH(ctx);
+    if (where == S4G_HOST) {
+        memcpy(out_coords, h_coords.data(), sizeof(int32_t) * 4 * n_pairs);
+        S4G_CUDA(ctx, cudaMemcpyAsync(out_paths, d_paths, (size_t)h_total, cudaMemcpyDeviceToHost, st));
+        S4G_CUDA(ctx, cudaMemcpyAsync(out_path_offsets, d_out_off, sizeof(int64_t) * (n_pairs + 1), cudaMemcpyDeviceToHost, st));
+        S4G_CUDA(ctx, cudaStreamSynchronize(st));
+    } else {
+        S4G_CUDA(ctx, cudaMemcpyAsync(out_path_offsets, d_out_off, sizeof(int64_t) * (n_pairs + 1), cudaMemcpyDeviceToDevice, st));
+    }
+    return S4G_OK;
 }
