@@ -13,6 +13,8 @@
 //        -> alignScoredPairCpu() (SSW / swAlign)  vendor/swsharp/swsharp/src/cpu_module.c:111
 //   ref_dump pipeline Q.fa DB.fa k max_candidates threads max_evalue max_alignments
 //        -> searchDatabase() + alignDatabase()    sift4g/src/main.cpp:203-220
+//   ref_dump matrix
+//        -> scorerCreateMatrix("BLOSUM_62") table   vendor/swsharp/swsharp/src/pre_proc.c:399, constants.c:87-114
 //   ref_dump scorebench Q.fa DB.fa CANDS.txt threads
 //        -> the reference's threaded scoring loop (tasks of 1000 targets, database.c:896-996) timed
 //
@@ -246,6 +248,18 @@ static int cmd_scorebench(int argc, char** argv) {
     return 0;
 }
 
+static int cmd_matrix(int argc, char** argv) {
+    int go = argc > 3 ? atoi(argv[2]) : 10, ge = argc > 3 ? atoi(argv[3]) : 1;
+    Scorer* scorer = nullptr;
+    scorerCreateMatrix(&scorer, (char*)"BLOSUM_62", go, ge);
+    const int* t = scorerGetTable(scorer);
+    int n = scorerGetMaxCode(scorer);
+    printf("%d", n);
+    for (int i = 0; i < n * n; ++i) printf(" %d", t[i]);
+    printf("\n");
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc < 2) { fprintf(stderr, "usage: ref_dump <candidates|scores|align|pipeline|scorebench> ...\n"); return 2; }
     std::string c = argv[1];
@@ -254,6 +268,7 @@ int main(int argc, char** argv) {
     if (c == "align") return cmd_align(argc, argv);
     if (c == "pipeline") return cmd_pipeline(argc, argv);
     if (c == "scorebench") return cmd_scorebench(argc, argv);
+    if (c == "matrix") return cmd_matrix(argc, argv);
     fprintf(stderr, "unknown command %s\n", argv[1]);
     return 2;
 }

@@ -1,0 +1,58 @@
+"""GPU end to end: the sift4g CLI with the B200 hot path (sift4g_b200/bin/sift4g_b200 = the reference's
+main/select_alignments/sift_prediction compiled unchanged around our searchDatabase/alignDatabase) must write
+byte-identical .SIFTprediction / alignments / aligned.fasta files (hashes of the reference CPU build, committed
+under tests/golden by make_golden.py)."""
+import hashlib
+import json
+import os
+import subprocess
+import tempfile
+
+import pytest
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "sift4g_b200", "bin", "sift4g_b200")
+
+
+def _run(args):
+    out = tempfile.mkdtemp()
+    r = subprocess.run([BIN] + args + ["--out", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return {f: hashlib.sha256(open(os.path.join(out, f), "rb").read()).hexdigest() for f in sorted(os.listdir(out))}
+
+
+def _expected(key):
+    return json.load(open(os.path.join(util.GOLDEN, "expected_hashes.json")))[key]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _binary():
+    assert os.path.exists(BIN), "sift4g_b200/bin/sift4g_b200 missing: build it with make -C sift4g_b200/host (build container)"
+
+
+def test_reference_fixture_with_subst_files():
+    tf = os.path.join(util.GOLDEN, "test_files")
+    got = _run(["-q", tf + "/query.fasta", "-d", tf + "/sample_protein_database.fa", "--subst", tf + "/", "--sub-results"])
+    assert got == _expected("test_files_subst")
+    # byte-for-byte against the committed files too
+    for f in got:
+        assert got[f] == hashlib.sha256(open(os.path.join(util.GOLDEN, "expected_test_files", f), "rb").read()).hexdigest()
+
+
+def test_reference_fixture_full_prediction_matrix():
+    tf = os.path.join(util.GOLDEN, "test_files")
+    assert _run(["-q", tf + "/query.fasta", "-d", tf + "/sample_protein_database.fa"]) == _expected("test_files_nosubst")
+
+
+def test_synthetic_database_default_flags():
+    sd = os.path.join(util.GOLDEN, "synth_e2e")
+    assert _run(["-q", sd + "/q.fa", "-d", sd + "/d.fa", "--sub-results"]) == _expected("synth_default")
+
+
+def test_synthetic_database_with_candidate_cutoff_and_fewer_alignments():
+    sd = os.path.join(util.GOLDEN, "synth_e2e")
+    got = _run(["-q", sd + "/q.fa", "-d", sd + "/d.fa", "--sub-results", "--max-candidates", "200", "--max-aligns", "50"])
+    assert got == _expected("synth_C200_M50")
