@@ -126,6 +126,22 @@ int s4g_sw_align(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_pairs, cons
                  int gap_open, int gap_extend, int32_t* out_coords, uint8_t* out_paths,
                  int64_t path_capacity, int64_t* out_path_offsets, int where);
 
+/* ---- between stage 2 and 3: E-value + hit selection (host side of the boundary) ------------------- */
+/* Restates extractThread / eValues / dbAlignmentDataCmp (sw/database.c:821-875,1043-1059,
+ * sw/evalue.cu:148-220,436-489) for callers that do not link the reference's host objects: for every
+ * query, E-values of its scored candidates in IEEE double with libm erf/exp/sqrt in the reference's
+ * operation order, then the k = min(#{E <= max_evalue}, max_alignments) best under
+ * (E asc, score desc, name asc).  `names` may be NULL: ties then fall back to ascending target id
+ * (equal to name order for zero-padded numeric names).  Runs on `n_threads` host threads (0 = all).
+ * Inputs are host pointers.  out_* arrays need capacity n_queries * max_alignments; hits of query q are
+ * written contiguously, out_offsets[n_queries+1] delimits them.  matrix_name: only "BLOSUM_62" rows are
+ * built in (other matrices use the reference's fallback row). */
+int s4g_select_hits(s4g_ctx* ctx, int32_t n_queries, const int32_t* query_lens, const uint32_t* cand_ids,
+                    const int64_t* cand_offsets, const int32_t* cand_scores, const int32_t* cand_lens,
+                    const char* const* cand_names, uint64_t db_residues, int gap_open, int gap_extend,
+                    double max_evalue, int max_alignments, int n_threads, uint32_t* out_q, uint32_t* out_t,
+                    int32_t* out_score, double* out_evalue, int64_t* out_offsets);
+
 /* ---- measurement helpers ------------------------------------------------------------------------ */
 /* Sustained issue rate of the DPX / integer ALU pipe (lane-operations per second of
  * VIADDMNMX.S16x2), measured for ~`millis` ms on the context's device: the denominator of the SW

@@ -41,6 +41,7 @@ SIGNATURES = {
     "s4g_merge_candidates": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "s4g_sw_score": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int64, _vp, C.c_int, C.c_int, _vp, C.c_int]),
     "s4g_sw_align": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int64, _vp, C.c_int]),
+    "s4g_select_hits": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, C.c_uint64, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "s4g_measure_dpx_peak": (C.c_int, [_vp, C.c_int, _f64p]),
     "s4g_last_sw_kernel_ms": (C.c_int, [_vp, _f32p]),
 }
@@ -240,3 +241,26 @@ def sw_align(ctx, db, q, pair_q, pair_t, pair_score, matrix, gap_open=10, gap_ex
     ctx.check(ctx.lib.s4g_sw_align(ctx.h, db.h, q.h, n, _ptr(pair_q), _ptr(pair_t), _ptr(pair_score), _ptr(matrix), gap_open, gap_extend,
                                    _ptr(coords), _ptr(paths), path_capacity, _ptr(off), S4G_HOST))
     return coords, [paths[off[i]:off[i + 1]].copy() for i in range(n)]
+
+
+def select_hits(ctx, query_lens, cand_ids, cand_offsets, cand_scores, cand_lens, db_residues, gap_open=10, gap_extend=1,
+                max_evalue=1e-4, max_alignments=400, names=None, n_threads=0):
+    """host: -> (pair_q, pair_t, pair_score, evalues, offsets[nq+1])"""
+    query_lens = np.ascontiguousarray(query_lens, dtype=np.int32)
+    cand_ids = np.ascontiguousarray(cand_ids, dtype=np.uint32)
+    cand_offsets = np.ascontiguousarray(cand_offsets, dtype=np.int64)
+    cand_scores = np.ascontiguousarray(cand_scores, dtype=np.int32)
+    cand_lens = np.ascontiguousarray(cand_lens, dtype=np.int32)
+    nq = len(query_lens)
+    cap = max(nq * max_alignments, 1)
+    oq = np.zeros(cap, dtype=np.uint32); ot = np.zeros(cap, dtype=np.uint32)
+    osc = np.zeros(cap, dtype=np.int32); oe = np.zeros(cap, dtype=np.float64)
+    off = np.zeros(nq + 1, dtype=np.int64)
+    name_arr = None
+    if names is not None:
+        name_arr = (C.c_char_p * max(len(names), 1))(*[n.encode() if isinstance(n, str) else n for n in names])
+    ctx.check(ctx.lib.s4g_select_hits(ctx.h, nq, _ptr(query_lens), _ptr(cand_ids), _ptr(cand_offsets), _ptr(cand_scores), _ptr(cand_lens),
+                                      C.cast(name_arr, _vp) if name_arr is not None else None, int(db_residues), gap_open, gap_extend,
+                                      max_evalue, max_alignments, n_threads, _ptr(oq), _ptr(ot), _ptr(osc), _ptr(oe), _ptr(off)))
+    n = int(off[-1])
+    return oq[:n], ot[:n], osc[:n], oe[:n], off

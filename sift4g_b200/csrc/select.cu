@@ -1,0 +1,130 @@
+// Between stage 2 and 3: E-values and hit selection, on the host side of the boundary (threaded C++).
+// Restates createEValueParams / calculateEValueProt (vendor/swsharp/swsharp/src/evalue.cu:73-88,148-220,
+// 436-489) and extractThread's ordering (database.c:847-869,1043-1059).  The C++ shims that link the
+// reference's host objects call the reference's own eValues() instead (sift4g_b200/host/database_alignment.cpp);
+// this entry point serves every other caller (Python binding, bench, multi-GPU pipeline).
+// Doubles: same operation order as the reference, libm erf/exp/sqrt, no FMA contraction (x86-64 baseline ISA).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <thread>
+
+#include "common.cuh"
+
+namespace {
+
+struct EvRow { int go, ge; double lambda, K, H, a, C, alpha, sigma; };
+const EvRow kB62[] = {
+    {-1, -1, 0.3176, 0.134, 0.4012, 0.7916, 0.623757, 4.964660, 4.964660},
+    {11, 2, 0.297, 0.082, 0.27, 1.1, 0.641766, 12.673800, 12.757600},
+    {10, 2, 0.291, 0.075, 0.23, 1.3, 0.649362, 16.474000, 16.602600},
+    {9, 2, 0.279, 0.058, 0.19, 1.5, 0.659245, 22.751900, 22.950000},
+    {8, 2, 0.264, 0.045, 0.15, 1.8, 0.672692, 35.483800, 35.821300},
+    {7, 2, 0.239, 0.027, 0.10, 2.5, 0.702056, 61.238300, 61.886000},
+    {6, 2, 0.201, 0.012, 0.061, 3.3, 0.740802, 140.417000, 141.882000},
+    {13, 1, 0.292, 0.071, 0.23, 1.2, 0.647715, 19.506300, 19.893100},
+    {12, 1, 0.283, 0.059, 0.19, 1.5, 0.656391, 27.856200, 28.469900},
+    {11, 1, 0.267, 0.041, 0.14, 1.9, 0.669720, 42.602800, 43.636200},
+    {10, 1, 0.243, 0.024, 0.10, 2.5, 0.693267, 83.178700, 85.065600},
+    {9, 1, 0.206, 0.010, 0.052, 4.0, 0.731887, 210.333000, 214.842000},
+};
+
+struct EvParams { double lambda, K, a, b, alpha, beta, sigma, tau; double length; };
+
+EvParams make_params(uint64_t db_residues, int go, int ge) {
+    int idx = 0;
+    for (int i = 0; i < (int)(sizeof(kB62) / sizeof(kB62[0])); ++i)
+        if (kB62[i].go == go && kB62[i].ge == ge) { idx = i; break; }
+    const EvRow& r = kB62[idx];
+    const double G = go + ge;
+    EvParams p;
+    p.lambda = r.lambda; p.K = r.K; p.a = r.a; p.alpha = r.alpha; p.sigma = r.sigma;
+    p.b = 2.0 * G * (kB62[0].a - r.a);
+    p.beta = 2.0 * G * (kB62[0].alpha - r.alpha);
+    p.tau = 2.0 * G * (kB62[0].alpha - r.sigma);
+    p.length = (double)(long long)db_residues;
+    return p;
+}
+
+inline double evalue(const EvParams& p, int score, int qlen, int tlen) {
+    const double y = score, m = qlen, n = tlen;
+    const double scale = p.length / (double)tlen;
+    const double c0 = 0.39894228040143267793994605993438;
+    double lm = m - (p.a * y + p.b);
+    double vm = std::max(2.0 * p.alpha / p.lambda, p.alpha * y + p.beta);
+    double sm = sqrt(vm);
+    double fm = lm / sm;
+    double pm = 0.5 + 0.5 * erf(fm);
+    double p1 = lm * pm + sm * c0 * exp(-0.5 * fm * fm);
+    double ln = n - (p.a * y + p.b);
+    double vn = std::max(2.0 * p.alpha / p.lambda, p.alpha * y + p.beta);
+    double sn = sqrt(vn);
+    double fn = ln / sn;
+    double pn = 0.5 + 0.5 * erf(fn);
+    double p2 = ln * pn + sn * c0 * exp(-0.5 * fn * fn);
+    double c = std::max(2.0 * p.sigma / p.lambda, p.sigma * y + p.tau);
+    double area = p1 * p2 + c * pm * pn;
+    return area * p.K * exp(-p.lambda * y) * scale;
+}
+
+struct Row { int64_t i; int score; double value; };
+
+}  // namespace
+
+extern "C" int s4g_select_hits(s4g_ctx* ctx, int32_t nq, const int32_t* query_lens, const uint32_t* cand_ids,
+                               const int64_t* cand_offsets, const int32_t* cand_scores, const int32_t* cand_lens,
+                               const char* const* cand_names, uint64_t db_residues, int gap_open, int gap_extend,
+                               double max_evalue, int max_alignments, int n_threads, uint32_t* out_q, uint32_t* out_t,
+                               int32_t* out_score, double* out_evalue, int64_t* out_offsets) {
+    if (nq < 0 || !query_lens || !cand_offsets || !out_offsets || max_alignments < 0) return S4G_ERR_ARG;
+    if (cand_offsets[nq] > 0 && (!cand_ids || !cand_scores || !cand_lens || !out_q || !out_t || !out_score || !out_evalue)) return S4G_ERR_ARG;
+    (void)ctx;
+    const EvParams P = make_params(db_residues, gap_open, gap_extend);
+    if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > nq) n_threads = nq > 0 ? nq : 1;
+    std::vector<int32_t> kept(nq, 0);
+    auto work = [&](int tid) {
+        std::vector<Row> rows;
+        for (int q = tid; q < nq; q += n_threads) {
+            const int64_t b = cand_offsets[q], e = cand_offsets[q + 1];
+            rows.resize(e - b);
+            int pass = 0;
+            for (int64_t i = b; i < e; ++i) {
+                rows[i - b] = {i, cand_scores[i], evalue(P, cand_scores[i], query_lens[q], cand_lens[i])};
+                if (rows[i - b].value <= max_evalue) ++pass;
+            }
+            const int k = std::min<int64_t>(std::min(pass, max_alignments), e - b);
+            auto less = [&](const Row& x, const Row& y) {
+                if (x.value == y.value) {
+                    if (x.score == y.score) {
+                        if (cand_names) { int c = strcmp(cand_names[x.i], cand_names[y.i]); if (c != 0) return c < 0; }
+                        return cand_ids[x.i] < cand_ids[y.i];
+                    }
+                    return x.score > y.score;
+                }
+                return x.value < y.value;
+            };
+            std::partial_sort(rows.begin(), rows.begin() + k, rows.end(), less);
+            uint32_t* oq = out_q + (size_t)q * max_alignments; uint32_t* ot = out_t + (size_t)q * max_alignments;
+            int32_t* os = out_score + (size_t)q * max_alignments; double* oe = out_evalue + (size_t)q * max_alignments;
+            for (int j = 0; j < k; ++j) { oq[j] = (uint32_t)q; ot[j] = cand_ids[rows[j].i]; os[j] = rows[j].score; oe[j] = rows[j].value; }
+            kept[q] = k;
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& t : pool) t.join();
+    // compact the per-query blocks (stride max_alignments) into contiguous output
+    int64_t w = 0;
+    out_offsets[0] = 0;
+    for (int q = 0; q < nq; ++q) {
+        const size_t src = (size_t)q * max_alignments;
+        if ((size_t)w != src)
+            for (int j = 0; j < kept[q]; ++j) { out_q[w + j] = out_q[src + j]; out_t[w + j] = out_t[src + j]; out_score[w + j] = out_score[src + j]; out_evalue[w + j] = out_evalue[src + j]; }
+        w += kept[q];
+        out_offsets[q + 1] = w;
+    }
+    return S4G_OK;
+}

@@ -1,0 +1,200 @@
+"""Host-side orchestration of the hot path over the C ABI (Python mirror of what the C++ shims in
+sift4g_b200/host do for the CLI): prefilter -> SW scores -> E-value selection -> traceback.
+
+Two entry points, same results:
+  * run_host(...)    -- host (numpy) buffers in and out; every call copies H2D/D2H inside the C ABI.
+                        This is the call a user of the library makes (bench.py's `e2e`).
+  * run_device(...)  -- inputs and intermediate results stay in HBM as torch tensors (bench.py's `value`);
+                        with torch.distributed initialised the database is sharded, one resident shard per
+                        rank, and the per-query candidate lists / kept hits are merged with two NCCL
+                        all-gathers (the only exchanges on the path).
+torch is plumbing here (device buffers, streams, NCCL); all compute is in libsift4g_b200.so.
+"""
+import numpy as np
+
+from . import capi
+
+
+class Result:
+    __slots__ = ("cand_ids", "cand_off", "scores", "pair_q", "pair_t", "pair_score", "evalue", "hit_off", "coords", "paths",
+                 "path_off", "sw_cells", "n_pairs", "timings", "h2d_bytes", "d2h_bytes")
+
+    def __init__(self):
+        for s in self.__slots__:
+            setattr(self, s, None)
+
+
+def _segment_sums(values, off):
+    cs = np.zeros(len(values) + 1, dtype=np.int64)
+    np.cumsum(values, out=cs[1:])
+    return cs[off[1:]] - cs[off[:-1]]
+
+
+def _ragged(ids2d, cnt):
+    nq, n = ids2d.shape
+    if int(cnt.min()) == n:
+        return ids2d.reshape(-1), np.arange(nq + 1, dtype=np.int64) * n
+    mask = np.arange(n)[None, :] < cnt[:, None]
+    off = np.zeros(nq + 1, dtype=np.int64)
+    off[1:] = np.cumsum(cnt)
+    return np.ascontiguousarray(ids2d[mask]), off
+
+
+def run_host(ctx, db, q_codes, q_off, matrix, db_lens, k=5, max_candidates=5000, gap_open=10, gap_extend=1, max_evalue=1e-4,
+             max_alignments=400, names=None, align=True):
+    """Whole hot path with host buffers.  db: capi.Database (resident shard covering the whole database)."""
+    r = Result()
+    q_lens = np.diff(q_off).astype(np.int32)
+    Q = ctx.queries(q_codes, q_off)
+    ids2d, _, cnt = capi.prefilter(ctx, db, Q, k, max_candidates, sorted_by_id=True)
+    r.cand_ids, r.cand_off = _ragged(ids2d, cnt)
+    r.scores = capi.sw_score(ctx, db, Q, r.cand_ids, r.cand_off, matrix, gap_open, gap_extend)
+    cand_lens = db_lens[r.cand_ids - db.id_base].astype(np.int32)
+    r.sw_cells = int(np.dot(q_lens.astype(np.int64), _segment_sums(cand_lens, r.cand_off)))
+    r.n_pairs = len(r.cand_ids)
+    cand_names = [names[i] for i in r.cand_ids] if names is not None else None
+    r.pair_q, r.pair_t, r.pair_score, r.evalue, r.hit_off = capi.select_hits(
+        ctx, q_lens, r.cand_ids, r.cand_off, r.scores, cand_lens, db.n_residues, gap_open, gap_extend, max_evalue, max_alignments, cand_names)
+    r.h2d_bytes = q_codes.nbytes + q_off.nbytes + r.cand_ids.nbytes + r.cand_off.nbytes
+    r.d2h_bytes = ids2d.nbytes + cnt.nbytes + r.scores.nbytes
+    if align and len(r.pair_q):
+        cap = int(q_lens[r.pair_q].astype(np.int64).sum() + db_lens[r.pair_t - db.id_base].astype(np.int64).sum()) + 16
+        r.coords, paths = _align_host(ctx, db, Q, r, matrix, gap_open, gap_extend, cap)
+        r.paths, r.path_off = paths
+        r.h2d_bytes += 3 * r.pair_q.nbytes
+        r.d2h_bytes += r.coords.nbytes + int(r.path_off[-1]) + r.path_off.nbytes
+    Q.close()
+    return r
+
+
+def _align_host(ctx, db, Q, r, matrix, go, ge, cap):
+    import ctypes as C
+    n = len(r.pair_q)
+    coords = np.zeros((n, 4), dtype=np.int32)
+    paths = np.zeros(cap, dtype=np.uint8)
+    off = np.zeros(n + 1, dtype=np.int64)
+    m = np.ascontiguousarray(matrix, dtype=np.int32)
+    ctx.check(ctx.lib.s4g_sw_align(ctx.h, db.h, Q.h, n, r.pair_q.ctypes.data, r.pair_t.ctypes.data, r.pair_score.ctypes.data, m.ctypes.data,
+                                   go, ge, coords.ctypes.data, paths.ctypes.data, cap, off.ctypes.data, capi.S4G_HOST))
+    return coords, (paths[:off[-1]], off)
+
+
+class DevicePipeline:
+    """Device-resident hot path for one rank.  With `dist` (torch.distributed, NCCL) every rank holds one
+    database shard; candidates and kept hits are merged across ranks."""
+
+    def __init__(self, ctx, db, q_codes, q_off, matrix, db_lens, total_residues, k=5, max_candidates=5000, gap_open=10, gap_extend=1,
+                 max_evalue=1e-4, max_alignments=400, dist=None):
+        import torch
+        self.torch = torch
+        self.ctx, self.db, self.matrix = ctx, db, np.ascontiguousarray(matrix, dtype=np.int32)
+        self.k, self.N, self.go, self.ge = k, max_candidates, gap_open, gap_extend
+        self.max_evalue, self.max_alignments = max_evalue, max_alignments
+        self.dist = dist
+        self.world = dist.get_world_size() if dist is not None else 1
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.dev = torch.device("cuda", ctx.device)
+        self.q_lens = np.diff(q_off).astype(np.int32)
+        self.nq = len(self.q_lens)
+        self.db_lens = db_lens                      # host, this shard
+        self.total_residues = int(total_residues)   # whole database (E-value length)
+        self.Q = ctx.queries(q_codes, q_off)
+        nq, N = self.nq, self.N
+        self.t_ids = torch.zeros((nq, N), dtype=torch.int32, device=self.dev)
+        self.t_sc = torch.zeros((nq, N), dtype=torch.float32, device=self.dev)
+        self.t_cnt = torch.zeros(nq, dtype=torch.int32, device=self.dev)
+        if self.world > 1:
+            self.g_ids = torch.zeros((self.world, nq, N), dtype=torch.int32, device=self.dev)
+            self.g_sc = torch.zeros((self.world, nq, N), dtype=torch.float32, device=self.dev)
+            self.g_cnt = torch.zeros((self.world, nq), dtype=torch.int32, device=self.dev)
+            self.m_ids = torch.zeros((nq, N), dtype=torch.int32, device=self.dev)
+            self.m_sc = torch.zeros((nq, N), dtype=torch.float32, device=self.dev)
+            self.m_cnt = torch.zeros(nq, dtype=torch.int32, device=self.dev)
+        ctx.set_stream(torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def close(self):
+        self.Q.close()
+
+    def step(self, align=True):
+        torch, ctx, db = self.torch, self.ctx, self.db
+        r = Result()
+        nq, N = self.nq, self.N
+        lo, hi = db.id_base, db.id_base + db.n_seqs
+        # ---- stage 1 ----
+        if self.world == 1:
+            capi.prefilter(ctx, db, self.Q, self.k, N, True, out=(self.t_ids, self.t_sc, self.t_cnt), where=capi.S4G_DEVICE)
+            ids, cnt = self.t_ids, self.t_cnt
+        else:
+            capi.prefilter(ctx, db, self.Q, self.k, N, False, out=(self.t_ids, self.t_sc, self.t_cnt), where=capi.S4G_DEVICE)
+            self.dist.all_gather_into_tensor(self.g_ids.view(-1), self.t_ids.view(-1))
+            self.dist.all_gather_into_tensor(self.g_sc.view(-1), self.t_sc.view(-1))
+            self.dist.all_gather_into_tensor(self.g_cnt.view(-1), self.t_cnt)
+            ctx.check(ctx.lib.s4g_merge_candidates(ctx.h, self.world, nq, N, self.g_ids.data_ptr(), self.g_sc.data_ptr(), self.g_cnt.data_ptr(),
+                                                   self.m_ids.data_ptr(), self.m_sc.data_ptr(), self.m_cnt.data_ptr()))
+            ids, cnt = self.m_ids, self.m_cnt
+        # candidates owned by this rank (ids are uint32 bit patterns in int32 tensors)
+        col = torch.arange(N, device=self.dev, dtype=torch.int32)[None, :]
+        ids64 = ids.to(torch.int64) & 0xffffffff
+        own = (col < cnt[:, None]) & (ids64 >= lo) & (ids64 < hi)
+        cand_ids = ids[own].contiguous()
+        cand_cnt = own.sum(dim=1)
+        cand_off = torch.zeros(nq + 1, dtype=torch.int64, device=self.dev)
+        cand_off[1:] = torch.cumsum(cand_cnt, 0)
+        n_pairs = int(cand_ids.numel())
+        scores = torch.empty(max(n_pairs, 1), dtype=torch.int32, device=self.dev)
+        # ---- stage 2 ----
+        if n_pairs:
+            capi.sw_score(ctx, db, self.Q, cand_ids, cand_off, self.matrix, self.go, self.ge, out=scores, where=capi.S4G_DEVICE)
+        # ---- E-value selection on the host ----
+        h_ids = cand_ids.cpu().numpy().view(np.uint32)
+        h_off = cand_off.cpu().numpy()
+        h_scores = scores[:n_pairs].cpu().numpy()
+        h_lens = self.db_lens[h_ids - lo].astype(np.int32) if n_pairs else np.zeros(0, np.int32)
+        r.n_pairs = n_pairs
+        r.sw_cells = int(np.dot(self.q_lens.astype(np.int64), _segment_sums(h_lens, h_off)))
+        pq, pt, ps, ev, hoff = capi.select_hits(ctx, self.q_lens, h_ids, h_off, h_scores, h_lens, self.total_residues, self.go, self.ge,
+                                                self.max_evalue, self.max_alignments)
+        if self.world > 1:
+            pq, pt, ps, ev, hoff = self._merge_hits(pq, pt, ps, ev, hoff, lo, hi)
+        r.pair_q, r.pair_t, r.pair_score, r.evalue, r.hit_off = pq, pt, ps, ev, hoff
+        r.cand_ids, r.cand_off, r.scores = h_ids, h_off, h_scores
+        # ---- stage 3 ----
+        if align and len(pq):
+            d_pq = torch.from_numpy(pq.view(np.int32)).to(self.dev)
+            d_pt = torch.from_numpy(pt.view(np.int32)).to(self.dev)
+            d_ps = torch.from_numpy(ps).to(self.dev)
+            cap = int(self.q_lens[pq].astype(np.int64).sum() + self.db_lens[pt - lo].astype(np.int64).sum()) + 16
+            d_coords = torch.empty((len(pq), 4), dtype=torch.int32, device=self.dev)
+            d_paths = torch.empty(cap, dtype=torch.uint8, device=self.dev)
+            d_poff = torch.empty(len(pq) + 1, dtype=torch.int64, device=self.dev)
+            ctx.check(ctx.lib.s4g_sw_align(ctx.h, db.h, self.Q.h, len(pq), d_pq.data_ptr(), d_pt.data_ptr(), d_ps.data_ptr(), self.matrix.ctypes.data,
+                                           self.go, self.ge, d_coords.data_ptr(), d_paths.data_ptr(), cap, d_poff.data_ptr(), capi.S4G_DEVICE))
+            r.coords, r.paths, r.path_off = d_coords, d_paths, d_poff
+        return r
+
+    def _merge_hits(self, pq, pt, ps, ev, hoff, lo, hi):
+        """Global top max_alignments per query over all ranks (value asc, score desc, id asc); every rank keeps
+        the hits whose targets it owns, so traceback needs no further exchange."""
+        torch = self.torch
+        nq, M, W = self.nq, self.max_alignments, self.world
+        loc = np.zeros((nq, M, 3), dtype=np.float64)      # value, score, id  (exact in double)
+        loc[:, :, 0] = np.inf
+        cnt = np.diff(hoff)
+        for q in range(nq):
+            a, b = hoff[q], hoff[q + 1]
+            loc[q, :b - a, 0] = ev[a:b]; loc[q, :b - a, 1] = ps[a:b]; loc[q, :b - a, 2] = pt[a:b]
+        t_loc = torch.from_numpy(loc).to(self.dev)
+        t_all = torch.empty((W,) + t_loc.shape, dtype=torch.float64, device=self.dev)
+        self.dist.all_gather_into_tensor(t_all.view(-1), t_loc.view(-1))
+        allh = t_all.cpu().numpy().transpose(1, 0, 2, 3).reshape(nq, W * M, 3)
+        oq, ot, osc, oev, off = [], [], [], [], [0]
+        for q in range(nq):
+            rows = allh[q]
+            rows = rows[np.isfinite(rows[:, 0])]
+            order = np.lexsort((rows[:, 2], -rows[:, 1], rows[:, 0]))[:M]
+            rows = rows[order]
+            mine = rows[(rows[:, 2] >= lo) & (rows[:, 2] < hi)]
+            oq.append(np.full(len(mine), q, dtype=np.uint32)); ot.append(mine[:, 2].astype(np.uint32))
+            osc.append(mine[:, 1].astype(np.int32)); oev.append(mine[:, 0]); off.append(off[-1] + len(mine))
+        cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt)
+        return cat(oq, np.uint32), cat(ot, np.uint32), cat(osc, np.int32), cat(oev, np.float64), np.array(off, dtype=np.int64)
