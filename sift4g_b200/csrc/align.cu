@@ -244,6 +244,151 @@ __global__ void al_band_kernel(AlParams P, BandParams B) {
     B.status[tid] = rc;
 }
 
+
+// Warp-parallel banded_sw: lanes own consecutive band columns of one row, rows are sequential.
+// Along a row the only serial dependency is F:  f[t] = max(hc[t-1] - go, f[t-1] - ge),  hc = max(g, f)  with
+// g = max(e+, Hdiag + S) >= 0, which for ge <= go collapses to f[t] = max(g[t-1] - go, f[t-1] - ge): a max-plus
+// prefix scan (5 shuffles).  Directions and values are the same integers banded_sw computes cell by cell.
+constexpr int kBandWarps = 4;
+constexpr int kNegBig = -(1 << 29);
+
+__global__ void __launch_bounds__(kBandWarps * 32) al_band_warp_kernel(AlParams P, BandParams B, unsigned long long* cursor) {
+    extern __shared__ int32_t rows[];
+    __shared__ int8_t smatT[32 * 32];            // [query letter][target letter]
+    for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) {
+        const int ql = i >> 5, tl = i & 31;
+        smatT[i] = tl <= S4G_PAD_CODE ? P.mat8[tl * 32 + ql] : 0;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned FULL = 0xffffffffu;
+    int32_t* bufA = rows + (size_t)warp * 3 * B.stride;
+    int32_t* bufB = bufA + B.stride;
+    int32_t* E = bufB + B.stride;
+    const int go = P.go, ge = P.ge;
+    while (true) {
+        unsigned long long wi = 0;
+        if (lane == 0) wi = atomicAdd(cursor, 1ull);
+        wi = __shfl_sync(FULL, wi, 0);
+        if (wi >= (unsigned long long)B.n_work) break;
+        const BandWork wk = B.work[wi];
+        const uint32_t p = wk.pair;
+        const int q0 = P.coords[4 * p + 0], q1 = P.coords[4 * p + 1], t0 = P.coords[4 * p + 2], t1 = P.coords[4 * p + 3];
+        const uint8_t* read = P.q_codes + P.q_off[P.pair_q[p]] + q0;
+        const uint8_t* ref = P.db_codes + P.db_off[P.pair_t[p] - P.id_base] + t0;
+        const int readLen = q1 - q0 + 1, refLen = t1 - t0 + 1;
+        const int score = P.pair_score[p];
+        const int w = wk.w, width = 2 * w + 3, width_d = 2 * w + 1;
+        uint8_t* dir = B.dir + wk.dir_off;
+        int32_t* prevH = bufA;
+        int32_t* curH = bufB;
+        for (int j = lane; j < width + 1; j += 32) { bufA[j] = 0; bufB[j] = 0; E[j] = 0; }
+        __syncwarp();
+        int best = 0;
+        const int f0 = max(-go, -ge);
+        for (int i = 0; i < readLen; ++i) {
+            const int beg = i - w > 0 ? i - w : 0;
+            const int end = i + w < refLen - 1 ? i + w : refLen - 1;
+            const int edge = end + 1 < width - 1 ? end + 1 : width - 1;
+            const int xp = (i - 1 - w > 0) ? i - 1 - w : 0;
+            if (lane == 0) { prevH[0] = 0; E[0] = 0; prevH[edge] = 0; E[edge] = 0; curH[0] = 0; }
+            __syncwarp();
+            const int8_t* mrow = smatT + (int)read[i] * 32;
+            uint8_t* line = dir + (size_t)width_d * i;
+            int carry_pm = kNegBig, carry_hc = 0, carry_f = 0;
+            for (int c0 = beg; c0 <= end; c0 += 32) {
+                const int j = c0 + lane;
+                const bool act = j <= end;
+                const int t = j - beg, u = t + 1, up = j - xp + 1;
+                int ph = 0, pe = 0, pd = 0, sc = 0;
+                if (act) { ph = prevH[up]; pe = E[up]; pd = prevH[up - 1]; sc = mrow[ref[j]]; }
+                const int open_e = i == 0 ? -go : ph - go;
+                const int ext_e = i == 0 ? -ge : pe - ge;
+                const int e = open_e > ext_e ? open_e : ext_e;
+                const unsigned de = open_e > ext_e ? 1u : 0u;
+                const int e1 = e > 0 ? e : 0;
+                const int dsc = pd + sc;
+                const int g = e1 > dsc ? e1 : dsc;
+                int a = act ? g - go + t * ge : kNegBig;
+                int incl = a;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl = max(incl, y); }
+                int excl = __shfl_up_sync(FULL, incl, 1);
+                if (lane == 0) excl = kNegBig;
+                excl = max(excl, carry_pm);
+                const int f = t == 0 ? f0 : max(f0 - t * ge, excl - (t - 1) * ge);
+                const int hc = g > f ? g : f;
+                int hc_left = __shfl_up_sync(FULL, hc, 1), f_left = __shfl_up_sync(FULL, f, 1);
+                if (lane == 0) { hc_left = carry_hc; f_left = carry_f; }
+                const unsigned df = (hc_left - go) > (f_left - ge) ? 1u : 0u;
+                const int f1 = f > 0 ? f : 0;
+                const int gap = e1 > f1 ? e1 : f1;
+                const unsigned sel = gap <= dsc ? 0u : (e1 > f1 ? 1u : 2u);
+                carry_pm = max(carry_pm, __shfl_sync(FULL, incl, 31));
+                carry_hc = __shfl_sync(FULL, hc, 31);
+                carry_f = __shfl_sync(FULL, f, 31);
+                __syncwarp();
+                if (act) {
+                    E[u] = e;
+                    curH[u] = hc;
+                    line[t] = (uint8_t)(de | (df << 1) | (sel << 2));
+                    best = max(best, hc);
+                }
+            }
+            __syncwarp();
+            int32_t* tmp = prevH; prevH = curH; curH = tmp;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(FULL, best, o));
+        if (best < score) { if (lane == 0) B.status[wi] = 0; continue; }
+        __threadfence_block();
+        __syncwarp();
+        // traceback: diagonal runs are taken 32 cells at a time (every lane probes one cell of the diagonal)
+        uint8_t* out = B.rev_paths + B.slot_off[p];
+        const int cap = (int)(B.slot_off[p + 1] - B.slot_off[p]);
+        int i = readLen - 1, j = refLen - 1, state = 2, n = 0, rc = 1;
+        while (i > 0) {
+            const int ii = i - lane, jj = j - lane;
+            unsigned d = 0xffu;
+            if (ii > 0 && jj >= 0) {
+                const int x = ii - w > 0 ? ii - w : 0;
+                const int hi = ii + w < refLen - 1 ? ii + w : refLen - 1;
+                if (jj >= x && jj <= hi) d = __ldcg(dir + (size_t)width_d * ii + (jj - x));
+            }
+            const unsigned d0 = __shfl_sync(FULL, d, 0);
+            if (d0 == 0xffu) { rc = -2; break; }
+            if (state == 2 && (d0 >> 2) == 0u) {
+                const unsigned nd = __ballot_sync(FULL, !(d != 0xffu && (d >> 2) == 0u));
+                int run = nd ? __ffs(nd) - 1 : 32;
+                if (run > i) run = i;
+                if (n + run >= cap) { rc = -2; break; }
+                if (lane < run) out[n + lane] = 1;
+                n += run; i -= run; j -= run;
+                continue;
+            }
+            unsigned code;
+            if (state == 0) code = (d0 & 1u) ? 3u : 2u;
+            else if (state == 1) code = (d0 & 2u) ? 5u : 4u;
+            else { const unsigned sel = d0 >> 2; code = sel == 1 ? ((d0 & 1u) ? 3u : 2u) : ((d0 & 2u) ? 5u : 4u); }
+            if (n + 1 >= cap) { rc = -2; break; }
+            uint8_t op;
+            switch (code) {
+                case 2: --i; state = 0; op = 3; break;
+                case 3: --i; state = 2; op = 3; break;
+                case 4: --j; state = 1; op = 2; break;
+                default: --j; state = 2; op = 2; break;
+            }
+            if (lane == 0) out[n] = op;
+            ++n;
+        }
+        if (lane == 0) {
+            if (rc == 1) { out[n++] = 1; B.path_len[p] = n; }
+            B.status[wi] = rc;
+        }
+        __syncwarp();
+    }
+}
+
 __global__ void al_slot_sizes_kernel(AlParams P, int64_t* sizes) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i > P.n_pairs) return;
@@ -408,10 +553,11 @@ extern "C" int s4g_sw_align(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_
                 ++end;
             }
             int stride = (2 * w_max + 5) | 1;
+            const bool warp_path = gap_extend <= gap_open && (size_t)kBandWarps * 3 * stride * 4 <= smem_limit;
             int tpb = threads;
             while (tpb > 1 && (size_t)tpb * 3 * stride * 4 > smem_limit) tpb >>= 1;
-            if ((size_t)tpb * 3 * stride * 4 > smem_limit) { s4g_set_error(ctx, "s4g_sw_align: band %d too wide for this build", w_max); return S4G_ERR_CAPACITY; }
-            const size_t smem = (size_t)tpb * 3 * stride * 4;
+            if (!warp_path && (size_t)tpb * 3 * stride * 4 > smem_limit) { s4g_set_error(ctx, "s4g_sw_align: band %d too wide for this build", w_max); return S4G_ERR_CAPACITY; }
+            const size_t smem = warp_path ? (size_t)kBandWarps * 3 * stride * 4 : (size_t)tpb * 3 * stride * 4;
             BandWork* d_work = (BandWork*)s4g_scratch(ctx, SLOT_AL_WORK, sizeof(BandWork) * work.size() + sizeof(int32_t) * work.size() + 64);
             uint8_t* d_dir = (uint8_t*)s4g_scratch(ctx, SLOT_AL_DIR, dir_bytes + 64);
             if (!d_work || !d_dir) return S4G_ERR_NOMEM;
@@ -420,8 +566,18 @@ extern "C" int s4g_sw_align(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_
             BandParams B;
             B.work = d_work; B.n_work = (int32_t)work.size(); B.stride = stride; B.dir = d_dir; B.rev_paths = d_rev;
             B.slot_off = d_slot_off; B.path_len = d_path_len; B.status = d_status;
-            S4G_CUDA(ctx, cudaFuncSetAttribute(al_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
-            al_band_kernel<<<(unsigned)((work.size() + tpb - 1) / tpb), tpb, smem, st>>>(P, B);
+            if (warp_path) {
+                S4G_CUDA(ctx, cudaFuncSetAttribute(al_band_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
+                S4G_CUDA(ctx, cudaMemsetAsync(d_counters + 2, 0, 8, st));
+                int per_sm = 0;
+                S4G_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, al_band_warp_kernel, kBandWarps * 32, smem));
+                if (per_sm < 1) per_sm = 1;
+                unsigned grid = (unsigned)std::min<size_t>((work.size() + kBandWarps - 1) / kBandWarps, (size_t)ctx->sm_count * per_sm);
+                al_band_warp_kernel<<<grid, kBandWarps * 32, smem, st>>>(P, B, d_counters + 2);
+            } else {
+                S4G_CUDA(ctx, cudaFuncSetAttribute(al_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
+                al_band_kernel<<<(unsigned)((work.size() + tpb - 1) / tpb), tpb, smem, st>>>(P, B);
+            }
             S4G_CHECK_LAUNCH(ctx);
             std::vector<int32_t> h_status(work.size());
             S4G_CUDA(ctx, cudaMemcpyAsync(h_status.data(), d_status, sizeof(int32_t) * work.size(), cudaMemcpyDeviceToHost, st));
