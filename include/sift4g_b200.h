@@ -142,6 +142,18 @@ int s4g_select_hits(s4g_ctx* ctx, int32_t n_queries, const int32_t* query_lens, 
                     double max_evalue, int max_alignments, int n_threads, uint32_t* out_q, uint32_t* out_t,
                     int32_t* out_score, double* out_evalue, int64_t* out_offsets);
 
+/* GPU pre-screen in front of s4g_select_hits (optional, changes no result): evaluates the E-value of every
+ * scored candidate on the device in double (CUDA libm, within a few ulp of the host's) and keeps those with
+ * E <= max_evalue * (1 + 1e-6), compacted in candidate order.  Survivors are re-evaluated exactly on the host
+ * by s4g_select_hits, so the final hit lists equal a host-only evaluation of every candidate; what the screen
+ * saves is the D2H copy and the host libm work for the ~95 % of candidates that cannot pass.
+ * cand_ids / cand_offsets / scores: device pointers (as given to / produced by s4g_sw_score with S4G_DEVICE).
+ * out_*: device arrays of capacity n_pairs; out_count: device uint32. */
+int s4g_evalue_screen(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, const uint32_t* cand_ids, const int64_t* cand_offsets,
+                      int64_t n_pairs, const int32_t* scores, uint64_t db_residues, int gap_open, int gap_extend,
+                      double max_evalue, uint32_t* out_query, uint32_t* out_id, int32_t* out_score, int32_t* out_tlen,
+                      uint32_t* out_count);
+
 /* ---- measurement helpers ------------------------------------------------------------------------ */
 /* Sustained issue rate of the DPX / integer ALU pipe (lane-operations per second of
  * VIADDMNMX.S16x2), measured for ~`millis` ms on the context's device: the denominator of the SW

@@ -42,6 +42,7 @@ SIGNATURES = {
     "s4g_sw_score": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int64, _vp, C.c_int, C.c_int, _vp, C.c_int]),
     "s4g_sw_align": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int64, _vp, C.c_int]),
     "s4g_select_hits": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, C.c_uint64, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "s4g_evalue_screen": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int64, _vp, C.c_uint64, C.c_int, C.c_int, C.c_double, _vp, _vp, _vp, _vp, _vp]),
     "s4g_measure_dpx_peak": (C.c_int, [_vp, C.c_int, _f64p]),
     "s4g_last_sw_kernel_ms": (C.c_int, [_vp, _f32p]),
 }

@@ -9,6 +9,8 @@
 #include <cstring>
 #include <thread>
 
+#include <cub/cub.cuh>
+
 #include "common.cuh"
 
 namespace {
@@ -69,6 +71,43 @@ inline double evalue(const EvParams& p, int score, int qlen, int tlen) {
 
 struct Row { int64_t i; int score; double value; };
 
+__global__ void ev_flag_kernel(EvParams P, const uint32_t* cand_ids, const int64_t* cand_off, int nq, int64_t n, const int32_t* scores,
+                               const int64_t* q_off, const int64_t* db_off, uint32_t id_base, double limit, uint8_t* flags,
+                               uint32_t* qidx, int32_t* tlens) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int lo = 0, hi = nq;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (cand_off[mid] <= i) lo = mid; else hi = mid; }
+    const int qlen = (int)(q_off[lo + 1] - q_off[lo]);
+    const uint32_t t = cand_ids[i] - id_base;
+    const int tlen = (int)(db_off[t + 1] - db_off[t]);
+    const double y = scores[i], m = qlen, nn = tlen;
+    const double c0 = 0.39894228040143267793994605993438;
+    const double lm = m - (P.a * y + P.b);
+    const double vm = fmax(2.0 * P.alpha / P.lambda, P.alpha * y + P.beta);
+    const double sm = sqrt(vm), fm = lm / sm;
+    const double pm = 0.5 + 0.5 * erf(fm);
+    const double p1 = lm * pm + sm * c0 * exp(-0.5 * fm * fm);
+    const double ln = nn - (P.a * y + P.b);
+    const double fn = ln / sm;
+    const double pn = 0.5 + 0.5 * erf(fn);
+    const double p2 = ln * pn + sm * c0 * exp(-0.5 * fn * fn);
+    const double c = fmax(2.0 * P.sigma / P.lambda, P.sigma * y + P.tau);
+    const double e = (p1 * p2 + c * pm * pn) * P.K * exp(-P.lambda * y) * (P.length / nn);
+    flags[i] = (e <= limit) ? 1 : 0;
+    qidx[i] = (uint32_t)lo;
+    tlens[i] = tlen;
+}
+
+__global__ void ev_gather_kernel(const uint32_t* sel, const uint32_t* n_sel, const uint32_t* cand_ids, const int32_t* scores,
+                                 const uint32_t* qidx, const int32_t* tlens, uint32_t* out_q, uint32_t* out_id, int32_t* out_score,
+                                 int32_t* out_tlen) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *n_sel) return;
+    const uint32_t s = sel[i];
+    out_q[i] = qidx[s]; out_id[i] = cand_ids[s]; out_score[i] = scores[s]; out_tlen[i] = tlens[s];
+}
+
 }  // namespace
 
 extern "C" int s4g_select_hits(s4g_ctx* ctx, int32_t nq, const int32_t* query_lens, const uint32_t* cand_ids,
@@ -126,5 +165,38 @@ extern "C" int s4g_select_hits(s4g_ctx* ctx, int32_t nq, const int32_t* query_le
         w += kept[q];
         out_offsets[q + 1] = w;
     }
+    return S4G_OK;
+}
+
+extern "C" int s4g_evalue_screen(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, const uint32_t* cand_ids, const int64_t* cand_offsets,
+                                 int64_t n_pairs, const int32_t* scores, uint64_t db_residues, int gap_open, int gap_extend,
+                                 double max_evalue, uint32_t* out_query, uint32_t* out_id, int32_t* out_score, int32_t* out_tlen,
+                                 uint32_t* out_count) {
+    if (!ctx || !db || !q || !cand_offsets || !out_count || n_pairs < 0) return S4G_ERR_ARG;
+    S4G_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    if (n_pairs == 0) { S4G_CUDA(ctx, cudaMemsetAsync(out_count, 0, 4, st)); return S4G_OK; }
+    if (n_pairs >= (1ll << 31)) { s4g_set_error(ctx, "s4g_evalue_screen: more than 2^31 pairs"); return S4G_ERR_ARG; }
+    const EvParams P = make_params(db_residues, gap_open, gap_extend);
+    char* buf = (char*)s4g_scratch(ctx, SLOT_AL_WORK, (size_t)n_pairs * (1 + 4 + 4 + 4) + 256);
+    if (!buf) return S4G_ERR_NOMEM;
+    uint32_t* qidx = (uint32_t*)buf;
+    int32_t* tlens = (int32_t*)(qidx + n_pairs);
+    uint32_t* sel = (uint32_t*)(tlens + n_pairs);
+    uint8_t* flags = (uint8_t*)(sel + n_pairs);
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((n_pairs + threads - 1) / threads);
+    ev_flag_kernel<<<blocks, threads, 0, st>>>(P, cand_ids, cand_offsets, q->n, n_pairs, scores, q->d_off, db->d_off, db->id_base,
+                                              max_evalue * (1.0 + 1e-6), flags, qidx, tlens);
+    S4G_CHECK_LAUNCH(ctx);
+    size_t tmp = 0;
+    cub::CountingInputIterator<uint32_t> it(0);
+    cub::DeviceSelect::Flagged(nullptr, tmp, it, flags, sel, out_count, (int)n_pairs, st);
+    void* d_tmp = s4g_scratch(ctx, SLOT_SW_CUB, tmp);
+    if (!d_tmp) return S4G_ERR_NOMEM;
+    S4G_CUDA(ctx, cub::DeviceSelect::Flagged(d_tmp, tmp, it, flags, sel, out_count, (int)n_pairs, st));
+    ctx->launches += 2;
+    ev_gather_kernel<<<blocks, threads, 0, st>>>(sel, out_count, cand_ids, scores, qidx, tlens, out_query, out_id, out_score, out_tlen);
+    S4G_CHECK_LAUNCH(ctx);
     return S4G_OK;
 }

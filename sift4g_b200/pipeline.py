@@ -110,14 +110,23 @@ class DevicePipeline:
             self.m_ids = torch.zeros((nq, N), dtype=torch.int32, device=self.dev)
             self.m_sc = torch.zeros((nq, N), dtype=torch.float32, device=self.dev)
             self.m_cnt = torch.zeros(nq, dtype=torch.int32, device=self.dev)
+        self.t_db_lens = torch.from_numpy(np.ascontiguousarray(db_lens, dtype=np.int64)).to(self.dev)
+        self.t_q_lens = torch.from_numpy(self.q_lens.astype(np.int64)).to(self.dev)
+        self.q_host = (q_codes, q_off)
         ctx.set_stream(torch.cuda.current_stream(self.dev).cuda_stream)
 
     def close(self):
         self.Q.close()
 
-    def step(self, align=True):
+    def step(self, align=True, e2e=False):
+        """One pass of the hot path.  e2e=True: the query batch is uploaded from host memory first and every
+        result (candidate lists, survivor scores, alignments) is copied back to the host at the end."""
         torch, ctx, db = self.torch, self.ctx, self.db
         r = Result()
+        if e2e:
+            self.Q.close()
+            self.Q = ctx.queries(*self.q_host)
+            r.h2d_bytes = self.q_host[0].nbytes + self.q_host[1].nbytes
         nq, N = self.nq, self.N
         lo, hi = db.id_base, db.id_base + db.n_seqs
         # ---- stage 1 ----
@@ -145,19 +154,37 @@ class DevicePipeline:
         # ---- stage 2 ----
         if n_pairs:
             capi.sw_score(ctx, db, self.Q, cand_ids, cand_off, self.matrix, self.go, self.ge, out=scores, where=capi.S4G_DEVICE)
-        # ---- E-value selection on the host ----
-        h_ids = cand_ids.cpu().numpy().view(np.uint32)
-        h_off = cand_off.cpu().numpy()
-        h_scores = scores[:n_pairs].cpu().numpy()
-        h_lens = self.db_lens[h_ids - lo].astype(np.int32) if n_pairs else np.zeros(0, np.int32)
+        # ---- E-value screen on the device, exact selection of the survivors on the host ----
+        cap = max(n_pairs, 1)
+        if getattr(self, "_scr_cap", 0) < cap:
+            self._scr = [torch.empty(cap, dtype=torch.int32, device=self.dev) for _ in range(4)]
+            self._scr_cnt = torch.zeros(1, dtype=torch.int32, device=self.dev)
+            self._scr_cap = cap
+        s_q, s_id, s_sc, s_tl = self._scr
+        ctx.check(ctx.lib.s4g_evalue_screen(ctx.h, db.h, self.Q.h, cand_ids.data_ptr(), cand_off.data_ptr(), n_pairs, scores.data_ptr(),
+                                            self.total_residues, self.go, self.ge, self.max_evalue, s_q.data_ptr(), s_id.data_ptr(),
+                                            s_sc.data_ptr(), s_tl.data_ptr(), self._scr_cnt.data_ptr()))
+        # algorithmic SW cells of this step (statistic): sum_q len(q) * sum_{t in cand(q)} len(t)
+        if n_pairs:
+            lens_dev = self.t_db_lens[(cand_ids.to(torch.int64) & 0xffffffff) - lo]
+            cs = torch.zeros(n_pairs + 1, dtype=torch.int64, device=self.dev)
+            cs[1:] = torch.cumsum(lens_dev, 0)
+            seg = cs[cand_off[1:]] - cs[cand_off[:-1]]
+            cells_dev = (seg * self.t_q_lens).sum()
+        n_s = int(self._scr_cnt.item())
+        h_q = s_q[:n_s].cpu().numpy().view(np.uint32)
+        h_ids = s_id[:n_s].cpu().numpy().view(np.uint32)
+        h_scores = s_sc[:n_s].cpu().numpy()
+        h_lens = s_tl[:n_s].cpu().numpy()
+        h_off = np.searchsorted(h_q, np.arange(nq + 1), side="left").astype(np.int64)
         r.n_pairs = n_pairs
-        r.sw_cells = int(np.dot(self.q_lens.astype(np.int64), _segment_sums(h_lens, h_off)))
+        r.sw_cells = int(cells_dev.item()) if n_pairs else 0
         pq, pt, ps, ev, hoff = capi.select_hits(ctx, self.q_lens, h_ids, h_off, h_scores, h_lens, self.total_residues, self.go, self.ge,
                                                 self.max_evalue, self.max_alignments)
         if self.world > 1:
             pq, pt, ps, ev, hoff = self._merge_hits(pq, pt, ps, ev, hoff, lo, hi)
         r.pair_q, r.pair_t, r.pair_score, r.evalue, r.hit_off = pq, pt, ps, ev, hoff
-        r.cand_ids, r.cand_off, r.scores = h_ids, h_off, h_scores
+        r.cand_ids, r.cand_off, r.scores = cand_ids, cand_off, scores     # device tensors (all candidates)
         # ---- stage 3 ----
         if align and len(pq):
             d_pq = torch.from_numpy(pq.view(np.int32)).to(self.dev)
@@ -170,31 +197,43 @@ class DevicePipeline:
             ctx.check(ctx.lib.s4g_sw_align(ctx.h, db.h, self.Q.h, len(pq), d_pq.data_ptr(), d_pt.data_ptr(), d_ps.data_ptr(), self.matrix.ctypes.data,
                                            self.go, self.ge, d_coords.data_ptr(), d_paths.data_ptr(), cap, d_poff.data_ptr(), capi.S4G_DEVICE))
             r.coords, r.paths, r.path_off = d_coords, d_paths, d_poff
+        if e2e:
+            host = [ids.cpu(), cnt.cpu()]
+            r.d2h_bytes = ids.numel() * 4 + cnt.numel() * 4 + n_s * 16 + 4
+            r.h2d_bytes += 3 * 4 * len(pq)
+            if r.coords is not None:
+                n_path = int(r.path_off[-1].item())
+                host += [r.coords.cpu(), r.paths[:n_path].cpu(), r.path_off.cpu()]
+                r.d2h_bytes += r.coords.numel() * 4 + n_path + r.path_off.numel() * 8
+            r.timings = host
         return r
 
     def _merge_hits(self, pq, pt, ps, ev, hoff, lo, hi):
-        """Global top max_alignments per query over all ranks (value asc, score desc, id asc); every rank keeps
-        the hits whose targets it owns, so traceback needs no further exchange."""
-        torch = self.torch
-        nq, M, W = self.nq, self.max_alignments, self.world
-        loc = np.zeros((nq, M, 3), dtype=np.float64)      # value, score, id  (exact in double)
-        loc[:, :, 0] = np.inf
-        cnt = np.diff(hoff)
-        for q in range(nq):
-            a, b = hoff[q], hoff[q + 1]
-            loc[q, :b - a, 0] = ev[a:b]; loc[q, :b - a, 1] = ps[a:b]; loc[q, :b - a, 2] = pt[a:b]
-        t_loc = torch.from_numpy(loc).to(self.dev)
-        t_all = torch.empty((W,) + t_loc.shape, dtype=torch.float64, device=self.dev)
-        self.dist.all_gather_into_tensor(t_all.view(-1), t_loc.view(-1))
-        allh = t_all.cpu().numpy().transpose(1, 0, 2, 3).reshape(nq, W * M, 3)
-        oq, ot, osc, oev, off = [], [], [], [], [0]
-        for q in range(nq):
-            rows = allh[q]
-            rows = rows[np.isfinite(rows[:, 0])]
-            order = np.lexsort((rows[:, 2], -rows[:, 1], rows[:, 0]))[:M]
-            rows = rows[order]
-            mine = rows[(rows[:, 2] >= lo) & (rows[:, 2] < hi)]
-            oq.append(np.full(len(mine), q, dtype=np.uint32)); ot.append(mine[:, 2].astype(np.uint32))
-            osc.append(mine[:, 1].astype(np.int32)); oev.append(mine[:, 0]); off.append(off[-1] + len(mine))
-        cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt)
-        return cat(oq, np.uint32), cat(ot, np.uint32), cat(osc, np.int32), cat(oev, np.float64), np.array(off, dtype=np.int64)
+        return merge_hits(self.torch, self.dist, self.dev, self.nq, self.max_alignments, pq, pt, ps, ev, hoff, lo, hi)
+
+
+def merge_hits(torch, dist, dev, nq, M, pq, pt, ps, ev, hoff, lo, hi):
+    """Global top M hits per query over all ranks under (E asc, score desc, id asc); every rank keeps the hits
+    whose targets it owns ([lo, hi)), so the traceback needs no further exchange.  One all-gather of
+    (E, score, id)[nq][M] doubles per rank."""
+    W = dist.get_world_size()
+    loc = np.zeros((nq, M, 3), dtype=np.float64)      # value, score, id  (all exact in double)
+    loc[:, :, 0] = np.inf
+    for q in range(nq):
+        a, b = hoff[q], hoff[q + 1]
+        loc[q, :b - a, 0] = ev[a:b]; loc[q, :b - a, 1] = ps[a:b]; loc[q, :b - a, 2] = pt[a:b]
+    t_loc = torch.from_numpy(loc).to(dev)
+    t_all = torch.empty((W,) + tuple(t_loc.shape), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(t_all.view(-1), t_loc.view(-1))
+    allh = t_all.cpu().numpy().transpose(1, 0, 2, 3).reshape(nq, W * M, 3)
+    oq, ot, osc, oev, off = [], [], [], [], [0]
+    for q in range(nq):
+        rows = allh[q]
+        rows = rows[np.isfinite(rows[:, 0])]
+        order = np.lexsort((rows[:, 2], -rows[:, 1], rows[:, 0]))[:M]
+        rows = rows[order]
+        mine = rows[(rows[:, 2] >= lo) & (rows[:, 2] < hi)]
+        oq.append(np.full(len(mine), q, dtype=np.uint32)); ot.append(mine[:, 2].astype(np.uint32))
+        osc.append(mine[:, 1].astype(np.int32)); oev.append(mine[:, 0]); off.append(off[-1] + len(mine))
+    cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt)
+    return cat(oq, np.uint32), cat(ot, np.uint32), cat(osc, np.int32), cat(oev, np.float64), np.array(off, dtype=np.int64)
