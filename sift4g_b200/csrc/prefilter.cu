@@ -25,7 +25,7 @@
 namespace {
 
 constexpr int kWarps = 8;
-constexpr int kSCap = 1024;            // hits per sequence handled in shared memory
+constexpr int kSCap = 512;             // hits per sequence handled in shared memory
 constexpr int kSeqBatch = 4;           // sequences claimed per atomic
 constexpr unsigned long long kNoThr = ~0ull;
 
@@ -99,10 +99,10 @@ __device__ int lis_inplace(unsigned long long* buf, int a, int n) {
     int len = 0;
     for (int i = 0; i < n; ++i) {
         const uint32_t x = (uint32_t)(buf[a + i] & 0x3fffffu);
-        int lo = 0, hi = len;
+        if (len == 0 || tails[len - 1] < x) { tails[len++] = x; continue; }     // collinear hits: O(1)
+        int lo = 0, hi = len - 1;
         while (lo < hi) { int mid = (lo + hi) >> 1; if (tails[mid] < x) lo = mid + 1; else hi = mid; }
         tails[lo] = x;
-        if (lo == len) ++len;
     }
     return len;
 }
@@ -126,23 +126,59 @@ __global__ void __launch_bounds__(kWarps * 32) pf_scan_kernel(PfParams P) {
             const int npos = len - k + 1;
             uint32_t T = 0, carry = 0xffffffffu;
             bool overflow = false;
-            for (int base = 0; base < npos; base += 32) {
-                const int j = base + lane;
-                const bool valid = j < npos;
-                const uint32_t kmer = valid ? kmer_at(seq, j, k) : 0xfffffffeu;
-                uint32_t prevk = __shfl_up_sync(FULL, kmer, 1);
-                if (lane == 0) prevk = carry;
-                carry = __shfl_sync(FULL, kmer, 31);
-                uint32_t b = 0, c = 0;
-                if (valid && !(j > 0 && kmer == prevk)) lookup(P, kmer, b, c);      // database_search.cpp:212-214
+            // 128 k-mer positions per step, 4 consecutive positions per lane: the 4 index probes of a lane are
+            // independent loads (memory-level parallelism), emission order = position order
+            for (int base = 0; base < npos; base += 128) {
+                const int j0 = base + 4 * lane;
+                uint32_t by[8];
+#pragma unroll
+                for (int x = 0; x < 8; ++x) by[x] = (j0 + x < len) ? (uint32_t)seq[j0 + x] : 0u;
+                uint32_t km[4];
+                {
+                    uint32_t v = (((by[0] << 5) | by[1]) << 5) | by[2];
+                    if (k >= 4) v = (v << 5) | by[3];
+                    if (k >= 5) v = (v << 5) | by[4];
+                    km[0] = v;
+#pragma unroll
+                    for (int i = 1; i < 4; ++i) {
+                        const uint32_t nb = k == 5 ? by[i + 4] : (k == 4 ? by[i + 3] : by[i + 2]);
+                        km[i] = ((km[i - 1] << 5) | nb) & P.mask;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) if (j0 + i >= npos) km[i] = 0xfffffffeu;
+                uint32_t prev0 = __shfl_up_sync(FULL, km[3], 1);
+                if (lane == 0) prev0 = carry;
+                carry = __shfl_sync(FULL, km[3], 31);
+                bool probe[4];
+                probe[0] = j0 < npos && !(j0 > 0 && km[0] == prev0);
+#pragma unroll
+                for (int i = 1; i < 4; ++i) probe[i] = (j0 + i < npos) && km[i] != km[i - 1];      // database_search.cpp:212-214
+                uint2 br[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) br[i] = probe[i] ? __ldg(P.bitrank + (km[i] >> 5)) : make_uint2(0u, 0u);
+                uint32_t hb[4], hc[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t bit = km[i] & 31u;
+                    hb[i] = 0; hc[i] = 0;
+                    if (probe[i] && ((br[i].x >> bit) & 1u)) {
+                        const uint32_t r = br[i].y + __popc(br[i].x & ((1u << bit) - 1u));
+                        hb[i] = __ldg(P.bucket_start + r);
+                        hc[i] = __ldg(P.bucket_start + r + 1) - hb[i];
+                    }
+                }
+                const uint32_t c = hc[0] + hc[1] + hc[2] + hc[3];
                 uint32_t total;
                 const uint32_t excl = warp_excl_scan(c, lane, total);
                 if (!overflow && T + total <= (uint32_t)kSCap) {
-                    for (uint32_t t = 0; t < c; ++t) {
-                        const unsigned long long h = __ldg(P.hits + b + t);
-                        const uint32_t ord = T + excl + t;
-                        buf[ord] = ((h >> 32) << 44) | ((unsigned long long)ord << 22) | (h & 0x3fffffu);
-                    }
+                    uint32_t ord = T + excl;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        for (uint32_t t = 0; t < hc[i]; ++t, ++ord) {
+                            const unsigned long long h = __ldg(P.hits + hb[i] + t);
+                            buf[ord] = ((h >> 32) << 44) | ((unsigned long long)ord << 22) | (h & 0x3fffffu);
+                        }
                 } else if (total) overflow = true;
                 T += total;
             }
@@ -162,9 +198,9 @@ __global__ void __launch_bounds__(kWarps * 32) pf_scan_kernel(PfParams P) {
             for (int i = T + lane; i < P2; i += 32) buf[i] = ~0ull;
             __syncwarp();
             for (int size = 2; size <= P2; size <<= 1) {
-                for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int stride = size >> 1, lg = 31 - __clz(size >> 1); stride > 0; stride >>= 1, --lg) {
                     for (int t = lane; t < (P2 >> 1); t += 32) {
-                        const int lo = ((t / stride) * stride * 2) + (t % stride);
+                        const int lo = ((t >> lg) << (lg + 1)) | (t & (stride - 1));
                         const int hi = lo + stride;
                         const bool up = ((lo & size) == 0);
                         const unsigned long long x = buf[lo], y = buf[hi];
@@ -506,8 +542,10 @@ int s4g_prefilter_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int ma
     // ---- candidate buffers ----
     // chunk of sequences per scan launch; every buffer can take a whole chunk on top of N + slack
     const uint32_t slack = N / 4 > 256 ? N / 4 : 256;
-    int64_t chunk = 131072;
-    const size_t budget = (size_t)6 << 30;   // bytes for both candidate buffers
+    // the scan runs in chunks of sequences; chunk sizes grow geometrically (cut-offs settle on the first small
+    // chunks, later chunks append little) up to what the candidate-buffer budget allows
+    int64_t chunk = 1 << 20;
+    const size_t budget = (size_t)12 << 30;   // bytes for both candidate buffers
     while (chunk > 4096 && (size_t)nq * (size_t)(N + slack + chunk) * 16 > budget) chunk >>= 1;
     if (chunk > db->n) chunk = db->n > 0 ? db->n : 1;
     const uint32_t cap = (uint32_t)(N + slack + chunk);
@@ -543,9 +581,12 @@ int s4g_prefilter_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int ma
     if (per_sm < 1) per_sm = 1;
     const int grid = ctx->sm_count * per_sm;
 
-    for (int64_t s0 = 0; s0 < db->n && n_hits > 0; s0 += chunk) {
+    int64_t this_chunk = chunk < 16384 ? chunk : 16384;
+    for (int64_t s0 = 0; s0 < db->n && n_hits > 0; ) {
         P.seq_begin = s0;
-        P.seq_end = s0 + chunk < db->n ? s0 + chunk : db->n;
+        P.seq_end = s0 + this_chunk < db->n ? s0 + this_chunk : db->n;
+        s0 = P.seq_end;
+        this_chunk = this_chunk * 2 < chunk ? this_chunk * 2 : chunk;
         S4G_CUDA(ctx, cudaMemsetAsync(d_counters, 0, 32, st));
         // the pool is only allocated once a chunk needs it (first pass counts; see below)
         P.pool_keys = (unsigned long long*)ctx->slot_ptr[SLOT_PF_HITS];
