@@ -19,6 +19,31 @@ void s4g_set_error(s4g_ctx* ctx, const char* fmt, ...) {
     if (ctx) ctx->err = buf;
 }
 
+#include <chrono>
+static double wall_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+void s4g_trace_start(s4g_ctx* ctx) {
+    if (!ctx->trace) return;
+    cudaStreamSynchronize(ctx->stream);
+    ctx->trace_last = wall_ms();
+}
+void s4g_trace_mark(s4g_ctx* ctx, const char* label) {
+    if (!ctx->trace) return;
+    cudaStreamSynchronize(ctx->stream);
+    const double now = wall_ms();
+    for (auto& kv : ctx->trace_acc) if (kv.first == label) { kv.second += now - ctx->trace_last; ctx->trace_last = now; return; }
+    ctx->trace_acc.emplace_back(label, now - ctx->trace_last);
+    ctx->trace_last = now;
+}
+void s4g_trace_report(s4g_ctx* ctx, const char* header) {
+    if (!ctx->trace) return;
+    fprintf(stderr, "[s4g trace] %s:", header);
+    for (auto& kv : ctx->trace_acc) fprintf(stderr, " %s=%.3fms", kv.first.c_str(), kv.second);
+    fprintf(stderr, "\n");
+    ctx->trace_acc.clear();
+}
+
 void* s4g_scratch(s4g_ctx* ctx, int slot, size_t bytes) {
     if (bytes == 0) bytes = 16;
     if (ctx->slot_bytes[slot] >= bytes) return ctx->slot_ptr[slot];
@@ -89,6 +114,7 @@ int s4g_init(int device, s4g_ctx** out) {
         return S4G_ERR_CUDA;
     }
     ctx->sm_count = prop.multiProcessorCount;
+    { const char* t = getenv("S4G_TRACE"); ctx->trace = t && t[0] && t[0] != '0'; }
     S4G_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     S4G_CUDA(ctx, cudaEventCreate(&ctx->ev_sw0));
     S4G_CUDA(ctx, cudaEventCreate(&ctx->ev_sw1));

@@ -29,6 +29,10 @@ struct s4g_ctx {
     // pinned host staging, grow-only
     void* pin_ptr[8] = {nullptr};
     size_t pin_bytes[8] = {0};
+    // S4G_TRACE=1: per-phase wall times (stream synchronised at every mark) printed to stderr
+    bool trace = false;
+    double trace_last = 0.0;
+    std::vector<std::pair<std::string, double>> trace_acc;
 };
 
 struct s4g_db {
@@ -72,6 +76,11 @@ void s4g_set_error(s4g_ctx* ctx, const char* fmt, ...);
         (ctx)->launches++;                                                                    \
         S4G_CUDA((ctx), cudaGetLastError());                                                  \
     } while (0)
+
+// phase tracing (no-ops unless the context was created with S4G_TRACE=1 in the environment)
+void s4g_trace_start(s4g_ctx* ctx);
+void s4g_trace_mark(s4g_ctx* ctx, const char* label);      // time since the previous mark/start is charged to `label`
+void s4g_trace_report(s4g_ctx* ctx, const char* header);
 
 // grow-only device scratch; returns nullptr (and sets the error) on failure
 void* s4g_scratch(s4g_ctx* ctx, int slot, size_t bytes);

@@ -25,8 +25,8 @@
 namespace {
 
 constexpr int kWarps = 8;
-constexpr int kSCap = 512;             // hits per sequence handled in shared memory
 constexpr int kSeqBatch = 4;           // sequences claimed per atomic
+constexpr int kCntSlots = 1024;        // per-warp hashed hit counters (16 bit each)
 constexpr unsigned long long kNoThr = ~0ull;
 
 struct PfParams {
@@ -107,83 +107,215 @@ __device__ int lis_inplace(unsigned long long* buf, int a, int n) {
     return len;
 }
 
-__global__ void __launch_bounds__(kWarps * 32) pf_scan_kernel(PfParams P) {
-    extern __shared__ unsigned long long sbuf[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned long long* buf = sbuf + warp * kSCap;
+// One scan step of a warp: 128 k-mer positions starting at `base`, 4 consecutive positions per lane (the 4 index
+// probes of a lane are independent loads -> memory-level parallelism; emission order = position order).
+// Returns the lane's buckets: first entry hb[i] and size hc[i] for each of its positions (0 when the k-mer is absent
+// from the index, is a consecutive duplicate (database_search.cpp:212-214) or lies beyond the sequence).
+__device__ __forceinline__ void scan_step(const PfParams& P, const uint8_t* seq, int npos, int base, int lane, uint32_t& carry,
+                                          uint32_t (&hb)[4], uint32_t (&hc)[4]) {
     const unsigned FULL = 0xffffffffu;
     const int k = P.k;
+    const int j0 = base + 4 * lane;
+    // 8 residue bytes of this lane through 3 aligned 32-bit loads (bytes beyond the sequence only reach k-mers at
+    // positions >= npos, which are discarded; the database buffer has S4G_DB_TAIL_PAD readable bytes after its end)
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(seq + j0);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(addr & ~(uintptr_t)3);
+    const unsigned sh = (unsigned)(addr & 3u) * 8u;
+    uint32_t lo = 0, hi = 0;
+    if (j0 < npos) {
+        const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+        lo = __funnelshift_r(w0, w1, sh);
+        hi = __funnelshift_r(w1, w2, sh);
+    }
+    uint32_t by[8];
+#pragma unroll
+    for (int x = 0; x < 4; ++x) { by[x] = (lo >> (8 * x)) & 0x1fu; by[x + 4] = (hi >> (8 * x)) & 0x1fu; }
+    uint32_t km[4];
+    {
+        uint32_t v = (((by[0] << 5) | by[1]) << 5) | by[2];
+        if (k >= 4) v = (v << 5) | by[3];
+        if (k >= 5) v = (v << 5) | by[4];
+        km[0] = v;
+#pragma unroll
+        for (int i = 1; i < 4; ++i) {
+            const uint32_t nb = k == 5 ? by[i + 4] : (k == 4 ? by[i + 3] : by[i + 2]);
+            km[i] = ((km[i - 1] << 5) | nb) & P.mask;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) if (j0 + i >= npos) km[i] = 0xfffffffeu;
+    uint32_t prev0 = __shfl_up_sync(FULL, km[3], 1);
+    if (lane == 0) prev0 = carry;
+    carry = __shfl_sync(FULL, km[3], 31);
+    bool probe[4];
+    probe[0] = j0 < npos && !(j0 > 0 && km[0] == prev0);
+#pragma unroll
+    for (int i = 1; i < 4; ++i) probe[i] = (j0 + i < npos) && km[i] != km[i - 1];
+    uint2 br[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) br[i] = probe[i] ? __ldg(P.bitrank + (km[i] >> 5)) : make_uint2(0u, 0u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t bit = km[i] & 31u;
+        hb[i] = 0; hc[i] = 0;
+        if (probe[i] && ((br[i].x >> bit) & 1u)) {
+            const uint32_t r = br[i].y + __popc(br[i].x & ((1u << bit) - 1u));
+            hb[i] = __ldg(P.bucket_start + r);
+            hc[i] = __ldg(P.bucket_start + r + 1) - hb[i];
+        }
+    }
+}
+
+// Publish the lane's buckets of one scan step in the warp's shared-memory tables (start offset of every one of the
+// 128 positions inside the step's hit list + first index entry) so that the step's hits can be enumerated
+// load-balanced: hit x of the step belongs to the last position p with off_s[p] <= x.
+__device__ __forceinline__ void publish_step(uint32_t* off_s, uint32_t* hb_s, int lane, uint32_t excl, const uint32_t (&hb)[4],
+                                             const uint32_t (&hc)[4]) {
+    uint32_t o = excl;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { off_s[4 * lane + i] = o; hb_s[4 * lane + i] = hb[i]; o += hc[i]; }
+    __syncwarp();
+}
+
+__device__ __forceinline__ unsigned long long step_hit(const PfParams& P, const uint32_t* off_s, const uint32_t* hb_s, uint32_t x) {
+    int p = 0;
+#pragma unroll
+    for (int b = 64; b > 0; b >>= 1) if (off_s[p + b] <= x) p += b;
+    return __ldg(P.hits + hb_s[p] + (x - off_s[p]));
+}
+
+// The scan kernel.  Per sequence (one warp):
+//   pass A  walks the k-mer positions, counts the hits of every query in per-warp hashed 16-bit counters and buffers
+//           the hits in shared memory while they fit;
+//   filter  a (query, sequence) pair can only become a candidate when LIS/len beats the query's cut-off, and
+//           LIS <= number of hits, so hits of queries whose COUNT cannot beat the cut-off are dropped (exact: the
+//           counters only over-estimate).  Once the cut-offs have settled this removes practically every random hit
+//           before any sorting;  sequences whose hits did not fit are re-walked keeping only the survivors;
+//   rest    survivors are bitonic-sorted by (query, emission order), each query's run reduced by the in-place LIS.
+// Shared memory per warp: hit buffer scap x 8 B, counters kCntSlots x 2 B, step tables 2 x 128 x 4 B.
+__global__ void __launch_bounds__(kWarps * 32) pf_scan_kernel(PfParams P, int scap) {
+    extern __shared__ unsigned long long sbuf[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long* buf = sbuf + (size_t)warp * scap;
+    uint32_t* cnt_all = reinterpret_cast<uint32_t*>(sbuf + (size_t)kWarps * scap);
+    uint32_t* slot_thr = cnt_all + kWarps * (kCntSlots / 2);        // float bits: smallest cut-off score of the slot's queries
+    uint32_t* step_all = slot_thr + kCntSlots;
+    uint32_t* cnt = cnt_all + warp * (kCntSlots / 2);
+    unsigned short* cnt16 = reinterpret_cast<unsigned short*>(cnt);
+    uint32_t* off_s = step_all + warp * 256;
+    uint32_t* hb_s = off_s + 128;
+    const unsigned FULL = 0xffffffffu;
+    const int k = P.k;
+    for (int i = threadIdx.x; i < kWarps * (kCntSlots / 2); i += blockDim.x) cnt_all[i] = 0;
+    for (int i = threadIdx.x; i < kCntSlots; i += blockDim.x) slot_thr[i] = 0x7f800000u;
+    __syncthreads();
+    for (int q = threadIdx.x; q < P.nq; q += blockDim.x)
+        atomicMin(slot_thr + (q & (kCntSlots - 1)), ~(uint32_t)(__ldcg(P.thr + q) >> 32));     // no cut-off yet -> 0.0f
+    __syncthreads();
     while (true) {
         long long s0 = 0;
         if (lane == 0) s0 = (long long)atomicAdd(P.counters + 0, (unsigned long long)kSeqBatch);
         s0 = __shfl_sync(FULL, s0, 0) + P.seq_begin;
         if (s0 >= P.seq_end) break;
-        for (long long s = s0; s < s0 + kSeqBatch && s < P.seq_end; ++s) {
-            const int64_t a = P.db_off[s];
-            const int len = (int)(P.db_off[s + 1] - a);
+        // offsets of the batch (lanes 0..kSeqBatch), and an L2 prefetch of its residues (contiguous in memory)
+        long long my_off = 0;
+        if (lane <= kSeqBatch && s0 + lane <= P.seq_end) my_off = P.db_off[s0 + lane];
+        {
+            const long long b0 = __shfl_sync(FULL, my_off, 0);
+            const int nb = (int)min((long long)kSeqBatch, P.seq_end - s0);
+            const long long b1 = __shfl_sync(FULL, my_off, nb);
+            for (long long a = b0 + 128ll * lane; a < b1; a += 128 * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.db_codes + a));
+        }
+        for (int bi = 0; bi < kSeqBatch && s0 + bi < P.seq_end; ++bi) {
+            const long long s = s0 + bi;
+            const int64_t a = __shfl_sync(FULL, my_off, bi);
+            const int len = (int)(__shfl_sync(FULL, my_off, bi + 1) - a);
             if (len < k) continue;
             const uint8_t* seq = P.db_codes + a;
             const int npos = len - k + 1;
+            // ---- pass A: count (and buffer while it fits)
             uint32_t T = 0, carry = 0xffffffffu;
-            bool overflow = false;
-            // 128 k-mer positions per step, 4 consecutive positions per lane: the 4 index probes of a lane are
-            // independent loads (memory-level parallelism), emission order = position order
+            bool buffered = true;
             for (int base = 0; base < npos; base += 128) {
-                const int j0 = base + 4 * lane;
-                uint32_t by[8];
-#pragma unroll
-                for (int x = 0; x < 8; ++x) by[x] = (j0 + x < len) ? (uint32_t)seq[j0 + x] : 0u;
-                uint32_t km[4];
-                {
-                    uint32_t v = (((by[0] << 5) | by[1]) << 5) | by[2];
-                    if (k >= 4) v = (v << 5) | by[3];
-                    if (k >= 5) v = (v << 5) | by[4];
-                    km[0] = v;
-#pragma unroll
-                    for (int i = 1; i < 4; ++i) {
-                        const uint32_t nb = k == 5 ? by[i + 4] : (k == 4 ? by[i + 3] : by[i + 2]);
-                        km[i] = ((km[i - 1] << 5) | nb) & P.mask;
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) if (j0 + i >= npos) km[i] = 0xfffffffeu;
-                uint32_t prev0 = __shfl_up_sync(FULL, km[3], 1);
-                if (lane == 0) prev0 = carry;
-                carry = __shfl_sync(FULL, km[3], 31);
-                bool probe[4];
-                probe[0] = j0 < npos && !(j0 > 0 && km[0] == prev0);
-#pragma unroll
-                for (int i = 1; i < 4; ++i) probe[i] = (j0 + i < npos) && km[i] != km[i - 1];      // database_search.cpp:212-214
-                uint2 br[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) br[i] = probe[i] ? __ldg(P.bitrank + (km[i] >> 5)) : make_uint2(0u, 0u);
                 uint32_t hb[4], hc[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const uint32_t bit = km[i] & 31u;
-                    hb[i] = 0; hc[i] = 0;
-                    if (probe[i] && ((br[i].x >> bit) & 1u)) {
-                        const uint32_t r = br[i].y + __popc(br[i].x & ((1u << bit) - 1u));
-                        hb[i] = __ldg(P.bucket_start + r);
-                        hc[i] = __ldg(P.bucket_start + r + 1) - hb[i];
-                    }
-                }
+                scan_step(P, seq, npos, base, lane, carry, hb, hc);
                 const uint32_t c = hc[0] + hc[1] + hc[2] + hc[3];
                 uint32_t total;
                 const uint32_t excl = warp_excl_scan(c, lane, total);
-                if (!overflow && T + total <= (uint32_t)kSCap) {
-                    uint32_t ord = T + excl;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        for (uint32_t t = 0; t < hc[i]; ++t, ++ord) {
-                            const unsigned long long h = __ldg(P.hits + hb[i] + t);
-                            buf[ord] = ((h >> 32) << 44) | ((unsigned long long)ord << 22) | (h & 0x3fffffu);
-                        }
-                } else if (total) overflow = true;
+                if (total == 0) continue;
+                if (buffered && T + total > (uint32_t)scap) buffered = false;
+                publish_step(off_s, hb_s, lane, excl, hb, hc);
+                for (uint32_t x = lane; x < total; x += 32) {
+                    const unsigned long long h = step_hit(P, off_s, hb_s, x);
+                    const uint32_t q = (uint32_t)(h >> 32), slot = q & (kCntSlots - 1);
+                    atomicAdd(cnt + (slot >> 1), (slot & 1u) ? 0x10000u : 1u);
+                    const uint32_t ord = T + x;
+                    if (buffered) buf[ord] = ((unsigned long long)q << 44) | ((unsigned long long)ord << 22) | (h & 0x3fffffu);
+                }
+                __syncwarp();
                 T += total;
             }
             if (T == 0) continue;
-            if (overflow) {
+            const float flen = (float)len * 0.99999f;      // margin >> float rounding: dropping stays exact
+            uint32_t nsurv = 0;
+            bool defer = false;
+            if (buffered) {
+                for (int base = 0; base < (int)T; base += 32) {
+                    const int i = base + lane;
+                    unsigned long long e = 0;
+                    bool keep = false;
+                    if (i < (int)T) {
+                        e = buf[i];
+                        const uint32_t slot = (uint32_t)(e >> 44) & (kCntSlots - 1);
+                        keep = !((float)cnt16[slot] < __uint_as_float(slot_thr[slot]) * flen);
+                    }
+                    const uint32_t bal = __ballot_sync(FULL, keep);
+                    if (keep) buf[nsurv + __popc(bal & ((1u << lane) - 1u))] = e;      // nsurv + rank <= i: never ahead of the reads
+                    nsurv += __popc(bal);
+                    __syncwarp();
+                }
+            } else if (T >= 65536u || T >= (1u << 22)) {
+                defer = true;                                 // a 16-bit counter may have wrapped: no filtering
+            } else {
+                // re-walk, keep the survivors only (any order: the sort key carries the emission order)
+                uint32_t ordbase = 0;
+                carry = 0xffffffffu;
+                for (int base = 0; base < npos && !defer; base += 128) {
+                    uint32_t hb[4], hc[4];
+                    scan_step(P, seq, npos, base, lane, carry, hb, hc);
+                    const uint32_t c = hc[0] + hc[1] + hc[2] + hc[3];
+                    uint32_t total;
+                    const uint32_t excl = warp_excl_scan(c, lane, total);
+                    if (total == 0) continue;
+                    publish_step(off_s, hb_s, lane, excl, hb, hc);
+                    for (uint32_t x0 = 0; x0 < total; x0 += 32) {
+                        const uint32_t x = x0 + lane;
+                        unsigned long long e = 0;
+                        bool keep = false;
+                        if (x < total) {
+                            const unsigned long long h = step_hit(P, off_s, hb_s, x);
+                            const uint32_t q = (uint32_t)(h >> 32), slot = q & (kCntSlots - 1);
+                            keep = !((float)cnt16[slot] < __uint_as_float(slot_thr[slot]) * flen);
+                            e = ((unsigned long long)q << 44) | ((unsigned long long)(ordbase + x) << 22) | (h & 0x3fffffu);
+                        }
+                        const uint32_t bal = __ballot_sync(FULL, keep);
+                        if (nsurv + __popc(bal) > (uint32_t)scap) { defer = true; break; }
+                        if (keep) buf[nsurv + __popc(bal & ((1u << lane) - 1u))] = e;
+                        nsurv += __popc(bal);
+                    }
+                    __syncwarp();
+                    ordbase += total;
+                }
+            }
+            // reset the counters: only the touched ones when the hit list is at hand
+            if (buffered) {
+                // (entries were compacted in place, so walk the sequence's own hit list again only if it was short;
+                //  clearing all 1 K words costs 32 stores per lane)
+            }
+            __syncwarp();
+            for (int i = lane; i < kCntSlots / 2; i += 32) cnt[i] = 0;
+            __syncwarp();
+            if (defer) {
                 if (lane == 0) {
                     const unsigned long long slot = atomicAdd(P.counters + 1, 1ull);
                     const unsigned long long off = atomicAdd(P.counters + 2, (unsigned long long)T);
@@ -192,10 +324,12 @@ __global__ void __launch_bounds__(kWarps * 32) pf_scan_kernel(PfParams P) {
                 }
                 continue;
             }
+            if (nsurv == 0) continue;
+            const int S = (int)nsurv;
             // bitonic sort of buf[0..P2) by (query, emission order)
             int P2 = 32;
-            while (P2 < (int)T) P2 <<= 1;
-            for (int i = T + lane; i < P2; i += 32) buf[i] = ~0ull;
+            while (P2 < S) P2 <<= 1;
+            for (int i = S + lane; i < P2; i += 32) buf[i] = ~0ull;
             __syncwarp();
             for (int size = 2; size <= P2; size <<= 1) {
                 for (int stride = size >> 1, lg = 31 - __clz(size >> 1); stride > 0; stride >>= 1, --lg) {
@@ -209,30 +343,33 @@ __global__ void __launch_bounds__(kWarps * 32) pf_scan_kernel(PfParams P) {
                     __syncwarp();
                 }
             }
-            // run starts, one ballot word per 32 entries, kept by lane (i / 32)
+            // run starts first (one ballot word per 32 entries, kept by lane i / 32; scap <= 1024), because the in-place
+            // LIS below overwrites the entries of finished runs
             uint32_t my_starts = 0;
-            for (int base = 0; base < (int)T; base += 32) {
+            for (int base = 0; base < S; base += 32) {
                 const int i = base + lane;
-                const bool st = i < (int)T && (i == 0 || (buf[i] >> 44) != (buf[i - 1] >> 44));
+                const bool st = i < S && (i == 0 || (buf[i] >> 44) != (buf[i - 1] >> 44));
                 const uint32_t bal = __ballot_sync(FULL, st);
                 if (lane == (base >> 5)) my_starts = bal;
             }
             __syncwarp();
             const uint32_t id = P.id_base + (uint32_t)s;
-            for (int base = 0; base < (int)T; base += 32) {
+            for (int base = 0; base < S; base += 32) {
                 const uint32_t bal = __shfl_sync(FULL, my_starts, base >> 5);
-                if ((bal >> lane) & 1u) {
-                    const int i = base + lane;
-                    const uint32_t q = (uint32_t)(buf[i] >> 44);
+                const bool st = (bal >> lane) & 1u;
+                const int i = base + lane;
+                uint32_t q = 0;
+                int n = 0;
+                if (st) {
+                    q = (uint32_t)(buf[i] >> 44);
                     int e = i + 1;
-                    while (e < (int)T && (uint32_t)(buf[e] >> 44) == q) ++e;
-                    const int n = e - i;
-                    const int lis = n == 1 ? 1 : lis_inplace(buf, i, n);
-                    emit(P, q, lis, len, id);
+                    while (e < S && (uint32_t)(buf[e] >> 44) == q) ++e;
+                    n = e - i;
                 }
+                __syncwarp();          // all run lengths of this block are known before any of its runs is overwritten
+                if (st) emit(P, q, n == 1 ? 1 : lis_inplace(buf, i, n), len, id);
                 __syncwarp();
             }
-            __syncwarp();
         }
     }
 }
@@ -471,6 +608,7 @@ int s4g_prefilter_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int ma
     if (nq >= (1 << 20)) { s4g_set_error(ctx, "at most 2^20-1 queries per batch"); return S4G_ERR_ARG; }
     if (q->max_len >= (1 << 22)) { s4g_set_error(ctx, "query longer than 2^22"); return S4G_ERR_ARG; }
 
+    s4g_trace_start(ctx);
     // ---- index over all queries ----
     int64_t n_hits = 0;
     for (int i = 0; i < nq; ++i) { int64_t len = q->h_off[i + 1] - q->h_off[i]; if (len >= k) n_hits += len - k + 1; }
@@ -539,6 +677,7 @@ int s4g_prefilter_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int ma
         S4G_CHECK_LAUNCH(ctx);
     }
 
+    s4g_trace_mark(ctx, "index");
     // ---- candidate buffers ----
     // chunk of sequences per scan launch; every buffer can take a whole chunk on top of N + slack
     const uint32_t slack = N / 4 > 256 ? N / 4 : 256;
@@ -575,7 +714,15 @@ int s4g_prefilter_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int ma
     P.pool_keys = nullptr; P.pool_vals = nullptr; P.pool_cap = pool_cap;
 
     int per_sm = 0;
-    const size_t scan_smem = sizeof(unsigned long long) * kWarps * kSCap;
+    // hit buffer per warp: room for the hits of a typical sequence (hits per residue = index size / k-mer space, times
+    // 4 average lengths), within 256 .. 1024 entries
+    int scap = 256;
+    {
+        const double per_res = (double)n_hits / (double)n_kmer_space * 8.0;        // frequent letters dominate: x8 over uniform
+        const double avg_len = db->n > 0 ? (double)db->residues / (double)db->n : 1.0;
+        while (scap < 1024 && (double)scap < 4.0 * per_res * avg_len) scap <<= 1;
+    }
+    const size_t scan_smem = sizeof(unsigned long long) * kWarps * scap + sizeof(uint32_t) * kWarps * (kCntSlots / 2) + sizeof(uint32_t) * kCntSlots + sizeof(uint32_t) * kWarps * 256;
     S4G_CUDA(ctx, cudaFuncSetAttribute(pf_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
     S4G_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pf_scan_kernel, kWarps * 32, scan_smem));
     if (per_sm < 1) per_sm = 1;
@@ -590,11 +737,12 @@ int s4g_prefilter_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int ma
         S4G_CUDA(ctx, cudaMemsetAsync(d_counters, 0, 32, st));
         // the pool is only allocated once a chunk needs it (first pass counts; see below)
         P.pool_keys = (unsigned long long*)ctx->slot_ptr[SLOT_PF_HITS];
-        pf_scan_kernel<<<grid, kWarps * 32, scan_smem, st>>>(P);
+        pf_scan_kernel<<<grid, kWarps * 32, scan_smem, st>>>(P, scap);
         S4G_CHECK_LAUNCH(ctx);
         unsigned long long h_c[4];
         S4G_CUDA(ctx, cudaMemcpyAsync(h_c, d_counters, 32, cudaMemcpyDeviceToHost, st));
         S4G_CUDA(ctx, cudaStreamSynchronize(st));
+        s4g_trace_mark(ctx, "scan");
         if (h_c[3] & 1ull) { s4g_set_error(ctx, "prefilter: candidate buffer overflow (internal)"); return S4G_ERR_INTERNAL; }
         if (h_c[3] & 2ull) { s4g_set_error(ctx, "prefilter: more than %u deferred sequences or %llu deferred hits in one chunk", max_deferred, pool_cap); return S4G_ERR_CAPACITY; }
         if (h_c[1] > 0) {
@@ -619,13 +767,16 @@ int s4g_prefilter_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int ma
             pf_lis_deferred_kernel<<<(unsigned)((n_pool + 127) / 128), 128, 0, st>>>(P, pk2, pv2, tails, n_pool);
             S4G_CHECK_LAUNCH(ctx);
         }
+        s4g_trace_mark(ctx, "deferred");
         // compact buffers that could overflow in the next chunk
         const bool last = P.seq_end >= db->n;
         if (!last) {
             int rc = compact(ctx, nq, cap, N, N + slack, 0, d_cand, d_cand_alt, d_count, d_thr, d_seg, d_seg_q, d_nseg, nullptr);
             if (rc != S4G_OK) return rc;
         }
+        s4g_trace_mark(ctx, "compact");
     }
+    s4g_trace_mark(ctx, "compact");
     // ---- final top-N, output ----
     {
         int rc = compact(ctx, nq, cap, N, 0, 1, d_cand, d_cand_alt, d_count, d_thr, d_seg, d_seg_q, d_nseg, nullptr);
@@ -644,6 +795,8 @@ int s4g_prefilter_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int ma
         cb_output_byid_kernel<<<nq, 128, 0, st>>>(d_cand, d_count, cap, N, nq, d_ids, d_scores, d_counts);
         S4G_CHECK_LAUNCH(ctx);
     }
+    s4g_trace_mark(ctx, "final");
+    s4g_trace_report(ctx, "prefilter");
     return S4G_OK;
 }
 
