@@ -23,7 +23,7 @@ struct s4g_ctx {
     cudaEvent_t ev_sw0 = nullptr, ev_sw1 = nullptr;
     bool sw_timed = false;
     // grow-only scratch arena, one buffer per slot (device memory)
-    static const int kSlots = 32;
+    static const int kSlots = 40;
     void* slot_ptr[kSlots] = {nullptr};
     size_t slot_bytes[kSlots] = {0};
     // pinned host staging, grow-only
@@ -92,7 +92,7 @@ enum {
     SLOT_SW_KEYS, SLOT_SW_KEYS2, SLOT_SW_VALS, SLOT_SW_VALS2, SLOT_SW_CUB, SLOT_SW_TILES,
     SLOT_SW_MISC, SLOT_SW_OVF, SLOT_SW_BOUND, SLOT_SW_MAT,
     SLOT_PF_INDEX, SLOT_PF_BITMAP, SLOT_PF_RANK, SLOT_PF_BUCKET, SLOT_PF_HITS, SLOT_PF_CAND,
-    SLOT_PF_COUNT, SLOT_PF_THR, SLOT_PF_CUB, SLOT_PF_TMP, SLOT_PF_TMP2, SLOT_PF_SPILL,
+    SLOT_PF_COUNT, SLOT_PF_THR, SLOT_PF_CUB, SLOT_PF_TMP, SLOT_PF_TMP2, SLOT_PF_SPILL, SLOT_PF_GBUF,
     SLOT_AL_WORK, SLOT_AL_DIR, SLOT_AL_MISC, SLOT_AL_OUT
 };
 

@@ -26,6 +26,7 @@ namespace {
 
 constexpr int kWarps = 8;
 constexpr int kSeqBatch = 4;           // sequences claimed per atomic
+constexpr int kGCap = 1024;             // surviving hits per sequence handled in the per-warp global scratch
 constexpr int kCntSlots = 1024;        // per-warp hashed hit counters (16 bit each)
 constexpr unsigned long long kNoThr = ~0ull;
 
@@ -51,6 +52,7 @@ struct PfParams {
     unsigned long long* pool_keys;    // (slot << 50 | q << 30 | order)
     uint32_t* pool_vals;              // query position
     unsigned long long pool_cap;
+    unsigned long long* gbuf;         // per-warp global scratch (kGCap entries) for sequences with many surviving hits
 };
 
 __device__ __forceinline__ unsigned long long cand_key(float score, uint32_t id) {
@@ -259,6 +261,7 @@ __global__ void __launch_bounds__(kWarps * 32) pf_scan_kernel(PfParams P, int sc
             const float flen = (float)len * 0.99999f;      // margin >> float rounding: dropping stays exact
             uint32_t nsurv = 0;
             bool defer = false;
+            unsigned long long* wb = buf;        // where the survivors are: shared buffer or global scratch
             if (buffered) {
                 for (int base = 0; base < (int)T; base += 32) {
                     const int i = base + lane;
@@ -277,7 +280,9 @@ __global__ void __launch_bounds__(kWarps * 32) pf_scan_kernel(PfParams P, int sc
             } else if (T >= 65536u || T >= (1u << 22)) {
                 defer = true;                                 // a 16-bit counter may have wrapped: no filtering
             } else {
-                // re-walk, keep the survivors only (any order: the sort key carries the emission order)
+                // re-walk, keep the survivors only (any order: the sort key carries the emission order); they go to the
+                // warp's global scratch, which holds what a strong homolog of a long query produces
+                wb = P.gbuf + (size_t)(blockIdx.x * kWarps + warp) * kGCap;
                 uint32_t ordbase = 0;
                 carry = 0xffffffffu;
                 for (int base = 0; base < npos && !defer; base += 128) {
@@ -299,18 +304,13 @@ __global__ void __launch_bounds__(kWarps * 32) pf_scan_kernel(PfParams P, int sc
                             e = ((unsigned long long)q << 44) | ((unsigned long long)(ordbase + x) << 22) | (h & 0x3fffffu);
                         }
                         const uint32_t bal = __ballot_sync(FULL, keep);
-                        if (nsurv + __popc(bal) > (uint32_t)scap) { defer = true; break; }
-                        if (keep) buf[nsurv + __popc(bal & ((1u << lane) - 1u))] = e;
+                        if (nsurv + __popc(bal) > (uint32_t)kGCap) { defer = true; break; }
+                        if (keep) wb[nsurv + __popc(bal & ((1u << lane) - 1u))] = e;
                         nsurv += __popc(bal);
                     }
                     __syncwarp();
                     ordbase += total;
                 }
-            }
-            // reset the counters: only the touched ones when the hit list is at hand
-            if (buffered) {
-                // (entries were compacted in place, so walk the sequence's own hit list again only if it was short;
-                //  clearing all 1 K words costs 32 stores per lane)
             }
             __syncwarp();
             for (int i = lane; i < kCntSlots / 2; i += 32) cnt[i] = 0;
@@ -326,10 +326,10 @@ __global__ void __launch_bounds__(kWarps * 32) pf_scan_kernel(PfParams P, int sc
             }
             if (nsurv == 0) continue;
             const int S = (int)nsurv;
-            // bitonic sort of buf[0..P2) by (query, emission order)
+            // bitonic sort of wb[0..P2) by (query, emission order)
             int P2 = 32;
             while (P2 < S) P2 <<= 1;
-            for (int i = S + lane; i < P2; i += 32) buf[i] = ~0ull;
+            for (int i = S + lane; i < P2; i += 32) wb[i] = ~0ull;
             __syncwarp();
             for (int size = 2; size <= P2; size <<= 1) {
                 for (int stride = size >> 1, lg = 31 - __clz(size >> 1); stride > 0; stride >>= 1, --lg) {
@@ -337,8 +337,8 @@ __global__ void __launch_bounds__(kWarps * 32) pf_scan_kernel(PfParams P, int sc
                         const int lo = ((t >> lg) << (lg + 1)) | (t & (stride - 1));
                         const int hi = lo + stride;
                         const bool up = ((lo & size) == 0);
-                        const unsigned long long x = buf[lo], y = buf[hi];
-                        if ((x > y) == up) { buf[lo] = y; buf[hi] = x; }
+                        const unsigned long long x = wb[lo], y = wb[hi];
+                        if ((x > y) == up) { wb[lo] = y; wb[hi] = x; }
                     }
                     __syncwarp();
                 }
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(kWarps * 32) pf_scan_kernel(PfParams P, int sc
             uint32_t my_starts = 0;
             for (int base = 0; base < S; base += 32) {
                 const int i = base + lane;
-                const bool st = i < S && (i == 0 || (buf[i] >> 44) != (buf[i - 1] >> 44));
+                const bool st = i < S && (i == 0 || (wb[i] >> 44) != (wb[i - 1] >> 44));
                 const uint32_t bal = __ballot_sync(FULL, st);
                 if (lane == (base >> 5)) my_starts = bal;
             }
@@ -361,13 +361,13 @@ __global__ void __launch_bounds__(kWarps * 32) pf_scan_kernel(PfParams P, int sc
                 uint32_t q = 0;
                 int n = 0;
                 if (st) {
-                    q = (uint32_t)(buf[i] >> 44);
+                    q = (uint32_t)(wb[i] >> 44);
                     int e = i + 1;
-                    while (e < S && (uint32_t)(buf[e] >> 44) == q) ++e;
+                    while (e < S && (uint32_t)(wb[e] >> 44) == q) ++e;
                     n = e - i;
                 }
                 __syncwarp();          // all run lengths of this block are known before any of its runs is overwritten
-                if (st) emit(P, q, n == 1 ? 1 : lis_inplace(buf, i, n), len, id);
+                if (st) emit(P, q, n == 1 ? 1 : lis_inplace(wb, i, n), len, id);
                 __syncwarp();
             }
         }
@@ -727,6 +727,8 @@ int s4g_prefilter_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int ma
     S4G_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pf_scan_kernel, kWarps * 32, scan_smem));
     if (per_sm < 1) per_sm = 1;
     const int grid = ctx->sm_count * per_sm;
+    P.gbuf = (unsigned long long*)s4g_scratch(ctx, SLOT_PF_GBUF, sizeof(unsigned long long) * (size_t)grid * kWarps * kGCap);
+    if (!P.gbuf) return S4G_ERR_NOMEM;
 
     int64_t this_chunk = chunk < 16384 ? chunk : 16384;
     for (int64_t s0 = 0; s0 < db->n && n_hits > 0; ) {
@@ -743,6 +745,7 @@ int s4g_prefilter_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int ma
         S4G_CUDA(ctx, cudaMemcpyAsync(h_c, d_counters, 32, cudaMemcpyDeviceToHost, st));
         S4G_CUDA(ctx, cudaStreamSynchronize(st));
         s4g_trace_mark(ctx, "scan");
+        if (ctx->trace) fprintf(stderr, "[s4g trace] chunk [%lld,%lld): deferred %llu sequences, %llu hits\n", (long long)P.seq_begin, (long long)P.seq_end, h_c[1], h_c[2]);
         if (h_c[3] & 1ull) { s4g_set_error(ctx, "prefilter: candidate buffer overflow (internal)"); return S4G_ERR_INTERNAL; }
         if (h_c[3] & 2ull) { s4g_set_error(ctx, "prefilter: more than %u deferred sequences or %llu deferred hits in one chunk", max_deferred, pool_cap); return S4G_ERR_CAPACITY; }
         if (h_c[1] > 0) {

@@ -122,21 +122,30 @@ __device__ __forceinline__ unsigned score_pair_packed(const unsigned* __restrict
             unsigned h_up = __shfl_up_sync(FULL, h_last, 1);
             unsigned f = __shfl_up_sync(FULL, f_out, 1);
             if (lane == 0) { h_up = 0; f = 0; }
-            unsigned hd = diag_in;
+            // Row r needs t_r = Hdiag + S = H_old[r-1] + S[r]; it is formed one row ahead (VIADD.16x2, which issues on the
+            // FMA pipe) so that H[r] can be overwritten in place without register moves, and the cell update itself
+            // is three DPX instructions on the ALU pipe: VIMNMX3.RELU, VIADDMNMX, VIADDMNMX.
+            unsigned t = __vadd2(diag_in, prmt(w1[0], w2[0], 0xC480u)), t_prev = 0;
             diag_in = h_up;
 #pragma unroll
             for (int r = 0; r < K; ++r) {
-                const unsigned sel = (r & 3) == 0 ? 0xC480u : (r & 3) == 1 ? 0xD591u : (r & 3) == 2 ? 0xE6A2u : 0xF7B3u;
-                const unsigned sc = prmt(w1[r >> 2], w2[r >> 2], sel);
-                const unsigned m = __viaddmax_s16x2_relu(hd, sc, E[r]);   // max(Hdiag + S, E, 0)
-                const unsigned h = __vmaxs2(m, f);                         // H
-                hd = H[r];
+                unsigned t_next = 0;
+                if (r + 1 < K) {
+                    const unsigned sel = ((r + 1) & 3) == 0 ? 0xC480u : ((r + 1) & 3) == 1 ? 0xD591u : ((r + 1) & 3) == 2 ? 0xE6A2u : 0xF7B3u;
+                    t_next = __vadd2(H[r], prmt(w1[(r + 1) >> 2], w2[(r + 1) >> 2], sel));
+                }
+                const unsigned h = __vimax3_s16x2_relu(t, E[r], f);          // H = max(Hdiag + S, E, F, 0)
                 H[r] = h;
                 const unsigned hq = __vadd2(h, negQ);                      // H - Q
                 E[r] = __viaddmax_s16x2(E[r], negR, hq);                   // E of the next column
                 f = __viaddmax_s16x2(f, negR, hq);                         // F of the next row
-                if (r & 1) best = __vimax3_s16x2(best, H[r - 1], h);
-                else if (r == K - 1) best = __vmaxs2(best, h);
+                // the matrix maximum is always reached by a diagonal step (gaps only lower a score), so tracking
+                // t = Hdiag + S instead of H finds the same maximum -- and gives the add a second consumer, which keeps
+                // ptxas from folding it back into a VIADDMNMX on the ALU pipe
+                if (r & 1) best = __vimax3_s16x2(best, t_prev, t);
+                else if (r == K - 1) best = __vmaxs2(best, t);
+                t_prev = t;
+                t = t_next;
             }
             h_last = H[K - 1];
             f_out = f;
