@@ -22,7 +22,6 @@
 namespace {
 
 constexpr int kWarps = 8;
-constexpr int kRows = 8;     // query rows per lane in the endpoint sweep
 
 struct AlParams {
     const uint8_t* db_codes;
@@ -42,81 +41,161 @@ struct AlParams {
     int64_t bound_stride;
 };
 
-// Sweep: Gotoh local alignment of q[0..qlen) (index i -> q[qbase + i*qstep]) against t (j -> t[tbase + j*tstep]);
-// returns the lexicographically smallest (column, row) whose H equals `score` (packed col << 32 | row), or ~0.
-__device__ unsigned long long sweep_first_cell(const uint8_t* q, int qstep, int qlen, const uint8_t* t, int tstep, int tlen,
-                                               int score, const int8_t* smat, int Q, int R, int32_t* bH, int32_t* bF, int lane) {
+// 32-bit systolic sweep, one warp per hit: Gotoh local alignment of rows i -> q[i * qstep] (i < rows) against
+// columns j -> t[j * tstep] (j < cols); finds the lexicographically smallest (column, row) whose H equals `score`
+// and stops once every lane has passed that column.  Lanes own 8 consecutive rows (256 rows per pass; the boundary
+// row travels between passes through a per-warp global scratch, staged through shared memory 64 columns at a time).
+// The lane's rows x 27 letters substitution scores sit in a per-warp shared-memory profile (4 int8 per word,
+// conflict free), rebuilt per pass.  Per cell: IADD (Hdiag + S), VIMNMX3.RELU, IADD (H - Q), 2 x VIADDMNMX.
+constexpr int kSwWarps = 8;
+constexpr int kSwRows = 8;
+constexpr int kSwRing = 64;
+constexpr int kSwProfWords = (S4G_PAD_CODE + 1) * 2 * 32;
+constexpr int kSwWarpBytes = kSwProfWords * 4 + 2 * kSwRing * 2 + 2 * kSwRing * 4 + 4 * kSwRing * 4;
+constexpr int kSwSmatBytes = 896;
+
+struct SweepSmem {
+    unsigned* prof;          // [27][2][32]
+    unsigned short* ring;    // [128] byte offset of the column letter's profile row
+    int *inH, *inF;          // [64] boundary row of the previous pass for the current block of columns
+    int *outH, *outF;        // [128] boundary row produced by lane 31
+};
+
+__device__ unsigned long long sweep32(const SweepSmem& S, const int8_t* smat, const uint8_t* q, int qstep, int rows, const uint8_t* t,
+                                      int tstep, int cols, int score, int Q, int R, int32_t* bH, int32_t* bF, int lane) {
     const unsigned FULL = 0xffffffffu;
     unsigned long long found = ~0ull;
-    const int npass = (qlen + 32 * kRows - 1) / (32 * kRows);
+    int jlim = cols;                                   // columns [0, jlim) can still hold the answer
+    const int npass = (rows + 32 * kSwRows - 1) / (32 * kSwRows);
+    const char* prof_b = reinterpret_cast<const char*>(S.prof) + lane * 4;
     for (int pass = 0; pass < npass; ++pass) {
-        const int row0 = pass * 32 * kRows + lane * kRows;
-        int ql[kRows];
-#pragma unroll
-        for (int r = 0; r < kRows; ++r) ql[r] = row0 + r < qlen ? (int)q[(long long)(row0 + r) * qstep] : -1;
-        int H[kRows], E[kRows];
-#pragma unroll
-        for (int r = 0; r < kRows; ++r) { H[r] = 0; E[r] = 0; }
-        int h_last = 0, f_out = 0, diag_in = 0;
+        const int row0 = pass * 32 * kSwRows + lane * kSwRows;
         const bool first = pass == 0, last = pass == npass - 1;
-        for (int s = 0; s < tlen + 31; ++s) {
-            const int j = s - lane;
-            int h_up = __shfl_up_sync(FULL, h_last, 1);
-            int f = __shfl_up_sync(FULL, f_out, 1);
-            const bool live = j >= 0 && j < tlen;
-            if (lane == 0) {
-                if (first || !live) { h_up = 0; f = 0; }
-                else { h_up = __ldcg(bH + j); f = __ldcg(bF + j); }
-            }
-            int hd = diag_in;
-            diag_in = h_up;
-            const int8_t* srow = smat + (live ? (int)t[(long long)j * tstep] : S4G_PAD_CODE) * 32;
-            int colmax = 0;
+        // profile of this lane's rows
+        {
+            int ql[kSwRows];
 #pragma unroll
-            for (int r = 0; r < kRows; ++r) {
-                const int sc = ql[r] >= 0 ? (int)srow[ql[r]] : -1;
-                int h = __vimax3_s32_relu(hd + sc, E[r], f);
-                if (!live || ql[r] < 0) h = 0;
-                hd = H[r];
-                H[r] = h;
-                const int hq = h - Q;
-                E[r] = __viaddmax_s32_relu(E[r], -R, hq);      // SSW keeps E, F >= 0 (saturating subtract)
-                f = __viaddmax_s32_relu(f, -R, hq);
-                colmax = max(colmax, h);
-            }
-            h_last = H[kRows - 1];
-            f_out = f;
-            if (lane == 31 && !last && live) { __stcg(bH + j, h_last); __stcg(bF + j, f_out); }
-            if (colmax == score && live) {
-                int rr = 0;
+            for (int r = 0; r < kSwRows; ++r) ql[r] = row0 + r < rows ? (int)q[(long long)(row0 + r) * qstep] : -1;
+            for (int letter = 0; letter <= S4G_PAD_CODE; ++letter) {
 #pragma unroll
-                for (int r = kRows - 1; r >= 0; --r) if (H[r] == score) rr = r;
-                const unsigned long long cand = ((unsigned long long)(unsigned)j << 32) | (unsigned)(row0 + rr);
-                if (cand < found) found = cand;
+                for (int m = 0; m < 2; ++m) {
+                    unsigned word = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int v = ql[4 * m + b] >= 0 ? (int)smat[letter * 32 + ql[4 * m + b]] : -128;
+                        word |= (unsigned)(v & 0xff) << (8 * b);
+                    }
+                    S.prof[(letter * 2 + m) * 32 + lane] = word;
+                }
             }
         }
-        __syncwarp();
-    }
+        for (int c = lane; c < kSwRing; c += 32) S.ring[kSwRing + c] = (unsigned short)(S4G_PAD_CODE * 256);   // columns -64..-1
+        int H[kSwRows], E[kSwRows];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long other = __shfl_xor_sync(FULL, found, o);
-        if (other < found) found = other;
+        for (int r = 0; r < kSwRows; ++r) { H[r] = 0; E[r] = 0; }
+        int h_last = 0, f_out = 0, diag_in = 0;
+        const int nsteps = jlim + 31;
+        int flushed = 0;
+        for (int s0 = 0; s0 < nsteps; s0 += kSwRing) {
+            // boundary row of the columns every lane has finished -> global (for the next pass)
+            if (!last) {
+                const int upto = min(jlim, s0 - 31);
+                for (int c = flushed + lane; c < upto; c += 32) { bH[c] = S.outH[c & (2 * kSwRing - 1)]; bF[c] = S.outF[c & (2 * kSwRing - 1)]; }
+                if (upto > flushed) flushed = upto;
+            }
+            if (s0 > 0) {
+                unsigned long long fm = found;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { const unsigned long long x = __shfl_xor_sync(FULL, fm, o); if (x < fm) fm = x; }
+                if (fm != ~0ull && (int)(fm >> 32) + 32 <= s0) break;
+            }
+            {
+                const int base = s0 & (2 * kSwRing - 1);
+#pragma unroll
+                for (int c = 0; c < kSwRing; c += 32) {
+                    const int j = s0 + c + lane;
+                    S.ring[base + c + lane] = (unsigned short)((j < jlim ? (unsigned)t[(long long)j * tstep] : (unsigned)S4G_PAD_CODE) * 256u);
+                    if (!first) { S.inH[c + lane] = j < jlim ? bH[j] : 0; S.inF[c + lane] = j < jlim ? bF[j] : 0; }
+                }
+            }
+            __syncwarp();
+            const int send = (nsteps - s0) < kSwRing ? (nsteps - s0) : kSwRing;
+#pragma unroll 1
+            for (int ss = 0; ss < send; ++ss) {
+                const int j = s0 + ss - lane;
+                const unsigned o = S.ring[j & (2 * kSwRing - 1)];
+                const unsigned w0 = *reinterpret_cast<const unsigned*>(prof_b + o);
+                const unsigned w1 = *reinterpret_cast<const unsigned*>(prof_b + o + 128);
+                int h_up = __shfl_up_sync(FULL, h_last, 1);
+                int f = __shfl_up_sync(FULL, f_out, 1);
+                if (lane == 0) { h_up = first ? 0 : S.inH[ss]; f = first ? 0 : S.inF[ss]; }
+                int tt = diag_in + (int)(int8_t)(w0 & 0xffu), t_prev = 0, cm = 0;
+                diag_in = h_up;
+#pragma unroll
+                for (int r = 0; r < kSwRows; ++r) {
+                    int t_next = 0;
+                    if (r + 1 < kSwRows) {
+                        const unsigned w = (r + 1) < 4 ? w0 : w1;
+                        t_next = H[r] + (int)(int8_t)((w >> (8 * ((r + 1) & 3))) & 0xffu);
+                    }
+                    const int h = __vimax3_s32_relu(tt, E[r], f);
+                    H[r] = h;
+                    const int hq = h - Q;
+                    E[r] = __viaddmax_s32(E[r], -R, hq);
+                    f = __viaddmax_s32(f, -R, hq);
+                    if (r & 1) cm = __vimax3_s32(cm, t_prev, tt);        // the maximum is reached by a diagonal step
+                    t_prev = tt;
+                    tt = t_next;
+                }
+                h_last = H[kSwRows - 1];
+                f_out = f;
+                if (lane == 31 && !last && j >= 0 && j < jlim) { S.outH[j & (2 * kSwRing - 1)] = h_last; S.outF[j & (2 * kSwRing - 1)] = f_out; }
+                if (cm == score && j >= 0 && j < jlim) {
+                    int rr = -1;
+#pragma unroll
+                    for (int r = kSwRows - 1; r >= 0; --r) if (H[r] == score && row0 + r < rows) rr = r;
+                    if (rr >= 0) {
+                        const unsigned long long cand = ((unsigned long long)(unsigned)j << 32) | (unsigned)(row0 + rr);
+                        if (cand < found) found = cand;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const unsigned long long x = __shfl_xor_sync(FULL, found, o); if (x < found) found = x; }
+        if (found != ~0ull) jlim = (int)(found >> 32) + 1;
+        if (!last) {
+            for (int c = flushed + lane; c < jlim; c += 32) { bH[c] = S.outH[c & (2 * kSwRing - 1)]; bF[c] = S.outF[c & (2 * kSwRing - 1)]; }
+        }
+        __syncwarp();
     }
     return found;
 }
 
-__global__ void __launch_bounds__(kWarps * 32) al_endpoints_kernel(AlParams P) {
-    __shared__ int8_t smat[(S4G_PAD_CODE + 1) * 32];
+// mode 0: begin cells of all hits (reverse sweep from the end cell; coords[1], coords[3] must be set)
+// mode 1: end cells of the hits whose query is longer than `long_rows` (forward sweep; the packed kernel did the rest)
+__global__ void __launch_bounds__(kSwWarps * 32) al_sweep32_kernel(AlParams P, int mode, int long_rows, unsigned long long* cursor) {
+    extern __shared__ __align__(16) unsigned char ssm[];
+    int8_t* smat = reinterpret_cast<int8_t*>(ssm);
     for (int i = threadIdx.x; i < (S4G_PAD_CODE + 1) * 32; i += blockDim.x) smat[i] = P.mat8[i];
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int gwarp = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* wb = ssm + kSwSmatBytes + warp * kSwWarpBytes;
+    SweepSmem S;
+    S.prof = reinterpret_cast<unsigned*>(wb);
+    S.ring = reinterpret_cast<unsigned short*>(S.prof + kSwProfWords);
+    S.inH = reinterpret_cast<int*>(S.ring + 2 * kSwRing);
+    S.inF = S.inH + kSwRing;
+    S.outH = S.inF + kSwRing;
+    S.outF = S.outH + 2 * kSwRing;
+    const int gwarp = blockIdx.x * kSwWarps + warp;
     int32_t* bH = P.bound + (int64_t)gwarp * P.bound_stride;
     int32_t* bF = bH + P.bound_stride / 2;
     const unsigned FULL = 0xffffffffu;
     while (true) {
         unsigned long long w = 0;
-        if (lane == 0) w = atomicAdd(P.counters + 0, 1ull);
+        if (lane == 0) w = atomicAdd(cursor, 1ull);
         w = __shfl_sync(FULL, w, 0);
         if ((long long)w >= P.n_pairs) break;
         const uint32_t qi = P.pair_q[w], ti = P.pair_t[w] - P.id_base;
@@ -125,24 +204,25 @@ __global__ void __launch_bounds__(kWarps * 32) al_endpoints_kernel(AlParams P) {
         const uint8_t* t = P.db_codes + P.db_off[ti];
         const int tlen = (int)(P.db_off[ti + 1] - P.db_off[ti]);
         const int score = P.pair_score[w];
-        int c0 = -1, c1 = -1, c2 = -1, c3 = -1;
-        if (score > 0) {
-            const unsigned long long e = sweep_first_cell(q, 1, qlen, t, 1, tlen, score, smat, P.go, P.ge, bH, bF, lane);
-            if (e != ~0ull) {
-                const int t_end = (int)(e >> 32), q_end = (int)(e & 0xffffffffu);
-                const unsigned long long b = sweep_first_cell(q + q_end, -1, q_end + 1, t + t_end, -1, t_end + 1, score, smat, P.go,
-                                                              P.ge, bH, bF, lane);
-                if (b != ~0ull) {
-                    c1 = q_end; c3 = t_end;
-                    c0 = q_end - (int)(b & 0xffffffffu);
-                    c2 = t_end - (int)(b >> 32);
-                }
+        if (mode == 1) {
+            if (qlen <= long_rows) continue;
+            const unsigned long long e = score > 0 ? sweep32(S, smat, q, 1, qlen, t, 1, tlen, score, P.go, P.ge, bH, bF, lane) : ~0ull;
+            if (lane == 0) {
+                if (e == ~0ull) atomicOr(P.counters + 1, 1ull);
+                P.coords[4 * w + 1] = e == ~0ull ? -1 : (int)(e & 0xffffffffu);
+                P.coords[4 * w + 3] = e == ~0ull ? -1 : (int)(e >> 32);
+            }
+        } else {
+            const int q_end = P.coords[4 * w + 1], t_end = P.coords[4 * w + 3];
+            unsigned long long b = ~0ull;
+            if (q_end >= 0 && t_end >= 0) b = sweep32(S, smat, q + q_end, -1, q_end + 1, t + t_end, -1, t_end + 1, score, P.go, P.ge, bH, bF, lane);
+            if (lane == 0) {
+                if (b == ~0ull) atomicOr(P.counters + 1, 1ull);
+                P.coords[4 * w + 0] = b == ~0ull ? -1 : q_end - (int)(b & 0xffffffffu);
+                P.coords[4 * w + 2] = b == ~0ull ? -1 : t_end - (int)(b >> 32);
             }
         }
-        if (lane == 0) {
-            if (c0 < 0) atomicOr(P.counters + 1, 1ull);
-            P.coords[4 * w + 0] = c0; P.coords[4 * w + 1] = c1; P.coords[4 * w + 2] = c2; P.coords[4 * w + 3] = c3;
-        }
+        __syncwarp();
     }
 }
 
@@ -471,10 +551,15 @@ extern "C" int s4g_sw_align(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_
         }
     for (int b = 0; b < 32; ++b) h_mat8[S4G_PAD_CODE * 32 + b] = (int8_t)(min_s < -1 ? min_s : -1);
 
-    const int ep_blocks = ctx->sm_count * 4;
+    const size_t sw_smem = kSwSmatBytes + (size_t)kSwWarps * kSwWarpBytes;
+    S4G_CUDA(ctx, cudaFuncSetAttribute(al_sweep32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw_smem));
+    int sw_per_sm = 0;
+    S4G_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sw_per_sm, al_sweep32_kernel, kSwWarps * 32, sw_smem));
+    if (sw_per_sm < 1) sw_per_sm = 1;
+    const int sw_blocks = ctx->sm_count * sw_per_sm;
     const int64_t bound_stride = 2 * ((int64_t)db->max_len + 64);
     char* misc = (char*)s4g_scratch(ctx, SLOT_AL_MISC, 256 + sizeof(h_mat8) + sizeof(int64_t) * 4 * (n_pairs + 1) + sizeof(int32_t) * 6 * n_pairs);
-    int32_t* d_bound = (int32_t*)s4g_scratch(ctx, SLOT_SW_BOUND, sizeof(int32_t) * bound_stride * ep_blocks * kWarps);
+    int32_t* d_bound = (int32_t*)s4g_scratch(ctx, SLOT_SW_BOUND, sizeof(int32_t) * bound_stride * sw_blocks * kSwWarps);
     if (!misc || !d_bound) return S4G_ERR_NOMEM;
     unsigned long long* d_counters = (unsigned long long*)misc;
     int8_t* d_mat8 = (int8_t*)(misc + 64);
@@ -489,6 +574,7 @@ extern "C" int s4g_sw_align(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_
     S4G_CUDA(ctx, cudaMemsetAsync(d_counters, 0, 64, st));
     S4G_CUDA(ctx, cudaMemcpyAsync(d_mat8, h_mat8, sizeof(h_mat8), cudaMemcpyHostToDevice, st));
     S4G_CUDA(ctx, cudaMemsetAsync(d_path_len, 0xff, sizeof(int32_t) * n_pairs, st));
+    S4G_CUDA(ctx, cudaMemsetAsync(d_coords, 0xff, sizeof(int32_t) * 4 * n_pairs, st));
 
     AlParams P;
     P.db_codes = db->d_codes; P.db_off = db->d_off; P.id_base = db->id_base;
@@ -497,9 +583,21 @@ extern "C" int s4g_sw_align(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_
     P.mat8 = d_mat8; P.go = gap_open; P.ge = gap_extend; P.coords = d_coords; P.counters = d_counters;
     P.bound = d_bound; P.bound_stride = bound_stride;
 
-    // 1+2: end and begin cells
-    al_endpoints_kernel<<<ep_blocks, kWarps * 32, 0, st>>>(P);
+    s4g_trace_start(ctx);
+    // 1: end cells -- packed s16x2 sweep, two hits of a query per warp; 32-bit sweep for queries beyond its reach
+    {
+        int rc = s4g_sw_forward_ends_device(ctx, db, q, n_pairs, d_pq, d_pt, d_ps, d_mat8, gap_open, gap_extend, d_coords, d_counters + 1);
+        if (rc != S4G_OK) return rc;
+        if (q->max_len > s4g_sw_long_query_rows()) {
+            al_sweep32_kernel<<<sw_blocks, kSwWarps * 32, sw_smem, st>>>(P, 1, s4g_sw_long_query_rows(), d_counters + 3);
+            S4G_CHECK_LAUNCH(ctx);
+        }
+    }
+    s4g_trace_mark(ctx, "ends");
+    // 2: begin cells -- reverse 32-bit sweep from the end cell, stopped at the first column that holds the score
+    al_sweep32_kernel<<<sw_blocks, kSwWarps * 32, sw_smem, st>>>(P, 0, 0, d_counters + 0);
     S4G_CHECK_LAUNCH(ctx);
+    s4g_trace_mark(ctx, "begins");
     std::vector<int32_t> h_coords(4 * n_pairs);
     unsigned long long h_counters[2];
     S4G_CUDA(ctx, cudaMemcpyAsync(h_coords.data(), d_coords, sizeof(int32_t) * 4 * n_pairs, cudaMemcpyDeviceToHost, st));
@@ -591,6 +689,7 @@ extern "C" int s4g_sw_align(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_
         pending.swap(next);
     }
 
+    s4g_trace_mark(ctx, "band");
     // pack: path offsets = exclusive scan of the lengths, then forward-order copy
     al_len64_kernel<<<(unsigned)((n_pairs + 1 + 255) / 256), 256, 0, st>>>(d_path_len, n_pairs, d_len64);
     S4G_CHECK_LAUNCH(ctx);
@@ -618,5 +717,7 @@ extern "C" int s4g_sw_align(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_
     } else {
         S4G_CUDA(ctx, cudaMemcpyAsync(out_path_offsets, d_out_off, sizeof(int64_t) * (n_pairs + 1), cudaMemcpyDeviceToDevice, st));
     }
+    s4g_trace_mark(ctx, "pack");
+    s4g_trace_report(ctx, "align");
     return S4G_OK;
 }

@@ -101,6 +101,11 @@ int s4g_sw_score_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, const uint32_t
                         const int64_t* d_cand_off, int64_t n_pairs, const int32_t* h_matrix, int gap_open,
                         int gap_extend, int32_t* d_out);
 
+int s4g_sw_forward_ends_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n, const uint32_t* d_pair_q, const uint32_t* d_pair_t,
+                               const int32_t* d_pair_score, const int8_t* d_mat8, int gap_open, int gap_extend, int32_t* d_coords,
+                               unsigned long long* d_flags);
+int s4g_sw_long_query_rows();      // queries longer than this many residues are not handled by the packed kernels
+
 int s4g_prefilter_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int max_candidates,
                          int sorted_by_id, uint32_t* d_ids, float* d_scores, uint32_t* d_counts);
 

@@ -63,17 +63,27 @@ struct ScoreParams {
     int64_t bound_stride;           // ints per warp
     int32_t gap_open, gap_extend;
     int32_t ovf_limit;              // 32767 - max(matrix)
+    // end-cell mode (stage 3, step 1): cand_ids = targets of the kept hits, out = coords (4 per hit)
+    const int32_t* pair_score;
 };
 
 // ------------------------------------------------------------------------------------------------------
 // packed s16x2 kernel body for one pair, K rows per lane
 
-template <int K>
+// TRACK = false: returns the packed maxima of the two targets.
+// TRACK = true : the scores are known (score2, packed); finds for each target the first column, then the first row in
+//                it, whose H equals the score -- SSW's end cell (ssw.c:283-308,491-512) -- as (col << 10 | row) in
+//                found1 / found2, and stops as soon as both are settled.
+constexpr unsigned kNotFound = 0xffffffffu;
+
+template <int K, bool TRACK>
 __device__ __forceinline__ unsigned score_pair_packed(const unsigned* __restrict__ prof_lane,   // smem, + lane
                                                       unsigned short* ring1, unsigned short* ring2,
                                                       const uint8_t* __restrict__ t1, int len1,
                                                       const uint8_t* __restrict__ t2, int len2,
-                                                      unsigned negQ, unsigned negR, int lane) {
+                                                      unsigned negQ, unsigned negR, int lane,
+                                                      unsigned score2 = 0, int qlen = 0, unsigned* found1 = nullptr,
+                                                      unsigned* found2 = nullptr) {
     constexpr int KW = (K + 3) / 4;
     constexpr unsigned kRowBytes = KW * 128;             // bytes per profile letter row
     constexpr unsigned kPadOff = S4G_PAD_CODE * kRowBytes;
@@ -84,6 +94,7 @@ __device__ __forceinline__ unsigned score_pair_packed(const unsigned* __restrict
 #pragma unroll
     for (int r = 0; r < K; ++r) { H[r] = 0; E[r] = 0; }
     unsigned best = 0, h_last = 0, f_out = 0, diag_in = 0;
+    unsigned fnd1 = kNotFound, fnd2 = kNotFound;
 
     const int maxlen = len1 > len2 ? len1 : len2;
     const int nsteps = maxlen + 31;
@@ -94,6 +105,15 @@ __device__ __forceinline__ unsigned score_pair_packed(const unsigned* __restrict
     const char* prof_bytes = reinterpret_cast<const char*>(prof_lane);
 
     for (int s0 = 0; s0 < nsteps; s0 += kRing) {
+        if (TRACK && s0 > 0) {
+            // a target is settled once every lane has passed the column of its first hit (or its end)
+            unsigned m1 = fnd1, m2 = fnd2;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { m1 = min(m1, __shfl_xor_sync(FULL, m1, o)); m2 = min(m2, __shfl_xor_sync(FULL, m2, o)); }
+            const bool d1 = (m1 != kNotFound && (int)(m1 >> 10) + 32 <= s0) || len1 + 31 <= s0;
+            const bool d2 = (m2 != kNotFound && (int)(m2 >> 10) + 32 <= s0) || len2 + 31 <= s0;
+            if (d1 && d2) break;
+        }
         // refill: columns s0 .. s0+kRing-1 into ring slot (s0/kRing)&1
         {
             const int base = s0 & kRingMask;
@@ -127,6 +147,7 @@ __device__ __forceinline__ unsigned score_pair_packed(const unsigned* __restrict
             // is three DPX instructions on the ALU pipe: VIMNMX3.RELU, VIADDMNMX, VIADDMNMX.
             unsigned t = __vadd2(diag_in, prmt(w1[0], w2[0], 0xC480u)), t_prev = 0;
             diag_in = h_up;
+            if (TRACK) best = 0;                                            // per-column maximum in end-cell mode
 #pragma unroll
             for (int r = 0; r < K; ++r) {
                 unsigned t_next = 0;
@@ -149,8 +170,32 @@ __device__ __forceinline__ unsigned score_pair_packed(const unsigned* __restrict
             }
             h_last = H[K - 1];
             f_out = f;
+            if (TRACK) {
+                const unsigned eq = __vcmpeq2(best, score2);
+                if (eq) {
+                    const int col = s0 + ss - lane;
+                    if ((eq & 0xffffu) && col < len1) {
+                        int rr = -1;
+#pragma unroll
+                        for (int r = K - 1; r >= 0; --r) if ((H[r] & 0xffffu) == (score2 & 0xffffu) && lane * K + r < qlen) rr = r;
+                        if (rr >= 0) fnd1 = min(fnd1, ((unsigned)col << 10) | (unsigned)(lane * K + rr));
+                    }
+                    if ((eq >> 16) && col < len2) {
+                        int rr = -1;
+#pragma unroll
+                        for (int r = K - 1; r >= 0; --r) if ((H[r] >> 16) == (score2 >> 16) && lane * K + r < qlen) rr = r;
+                        if (rr >= 0) fnd2 = min(fnd2, ((unsigned)col << 10) | (unsigned)(lane * K + rr));
+                    }
+                }
+            }
         }
         __syncwarp();
+    }
+    if (TRACK) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { fnd1 = min(fnd1, __shfl_xor_sync(FULL, fnd1, o)); fnd2 = min(fnd2, __shfl_xor_sync(FULL, fnd2, o)); }
+        *found1 = fnd1; *found2 = fnd2;
+        return 0;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best = __vmaxs2(best, __shfl_xor_sync(FULL, best, o));
@@ -177,7 +222,7 @@ __device__ void build_profile(unsigned* prof, const int8_t* smat, const uint8_t*
     }
 }
 
-template <int K>
+template <int K, bool TRACK>
 __device__ void run_tile(const ScoreParams& P, unsigned* prof, const int8_t* smat, unsigned short* rings,
                          int* s_next, int q, int pair_begin, int pair_end) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -202,8 +247,26 @@ __device__ void run_tile(const ScoreParams& P, unsigned* prof, const int8_t* sma
         const uint32_t c2 = has2 ? P.sorted_idx[i2] : c1;
         const int64_t a1 = P.db_off[P.cand_ids[c1] - P.id_base], b1 = P.db_off[P.cand_ids[c1] - P.id_base + 1];
         const int64_t a2 = P.db_off[P.cand_ids[c2] - P.id_base], b2 = P.db_off[P.cand_ids[c2] - P.id_base + 1];
-        const unsigned best = score_pair_packed<K>(prof + lane, ring1, ring2, P.db_codes + a1, (int)(b1 - a1),
-                                                   P.db_codes + a2, has2 ? (int)(b2 - a2) : 0, negQ, negR, lane);
+        if (TRACK) {
+            // missing second target: a score no cell can reach
+            const unsigned sc2 = ((unsigned)P.pair_score[c1] & 0xffffu) | (has2 ? (unsigned)P.pair_score[c2] << 16 : 0x7fff0000u);
+            unsigned f1, f2;
+            score_pair_packed<K, true>(prof + lane, ring1, ring2, P.db_codes + a1, (int)(b1 - a1), P.db_codes + a2,
+                                       has2 ? (int)(b2 - a2) : 0, negQ, negR, lane, sc2, qlen, &f1, &f2);
+            if (lane == 0) {
+                if (f1 == kNotFound) atomicOr(&P.counters[3], 1ull);
+                P.out[4 * (int64_t)c1 + 1] = f1 == kNotFound ? -1 : (int)(f1 & 1023u);
+                P.out[4 * (int64_t)c1 + 3] = f1 == kNotFound ? -1 : (int)(f1 >> 10);
+                if (has2) {
+                    if (f2 == kNotFound) atomicOr(&P.counters[3], 1ull);
+                    P.out[4 * (int64_t)c2 + 1] = f2 == kNotFound ? -1 : (int)(f2 & 1023u);
+                    P.out[4 * (int64_t)c2 + 3] = f2 == kNotFound ? -1 : (int)(f2 >> 10);
+                }
+            }
+            continue;
+        }
+        const unsigned best = score_pair_packed<K, false>(prof + lane, ring1, ring2, P.db_codes + a1, (int)(b1 - a1),
+                                                          P.db_codes + a2, has2 ? (int)(b2 - a2) : 0, negQ, negR, lane);
         if (lane == 0) {
             const int s1 = (int)(best & 0xffffu), s2 = (int)(best >> 16);
             if (s1 > P.ovf_limit) P.overflow[atomicAdd(&P.counters[1], 1ull)] = c1; else P.out[c1] = s1;
@@ -213,7 +276,8 @@ __device__ void run_tile(const ScoreParams& P, unsigned* prof, const int8_t* sma
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kWarps * 32, 2) sw_score_packed_kernel(ScoreParams P) {
+template <bool TRACK>
+__device__ __forceinline__ void packed_kernel_body(const ScoreParams& P) {
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned* prof = reinterpret_cast<unsigned*>(smem);                                   // 27*8*32 words max
     int8_t* smat = reinterpret_cast<int8_t*>(smem + (S4G_PAD_CODE + 1) * 8 * 32 * 4);      // 27*32
@@ -239,25 +303,30 @@ __global__ void __launch_bounds__(kWarps * 32, 2) sw_score_packed_kernel(ScorePa
         const int pe = pb + kTilePairs < n_pairs ? pb + kTilePairs : n_pairs;
         const int K = (qlen + 31) >> 5;
         switch ((K + 1) >> 1) {
-            case 0: case 1: run_tile<2>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 2: run_tile<4>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 3: run_tile<6>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 4: run_tile<8>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 5: run_tile<10>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 6: run_tile<12>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 7: run_tile<14>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 8: run_tile<16>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 9: run_tile<18>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 10: run_tile<20>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 11: run_tile<22>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 12: run_tile<24>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 13: run_tile<26>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 14: run_tile<28>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 15: run_tile<30>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            default: run_tile<32>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 0: case 1: run_tile<2, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 2: run_tile<4, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 3: run_tile<6, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 4: run_tile<8, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 5: run_tile<10, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 6: run_tile<12, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 7: run_tile<14, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 8: run_tile<16, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 9: run_tile<18, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 10: run_tile<20, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 11: run_tile<22, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 12: run_tile<24, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 13: run_tile<26, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 14: run_tile<28, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 15: run_tile<30, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            default: run_tile<32, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
         }
     }
 }
+
+__global__ void __launch_bounds__(kWarps * 32, 2) sw_score_packed_kernel(ScoreParams P) { packed_kernel_body<false>(P); }
+
+// End cells of the kept hits with the same systolic sweep (stage 3, step 1).
+__global__ void __launch_bounds__(kWarps * 32, 2) al_forward_packed_kernel(ScoreParams P) { packed_kernel_body<true>(P); }
 
 // ------------------------------------------------------------------------------------------------------
 // exact 32-bit kernel: one warp per (query, target), any query length (256-row passes, the boundary row
@@ -386,6 +455,27 @@ __global__ void gather_long_kernel(ScoreParams P, const int64_t* long_start, con
     for (int64_t i = b + threadIdx.x; i < e; i += blockDim.x) long_idx[long_start[q] + (i - b)] = sorted_idx[i];
 }
 
+// ---- end-cell mode: the kept hits as (query, target) work, grouped by query and sorted by target length ----
+
+__global__ void hit_keys_kernel(ScoreParams P, const uint32_t* pair_q, int64_t n, unsigned long long* keys, uint32_t* vals) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t t = P.cand_ids[i] - P.id_base;
+    const unsigned len = (unsigned)(P.db_off[t + 1] - P.db_off[t]);
+    keys[i] = ((unsigned long long)pair_q[i] << 32) | (unsigned long long)(0xffffffffu - len);
+    vals[i] = (uint32_t)i;
+}
+
+// first position of every query in the sorted key list (nq + 1 entries)
+__global__ void hit_qstart_kernel(const unsigned long long* sorted_keys, int64_t n, int nq, int64_t* qstart) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q > nq) return;
+    const unsigned long long want = (unsigned long long)q << 32;
+    int64_t lo = 0, hi = n;
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (sorted_keys[mid] < want) lo = mid + 1; else hi = mid; }
+    qstart[q] = lo;
+}
+
 }  // namespace
 
 int s4g_sw_score_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, const uint32_t* d_cand_ids,
@@ -498,3 +588,67 @@ int s4g_sw_score_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, const uint32_t
     }
     return S4G_OK;
 }
+
+// Stage 3, step 1 for queries of at most 32 * kMaxK residues: end cell (query row -> coords[4i+1], target column ->
+// coords[4i+3]) of every kept hit, two hits of the same query per warp.  Hits of longer queries are left untouched
+// (align.cu sweeps them with its 32-bit kernel).  d_flags[0] bit 0 is set when a score is not attained.
+int s4g_sw_forward_ends_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n, const uint32_t* d_pair_q, const uint32_t* d_pair_t,
+                               const int32_t* d_pair_score, const int8_t* d_mat8, int gap_open, int gap_extend, int32_t* d_coords,
+                               unsigned long long* d_flags) {
+    cudaStream_t st = ctx->stream;
+    const int nq = q->n;
+    unsigned long long* d_keys = (unsigned long long*)s4g_scratch(ctx, SLOT_SW_KEYS, sizeof(unsigned long long) * n);
+    unsigned long long* d_keys2 = (unsigned long long*)s4g_scratch(ctx, SLOT_SW_KEYS2, sizeof(unsigned long long) * n);
+    uint32_t* d_vals = (uint32_t*)s4g_scratch(ctx, SLOT_SW_VALS, sizeof(uint32_t) * n);
+    uint32_t* d_vals2 = (uint32_t*)s4g_scratch(ctx, SLOT_SW_VALS2, sizeof(uint32_t) * n);
+    int64_t* d_tiles = (int64_t*)s4g_scratch(ctx, SLOT_SW_TILES, sizeof(int64_t) * 5 * (nq + 1));
+    unsigned long long* d_counters = (unsigned long long*)s4g_scratch(ctx, SLOT_SW_MISC, 64);
+    if (!d_keys || !d_keys2 || !d_vals || !d_vals2 || !d_tiles || !d_counters) return S4G_ERR_NOMEM;
+    int64_t* d_tile_cnt = d_tiles, *d_tile_start = d_tiles + (nq + 1), *d_long_cnt = d_tiles + 2 * (nq + 1), *d_qstart = d_tiles + 4 * (nq + 1);
+    S4G_CUDA(ctx, cudaMemsetAsync(d_counters, 0, 64, st));
+
+    ScoreParams P;
+    memset(&P, 0, sizeof(P));
+    P.db_codes = db->d_codes; P.db_off = db->d_off; P.id_base = db->id_base;
+    P.q_codes = q->d_codes; P.q_off = q->d_off; P.nq = nq;
+    P.cand_ids = d_pair_t; P.cand_off = d_qstart;
+    P.sorted_idx = d_vals2; P.tile_start = d_tile_start; P.mat8 = d_mat8; P.out = d_coords;
+    P.counters = d_counters; P.gap_open = gap_open; P.gap_extend = gap_extend; P.pair_score = d_pair_score;
+
+    hit_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, d_pair_q, n, d_keys, d_vals);
+    S4G_CHECK_LAUNCH(ctx);
+    {
+        int qbits = 1;
+        while ((1ll << qbits) < nq) ++qbits;
+        size_t tmp_bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, (int)n, 0, 32 + qbits, st);
+        void* d_tmp = s4g_scratch(ctx, SLOT_SW_CUB, tmp_bytes);
+        if (!d_tmp) return S4G_ERR_NOMEM;
+        S4G_CUDA(ctx, cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, (int)n, 0, 32 + qbits, st));
+        ctx->launches += 4;
+    }
+    hit_qstart_kernel<<<(nq + 1 + 255) / 256, 256, 0, st>>>(d_keys2, n, nq, d_qstart);
+    S4G_CHECK_LAUNCH(ctx);
+    count_tiles_kernel<<<(nq + 1 + 255) / 256, 256, 0, st>>>(P, d_tile_cnt, d_long_cnt);
+    S4G_CHECK_LAUNCH(ctx);
+    {
+        size_t tmp_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_tile_cnt, d_tile_start, nq + 1, st);
+        void* d_tmp = s4g_scratch(ctx, SLOT_SW_CUB, tmp_bytes);
+        if (!d_tmp) return S4G_ERR_NOMEM;
+        S4G_CUDA(ctx, cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_tile_cnt, d_tile_start, nq + 1, st));
+        ctx->launches += 1;
+    }
+    const size_t smem = (S4G_PAD_CODE + 1) * 8 * 32 * 4 + (S4G_PAD_CODE + 1) * 32 + kWarps * 4 * kRing * sizeof(unsigned short);
+    S4G_CUDA(ctx, cudaFuncSetAttribute(al_forward_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    S4G_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, al_forward_packed_kernel, kWarps * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    al_forward_packed_kernel<<<ctx->sm_count * per_sm, kWarps * 32, smem, st>>>(P);
+    S4G_CHECK_LAUNCH(ctx);
+    // fold the error flag into the caller's flag word
+    S4G_CUDA(ctx, cudaMemcpyAsync(d_flags, d_counters + 3, 8, cudaMemcpyDeviceToDevice, st));
+    return S4G_OK;
+}
+
+int s4g_sw_long_query_rows() { return 32 * kMaxK; }
