@@ -332,6 +332,125 @@ __global__ void al_band_kernel(AlParams P, BandParams B) {
 constexpr int kBandWarps = 4;
 constexpr int kNegBig = -(1 << 29);
 
+// One banded_sw attempt of a warp with half band width w: fills the direction bytes, returns the banded maximum.
+// bufA / bufB / E: three band rows of `2 * w + 4` ints (shared memory).
+__device__ int band_fill(const int8_t* smatT, const uint8_t* read, int readLen, const uint8_t* ref, int refLen, int w, int go, int ge,
+                         int32_t* bufA, int32_t* bufB, int32_t* E, uint8_t* dir, int lane) {
+    const unsigned FULL = 0xffffffffu;
+    const int width = 2 * w + 3, width_d = 2 * w + 1;
+    int32_t* prevH = bufA;
+    int32_t* curH = bufB;
+    for (int j = lane; j < width + 1; j += 32) { bufA[j] = 0; bufB[j] = 0; E[j] = 0; }
+    __syncwarp();
+    int best = 0;
+    const int f0 = max(-go, -ge);
+    for (int i = 0; i < readLen; ++i) {
+        const int beg = i - w > 0 ? i - w : 0;
+        const int end = i + w < refLen - 1 ? i + w : refLen - 1;
+        const int edge = end + 1 < width - 1 ? end + 1 : width - 1;
+        const int xp = (i - 1 - w > 0) ? i - 1 - w : 0;
+        if (lane == 0) { prevH[0] = 0; E[0] = 0; prevH[edge] = 0; E[edge] = 0; curH[0] = 0; }
+        __syncwarp();
+        const int8_t* mrow = smatT + (int)read[i] * 32;
+        uint8_t* line = dir + (size_t)width_d * i;
+        int carry_pm = kNegBig, carry_hc = 0, carry_f = 0;
+        for (int c0 = beg; c0 <= end; c0 += 32) {
+            const int j = c0 + lane;
+            const bool act = j <= end;
+            const int t = j - beg, u = t + 1, up = j - xp + 1;
+            int ph = 0, pe = 0, pd = 0, sc = 0;
+            if (act) { ph = prevH[up]; pe = E[up]; pd = prevH[up - 1]; sc = mrow[ref[j]]; }
+            const int open_e = i == 0 ? -go : ph - go;
+            const int ext_e = i == 0 ? -ge : pe - ge;
+            const int e = open_e > ext_e ? open_e : ext_e;
+            const unsigned de = open_e > ext_e ? 1u : 0u;
+            const int e1 = e > 0 ? e : 0;
+            const int dsc = pd + sc;
+            const int g = e1 > dsc ? e1 : dsc;
+            int a = act ? g - go + t * ge : kNegBig;
+            int incl = a;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl = max(incl, y); }
+            int excl = __shfl_up_sync(FULL, incl, 1);
+            if (lane == 0) excl = kNegBig;
+            excl = max(excl, carry_pm);
+            const int f = t == 0 ? f0 : max(f0 - t * ge, excl - (t - 1) * ge);
+            const int hc = g > f ? g : f;
+            int hc_left = __shfl_up_sync(FULL, hc, 1), f_left = __shfl_up_sync(FULL, f, 1);
+            if (lane == 0) { hc_left = carry_hc; f_left = carry_f; }
+            const unsigned df = (hc_left - go) > (f_left - ge) ? 1u : 0u;
+            const int f1 = f > 0 ? f : 0;
+            const int gap = e1 > f1 ? e1 : f1;
+            const unsigned sel = gap <= dsc ? 0u : (e1 > f1 ? 1u : 2u);
+            carry_pm = max(carry_pm, __shfl_sync(FULL, incl, 31));
+            carry_hc = __shfl_sync(FULL, hc, 31);
+            carry_f = __shfl_sync(FULL, f, 31);
+            __syncwarp();
+            if (act) {
+                E[u] = e;
+                curH[u] = hc;
+                line[t] = (uint8_t)(de | (df << 1) | (sel << 2));
+                best = max(best, hc);
+            }
+        }
+        __syncwarp();
+        int32_t* tmp = prevH; prevH = curH; curH = tmp;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(FULL, best, o));
+    return best;
+}
+
+// Traceback over the direction bytes of a successful attempt (ssw.c:634-706): from the bottom-right corner in state H
+// until row 0; diagonal runs are taken 32 cells at a time (every lane probes one cell of the diagonal).
+// Writes the reversed path; returns its length or -2 when the walk leaves the band / the slot.
+__device__ int band_trace(const uint8_t* dir, int readLen, int refLen, int w, uint8_t* out, int cap, int lane) {
+    const unsigned FULL = 0xffffffffu;
+    const int width_d = 2 * w + 1;
+    int i = readLen - 1, j = refLen - 1, state = 2, n = 0;
+    while (i > 0) {
+        const int ii = i - lane, jj = j - lane;
+        unsigned d = 0xffu;
+        if (ii > 0 && jj >= 0) {
+            const int x = ii - w > 0 ? ii - w : 0;
+            const int hi = ii + w < refLen - 1 ? ii + w : refLen - 1;
+            if (jj >= x && jj <= hi) d = __ldcg(dir + (size_t)width_d * ii + (jj - x));
+        }
+        const unsigned d0 = __shfl_sync(FULL, d, 0);
+        if (d0 == 0xffu) return -2;
+        if (state == 2 && (d0 >> 2) == 0u) {
+            const unsigned nd = __ballot_sync(FULL, !(d != 0xffu && (d >> 2) == 0u));
+            int run = nd ? __ffs(nd) - 1 : 32;
+            if (run > i) run = i;
+            if (n + run >= cap) return -2;
+            if (lane < run) out[n + lane] = 1;
+            n += run; i -= run; j -= run;
+            continue;
+        }
+        unsigned code;
+        if (state == 0) code = (d0 & 1u) ? 3u : 2u;
+        else if (state == 1) code = (d0 & 2u) ? 5u : 4u;
+        else { const unsigned sel = d0 >> 2; code = sel == 1 ? ((d0 & 1u) ? 3u : 2u) : ((d0 & 2u) ? 5u : 4u); }
+        if (n + 1 >= cap) return -2;
+        uint8_t op;
+        switch (code) {
+            case 2: --i; state = 0; op = 3; break;
+            case 3: --i; state = 2; op = 3; break;
+            case 4: --j; state = 1; op = 2; break;
+            default: --j; state = 2; op = 2; break;
+        }
+        if (lane == 0) out[n] = op;
+        ++n;
+    }
+    if (lane == 0) out[n] = 1;            // the remaining cell is closed as one more match
+    return n + 1;
+}
+
+// Warp-parallel banded_sw: lanes own consecutive band columns of one row, rows are sequential.
+// Along a row the only serial dependency is F:  f[t] = max(hc[t-1] - go, f[t-1] - ge),  hc = max(g, f)  with
+// g = max(e+, Hdiag + S) >= 0, which for ge <= go collapses to f[t] = max(g[t-1] - go, f[t-1] - ge): a max-plus
+// prefix scan (5 shuffles).  Directions and values are the same integers banded_sw computes cell by cell.
+// Host-sequenced variant: one attempt per work item (used for the bands the persistent kernel below hands back).
 __global__ void __launch_bounds__(kBandWarps * 32) al_band_warp_kernel(AlParams P, BandParams B, unsigned long long* cursor) {
     extern __shared__ int32_t rows[];
     __shared__ int8_t smatT[32 * 32];            // [query letter][target letter]
@@ -345,7 +464,6 @@ __global__ void __launch_bounds__(kBandWarps * 32) al_band_warp_kernel(AlParams 
     int32_t* bufA = rows + (size_t)warp * 3 * B.stride;
     int32_t* bufB = bufA + B.stride;
     int32_t* E = bufB + B.stride;
-    const int go = P.go, ge = P.ge;
     while (true) {
         unsigned long long wi = 0;
         if (lane == 0) wi = atomicAdd(cursor, 1ull);
@@ -357,113 +475,80 @@ __global__ void __launch_bounds__(kBandWarps * 32) al_band_warp_kernel(AlParams 
         const uint8_t* read = P.q_codes + P.q_off[P.pair_q[p]] + q0;
         const uint8_t* ref = P.db_codes + P.db_off[P.pair_t[p] - P.id_base] + t0;
         const int readLen = q1 - q0 + 1, refLen = t1 - t0 + 1;
-        const int score = P.pair_score[p];
-        const int w = wk.w, width = 2 * w + 3, width_d = 2 * w + 1;
         uint8_t* dir = B.dir + wk.dir_off;
-        int32_t* prevH = bufA;
-        int32_t* curH = bufB;
-        for (int j = lane; j < width + 1; j += 32) { bufA[j] = 0; bufB[j] = 0; E[j] = 0; }
-        __syncwarp();
-        int best = 0;
-        const int f0 = max(-go, -ge);
-        for (int i = 0; i < readLen; ++i) {
-            const int beg = i - w > 0 ? i - w : 0;
-            const int end = i + w < refLen - 1 ? i + w : refLen - 1;
-            const int edge = end + 1 < width - 1 ? end + 1 : width - 1;
-            const int xp = (i - 1 - w > 0) ? i - 1 - w : 0;
-            if (lane == 0) { prevH[0] = 0; E[0] = 0; prevH[edge] = 0; E[edge] = 0; curH[0] = 0; }
-            __syncwarp();
-            const int8_t* mrow = smatT + (int)read[i] * 32;
-            uint8_t* line = dir + (size_t)width_d * i;
-            int carry_pm = kNegBig, carry_hc = 0, carry_f = 0;
-            for (int c0 = beg; c0 <= end; c0 += 32) {
-                const int j = c0 + lane;
-                const bool act = j <= end;
-                const int t = j - beg, u = t + 1, up = j - xp + 1;
-                int ph = 0, pe = 0, pd = 0, sc = 0;
-                if (act) { ph = prevH[up]; pe = E[up]; pd = prevH[up - 1]; sc = mrow[ref[j]]; }
-                const int open_e = i == 0 ? -go : ph - go;
-                const int ext_e = i == 0 ? -ge : pe - ge;
-                const int e = open_e > ext_e ? open_e : ext_e;
-                const unsigned de = open_e > ext_e ? 1u : 0u;
-                const int e1 = e > 0 ? e : 0;
-                const int dsc = pd + sc;
-                const int g = e1 > dsc ? e1 : dsc;
-                int a = act ? g - go + t * ge : kNegBig;
-                int incl = a;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl = max(incl, y); }
-                int excl = __shfl_up_sync(FULL, incl, 1);
-                if (lane == 0) excl = kNegBig;
-                excl = max(excl, carry_pm);
-                const int f = t == 0 ? f0 : max(f0 - t * ge, excl - (t - 1) * ge);
-                const int hc = g > f ? g : f;
-                int hc_left = __shfl_up_sync(FULL, hc, 1), f_left = __shfl_up_sync(FULL, f, 1);
-                if (lane == 0) { hc_left = carry_hc; f_left = carry_f; }
-                const unsigned df = (hc_left - go) > (f_left - ge) ? 1u : 0u;
-                const int f1 = f > 0 ? f : 0;
-                const int gap = e1 > f1 ? e1 : f1;
-                const unsigned sel = gap <= dsc ? 0u : (e1 > f1 ? 1u : 2u);
-                carry_pm = max(carry_pm, __shfl_sync(FULL, incl, 31));
-                carry_hc = __shfl_sync(FULL, hc, 31);
-                carry_f = __shfl_sync(FULL, f, 31);
-                __syncwarp();
-                if (act) {
-                    E[u] = e;
-                    curH[u] = hc;
-                    line[t] = (uint8_t)(de | (df << 1) | (sel << 2));
-                    best = max(best, hc);
-                }
-            }
-            __syncwarp();
-            int32_t* tmp = prevH; prevH = curH; curH = tmp;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(FULL, best, o));
-        if (best < score) { if (lane == 0) B.status[wi] = 0; continue; }
+        const int best = band_fill(smatT, read, readLen, ref, refLen, wk.w, P.go, P.ge, bufA, bufB, E, dir, lane);
+        if (best < P.pair_score[p]) { if (lane == 0) B.status[wi] = 0; continue; }
         __threadfence_block();
         __syncwarp();
-        // traceback: diagonal runs are taken 32 cells at a time (every lane probes one cell of the diagonal)
-        uint8_t* out = B.rev_paths + B.slot_off[p];
-        const int cap = (int)(B.slot_off[p + 1] - B.slot_off[p]);
-        int i = readLen - 1, j = refLen - 1, state = 2, n = 0, rc = 1;
-        while (i > 0) {
-            const int ii = i - lane, jj = j - lane;
-            unsigned d = 0xffu;
-            if (ii > 0 && jj >= 0) {
-                const int x = ii - w > 0 ? ii - w : 0;
-                const int hi = ii + w < refLen - 1 ? ii + w : refLen - 1;
-                if (jj >= x && jj <= hi) d = __ldcg(dir + (size_t)width_d * ii + (jj - x));
-            }
-            const unsigned d0 = __shfl_sync(FULL, d, 0);
-            if (d0 == 0xffu) { rc = -2; break; }
-            if (state == 2 && (d0 >> 2) == 0u) {
-                const unsigned nd = __ballot_sync(FULL, !(d != 0xffu && (d >> 2) == 0u));
-                int run = nd ? __ffs(nd) - 1 : 32;
-                if (run > i) run = i;
-                if (n + run >= cap) { rc = -2; break; }
-                if (lane < run) out[n + lane] = 1;
-                n += run; i -= run; j -= run;
-                continue;
-            }
-            unsigned code;
-            if (state == 0) code = (d0 & 1u) ? 3u : 2u;
-            else if (state == 1) code = (d0 & 2u) ? 5u : 4u;
-            else { const unsigned sel = d0 >> 2; code = sel == 1 ? ((d0 & 1u) ? 3u : 2u) : ((d0 & 2u) ? 5u : 4u); }
-            if (n + 1 >= cap) { rc = -2; break; }
-            uint8_t op;
-            switch (code) {
-                case 2: --i; state = 0; op = 3; break;
-                case 3: --i; state = 2; op = 3; break;
-                case 4: --j; state = 1; op = 2; break;
-                default: --j; state = 2; op = 2; break;
-            }
-            if (lane == 0) out[n] = op;
-            ++n;
-        }
+        const int n = band_trace(dir, readLen, refLen, wk.w, B.rev_paths + B.slot_off[p], (int)(B.slot_off[p + 1] - B.slot_off[p]), lane);
         if (lane == 0) {
-            if (rc == 1) { out[n++] = 1; B.path_len[p] = n; }
-            B.status[wi] = rc;
+            if (n > 0) B.path_len[p] = n;
+            B.status[wi] = n > 0 ? 1 : -2;
+        }
+        __syncwarp();
+    }
+}
+
+// Persistent variant: one warp takes a hit through ALL its band-doubling attempts (ssw.c:570-631) and the traceback,
+// with its direction bytes in a per-warp scratch region that is reused from hit to hit.  Hits whose band outgrows the
+// shared-memory rows (w > w_max) or the region are handed back in `overflow` (pair index, band width reached) for the
+// host-sequenced kernel above.
+struct PersistParams {
+    int32_t w_max;               // largest half band width the shared-memory rows hold
+    int64_t dir_per_warp;        // bytes of direction scratch per warp
+    uint8_t* dir;
+    uint8_t* rev_paths;
+    const int64_t* slot_off;
+    int32_t* path_len;
+    unsigned long long* cursor;  // [0] work cursor, [1] overflow count, [2] error flags
+    uint2* overflow;             // (pair, w)
+    const uint32_t* order;       // processing order (largest hits first), or nullptr
+};
+
+__global__ void __launch_bounds__(kBandWarps * 32) al_band_persistent_kernel(AlParams P, PersistParams B) {
+    extern __shared__ int32_t rows[];
+    __shared__ int8_t smatT[32 * 32];
+    for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) {
+        const int ql = i >> 5, tl = i & 31;
+        smatT[i] = tl <= S4G_PAD_CODE ? P.mat8[tl * 32 + ql] : 0;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned FULL = 0xffffffffu;
+    const int stride = 2 * B.w_max + 5;
+    int32_t* bufA = rows + (size_t)warp * 3 * stride;
+    int32_t* bufB = bufA + stride;
+    int32_t* E = bufB + stride;
+    uint8_t* dir = B.dir + (size_t)(blockIdx.x * kBandWarps + warp) * B.dir_per_warp;
+    while (true) {
+        unsigned long long wi = 0;
+        if (lane == 0) wi = atomicAdd(B.cursor, 1ull);
+        wi = __shfl_sync(FULL, wi, 0);
+        if ((long long)wi >= P.n_pairs) break;
+        const uint32_t p = B.order ? B.order[wi] : (uint32_t)wi;
+        const int q0 = P.coords[4 * p + 0], q1 = P.coords[4 * p + 1], t0 = P.coords[4 * p + 2], t1 = P.coords[4 * p + 3];
+        if (q0 < 0 || t0 < 0) continue;                      // reported by the sweeps
+        const uint8_t* read = P.q_codes + P.q_off[P.pair_q[p]] + q0;
+        const uint8_t* ref = P.db_codes + P.db_off[P.pair_t[p] - P.id_base] + t0;
+        const int readLen = q1 - q0 + 1, refLen = t1 - t0 + 1;
+        const int score = P.pair_score[p];
+        int w = abs(refLen - readLen) + 1;
+        for (int round = 0; ; ++round) {
+            if (round > 40) { if (lane == 0) atomicOr(B.cursor + 2, 2ull); break; }
+            if (w > B.w_max || (int64_t)(2 * w + 1) * readLen > B.dir_per_warp) {
+                if (lane == 0) B.overflow[atomicAdd(B.cursor + 1, 1ull)] = make_uint2(p, (uint32_t)w);
+                break;
+            }
+            const int best = band_fill(smatT, read, readLen, ref, refLen, w, P.go, P.ge, bufA, bufB, E, dir, lane);
+            if (best >= score) {
+                __threadfence_block();
+                __syncwarp();
+                const int n = band_trace(dir, readLen, refLen, w, B.rev_paths + B.slot_off[p], (int)(B.slot_off[p + 1] - B.slot_off[p]), lane);
+                if (lane == 0) { if (n > 0) B.path_len[p] = n; else atomicOr(B.cursor + 2, 4ull); }
+                break;
+            }
+            w *= 2;
+            __syncwarp();
         }
         __syncwarp();
     }
@@ -598,11 +683,7 @@ extern "C" int s4g_sw_align(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_
     al_sweep32_kernel<<<sw_blocks, kSwWarps * 32, sw_smem, st>>>(P, 0, 0, d_counters + 0);
     S4G_CHECK_LAUNCH(ctx);
     s4g_trace_mark(ctx, "begins");
-    std::vector<int32_t> h_coords(4 * n_pairs);
-    unsigned long long h_counters[2];
-    S4G_CUDA(ctx, cudaMemcpyAsync(h_coords.data(), d_coords, sizeof(int32_t) * 4 * n_pairs, cudaMemcpyDeviceToHost, st));
-    S4G_CUDA(ctx, cudaMemcpyAsync(h_counters, d_counters, 16, cudaMemcpyDeviceToHost, st));
-    // slots for the reversed paths
+    // slots for the reversed paths (device scan; the host only needs an upper bound to size the buffer)
     al_slot_sizes_kernel<<<(unsigned)((n_pairs + 1 + 255) / 256), 256, 0, st>>>(P, d_sizes);
     S4G_CHECK_LAUNCH(ctx);
     {
@@ -613,19 +694,67 @@ extern "C" int s4g_sw_align(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_
         S4G_CUDA(ctx, cub::DeviceScan::ExclusiveSum(d_tmp, tmp, d_sizes, d_slot_off, (int)(n_pairs + 1), st));
         ctx->launches += 1;
     }
-    S4G_CUDA(ctx, cudaStreamSynchronize(st));
-    if (h_counters[1] & 1ull) { s4g_set_error(ctx, "s4g_sw_align: a pair's score is not attained by any cell (score does not belong to the pair)"); return S4G_ERR_ARG; }
     int64_t total_slots = 0;
-    for (int64_t i = 0; i < n_pairs; ++i) total_slots += (h_coords[4 * i + 1] - h_coords[4 * i] + 1) + (h_coords[4 * i + 3] - h_coords[4 * i + 2] + 1) + 2;
+    for (int64_t i = 0; i < n_pairs; ++i)
+        total_slots += (q->h_off[h_q[i] + 1] - q->h_off[h_q[i]]) + (db->h_off[h_t[i] - db->id_base + 1] - db->h_off[h_t[i] - db->id_base]) + 2;
     uint8_t* d_rev = (uint8_t*)s4g_scratch(ctx, SLOT_AL_OUT, (size_t)total_slots + 64);
     if (!d_rev) return S4G_ERR_NOMEM;
 
-    // 3: banded traceback, rounds of band doubling sequenced here
+    // 3: banded traceback.  Persistent kernel: every warp takes a hit through all its band-doubling attempts; what
+    // outgrows its shared-memory rows comes back in an overflow list for the host-sequenced rounds below.
     struct Pending { uint32_t pair; int32_t w, readLen, refLen; };
-    std::vector<Pending> pending(n_pairs);
-    for (int64_t i = 0; i < n_pairs; ++i) {
-        const int readLen = h_coords[4 * i + 1] - h_coords[4 * i] + 1, refLen = h_coords[4 * i + 3] - h_coords[4 * i + 2] + 1;
-        pending[i] = {(uint32_t)i, abs(refLen - readLen) + 1, readLen, refLen};
+    std::vector<Pending> pending;
+    std::vector<int32_t> h_coords;
+    const bool warp_rule = gap_extend <= gap_open;     // the max-plus scan of the warp kernels needs ge <= go
+    unsigned long long h_flags[4] = {0, 0, 0, 0};
+    if (warp_rule) {
+        const int w_max = 256;
+        const size_t p_smem = (size_t)kBandWarps * 3 * (2 * w_max + 5) * sizeof(int32_t);
+        int per_sm = 0;
+        S4G_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, al_band_persistent_kernel, kBandWarps * 32, p_smem));
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 8) per_sm = 8;
+        const int grid = (int)std::min<int64_t>((n_pairs + kBandWarps - 1) / kBandWarps, (int64_t)ctx->sm_count * per_sm);
+        const int64_t dir_per_warp = 640 * 1024;
+        uint8_t* d_dirp = (uint8_t*)s4g_scratch(ctx, SLOT_AL_DIR, (size_t)grid * kBandWarps * dir_per_warp + 64);
+        char* d_pw = (char*)s4g_scratch(ctx, SLOT_AL_WORK, 64 + sizeof(uint2) * n_pairs);
+        if (!d_dirp || !d_pw) return S4G_ERR_NOMEM;
+        S4G_CUDA(ctx, cudaMemsetAsync(d_pw, 0, 64, st));
+        PersistParams B;
+        B.w_max = w_max; B.dir_per_warp = dir_per_warp; B.dir = d_dirp; B.rev_paths = d_rev; B.slot_off = d_slot_off; B.path_len = d_path_len;
+        B.cursor = (unsigned long long*)d_pw; B.overflow = (uint2*)(d_pw + 64); B.order = nullptr;
+        al_band_persistent_kernel<<<grid, kBandWarps * 32, p_smem, st>>>(P, B);
+        S4G_CHECK_LAUNCH(ctx);
+        S4G_CUDA(ctx, cudaMemcpyAsync(h_flags, d_pw, 32, cudaMemcpyDeviceToHost, st));
+    }
+    unsigned long long h_counters[2];
+    S4G_CUDA(ctx, cudaMemcpyAsync(h_counters, d_counters, 16, cudaMemcpyDeviceToHost, st));
+    S4G_CUDA(ctx, cudaStreamSynchronize(st));
+    if (h_counters[1] & 1ull) { s4g_set_error(ctx, "s4g_sw_align: a pair's score is not attained by any cell (score does not belong to the pair)"); return S4G_ERR_ARG; }
+    if (h_flags[2] & 2ull) { s4g_set_error(ctx, "s4g_sw_align: band doubling did not converge"); return S4G_ERR_INTERNAL; }
+    if (h_flags[2] & 4ull) { s4g_set_error(ctx, "s4g_sw_align: traceback left the band (the reference's behaviour is undefined there)"); return S4G_ERR_INTERNAL; }
+    s4g_trace_mark(ctx, "band_persistent");
+    if (ctx->trace) fprintf(stderr, "[s4g trace] align: %lld hits, %llu handed back to the host-sequenced band rounds\n", (long long)n_pairs, h_flags[1]);
+    const bool need_host_rounds = !warp_rule || h_flags[1] > 0;
+    if (need_host_rounds || where == S4G_HOST) {
+        h_coords.resize(4 * n_pairs);
+        S4G_CUDA(ctx, cudaMemcpyAsync(h_coords.data(), d_coords, sizeof(int32_t) * 4 * n_pairs, cudaMemcpyDeviceToHost, st));
+        S4G_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    if (!warp_rule) {
+        pending.resize(n_pairs);
+        for (int64_t i = 0; i < n_pairs; ++i) {
+            const int readLen = h_coords[4 * i + 1] - h_coords[4 * i] + 1, refLen = h_coords[4 * i + 3] - h_coords[4 * i + 2] + 1;
+            pending[i] = {(uint32_t)i, abs(refLen - readLen) + 1, readLen, refLen};
+        }
+    } else if (h_flags[1] > 0) {
+        std::vector<uint2> ovf(h_flags[1]);
+        S4G_CUDA(ctx, cudaMemcpy(ovf.data(), (char*)ctx->slot_ptr[SLOT_AL_WORK] + 64, sizeof(uint2) * ovf.size(), cudaMemcpyDeviceToHost));
+        pending.resize(ovf.size());
+        for (size_t k = 0; k < ovf.size(); ++k) {
+            const int64_t i = ovf[k].x;
+            pending[k] = {(uint32_t)i, (int32_t)ovf[k].y, h_coords[4 * i + 1] - h_coords[4 * i] + 1, h_coords[4 * i + 3] - h_coords[4 * i + 2] + 1};
+        }
     }
     const size_t dir_budget = (size_t)4 << 30;
     const int threads = 64;
@@ -689,7 +818,7 @@ extern "C" int s4g_sw_align(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_
         pending.swap(next);
     }
 
-    s4g_trace_mark(ctx, "band");
+    s4g_trace_mark(ctx, "band_rounds");
     // pack: path offsets = exclusive scan of the lengths, then forward-order copy
     al_len64_kernel<<<(unsigned)((n_pairs + 1 + 255) / 256), 256, 0, st>>>(d_path_len, n_pairs, d_len64);
     S4G_CHECK_LAUNCH(ctx);
