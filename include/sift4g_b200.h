@@ -142,6 +142,17 @@ int s4g_select_hits(s4g_ctx* ctx, int32_t n_queries, const int32_t* query_lens, 
                     double max_evalue, int max_alignments, int n_threads, uint32_t* out_q, uint32_t* out_t,
                     int32_t* out_score, double* out_evalue, int64_t* out_offsets);
 
+/* Multi-GPU (one database shard per GPU): the global `max_alignments` best hits of every query out of the per-shard
+ * selections.  gathered: n_ranks blocks of rank_stride rows of 3 doubles {E-value, score, target id}; block r holds rank
+ * r's s4g_select_hits output (hits grouped by query, in order) and gathered_counts[r * n_queries + q] says how many rows
+ * query q has there -- what two all-gathers of every rank's selection give (host pointers).  Order and truncation are
+ * those of dbAlignmentsMerge (sw/post_proc.c:299-339,432-456): E asc, score desc, then name/id asc.  Only hits whose
+ * target id lies in [own_lo, own_hi) are written (the caller's shard; 0, 0xffffffff for all), in global order;
+ * out_* need capacity n_queries * max_alignments. */
+int s4g_merge_hits(s4g_ctx* ctx, int n_ranks, int32_t n_queries, int max_alignments, const double* gathered, int64_t rank_stride,
+                   const int64_t* gathered_counts, uint32_t own_lo, uint32_t own_hi, int n_threads, uint32_t* out_q, uint32_t* out_t,
+                   int32_t* out_score, double* out_evalue, int64_t* out_offsets);
+
 /* GPU pre-screen in front of s4g_select_hits (optional, changes no result): evaluates the E-value of every
  * scored candidate on the device in double (CUDA libm, within a few ulp of the host's) and keeps those with
  * E <= max_evalue * (1 + 1e-6), compacted in candidate order.  Survivors are re-evaluated exactly on the host

@@ -41,6 +41,7 @@ SIGNATURES = {
     "s4g_merge_candidates": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "s4g_sw_score": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int64, _vp, C.c_int, C.c_int, _vp, C.c_int]),
     "s4g_sw_align": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int64, _vp, C.c_int]),
+    "s4g_merge_hits": (C.c_int, [_vp, C.c_int, C.c_int32, C.c_int, _vp, C.c_int64, _vp, C.c_uint32, C.c_uint32, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "s4g_select_hits": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, C.c_uint64, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "s4g_evalue_screen": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int64, _vp, C.c_uint64, C.c_int, C.c_int, C.c_double, _vp, _vp, _vp, _vp, _vp]),
     "s4g_measure_dpx_peak": (C.c_int, [_vp, C.c_int, _f64p]),
@@ -263,5 +264,25 @@ def select_hits(ctx, query_lens, cand_ids, cand_offsets, cand_scores, cand_lens,
     ctx.check(ctx.lib.s4g_select_hits(ctx.h, nq, _ptr(query_lens), _ptr(cand_ids), _ptr(cand_offsets), _ptr(cand_scores), _ptr(cand_lens),
                                       C.cast(name_arr, _vp) if name_arr is not None else None, int(db_residues), gap_open, gap_extend,
                                       max_evalue, max_alignments, n_threads, _ptr(oq), _ptr(ot), _ptr(osc), _ptr(oe), _ptr(off)))
+    n = int(off[-1])
+    return oq[:n], ot[:n], osc[:n], oe[:n], off
+
+
+def merge_hits(ctx, gathered, counts, nq, max_alignments, own_lo=0, own_hi=0xffffffff, n_threads=0):
+    """host: gathered float64 [n_ranks][stride][3] rows {E, score, id} (rank r's hits grouped by query), counts int64
+    [n_ranks][nq] -> (pair_q, pair_t, pair_score, evalues, offsets[nq+1]) of the global top hits whose target lies in
+    [own_lo, own_hi)"""
+    gathered = np.ascontiguousarray(gathered, dtype=np.float64)
+    counts = np.ascontiguousarray(counts, dtype=np.int64)
+    n_ranks, stride = gathered.shape[0], gathered.shape[1]
+    cap = max(nq * max_alignments, 1)
+    oq = np.zeros(cap, dtype=np.uint32); ot = np.zeros(cap, dtype=np.uint32)
+    osc = np.zeros(cap, dtype=np.int32); oe = np.zeros(cap, dtype=np.float64)
+    off = np.zeros(nq + 1, dtype=np.int64)
+    lib = ctx.lib if ctx is not None else load()        # pure host code: usable without a context (CPU tests)
+    rc = lib.s4g_merge_hits(ctx.h if ctx is not None else None, n_ranks, nq, max_alignments, _ptr(gathered), stride, _ptr(counts),
+                            int(own_lo), int(own_hi), n_threads, _ptr(oq), _ptr(ot), _ptr(osc), _ptr(oe), _ptr(off))
+    if rc != 0:
+        raise S4GError("s4g_merge_hits failed (%d)" % rc)
     n = int(off[-1])
     return oq[:n], ot[:n], osc[:n], oe[:n], off

@@ -168,6 +168,67 @@ extern "C" int s4g_select_hits(s4g_ctx* ctx, int32_t nq, const int32_t* query_le
     return S4G_OK;
 }
 
+extern "C" int s4g_merge_hits(s4g_ctx* ctx, int n_ranks, int32_t nq, int max_alignments, const double* gathered, int64_t rank_stride,
+                              const int64_t* gathered_counts, uint32_t own_lo, uint32_t own_hi, int n_threads, uint32_t* out_q,
+                              uint32_t* out_t, int32_t* out_score, double* out_evalue, int64_t* out_offsets) {
+    (void)ctx;
+    if (n_ranks < 1 || nq < 0 || max_alignments < 0 || !gathered || !gathered_counts || !out_offsets) return S4G_ERR_ARG;
+    const int M = max_alignments;
+    if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 16) n_threads = 16;
+    if (n_threads > nq) n_threads = nq > 0 ? nq : 1;
+    // start of every (rank, query) run inside the rank's block
+    std::vector<int64_t> start((size_t)n_ranks * (nq + 1), 0);
+    for (int r = 0; r < n_ranks; ++r) {
+        int64_t* st = start.data() + (size_t)r * (nq + 1);
+        for (int q = 0; q < nq; ++q) st[q + 1] = st[q] + gathered_counts[(size_t)r * nq + q];
+        if (st[nq] > rank_stride) return S4G_ERR_ARG;
+    }
+    std::vector<int32_t> kept(nq, 0);
+    struct G { double value, score, id; };
+    auto work = [&](int tid) {
+        std::vector<G> rows;
+        for (int q = tid; q < nq; q += n_threads) {
+            rows.clear();
+            for (int r = 0; r < n_ranks; ++r) {
+                const int64_t* st = start.data() + (size_t)r * (nq + 1);
+                const double* src = gathered + ((size_t)r * rank_stride + st[q]) * 3;
+                for (int64_t j = 0; j < st[q + 1] - st[q]; ++j) rows.push_back({src[3 * j], src[3 * j + 1], src[3 * j + 2]});
+            }
+            const int k = std::min<int>((int)rows.size(), M);
+            std::partial_sort(rows.begin(), rows.begin() + k, rows.end(), [](const G& x, const G& y) {
+                if (x.value != y.value) return x.value < y.value;
+                if (x.score != y.score) return x.score > y.score;
+                return x.id < y.id;
+            });
+            int n = 0;
+            const size_t dst = (size_t)q * M;
+            for (int j = 0; j < k; ++j) {
+                const uint32_t id = (uint32_t)rows[j].id;
+                if (id < own_lo || id >= own_hi) continue;
+                out_q[dst + n] = (uint32_t)q; out_t[dst + n] = id; out_score[dst + n] = (int32_t)rows[j].score; out_evalue[dst + n] = rows[j].value;
+                ++n;
+            }
+            kept[q] = n;
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& t : pool) t.join();
+    int64_t w = 0;
+    out_offsets[0] = 0;
+    for (int q = 0; q < nq; ++q) {
+        const size_t src = (size_t)q * M;
+        if ((size_t)w != src)
+            for (int j = 0; j < kept[q]; ++j) { out_q[w + j] = out_q[src + j]; out_t[w + j] = out_t[src + j]; out_score[w + j] = out_score[src + j]; out_evalue[w + j] = out_evalue[src + j]; }
+        w += kept[q];
+        out_offsets[q + 1] = w;
+    }
+    return S4G_OK;
+}
+
 extern "C" int s4g_evalue_screen(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, const uint32_t* cand_ids, const int64_t* cand_offsets,
                                  int64_t n_pairs, const int32_t* scores, uint64_t db_residues, int gap_open, int gap_extend,
                                  double max_evalue, uint32_t* out_query, uint32_t* out_id, int32_t* out_score, int32_t* out_tlen,

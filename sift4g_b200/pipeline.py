@@ -10,6 +10,10 @@ Two entry points, same results:
                         all-gathers (the only exchanges on the path).
 torch is plumbing here (device buffers, streams, NCCL); all compute is in libsift4g_b200.so.
 """
+import os
+import sys
+import time
+
 import numpy as np
 
 from . import capi
@@ -123,6 +127,18 @@ class DevicePipeline:
         result (candidate lists, survivor scores, alignments) is copied back to the host at the end."""
         torch, ctx, db = self.torch, self.ctx, self.db
         r = Result()
+        trace = os.environ.get("S4G_TRACE", "") not in ("", "0")
+        marks = []
+        if trace:
+            torch.cuda.synchronize()
+            t_last = [time.time()]
+
+        def mark(name):
+            if trace:
+                torch.cuda.synchronize()
+                now = time.time()
+                marks.append("%s=%.3fms" % (name, (now - t_last[0]) * 1e3))
+                t_last[0] = now
         if e2e:
             self.Q.close()
             self.Q = ctx.queries(*self.q_host)
@@ -133,14 +149,18 @@ class DevicePipeline:
         if self.world == 1:
             capi.prefilter(ctx, db, self.Q, self.k, N, True, out=(self.t_ids, self.t_sc, self.t_cnt), where=capi.S4G_DEVICE)
             ids, cnt = self.t_ids, self.t_cnt
+            mark("prefilter")
         else:
             capi.prefilter(ctx, db, self.Q, self.k, N, False, out=(self.t_ids, self.t_sc, self.t_cnt), where=capi.S4G_DEVICE)
+            mark("prefilter")
             self.dist.all_gather_into_tensor(self.g_ids.view(-1), self.t_ids.view(-1))
             self.dist.all_gather_into_tensor(self.g_sc.view(-1), self.t_sc.view(-1))
             self.dist.all_gather_into_tensor(self.g_cnt.view(-1), self.t_cnt)
+            mark("gather_candidates")
             ctx.check(ctx.lib.s4g_merge_candidates(ctx.h, self.world, nq, N, self.g_ids.data_ptr(), self.g_sc.data_ptr(), self.g_cnt.data_ptr(),
                                                    self.m_ids.data_ptr(), self.m_sc.data_ptr(), self.m_cnt.data_ptr()))
             ids, cnt = self.m_ids, self.m_cnt
+            mark("merge_candidates")
         # candidates owned by this rank (ids are uint32 bit patterns in int32 tensors)
         col = torch.arange(N, device=self.dev, dtype=torch.int32)[None, :]
         ids64 = ids.to(torch.int64) & 0xffffffff
@@ -151,9 +171,11 @@ class DevicePipeline:
         cand_off[1:] = torch.cumsum(cand_cnt, 0)
         n_pairs = int(cand_ids.numel())
         scores = torch.empty(max(n_pairs, 1), dtype=torch.int32, device=self.dev)
+        mark("own_candidates")
         # ---- stage 2 ----
         if n_pairs:
             capi.sw_score(ctx, db, self.Q, cand_ids, cand_off, self.matrix, self.go, self.ge, out=scores, where=capi.S4G_DEVICE)
+        mark("sw_score")
         # ---- E-value screen on the device, exact selection of the survivors on the host ----
         cap = max(n_pairs, 1)
         if getattr(self, "_scr_cap", 0) < cap:
@@ -179,10 +201,13 @@ class DevicePipeline:
         h_off = np.searchsorted(h_q, np.arange(nq + 1), side="left").astype(np.int64)
         r.n_pairs = n_pairs
         r.sw_cells = int(cells_dev.item()) if n_pairs else 0
+        mark("screen_d2h")
         pq, pt, ps, ev, hoff = capi.select_hits(ctx, self.q_lens, h_ids, h_off, h_scores, h_lens, self.total_residues, self.go, self.ge,
                                                 self.max_evalue, self.max_alignments)
+        mark("select_hits")
         if self.world > 1:
             pq, pt, ps, ev, hoff = self._merge_hits(pq, pt, ps, ev, hoff, lo, hi)
+            mark("merge_hits")
         r.pair_q, r.pair_t, r.pair_score, r.evalue, r.hit_off = pq, pt, ps, ev, hoff
         r.cand_ids, r.cand_off, r.scores = cand_ids, cand_off, scores     # device tensors (all candidates)
         # ---- stage 3 ----
@@ -197,6 +222,9 @@ class DevicePipeline:
             ctx.check(ctx.lib.s4g_sw_align(ctx.h, db.h, self.Q.h, len(pq), d_pq.data_ptr(), d_pt.data_ptr(), d_ps.data_ptr(), self.matrix.ctypes.data,
                                            self.go, self.ge, d_coords.data_ptr(), d_paths.data_ptr(), cap, d_poff.data_ptr(), capi.S4G_DEVICE))
             r.coords, r.paths, r.path_off = d_coords, d_paths, d_poff
+        mark("align")
+        if trace and self.rank == 0:
+            print("[s4g trace] step: " + " ".join(marks), file=sys.stderr)
         if e2e:
             host = [ids.cpu(), cnt.cpu()]
             r.d2h_bytes = ids.numel() * 4 + cnt.numel() * 4 + n_s * 16 + 4
@@ -209,27 +237,50 @@ class DevicePipeline:
         return r
 
     def _merge_hits(self, pq, pt, ps, ev, hoff, lo, hi):
-        return merge_hits(self.torch, self.dist, self.dev, self.nq, self.max_alignments, pq, pt, ps, ev, hoff, lo, hi)
+        return merge_hits(self.torch, self.dist, self.dev, self.nq, self.max_alignments, pq, pt, ps, ev, hoff, lo, hi, ctx=self.ctx)
 
 
-def merge_hits(torch, dist, dev, nq, M, pq, pt, ps, ev, hoff, lo, hi):
+def merge_hits(torch, dist, dev, nq, M, pq, pt, ps, ev, hoff, lo, hi, ctx=None):
     """Global top M hits per query over all ranks under (E asc, score desc, id asc); every rank keeps the hits
-    whose targets it owns ([lo, hi)), so the traceback needs no further exchange.  One all-gather of
-    (E, score, id)[nq][M] doubles per rank."""
+    whose targets it owns ([lo, hi)), so the traceback needs no further exchange.  Two small all-gathers (per-query
+    counts, then the {E, score, id} rows padded to the largest rank), then s4g_merge_hits (threaded C++) everywhere."""
     W = dist.get_world_size()
-    loc = np.zeros((nq, M, 3), dtype=np.float64)      # value, score, id  (all exact in double)
-    loc[:, :, 0] = np.inf
-    for q in range(nq):
-        a, b = hoff[q], hoff[q + 1]
-        loc[q, :b - a, 0] = ev[a:b]; loc[q, :b - a, 1] = ps[a:b]; loc[q, :b - a, 2] = pt[a:b]
-    t_loc = torch.from_numpy(loc).to(dev)
-    t_all = torch.empty((W,) + tuple(t_loc.shape), dtype=torch.float64, device=dev)
-    dist.all_gather_into_tensor(t_all.view(-1), t_loc.view(-1))
-    allh = t_all.cpu().numpy().transpose(1, 0, 2, 3).reshape(nq, W * M, 3)
+    cuda = dev.type == "cuda"
+    cnt = torch.from_numpy(np.diff(hoff).astype(np.int64))
+    rows = np.empty((len(pq), 3), dtype=np.float64)
+    rows[:, 0] = ev; rows[:, 1] = ps; rows[:, 2] = pt
+    if cuda:
+        cnt = cnt.to(dev)
+        all_cnt = torch.empty((W, nq), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(all_cnt.view(-1), cnt)
+        all_cnt = all_cnt.cpu()
+    else:
+        parts = [torch.empty_like(cnt) for _ in range(W)]
+        dist.all_gather(parts, cnt)
+        all_cnt = torch.stack(parts)
+    stride = max(int(all_cnt.sum(dim=1).max()), 1)
+    loc = torch.zeros((stride, 3), dtype=torch.float64)
+    loc[:len(pq)] = torch.from_numpy(rows)
+    if cuda:
+        loc = loc.to(dev)
+        allh = torch.empty((W, stride, 3), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allh.view(-1), loc.view(-1))
+        allh = allh.cpu()
+    else:
+        parts = [torch.empty_like(loc) for _ in range(W)]
+        dist.all_gather(parts, loc)
+        allh = torch.stack(parts)
+    return capi.merge_hits(ctx, allh.numpy(), all_cnt.numpy(), nq, M, lo, hi)
+
+
+def merge_hits_numpy(allh, counts, nq, M, lo, hi):
+    """numpy statement of s4g_merge_hits (tests compare the two)."""
+    W = allh.shape[0]
+    start = np.zeros((W, nq + 1), dtype=np.int64)
+    start[:, 1:] = np.cumsum(counts, axis=1)
     oq, ot, osc, oev, off = [], [], [], [], [0]
     for q in range(nq):
-        rows = allh[q]
-        rows = rows[np.isfinite(rows[:, 0])]
+        rows = np.concatenate([allh[r, start[r, q]:start[r, q + 1]] for r in range(W)])
         order = np.lexsort((rows[:, 2], -rows[:, 1], rows[:, 0]))[:M]
         rows = rows[order]
         mine = rows[(rows[:, 2] >= lo) & (rows[:, 2] < hi)]

@@ -77,3 +77,28 @@ def test_merge_hits_world_size_2_gloo():
         assert len(got) == len(want)
         for g, w in zip(got, want):
             assert g[0] == w[0] and g[1] == w[1] and g[2] == w[2]
+
+
+def test_native_merge_equals_numpy_statement():
+    from sift4g_b200 import capi
+    rng = np.random.default_rng(9)
+    W, nq, M = 3, 11, 16
+    counts = rng.integers(0, M + 1, size=(W, nq)).astype(np.int64)
+    counts[1, 4] = 0
+    stride = int(counts.sum(axis=1).max()) + 2
+    allh = np.zeros((W, stride, 3), dtype=np.float64)
+    for r in range(W):
+        pos = 0
+        for q in range(nq):
+            n = int(counts[r, q])
+            sc = rng.integers(40, 60, size=n)
+            e = np.exp(-0.25 * sc)                      # equal scores -> equal E: exercises the tie keys
+            ids = rng.choice(3000, size=n, replace=False) + 3000 * r
+            order = np.lexsort((ids, -sc, e))
+            allh[r, pos:pos + n, 0] = e[order]; allh[r, pos:pos + n, 1] = sc[order]; allh[r, pos:pos + n, 2] = ids[order]
+            pos += n
+    for lo, hi in ((0, 0xffffffff), (3000, 6000)):
+        got = capi.merge_hits(None, allh, counts, nq, M, lo, hi, n_threads=3)
+        want = pipeline.merge_hits_numpy(allh, counts, nq, M, lo, hi)
+        for g, w in zip(got, want):
+            assert np.array_equal(g, w)
