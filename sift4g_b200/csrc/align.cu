@@ -39,7 +39,11 @@ struct AlParams {
     unsigned long long* counters;   // [0] work cursor, [1] error flags
     int32_t* bound;              // per-warp boundary rows for multi-pass sweeps
     int64_t bound_stride;
+    int32_t swalign_all;         // gap penalties outside SSW's range: every hit takes the swAlign rules (sse_module.c:215-236)
 };
+
+// which engine defines the path of a hit: SSW (score <= 32767, sse_module.c:181-185) or swsharp's swAlign
+__device__ __forceinline__ bool takes_swalign(const AlParams& P, int score) { return P.swalign_all || score > 32767; }
 
 // 32-bit systolic sweep, one warp per hit: Gotoh local alignment of rows i -> q[i * qstep] (i < rows) against
 // columns j -> t[j * tstep] (j < cols); finds the lexicographically smallest (column, row) whose H equals `score`
@@ -52,7 +56,7 @@ constexpr int kSwRows = 8;
 constexpr int kSwRing = 64;
 constexpr int kSwProfWords = (S4G_PAD_CODE + 1) * 2 * 32;
 constexpr int kSwWarpBytes = kSwProfWords * 4 + 2 * kSwRing * 2 + 2 * kSwRing * 4 + 4 * kSwRing * 4;
-constexpr int kSwSmatBytes = 896;
+constexpr int kSwSmatBytes = 2 * 896;      // substitution matrix and its transpose
 
 struct SweepSmem {
     unsigned* prof;          // [27][2][32]
@@ -177,8 +181,13 @@ __device__ unsigned long long sweep32(const SweepSmem& S, const int8_t* smat, co
 // mode 1: end cells of the hits whose query is longer than `long_rows` (forward sweep; the packed kernel did the rest)
 __global__ void __launch_bounds__(kSwWarps * 32) al_sweep32_kernel(AlParams P, int mode, int long_rows, unsigned long long* cursor) {
     extern __shared__ __align__(16) unsigned char ssm[];
-    int8_t* smat = reinterpret_cast<int8_t*>(ssm);
-    for (int i = threadIdx.x; i < (S4G_PAD_CODE + 1) * 32; i += blockDim.x) smat[i] = P.mat8[i];
+    int8_t* smat = reinterpret_cast<int8_t*>(ssm);            // [target letter][query letter]
+    int8_t* smatT = smat + 896;                               // [query letter][target letter], pad row copied
+    for (int i = threadIdx.x; i < (S4G_PAD_CODE + 1) * 32; i += blockDim.x) {
+        smat[i] = P.mat8[i];
+        const int a = i >> 5, b = i & 31;
+        smatT[i] = a == S4G_PAD_CODE ? P.mat8[i] : (b <= S4G_PAD_CODE ? P.mat8[b * 32 + a] : 0);
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* wb = ssm + kSwSmatBytes + warp * kSwWarpBytes;
@@ -205,7 +214,20 @@ __global__ void __launch_bounds__(kSwWarps * 32) al_sweep32_kernel(AlParams P, i
         const int tlen = (int)(P.db_off[ti + 1] - P.db_off[ti]);
         const int score = P.pair_score[w];
         if (mode == 1) {
-            if (qlen <= long_rows) continue;
+            const bool swa = takes_swalign(P, score);
+            if (qlen <= long_rows && !swa) continue;
+            if (swa) {
+                // swAlign's end cell: the first cell in query-major order that reaches the maximum (cpu_module.c:1320-1325)
+                // = the SSW rule on the transposed problem (rows = target, columns = query)
+                const unsigned long long e = score > 0 ? sweep32(S, smatT, t, 1, tlen, q, 1, qlen, score, P.go, P.ge, bH, bF, lane) : ~0ull;
+                if (lane == 0) {
+                    if (e == ~0ull) atomicOr(P.counters + 1, 1ull);
+                    P.coords[4 * w + 1] = e == ~0ull ? -1 : (int)(e >> 32);
+                    P.coords[4 * w + 3] = e == ~0ull ? -1 : (int)(e & 0xffffffffu);
+                }
+                __syncwarp();
+                continue;
+            }
             const unsigned long long e = score > 0 ? sweep32(S, smat, q, 1, qlen, t, 1, tlen, score, P.go, P.ge, bH, bF, lane) : ~0ull;
             if (lane == 0) {
                 if (e == ~0ull) atomicOr(P.counters + 1, 1ull);
@@ -213,6 +235,7 @@ __global__ void __launch_bounds__(kSwWarps * 32) al_sweep32_kernel(AlParams P, i
                 P.coords[4 * w + 3] = e == ~0ull ? -1 : (int)(e >> 32);
             }
         } else {
+            if (takes_swalign(P, score)) continue;
             const int q_end = P.coords[4 * w + 1], t_end = P.coords[4 * w + 3];
             unsigned long long b = ~0ull;
             if (q_end >= 0 && t_end >= 0) b = sweep32(S, smat, q + q_end, -1, q_end + 1, t + t_end, -1, t_end + 1, score, P.go, P.ge, bH, bF, lane);
@@ -554,11 +577,186 @@ __global__ void __launch_bounds__(kBandWarps * 32) al_band_persistent_kernel(AlP
     }
 }
 
+// ---- swAlign-rule paths (score > 32767, or gap penalties SSW cannot take) ----------------------------------------
+// Restates swAlign (vendor/swsharp/swsharp/src/cpu_module.c:1185-1413) on the rectangle [0..er] x [0..ec] that ends in
+// its end cell, in linear working memory plus 4 bits per cell: move (STOP/DIAG/LEFT/UP with the reference's priority
+// UP > LEFT > DIAG > STOP) and two flags saying whether the horizontal / vertical gap arriving in the cell was an
+// extension (open/extend ties count as extension, :1291-1305) -- the gap lengths the reference stores per cell are the
+// run lengths of these flags.  One warp per hit, same systolic sweep as above (lanes own 8 rows, 256 rows per pass).
+// Direction words: [pass][lane][column], nibble r of a word = row 8 * lane + r of the pass.
+constexpr int kSMIN = -1000000000;
+
+struct SwaWork { uint32_t pair; uint32_t pad; int64_t dir_off; };   // dir_off in 32-bit words
+
+__global__ void __launch_bounds__(kSwWarps * 32) al_swalign_kernel(AlParams P, const SwaWork* work, int n_work, uint32_t* dir_pool,
+                                                                    uint8_t* rev_paths, const int64_t* slot_off, int32_t* path_len,
+                                                                    unsigned long long* cursor) {
+    extern __shared__ __align__(16) unsigned char ssm[];
+    int8_t* smat = reinterpret_cast<int8_t*>(ssm);
+    for (int i = threadIdx.x; i < (S4G_PAD_CODE + 1) * 32; i += blockDim.x) smat[i] = P.mat8[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* wb = ssm + kSwSmatBytes + warp * kSwWarpBytes;
+    unsigned* prof = reinterpret_cast<unsigned*>(wb);
+    unsigned short* ring = reinterpret_cast<unsigned short*>(prof + kSwProfWords);
+    int* inH = reinterpret_cast<int*>(ring + 2 * kSwRing);
+    int* inF = inH + kSwRing;
+    int* outH = inF + kSwRing;
+    int* outF = outH + 2 * kSwRing;
+    const int gwarp = blockIdx.x * kSwWarps + warp;
+    int32_t* bH = P.bound + (int64_t)gwarp * P.bound_stride;
+    int32_t* bF = bH + P.bound_stride / 2;
+    const unsigned FULL = 0xffffffffu;
+    const int Q = P.go, R = P.ge;
+    const char* prof_b = reinterpret_cast<const char*>(prof) + lane * 4;
+    while (true) {
+        unsigned long long wi = 0;
+        if (lane == 0) wi = atomicAdd(cursor, 1ull);
+        wi = __shfl_sync(FULL, wi, 0);
+        if (wi >= (unsigned long long)n_work) break;
+        const uint32_t p = work[wi].pair;
+        uint32_t* dir = dir_pool + work[wi].dir_off;
+        const int er = P.coords[4 * p + 1], ec = P.coords[4 * p + 3];
+        const uint8_t* q = P.q_codes + P.q_off[P.pair_q[p]];
+        const uint8_t* t = P.db_codes + P.db_off[P.pair_t[p] - P.id_base];
+        const int rows = er + 1, cols = ec + 1;
+        const int npass = (rows + 32 * kSwRows - 1) / (32 * kSwRows);
+        // ---- fill
+        for (int pass = 0; pass < npass; ++pass) {
+            const int row0 = pass * 32 * kSwRows + lane * kSwRows;
+            const bool first = pass == 0, last = pass == npass - 1;
+            {
+                int ql[kSwRows];
+#pragma unroll
+                for (int r = 0; r < kSwRows; ++r) ql[r] = row0 + r < rows ? (int)q[row0 + r] : -1;
+                for (int letter = 0; letter <= S4G_PAD_CODE; ++letter) {
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) {
+                        unsigned word = 0;
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            const int v = ql[4 * m + b] >= 0 ? (int)smat[letter * 32 + ql[4 * m + b]] : -128;
+                            word |= (unsigned)(v & 0xff) << (8 * b);
+                        }
+                        prof[(letter * 2 + m) * 32 + lane] = word;
+                    }
+                }
+            }
+            for (int c = lane; c < kSwRing; c += 32) ring[kSwRing + c] = (unsigned short)(S4G_PAD_CODE * 256);
+            int Hl[kSwRows], A[kSwRows];                 // score and horizontal-gap value of the cell to the left
+#pragma unroll
+            for (int r = 0; r < kSwRows; ++r) { Hl[r] = 0; A[r] = kSMIN; }
+            int h_last = 0, d_last = kSMIN, diag_in = 0;
+            uint32_t* dline = dir + ((size_t)pass * 32 + lane) * cols;
+            const int nsteps = cols + 31;
+            int flushed = 0;
+            for (int s0 = 0; s0 < nsteps; s0 += kSwRing) {
+                if (!last) {
+                    const int upto = min(cols, s0 - 31);
+                    for (int c = flushed + lane; c < upto; c += 32) { bH[c] = outH[c & (2 * kSwRing - 1)]; bF[c] = outF[c & (2 * kSwRing - 1)]; }
+                    if (upto > flushed) flushed = upto;
+                }
+                {
+                    const int base = s0 & (2 * kSwRing - 1);
+#pragma unroll
+                    for (int c = 0; c < kSwRing; c += 32) {
+                        const int j = s0 + c + lane;
+                        ring[base + c + lane] = (unsigned short)((j < cols ? (unsigned)t[j] : (unsigned)S4G_PAD_CODE) * 256u);
+                        if (!first) { inH[c + lane] = j < cols ? bH[j] : 0; inF[c + lane] = j < cols ? bF[j] : kSMIN; }
+                    }
+                }
+                __syncwarp();
+                const int send = (nsteps - s0) < kSwRing ? (nsteps - s0) : kSwRing;
+#pragma unroll 1
+                for (int ss = 0; ss < send; ++ss) {
+                    const int j = s0 + ss - lane;
+                    const unsigned o = ring[j & (2 * kSwRing - 1)];
+                    const unsigned w0 = *reinterpret_cast<const unsigned*>(prof_b + o);
+                    const unsigned w1 = *reinterpret_cast<const unsigned*>(prof_b + o + 128);
+                    int hs = __shfl_up_sync(FULL, h_last, 1);        // score of the cell above the lane's first row
+                    int ha = __shfl_up_sync(FULL, d_last, 1);        // its vertical-gap value
+                    if (lane == 0) { hs = first ? 0 : inH[ss]; ha = first ? kSMIN : inF[ss]; }
+                    const bool live = j >= 0 && j < cols;
+                    if (!live) { hs = 0; ha = kSMIN; }
+                    int diag = diag_in;
+                    diag_in = hs;
+                    unsigned word = 0;
+#pragma unroll
+                    for (int r = 0; r < kSwRows; ++r) {
+                        const unsigned w = r < 4 ? w0 : w1;
+                        const int mch = diag + (int)(int8_t)((w >> (8 * (r & 3))) & 0xffu);
+                        const int ins_o = Hl[r] - Q, ins_e = A[r] - R;
+                        const int ins = max(ins_o, ins_e);
+                        const int del_o = hs - Q, del_e = ha - R;
+                        const int del = max(del_o, del_e);
+                        const int scr = max(max(0, mch), max(ins, del));
+                        const unsigned mv = del == scr ? 3u : ins == scr ? 2u : mch == scr ? 1u : 0u;
+                        word |= (mv | (ins == ins_e ? 4u : 0u) | (del == del_e ? 8u : 0u)) << (4 * r);
+                        diag = Hl[r];
+                        if (live) { Hl[r] = scr; A[r] = ins; }
+                        hs = scr; ha = del;
+                    }
+                    h_last = hs; d_last = ha;
+                    if (live) dline[j] = word;
+                    if (lane == 31 && !last && live) { outH[j & (2 * kSwRing - 1)] = h_last; outF[j & (2 * kSwRing - 1)] = d_last; }
+                }
+                __syncwarp();
+            }
+            if (!last) for (int c = flushed + lane; c < cols; c += 32) { bH[c] = outH[c & (2 * kSwRing - 1)]; bF[c] = outF[c & (2 * kSwRing - 1)]; }
+            __syncwarp();
+        }
+        __threadfence_block();
+        __syncwarp();
+        // ---- traceback (cpu_module.c:1349-1400): lane 0 walks, reading one nibble per step
+        if (lane == 0) {
+            uint8_t* out = rev_paths + slot_off[p];
+            const int cap = (int)(slot_off[p + 1] - slot_off[p]);
+            int r = er, c = ec, n = 0;
+            bool ok = true;
+            auto nib = [&](int rr, int cc) -> unsigned {
+                const int ps = rr / (32 * kSwRows), ln = (rr % (32 * kSwRows)) / kSwRows, k = rr % kSwRows;
+                return (__ldcg(dir + ((size_t)ps * 32 + ln) * cols + cc) >> (4 * k)) & 15u;
+            };
+            while (r >= 0 && c >= 0) {
+                const unsigned d = nib(r, c), mv = d & 3u;
+                if (mv == 1u) { if (n >= cap) { ok = false; break; } out[n++] = 1; --r; --c; }
+                else if (mv == 2u) {
+                    // LEFT: the gap consumes hGaps + 1 columns; hGaps = run of extension flags ending here
+                    unsigned f = d;
+                    while (true) {
+                        if (n >= cap) { ok = false; break; }
+                        out[n++] = 2; --c;
+                        if (!(f & 4u) || c < 0) break;
+                        f = nib(r, c);
+                    }
+                    if (!ok) break;
+                } else if (mv == 3u) {
+                    unsigned f = d;
+                    while (true) {
+                        if (n >= cap) { ok = false; break; }
+                        out[n++] = 3; --r;
+                        if (!(f & 8u) || r < 0) break;
+                        f = nib(r, c);
+                    }
+                    if (!ok) break;
+                } else { ++r; ++c; break; }
+            }
+            if (r == -1 || c == -1) { ++r; ++c; }
+            if (ok) { P.coords[4 * p + 0] = r; P.coords[4 * p + 2] = c; path_len[p] = n; }
+            else atomicOr(P.counters + 1, 4ull);
+        }
+        __syncwarp();
+    }
+}
+
 __global__ void al_slot_sizes_kernel(AlParams P, int64_t* sizes) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i > P.n_pairs) return;
     int64_t s = 0;
-    if (i < P.n_pairs && P.coords[4 * i] >= 0) s = (P.coords[4 * i + 1] - P.coords[4 * i] + 1) + (P.coords[4 * i + 3] - P.coords[4 * i + 2] + 1) + 2;
+    if (i < P.n_pairs) {
+        if (takes_swalign(P, P.pair_score[i])) { if (P.coords[4 * i + 1] >= 0) s = (int64_t)P.coords[4 * i + 1] + P.coords[4 * i + 3] + 4; }
+        else if (P.coords[4 * i] >= 0) s = (P.coords[4 * i + 1] - P.coords[4 * i] + 1) + (P.coords[4 * i + 3] - P.coords[4 * i + 2] + 1) + 2;
+    }
     sizes[i] = s;
 }
 
@@ -596,7 +794,7 @@ extern "C" int s4g_sw_align(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_
         else S4G_CUDA(ctx, cudaMemcpyAsync(out_path_offsets, &zero, 8, cudaMemcpyHostToDevice, st));
         return S4G_OK;
     }
-    if (abs(gap_open) > 127 || abs(gap_extend) > 127) { s4g_set_error(ctx, "gap penalties above 127 take the reference's swAlign path, which this build does not provide yet"); return S4G_ERR_ARG; }
+    const bool swalign_all = abs(gap_open) > 127 || abs(gap_extend) > 127;     // sse_module.c:215-236: SSW takes 8-bit penalties only
 
     // host copies of the pair arrays (the band rounds are sequenced on the host)
     std::vector<uint32_t> h_q(n_pairs), h_t(n_pairs);
@@ -621,7 +819,6 @@ extern "C" int s4g_sw_align(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_
     }
     for (int64_t i = 0; i < n_pairs; ++i) {
         if (h_q[i] >= (uint32_t)q->n || h_t[i] < db->id_base || h_t[i] - db->id_base >= (uint64_t)db->n) { s4g_set_error(ctx, "pair %lld references an unknown query or target", (long long)i); return S4G_ERR_ARG; }
-        if (h_s[i] > 32767) { s4g_set_error(ctx, "pair %lld: score %d > 32767 takes the reference's swAlign path (sw/cpu_module.c:1185), which this build does not provide yet", (long long)i, h_s[i]); return S4G_ERR_ARG; }
     }
 
     int8_t h_mat8[(S4G_PAD_CODE + 1) * 32];
@@ -642,7 +839,7 @@ extern "C" int s4g_sw_align(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_
     S4G_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sw_per_sm, al_sweep32_kernel, kSwWarps * 32, sw_smem));
     if (sw_per_sm < 1) sw_per_sm = 1;
     const int sw_blocks = ctx->sm_count * sw_per_sm;
-    const int64_t bound_stride = 2 * ((int64_t)db->max_len + 64);
+    const int64_t bound_stride = 2 * ((int64_t)std::max(db->max_len, q->max_len) + 64);
     char* misc = (char*)s4g_scratch(ctx, SLOT_AL_MISC, 256 + sizeof(h_mat8) + sizeof(int64_t) * 4 * (n_pairs + 1) + sizeof(int32_t) * 6 * n_pairs);
     int32_t* d_bound = (int32_t*)s4g_scratch(ctx, SLOT_SW_BOUND, sizeof(int32_t) * bound_stride * sw_blocks * kSwWarps);
     if (!misc || !d_bound) return S4G_ERR_NOMEM;
@@ -666,15 +863,19 @@ extern "C" int s4g_sw_align(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_
     P.q_codes = q->d_codes; P.q_off = q->d_off;
     P.pair_q = d_pq; P.pair_t = d_pt; P.pair_score = d_ps; P.n_pairs = n_pairs;
     P.mat8 = d_mat8; P.go = gap_open; P.ge = gap_extend; P.coords = d_coords; P.counters = d_counters;
-    P.bound = d_bound; P.bound_stride = bound_stride;
+    P.bound = d_bound; P.bound_stride = bound_stride; P.swalign_all = swalign_all ? 1 : 0;
+    int64_t n_swa = 0;
+    for (int64_t i = 0; i < n_pairs; ++i) n_swa += (swalign_all || h_s[i] > 32767) ? 1 : 0;
 
     s4g_trace_start(ctx);
     // 1: end cells -- packed s16x2 sweep, two hits of a query per warp; 32-bit sweep for queries beyond its reach
     {
-        int rc = s4g_sw_forward_ends_device(ctx, db, q, n_pairs, d_pq, d_pt, d_ps, d_mat8, gap_open, gap_extend, d_coords, d_counters + 1);
-        if (rc != S4G_OK) return rc;
-        if (q->max_len > s4g_sw_long_query_rows()) {
-            al_sweep32_kernel<<<sw_blocks, kSwWarps * 32, sw_smem, st>>>(P, 1, s4g_sw_long_query_rows(), d_counters + 3);
+        if (!swalign_all) {
+            int rc = s4g_sw_forward_ends_device(ctx, db, q, n_pairs, d_pq, d_pt, d_ps, d_mat8, gap_open, gap_extend, d_coords, d_counters + 1);
+            if (rc != S4G_OK) return rc;
+        }
+        if (swalign_all || n_swa > 0 || q->max_len > s4g_sw_long_query_rows()) {
+            al_sweep32_kernel<<<sw_blocks, kSwWarps * 32, sw_smem, st>>>(P, 1, swalign_all ? 0 : s4g_sw_long_query_rows(), d_counters + 3);
             S4G_CHECK_LAUNCH(ctx);
         }
     }
@@ -742,10 +943,11 @@ extern "C" int s4g_sw_align(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_
         S4G_CUDA(ctx, cudaStreamSynchronize(st));
     }
     if (!warp_rule) {
-        pending.resize(n_pairs);
+        pending.clear();
         for (int64_t i = 0; i < n_pairs; ++i) {
+            if (swalign_all || h_s[i] > 32767) continue;
             const int readLen = h_coords[4 * i + 1] - h_coords[4 * i] + 1, refLen = h_coords[4 * i + 3] - h_coords[4 * i + 2] + 1;
-            pending[i] = {(uint32_t)i, abs(refLen - readLen) + 1, readLen, refLen};
+            pending.push_back({(uint32_t)i, abs(refLen - readLen) + 1, readLen, refLen});
         }
     } else if (h_flags[1] > 0) {
         std::vector<uint2> ovf(h_flags[1]);
@@ -818,6 +1020,52 @@ extern "C" int s4g_sw_align(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_
         pending.swap(next);
     }
 
+    // 3b: swAlign-rule hits -- full direction rectangles, batched by memory
+    if (n_swa > 0) {
+        if (h_coords.empty()) {
+            h_coords.resize(4 * n_pairs);
+            S4G_CUDA(ctx, cudaMemcpyAsync(h_coords.data(), d_coords, sizeof(int32_t) * 4 * n_pairs, cudaMemcpyDeviceToHost, st));
+            S4G_CUDA(ctx, cudaStreamSynchronize(st));
+        }
+        S4G_CUDA(ctx, cudaFuncSetAttribute(al_swalign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw_smem));
+        const int64_t budget_words = (int64_t)2 << 30;          // 8 GiB of direction words per batch
+        std::vector<SwaWork> work;
+        int64_t used = 0;
+        auto flush = [&]() -> int {
+            if (work.empty()) return S4G_OK;
+            SwaWork* d_work = (SwaWork*)s4g_scratch(ctx, SLOT_AL_WORK, sizeof(SwaWork) * work.size() + 64);
+            uint32_t* d_dirw = (uint32_t*)s4g_scratch(ctx, SLOT_AL_DIR, sizeof(uint32_t) * (size_t)used + 64);
+            if (!d_work || !d_dirw) return S4G_ERR_NOMEM;
+            S4G_CUDA(ctx, cudaMemcpyAsync(d_work, work.data(), sizeof(SwaWork) * work.size(), cudaMemcpyHostToDevice, st));
+            S4G_CUDA(ctx, cudaMemsetAsync(d_counters + 4, 0, 8, st));
+            const int grid = (int)std::min<int64_t>((int64_t)(work.size() + kSwWarps - 1) / kSwWarps, sw_blocks);
+            al_swalign_kernel<<<grid, kSwWarps * 32, sw_smem, st>>>(P, d_work, (int)work.size(), d_dirw, d_rev, d_slot_off, d_path_len, d_counters + 4);
+            S4G_CHECK_LAUNCH(ctx);
+            S4G_CUDA(ctx, cudaStreamSynchronize(st));           // the host vector is reused by the next batch
+            work.clear();
+            used = 0;
+            return S4G_OK;
+        };
+        for (int64_t i = 0; i < n_pairs; ++i) {
+            if (!(swalign_all || h_s[i] > 32767)) continue;
+            const int64_t rows = (int64_t)h_coords[4 * i + 1] + 1, cols = (int64_t)h_coords[4 * i + 3] + 1;
+            if (rows <= 0 || cols <= 0) continue;
+            const int64_t words = ((rows + 32 * kSwRows - 1) / (32 * kSwRows)) * 32 * cols;
+            if (!work.empty() && used + words > budget_words) { int rc = flush(); if (rc != S4G_OK) return rc; }
+            work.push_back({(uint32_t)i, 0u, used});
+            used += words;
+        }
+        int rc = flush();
+        if (rc != S4G_OK) return rc;
+        unsigned long long h_err = 0;
+        S4G_CUDA(ctx, cudaMemcpy(&h_err, d_counters + 1, 8, cudaMemcpyDeviceToHost));
+        if (h_err & 4ull) { s4g_set_error(ctx, "s4g_sw_align: a swAlign-rule path does not fit its slot (internal)"); return S4G_ERR_INTERNAL; }
+        // coords of these hits changed on the device
+        if (where == S4G_HOST) {
+            S4G_CUDA(ctx, cudaMemcpyAsync(h_coords.data(), d_coords, sizeof(int32_t) * 4 * n_pairs, cudaMemcpyDeviceToHost, st));
+            S4G_CUDA(ctx, cudaStreamSynchronize(st));
+        }
+    }
     s4g_trace_mark(ctx, "band_rounds");
     // pack: path offsets = exclusive scan of the lengths, then forward-order copy
     al_len64_kernel<<<(unsigned)((n_pairs + 1 + 255) / 256), 256, 0, st>>>(d_path_len, n_pairs, d_len64);

@@ -84,3 +84,47 @@ def test_identical_and_single_residue_hits(ctx, blosum):
     queries = [q, w]
     db = [q.copy(), w.copy(), np.concatenate([synth.random_codes(rng, 5), w])]
     _align_and_check(ctx, blosum, queries, db, [(0, 0), (1, 1), (1, 2), (0, 2)])
+
+
+def test_swalign_rule_golden_paths_from_the_reference(ctx, blosum):
+    """Gap open 128 makes the reference leave SSW for swAlign (sse_module.c:215); tests/golden/seams.json holds the
+    reference's own coords/paths for 30 such pairs."""
+    from tests import util
+    s = util.seams()
+    _, queries, _, db = util.synth_e2e()
+    qc, qo = synth.pack(queries); dc, do = synth.pack(db)
+    D = ctx.database(dc, do); Q = ctx.queries(qc, qo)
+    al = [a for a in s["alignments_swalign_go128"] if a["score"] > 0]
+    pq = np.array([a["q"] for a in al], dtype=np.uint32); pt = np.array([a["t"] for a in al], dtype=np.uint32)
+    ps = np.array([a["score"] for a in al], dtype=np.int32)
+    coords, paths = capi.sw_align(ctx, D, Q, pq, pt, ps, blosum, 128, 1, q_lens=np.diff(qo), t_lens=np.diff(do))
+    Q.close(); D.close()
+    assert len(al) >= 20
+    for i, a in enumerate(al):
+        assert list(coords[i]) == a["coords"], a
+        assert util.path_str(paths[i]) == a["path"], a
+
+
+def test_swalign_rule_forced_by_large_gap_penalties(ctx, blosum):
+    queries, db = synth.make_dataset(36, 6, 120, q_len=(60, 700), homologs=(5, 9), rare_fraction=0.01)
+    pairs = []
+    for q in range(len(queries)):
+        sc = np.array([O.sw_score(queries[q], t, blosum, 128, 2) for t in db])
+        pairs += [(q, int(t)) for t in np.argsort(-sc)[:12]]
+    assert _align_and_check(ctx, blosum, queries, db, pairs, 128, 2) > 50
+    assert _align_and_check(ctx, blosum, queries, db, pairs[:30], 20, 130) > 10
+
+
+def test_scores_above_32767_take_the_swalign_rule(ctx, blosum):
+    """A near-identical copy of a 7 000-residue query scores > 32767: the reference switches to swAlign
+    (sse_module.c:181-185); mixed with an ordinary hit of the same query in one call."""
+    rng = np.random.default_rng(37)
+    q = synth.random_codes(rng, 7000)
+    t_big = synth.mutate(rng, q, identity=0.93, indel_rate=0.004)
+    t_big = np.concatenate([synth.random_codes(rng, 40), t_big, synth.random_codes(rng, 25)]).astype(np.uint8)
+    t_small = synth.mutate(rng, q[1000:1800], identity=0.7)
+    t_shift = np.concatenate([q[3000:], q[:3000]]).astype(np.uint8)            # two competing diagonals
+    queries = [q, synth.random_codes(rng, 300)]
+    db = [t_big, t_small, t_shift, synth.mutate(rng, queries[1], 0.8)]
+    assert O.sw_score(q, t_big, blosum) > 32767
+    _align_and_check(ctx, blosum, queries, db, [(0, 0), (0, 1), (0, 2), (1, 3)])
