@@ -18,6 +18,8 @@
 // thread per run).  Scored pairs that beat the query's current cut-off are appended to that query's
 // candidate buffer; buffers are compacted (segmented sort, keep the best N, raise the cut-off) whenever
 // they could overflow during the next chunk of sequences.
+#include <algorithm>
+#include <cstring>
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -25,9 +27,9 @@
 namespace {
 
 constexpr int kWarps = 8;
+constexpr int kMaxWarps = 16;            // scan kernel: warps per CTA when its shared-memory tables are large
 constexpr int kSeqBatch = 4;           // sequences claimed per atomic
 constexpr int kGCap = 1024;             // surviving hits per sequence handled in the per-warp global scratch
-constexpr int kCntSlots = 1024;        // per-warp hashed hit counters (16 bit each)
 constexpr unsigned long long kNoThr = ~0ull;
 
 struct PfParams {
@@ -49,7 +51,7 @@ struct PfParams {
     uint32_t* def_seq;                // deferred: local sequence index
     unsigned long long* def_off;      // deferred: offset into the pool
     uint32_t max_deferred;
-    unsigned long long* pool_keys;    // (slot << 50 | q << 30 | order)
+    unsigned long long* pool_keys;    // (slot << 48 | q << 28 | order)
     uint32_t* pool_vals;              // query position
     unsigned long long pool_cap;
     unsigned long long* gbuf;         // per-warp global scratch (kGCap entries) for sequences with many surviving hits
@@ -186,6 +188,14 @@ __device__ __forceinline__ unsigned long long step_hit(const PfParams& P, const 
     return __ldg(P.hits + hb_s[p] + (x - off_s[p]));
 }
 
+// Can a (query, sequence) pair still beat the query's cut-off?  cnt16 = hashed per-sequence hit counters (they only
+// over-estimate a query's hits); the query's cut-off score comes from the CTA's shared table (upper 16 bits of the
+// float, i.e. rounded down -- conservative) or, for batches too large for it, from global memory.
+__device__ __forceinline__ bool may_pass(const PfParams& P, const unsigned short* qthr, const unsigned short* cnt16, uint32_t cmask, uint32_t q, float flen) {
+    const float th = qthr ? __uint_as_float((uint32_t)qthr[q] << 16) : __uint_as_float(~(uint32_t)(__ldcg(P.thr + q) >> 32));
+    return !((float)cnt16[q & cmask] < th * flen);
+}
+
 // The scan kernel.  Per sequence (one warp):
 //   pass A  walks the k-mer positions, counts the hits of every query in per-warp hashed 16-bit counters and buffers
 //           the hits in shared memory while they fit;
@@ -194,25 +204,24 @@ __device__ __forceinline__ unsigned long long step_hit(const PfParams& P, const 
 //           counters only over-estimate).  Once the cut-offs have settled this removes practically every random hit
 //           before any sorting;  sequences whose hits did not fit are re-walked keeping only the survivors;
 //   rest    survivors are bitonic-sorted by (query, emission order), each query's run reduced by the in-place LIS.
-// Shared memory per warp: hit buffer scap x 8 B, counters kCntSlots x 2 B, step tables 2 x 128 x 4 B.
-__global__ void __launch_bounds__(kWarps * 32) pf_scan_kernel(PfParams P, int scap) {
+// Shared memory per warp: hit buffer scap x 8 B, counters cslots x 2 B (cslots = 1024 .. 4096 by batch size: the
+// fewer queries share a counter, the sharper the filter), step tables 2 x 128 x 4 B.
+__global__ void __launch_bounds__(kMaxWarps * 32) pf_scan_kernel(PfParams P, int scap, int cslots, int qthr_in_smem) {
     extern __shared__ unsigned long long sbuf[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     unsigned long long* buf = sbuf + (size_t)warp * scap;
-    uint32_t* cnt_all = reinterpret_cast<uint32_t*>(sbuf + (size_t)kWarps * scap);
-    uint32_t* slot_thr = cnt_all + kWarps * (kCntSlots / 2);        // float bits: smallest cut-off score of the slot's queries
-    uint32_t* step_all = slot_thr + kCntSlots;
-    uint32_t* cnt = cnt_all + warp * (kCntSlots / 2);
+    uint32_t* cnt_all = reinterpret_cast<uint32_t*>(sbuf + (size_t)nwarps * scap);
+    const uint32_t cmask = (uint32_t)cslots - 1u;
+    uint32_t* step_all = cnt_all + nwarps * (cslots / 2);
+    unsigned short* qthr = qthr_in_smem ? reinterpret_cast<unsigned short*>(step_all + nwarps * 256) : nullptr;
+    uint32_t* cnt = cnt_all + warp * (cslots / 2);
     unsigned short* cnt16 = reinterpret_cast<unsigned short*>(cnt);
     uint32_t* off_s = step_all + warp * 256;
     uint32_t* hb_s = off_s + 128;
     const unsigned FULL = 0xffffffffu;
     const int k = P.k;
-    for (int i = threadIdx.x; i < kWarps * (kCntSlots / 2); i += blockDim.x) cnt_all[i] = 0;
-    for (int i = threadIdx.x; i < kCntSlots; i += blockDim.x) slot_thr[i] = 0x7f800000u;
-    __syncthreads();
-    for (int q = threadIdx.x; q < P.nq; q += blockDim.x)
-        atomicMin(slot_thr + (q & (kCntSlots - 1)), ~(uint32_t)(__ldcg(P.thr + q) >> 32));     // no cut-off yet -> 0.0f
+    for (int i = threadIdx.x; i < nwarps * (cslots / 2); i += blockDim.x) cnt_all[i] = 0;
+    if (qthr) for (int q = threadIdx.x; q < P.nq; q += blockDim.x) qthr[q] = (unsigned short)((~(uint32_t)(__ldcg(P.thr + q) >> 32)) >> 16);   // no cut-off yet -> 0
     __syncthreads();
     while (true) {
         long long s0 = 0;
@@ -249,7 +258,7 @@ __global__ void __launch_bounds__(kWarps * 32) pf_scan_kernel(PfParams P, int sc
                 publish_step(off_s, hb_s, lane, excl, hb, hc);
                 for (uint32_t x = lane; x < total; x += 32) {
                     const unsigned long long h = step_hit(P, off_s, hb_s, x);
-                    const uint32_t q = (uint32_t)(h >> 32), slot = q & (kCntSlots - 1);
+                    const uint32_t q = (uint32_t)(h >> 32), slot = q & cmask;
                     atomicAdd(cnt + (slot >> 1), (slot & 1u) ? 0x10000u : 1u);
                     const uint32_t ord = T + x;
                     if (buffered) buf[ord] = ((unsigned long long)q << 44) | ((unsigned long long)ord << 22) | (h & 0x3fffffu);
@@ -269,8 +278,7 @@ __global__ void __launch_bounds__(kWarps * 32) pf_scan_kernel(PfParams P, int sc
                     bool keep = false;
                     if (i < (int)T) {
                         e = buf[i];
-                        const uint32_t slot = (uint32_t)(e >> 44) & (kCntSlots - 1);
-                        keep = !((float)cnt16[slot] < __uint_as_float(slot_thr[slot]) * flen);
+                        keep = may_pass(P, qthr, cnt16, cmask, (uint32_t)(e >> 44), flen);
                     }
                     const uint32_t bal = __ballot_sync(FULL, keep);
                     if (keep) buf[nsurv + __popc(bal & ((1u << lane) - 1u))] = e;      // nsurv + rank <= i: never ahead of the reads
@@ -282,7 +290,7 @@ __global__ void __launch_bounds__(kWarps * 32) pf_scan_kernel(PfParams P, int sc
             } else {
                 // re-walk, keep the survivors only (any order: the sort key carries the emission order); they go to the
                 // warp's global scratch, which holds what a strong homolog of a long query produces
-                wb = P.gbuf + (size_t)(blockIdx.x * kWarps + warp) * kGCap;
+                wb = P.gbuf + (size_t)(blockIdx.x * nwarps + warp) * kGCap;
                 uint32_t ordbase = 0;
                 carry = 0xffffffffu;
                 for (int base = 0; base < npos && !defer; base += 128) {
@@ -299,8 +307,8 @@ __global__ void __launch_bounds__(kWarps * 32) pf_scan_kernel(PfParams P, int sc
                         bool keep = false;
                         if (x < total) {
                             const unsigned long long h = step_hit(P, off_s, hb_s, x);
-                            const uint32_t q = (uint32_t)(h >> 32), slot = q & (kCntSlots - 1);
-                            keep = !((float)cnt16[slot] < __uint_as_float(slot_thr[slot]) * flen);
+                            const uint32_t q = (uint32_t)(h >> 32);
+                            keep = may_pass(P, qthr, cnt16, cmask, q, flen);
                             e = ((unsigned long long)q << 44) | ((unsigned long long)(ordbase + x) << 22) | (h & 0x3fffffu);
                         }
                         const uint32_t bal = __ballot_sync(FULL, keep);
@@ -313,7 +321,11 @@ __global__ void __launch_bounds__(kWarps * 32) pf_scan_kernel(PfParams P, int sc
                 }
             }
             __syncwarp();
-            for (int i = lane; i < kCntSlots / 2; i += 32) cnt[i] = 0;
+            for (int i = lane; i < cslots / 2; i += 32) cnt[i] = 0;
+            if (!defer && wb != buf && nsurv <= (uint32_t)scap) {       // few survivors: sort them in shared memory
+                for (int i = lane; i < (int)nsurv; i += 32) buf[i] = wb[i];
+                wb = buf;
+            }
             __syncwarp();
             if (defer) {
                 if (lane == 0) {
@@ -402,7 +414,7 @@ __global__ void __launch_bounds__(kWarps * 32) pf_fill_deferred_kernel(PfParams 
             for (uint32_t t = 0; t < c; ++t) {
                 const unsigned long long h = __ldg(P.hits + b + t);
                 const uint32_t ord = T + excl + t;
-                keys[ord] = ((unsigned long long)slot << 50) | ((h >> 32) << 30) | (unsigned long long)(ord & 0x3fffffffu);
+                keys[ord] = ((unsigned long long)slot << 48) | ((h >> 32) << 28) | (unsigned long long)(ord & 0xfffffffu);
                 vals[ord] = (uint32_t)h;
             }
             T += total;
@@ -415,12 +427,12 @@ __global__ void pf_lis_deferred_kernel(PfParams P, const unsigned long long* key
                                        unsigned long long n) {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const unsigned long long g = keys[i] >> 30;
-    if (i > 0 && (keys[i - 1] >> 30) == g) return;
+    const unsigned long long g = keys[i] >> 28;
+    if (i > 0 && (keys[i - 1] >> 28) == g) return;
     unsigned long long e = i + 1;
     int len = 0;
     uint32_t* tl = tails + i;
-    for (unsigned long long x = i; x < n && (keys[x] >> 30) == g; ++x) {
+    for (unsigned long long x = i; x < n && (keys[x] >> 28) == g; ++x) {
         const uint32_t v = vals[x];
         int lo = 0, hi = len;
         while (lo < hi) { int mid = (lo + hi) >> 1; if (tl[mid] < v) lo = mid + 1; else hi = mid; }
@@ -684,16 +696,25 @@ int s4g_prefilter_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int ma
     // the scan runs in chunks of sequences; chunk sizes grow geometrically (cut-offs settle on the first small
     // chunks, later chunks append little) up to what the candidate-buffer budget allows
     int64_t chunk = 1 << 20;
-    const size_t budget = (size_t)12 << 30;   // bytes for both candidate buffers
+    size_t budget = (size_t)12 << 30;         // bytes for both candidate buffers: a third of the free HBM, 12 .. 48 GiB
+    {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            free_b += ctx->slot_bytes[SLOT_PF_CAND] + ctx->slot_bytes[SLOT_PF_TMP];      // what this call may reuse
+            budget = std::min<size_t>(std::max<size_t>(free_b / 3, (size_t)12 << 30), (size_t)48 << 30);
+            if (budget > free_b / 2) budget = free_b / 2;
+        }
+    }
     while (chunk > 4096 && (size_t)nq * (size_t)(N + slack + chunk) * 16 > budget) chunk >>= 1;
     if (chunk > db->n) chunk = db->n > 0 ? db->n : 1;
     const uint32_t cap = (uint32_t)(N + slack + chunk);
     unsigned long long* d_cand = (unsigned long long*)s4g_scratch(ctx, SLOT_PF_CAND, sizeof(unsigned long long) * (size_t)nq * cap);
     unsigned long long* d_cand_alt = (unsigned long long*)s4g_scratch(ctx, SLOT_PF_TMP, sizeof(unsigned long long) * (size_t)nq * cap);
-    uint32_t* d_count = (uint32_t*)s4g_scratch(ctx, SLOT_PF_COUNT, sizeof(uint32_t) * nq);
+    uint32_t* d_count = (uint32_t*)s4g_scratch(ctx, SLOT_PF_COUNT, sizeof(uint32_t) * 2 * nq);
+    uint32_t* d_count_saved = d_count ? d_count + nq : nullptr;
     unsigned long long* d_thr = (unsigned long long*)s4g_scratch(ctx, SLOT_PF_THR, sizeof(unsigned long long) * nq + 64);
-    const uint32_t max_deferred = 1u << 14;
-    const unsigned long long pool_cap = 1ull << 26;   // 64 M hits per chunk through the deferred path
+    const uint32_t max_deferred = 1u << 16;
+    const unsigned long long pool_cap = 1ull << 27;   // 128 M hits per chunk through the deferred path (28-bit order field)
     char* spill = (char*)s4g_scratch(ctx, SLOT_PF_SPILL, 64 + sizeof(int64_t) * 2 * nq + sizeof(uint32_t) * nq + (sizeof(uint32_t) + sizeof(unsigned long long)) * max_deferred);
     if (!d_cand || !d_cand_alt || !d_count || !d_thr || !spill) return S4G_ERR_NOMEM;
     unsigned long long* d_counters = (unsigned long long*)spill;          // 8 counters
@@ -721,25 +742,37 @@ int s4g_prefilter_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int ma
         const double per_res = (double)n_hits / (double)n_kmer_space * 8.0;        // frequent letters dominate: x8 over uniform
         const double avg_len = db->n > 0 ? (double)db->residues / (double)db->n : 1.0;
         while (scap < 1024 && (double)scap < 4.0 * per_res * avg_len) scap <<= 1;
+        // batches so large that a typical sequence cannot be buffered anyway are counted first and re-walked;
+        // the buffer then only holds the survivors of the filter
+        if (4.0 * per_res * avg_len > 1024.0) scap = 512;
     }
-    const size_t scan_smem = sizeof(unsigned long long) * kWarps * scap + sizeof(uint32_t) * kWarps * (kCntSlots / 2) + sizeof(uint32_t) * kCntSlots + sizeof(uint32_t) * kWarps * 256;
+    // per-query cut-off table in shared memory (2 B per query) when it fits beside the per-warp buffers
+    const int qthr_in_smem = nq <= 32768 ? 1 : 0;
+    const size_t qthr_bytes = qthr_in_smem ? (((size_t)nq * 2 + 15) / 16) * 16 : 0;
+    const int cslots = nq <= 1024 ? 1024 : (nq <= 8192 ? 2048 : 4096);
+    if (cslots == 4096) scap = 256;
+    const size_t per_warp_smem = sizeof(unsigned long long) * scap + sizeof(uint32_t) * (cslots / 2) + sizeof(uint32_t) * 256;
+    // small tables: 8-warp CTAs, several per SM; a large cut-off table is shared by 16 warps
+    const int scan_warps = qthr_bytes > 16384 ? kMaxWarps : kWarps;
+    const size_t scan_smem = per_warp_smem * scan_warps + qthr_bytes;
     S4G_CUDA(ctx, cudaFuncSetAttribute(pf_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
-    S4G_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pf_scan_kernel, kWarps * 32, scan_smem));
+    S4G_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pf_scan_kernel, scan_warps * 32, scan_smem));
     if (per_sm < 1) per_sm = 1;
     const int grid = ctx->sm_count * per_sm;
-    P.gbuf = (unsigned long long*)s4g_scratch(ctx, SLOT_PF_GBUF, sizeof(unsigned long long) * (size_t)grid * kWarps * kGCap);
+    P.gbuf = (unsigned long long*)s4g_scratch(ctx, SLOT_PF_GBUF, sizeof(unsigned long long) * (size_t)grid * scan_warps * kGCap);
     if (!P.gbuf) return S4G_ERR_NOMEM;
 
     int64_t this_chunk = chunk < 16384 ? chunk : 16384;
+    int64_t ceiling = chunk;
+    int ceiling_hold = 0;
     for (int64_t s0 = 0; s0 < db->n && n_hits > 0; ) {
         P.seq_begin = s0;
         P.seq_end = s0 + this_chunk < db->n ? s0 + this_chunk : db->n;
-        s0 = P.seq_end;
-        this_chunk = this_chunk * 2 < chunk ? this_chunk * 2 : chunk;
         S4G_CUDA(ctx, cudaMemsetAsync(d_counters, 0, 32, st));
+        S4G_CUDA(ctx, cudaMemcpyAsync(d_count_saved, d_count, sizeof(uint32_t) * nq, cudaMemcpyDeviceToDevice, st));
         // the pool is only allocated once a chunk needs it (first pass counts; see below)
         P.pool_keys = (unsigned long long*)ctx->slot_ptr[SLOT_PF_HITS];
-        pf_scan_kernel<<<grid, kWarps * 32, scan_smem, st>>>(P, scap);
+        pf_scan_kernel<<<grid, scan_warps * 32, scan_smem, st>>>(P, scap, cslots, qthr_in_smem);
         S4G_CHECK_LAUNCH(ctx);
         unsigned long long h_c[4];
         S4G_CUDA(ctx, cudaMemcpyAsync(h_c, d_counters, 32, cudaMemcpyDeviceToHost, st));
@@ -747,7 +780,17 @@ int s4g_prefilter_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int ma
         s4g_trace_mark(ctx, "scan");
         if (ctx->trace) fprintf(stderr, "[s4g trace] chunk [%lld,%lld): deferred %llu sequences, %llu hits\n", (long long)P.seq_begin, (long long)P.seq_end, h_c[1], h_c[2]);
         if (h_c[3] & 1ull) { s4g_set_error(ctx, "prefilter: candidate buffer overflow (internal)"); return S4G_ERR_INTERNAL; }
-        if (h_c[3] & 2ull) { s4g_set_error(ctx, "prefilter: more than %u deferred sequences or %llu deferred hits in one chunk", max_deferred, pool_cap); return S4G_ERR_CAPACITY; }
+        if (h_c[3] & 2ull) {
+            if (P.seq_end - P.seq_begin <= 256) { s4g_set_error(ctx, "prefilter: more than %u deferred sequences or %llu deferred hits in a chunk of %lld sequences", max_deferred, pool_cap, (long long)(P.seq_end - P.seq_begin)); return S4G_ERR_CAPACITY; }
+            S4G_CUDA(ctx, cudaMemcpyAsync(d_count, d_count_saved, sizeof(uint32_t) * nq, cudaMemcpyDeviceToDevice, st));
+            this_chunk = (P.seq_end - P.seq_begin) / 2;
+            ceiling = this_chunk;
+            ceiling_hold = 8;
+            continue;
+        }
+        s0 = P.seq_end;
+        if (ceiling_hold > 0 && --ceiling_hold == 0) ceiling = chunk;
+        this_chunk = std::min<int64_t>(this_chunk * 2, std::min(chunk, ceiling));
         if (h_c[1] > 0) {
             const unsigned long long n_pool = h_c[2];
             const uint32_t n_def = (uint32_t)h_c[1];
@@ -780,6 +823,15 @@ int s4g_prefilter_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int ma
         s4g_trace_mark(ctx, "compact");
     }
     s4g_trace_mark(ctx, "compact");
+    if (ctx->trace) {
+        std::vector<unsigned long long> h_thr(nq);
+        cudaMemcpy(h_thr.data(), d_thr, sizeof(unsigned long long) * nq, cudaMemcpyDeviceToHost);
+        std::vector<float> sc;
+        int none = 0;
+        for (int i = 0; i < nq; ++i) { if (h_thr[i] == kNoThr) ++none; else { uint32_t b = ~(uint32_t)(h_thr[i] >> 32); float f; memcpy(&f, &b, 4); sc.push_back(f); } }
+        std::sort(sc.begin(), sc.end());
+        if (!sc.empty()) fprintf(stderr, "[s4g trace] cut-off scores: %d queries without, min %.4f p10 %.4f median %.4f max %.4f\n", none, sc.front(), sc[sc.size() / 10], sc[sc.size() / 2], sc.back());
+    }
     // ---- final top-N, output ----
     {
         int rc = compact(ctx, nq, cap, N, 0, 1, d_cand, d_cand_alt, d_count, d_thr, d_seg, d_seg_q, d_nseg, nullptr);
