@@ -37,6 +37,7 @@ constexpr int kTilePairs = 64;            // pairs per (query, tile)
 constexpr int kRing = 64;                 // ring refill granularity (columns), >= 32
 constexpr int kMaxK = 32;                 // rows per lane in the packed kernel -> queries up to 1024
 constexpr int kGenK = 8;                  // rows per lane in the 32-bit kernel (256 rows per pass)
+constexpr int kStripCols = 4096;          // longest target the striped kernel takes (longer ones: 32-bit kernel)
 
 __device__ __forceinline__ unsigned prmt(unsigned a, unsigned b, unsigned sel) {
     unsigned d;
@@ -65,6 +66,9 @@ struct ScoreParams {
     int32_t ovf_limit;              // 32767 - max(matrix)
     // end-cell mode (stage 3, step 1): cand_ids = targets of the kept hits, out = coords (4 per hit)
     const int32_t* pair_score;
+    // striped kernel (queries longer than 32 * kMaxK rows)
+    const int64_t* long_tile_start;   // nq+1: exclusive scan of its tiles per query
+    unsigned* strip_bound;            // per CTA: kTilePairs x 2 x kStripCols packed boundary rows (H, F)
 };
 
 // ------------------------------------------------------------------------------------------------------
@@ -329,6 +333,176 @@ __global__ void __launch_bounds__(kWarps * 32, 2) sw_score_packed_kernel(ScorePa
 __global__ void __launch_bounds__(kWarps * 32, 2) al_forward_packed_kernel(ScoreParams P) { packed_kernel_body<true>(P); }
 
 // ------------------------------------------------------------------------------------------------------
+// striped kernel for long queries (intra-sequence): the query is cut into stripes of 32 * kMaxK = 1024 rows; a stripe
+// is swept exactly like a short query (same packed cell update, two targets per warp, profile of the stripe shared by
+// the CTA), and the last row of a stripe (H and F, packed for both targets) is handed to the next stripe through a
+// per-pair boundary buffer in global memory, staged through shared memory 64 columns at a time.
+
+struct StripSmem {
+    unsigned short *ring1, *ring2;    // [128] profile row offsets of the two targets
+    unsigned *inH, *inF;              // [64]  boundary of the previous stripe for the current block of columns
+    unsigned *outH, *outF;            // [128] boundary produced by lane 31
+};
+constexpr int kStripWarpBytes = 4 * kRing * 2 + 2 * kRing * 4 + 4 * kRing * 4;
+
+__device__ __forceinline__ unsigned sweep_stripe(const unsigned* __restrict__ prof_lane, const StripSmem& S, const uint8_t* __restrict__ t1,
+                                                 int len1, const uint8_t* __restrict__ t2, int len2, unsigned negQ, unsigned negR,
+                                                 unsigned* bH, unsigned* bF, bool first, bool last, int lane) {
+    constexpr int K = kMaxK, KW = K / 4;
+    constexpr unsigned kRowBytes = KW * 128;
+    constexpr unsigned kPadOff = S4G_PAD_CODE * kRowBytes;
+    constexpr int kRingMask = 2 * kRing - 1;
+    const unsigned FULL = 0xffffffffu;
+    unsigned H[K], E[K];
+#pragma unroll
+    for (int r = 0; r < K; ++r) { H[r] = 0; E[r] = 0; }
+    unsigned best = 0, h_last = 0, f_out = 0, diag_in = 0;
+    const int maxlen = len1 > len2 ? len1 : len2;
+    const int nsteps = maxlen + 31;
+    for (int c = lane; c < kRing; c += 32) { S.ring1[kRing + c] = kPadOff; S.ring2[kRing + c] = kPadOff; }
+    const char* prof_bytes = reinterpret_cast<const char*>(prof_lane);
+    int flushed = 0;
+    for (int s0 = 0; s0 < nsteps; s0 += kRing) {
+        if (!last) {
+            const int upto = min(maxlen, s0 - 31);
+            for (int c = flushed + lane; c < upto; c += 32) { bH[c] = S.outH[c & kRingMask]; bF[c] = S.outF[c & kRingMask]; }
+            if (upto > flushed) flushed = upto;
+        }
+        {
+            const int base = s0 & kRingMask;
+#pragma unroll
+            for (int c = 0; c < kRing; c += 32) {
+                const int j = s0 + c + lane;
+                S.ring1[base + c + lane] = (unsigned short)(j < len1 ? (unsigned)t1[j] * kRowBytes : kPadOff);
+                S.ring2[base + c + lane] = (unsigned short)(j < len2 ? (unsigned)t2[j] * kRowBytes : kPadOff);
+                if (!first) { S.inH[c + lane] = j < maxlen ? bH[j] : 0u; S.inF[c + lane] = j < maxlen ? bF[j] : 0u; }
+            }
+        }
+        __syncwarp();
+        const int send = (nsteps - s0) < kRing ? (nsteps - s0) : kRing;
+#pragma unroll 1
+        for (int ss = 0; ss < send; ++ss) {
+            const int j = s0 + ss - lane;
+            const unsigned o1 = S.ring1[j & kRingMask];
+            const unsigned o2 = S.ring2[j & kRingMask];
+            unsigned w1[KW], w2[KW];
+#pragma unroll
+            for (int m = 0; m < KW; ++m) {
+                w1[m] = *reinterpret_cast<const unsigned*>(prof_bytes + o1 + m * 128);
+                w2[m] = *reinterpret_cast<const unsigned*>(prof_bytes + o2 + m * 128);
+            }
+            unsigned h_up = __shfl_up_sync(FULL, h_last, 1);
+            unsigned f = __shfl_up_sync(FULL, f_out, 1);
+            if (lane == 0) { h_up = first ? 0u : S.inH[ss]; f = first ? 0u : S.inF[ss]; }
+            unsigned t = __vadd2(diag_in, prmt(w1[0], w2[0], 0xC480u)), t_prev = 0;
+            diag_in = h_up;
+#pragma unroll
+            for (int r = 0; r < K; ++r) {
+                unsigned t_next = 0;
+                if (r + 1 < K) {
+                    const unsigned sel = ((r + 1) & 3) == 0 ? 0xC480u : ((r + 1) & 3) == 1 ? 0xD591u : ((r + 1) & 3) == 2 ? 0xE6A2u : 0xF7B3u;
+                    t_next = __vadd2(H[r], prmt(w1[(r + 1) >> 2], w2[(r + 1) >> 2], sel));
+                }
+                const unsigned h = __vimax3_s16x2_relu(t, E[r], f);
+                H[r] = h;
+                const unsigned hq = __vadd2(h, negQ);
+                E[r] = __viaddmax_s16x2(E[r], negR, hq);
+                f = __viaddmax_s16x2(f, negR, hq);
+                if (r & 1) best = __vimax3_s16x2(best, t_prev, t);
+                t_prev = t;
+                t = t_next;
+            }
+            h_last = H[K - 1];
+            f_out = f;
+            if (lane == 31 && !last && j >= 0 && j < maxlen) { S.outH[j & kRingMask] = h_last; S.outF[j & kRingMask] = f_out; }
+        }
+        __syncwarp();
+    }
+    if (!last) for (int c = flushed + lane; c < maxlen; c += 32) { bH[c] = S.outH[c & kRingMask]; bF[c] = S.outF[c & kRingMask]; }
+    __syncwarp();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = __vmaxs2(best, __shfl_xor_sync(FULL, best, o));
+    return best;
+}
+
+__global__ void __launch_bounds__(kWarps * 32, 2) sw_score_striped_kernel(ScoreParams P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned* prof = reinterpret_cast<unsigned*>(smem);
+    int8_t* smat = reinterpret_cast<int8_t*>(smem + (S4G_PAD_CODE + 1) * 8 * 32 * 4);
+    unsigned char* wbase = reinterpret_cast<unsigned char*>(smat + (S4G_PAD_CODE + 1) * 32);
+    __shared__ long long s_tile;
+    __shared__ unsigned s_best[kTilePairs];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    StripSmem S;
+    {
+        unsigned char* wb = wbase + warp * kStripWarpBytes;
+        S.ring1 = reinterpret_cast<unsigned short*>(wb);
+        S.ring2 = S.ring1 + 2 * kRing;
+        S.inH = reinterpret_cast<unsigned*>(S.ring2 + 2 * kRing);
+        S.inF = S.inH + kRing;
+        S.outH = S.inF + kRing;
+        S.outF = S.outH + 2 * kRing;
+    }
+    for (int i = threadIdx.x; i < (S4G_PAD_CODE + 1) * 32; i += blockDim.x) smat[i] = P.mat8[i];
+    const long long total = P.long_tile_start[P.nq];
+    const unsigned negQ = ((unsigned)(-P.gap_open) & 0xffffu) * 0x10001u;
+    const unsigned negR = ((unsigned)(-P.gap_extend) & 0xffffu) * 0x10001u;
+    unsigned* cta_bound = P.strip_bound + (size_t)blockIdx.x * kTilePairs * 2 * kStripCols;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = (long long)atomicAdd(&P.counters[4], 1ull);
+        __syncthreads();
+        const long long tile = s_tile;
+        if (tile >= total) break;
+        int lo = 0, hi = P.nq;
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (P.long_tile_start[mid] <= tile) lo = mid; else hi = mid; }
+        const int q = lo;
+        const int64_t qo = P.q_off[q];
+        const int qlen = (int)(P.q_off[q + 1] - qo);
+        const int64_t cbeg = P.cand_off[q], cend = P.cand_off[q + 1];
+        const int n_pairs = (int)((cend - cbeg + 1) >> 1);
+        const int pb = (int)(tile - P.long_tile_start[q]) * kTilePairs;
+        const int pe = pb + kTilePairs < n_pairs ? pb + kTilePairs : n_pairs;
+        const int npass = (qlen + 32 * kMaxK - 1) / (32 * kMaxK);
+        for (int i = threadIdx.x; i < kTilePairs; i += blockDim.x) s_best[i] = 0;
+        for (int pass = 0; pass < npass; ++pass) {
+            __syncthreads();
+            build_profile<kMaxK>(prof, smat, P.q_codes + qo + (int64_t)pass * 32 * kMaxK, qlen - pass * 32 * kMaxK);
+            __syncthreads();
+            for (int p = pb + warp; p < pe; p += kWarps) {
+                const int64_t i1 = cbeg + 2 * (int64_t)p, i2 = i1 + 1;
+                const uint32_t c1 = P.sorted_idx[i1];
+                const bool has2 = i2 < cend;
+                const uint32_t c2 = has2 ? P.sorted_idx[i2] : c1;
+                const int64_t a1 = P.db_off[P.cand_ids[c1] - P.id_base], b1 = P.db_off[P.cand_ids[c1] - P.id_base + 1];
+                const int64_t a2 = P.db_off[P.cand_ids[c2] - P.id_base], b2 = P.db_off[P.cand_ids[c2] - P.id_base + 1];
+                const int len1 = (int)(b1 - a1), len2 = has2 ? (int)(b2 - a2) : 0;
+                if (len1 > kStripCols || len2 > kStripCols) {           // too long for the boundary buffer: 32-bit kernel
+                    if (lane == 0) s_best[p - pb] = 0x7fff7fffu;
+                    continue;
+                }
+                unsigned* bH = cta_bound + (size_t)(p - pb) * 2 * kStripCols;
+                const unsigned best = sweep_stripe(prof + lane, S, P.db_codes + a1, len1, P.db_codes + a2, len2, negQ, negR, bH, bH + kStripCols,
+                                                   pass == 0, pass == npass - 1, lane);
+                if (lane == 0) s_best[p - pb] = __vmaxs2(s_best[p - pb], best);
+            }
+        }
+        __syncthreads();
+        for (int p = pb + threadIdx.x; p < pe; p += blockDim.x) {
+            const int64_t i1 = cbeg + 2 * (int64_t)p, i2 = i1 + 1;
+            const uint32_t c1 = P.sorted_idx[i1];
+            const unsigned best = s_best[p - pb];
+            const int s1 = (int)(best & 0xffffu), s2 = (int)(best >> 16);
+            if (s1 > P.ovf_limit) P.overflow[atomicAdd(&P.counters[1], 1ull)] = c1; else P.out[c1] = s1;
+            if (i2 < cend) {
+                const uint32_t c2 = P.sorted_idx[i2];
+                if (s2 > P.ovf_limit) P.overflow[atomicAdd(&P.counters[1], 1ull)] = c2; else P.out[c2] = s2;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // exact 32-bit kernel: one warp per (query, target), any query length (256-row passes, the boundary row
 // H/F travels through a per-warp global scratch that stays in L2).  Used for 16-bit overflow re-runs and
 // for queries longer than 32*kMaxK rows.
@@ -431,7 +605,7 @@ __global__ void make_keys_kernel(ScoreParams P, int64_t n_pairs, unsigned long l
     vals[i] = (uint32_t)i;
 }
 
-// tiles per query for the packed kernel (0 for long queries), and the number of long-query candidates
+// tiles per query for the packed kernel (0 for long queries) and for the striped kernel (0 for short ones)
 __global__ void count_tiles_kernel(ScoreParams P, int64_t* tiles, int64_t* long_cands) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q > P.nq) return;
@@ -440,20 +614,12 @@ __global__ void count_tiles_kernel(ScoreParams P, int64_t* tiles, int64_t* long_
         const int64_t n_c = P.cand_off[q + 1] - P.cand_off[q];
         const int qlen = (int)(P.q_off[q + 1] - P.q_off[q]);
         if (qlen <= 32 * kMaxK) t = ((n_c + 1) / 2 + kTilePairs - 1) / kTilePairs;
-        else l = n_c;
+        else l = ((n_c + 1) / 2 + kTilePairs - 1) / kTilePairs;      // tiles of the striped kernel
     }
     tiles[q] = t;
     long_cands[q] = l;
 }
 
-// positions (in sorted order) of the candidates of long queries
-__global__ void gather_long_kernel(ScoreParams P, const int64_t* long_start, const uint32_t* sorted_idx, uint32_t* long_idx) {
-    const int q = blockIdx.x;
-    const int qlen = (int)(P.q_off[q + 1] - P.q_off[q]);
-    if (qlen <= 32 * kMaxK) return;
-    const int64_t b = P.cand_off[q], e = P.cand_off[q + 1];
-    for (int64_t i = b + threadIdx.x; i < e; i += blockDim.x) long_idx[long_start[q] + (i - b)] = sorted_idx[i];
-}
 
 // ---- end-cell mode: the kept hits as (query, target) work, grouped by query and sorted by target length ----
 
@@ -503,11 +669,10 @@ int s4g_sw_score_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, const uint32_t
     unsigned long long* d_keys2 = (unsigned long long*)s4g_scratch(ctx, SLOT_SW_KEYS2, sizeof(unsigned long long) * n_pairs);
     uint32_t* d_vals = (uint32_t*)s4g_scratch(ctx, SLOT_SW_VALS, sizeof(uint32_t) * n_pairs);
     uint32_t* d_vals2 = (uint32_t*)s4g_scratch(ctx, SLOT_SW_VALS2, sizeof(uint32_t) * n_pairs);
-    int64_t* d_tiles = (int64_t*)s4g_scratch(ctx, SLOT_SW_TILES, sizeof(int64_t) * 4 * (nq + 1));
+    int64_t* d_tiles = (int64_t*)s4g_scratch(ctx, SLOT_SW_TILES, sizeof(int64_t) * 5 * (nq + 1));
     unsigned long long* d_counters = (unsigned long long*)s4g_scratch(ctx, SLOT_SW_MISC, 64);
     uint32_t* d_ovf = (uint32_t*)s4g_scratch(ctx, SLOT_SW_OVF, sizeof(uint32_t) * 2 * n_pairs);
     if (!d_mat8 || !d_keys || !d_keys2 || !d_vals || !d_vals2 || !d_tiles || !d_counters || !d_ovf) return S4G_ERR_NOMEM;
-    uint32_t* d_long_idx = d_ovf + n_pairs;
     int64_t* d_tile_cnt = d_tiles, *d_tile_start = d_tiles + (nq + 1), *d_long_cnt = d_tiles + 2 * (nq + 1), *d_long_start = d_tiles + 3 * (nq + 1);
 
     const int gen_blocks = ctx->sm_count * 2;
@@ -524,6 +689,7 @@ int s4g_sw_score_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, const uint32_t
     P.cand_ids = d_cand_ids; P.cand_off = d_cand_off;
     P.sorted_idx = d_vals2; P.tile_start = d_tile_start; P.mat8 = d_mat8; P.out = d_out;
     P.counters = d_counters; P.overflow = d_ovf; P.bound = d_bound; P.bound_stride = bound_stride;
+    P.long_tile_start = d_long_start; P.strip_bound = nullptr; P.pair_score = nullptr;
     P.gap_open = gap_open; P.gap_extend = gap_extend; P.ovf_limit = 32767 - max_s;
 
     // 1. sort candidates of each query by target length (longest first)
@@ -563,25 +729,26 @@ int s4g_sw_score_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, const uint32_t
         S4G_CUDA(ctx, cudaEventRecord(ctx->ev_sw0, st));
         sw_score_packed_kernel<<<ctx->sm_count * per_sm, kWarps * 32, smem, st>>>(P);
         S4G_CHECK_LAUNCH(ctx);
-        S4G_CUDA(ctx, cudaEventRecord(ctx->ev_sw1, st));
-        ctx->sw_timed = true;
     }
-    // 4. long queries (all their candidates) and 16-bit overflow re-runs, exact 32-bit kernel
+    // 4. long queries: striped kernel (stripes of 1024 rows, boundary rows through a per-CTA buffer)
+    if (q->max_len > 32 * kMaxK) {
+        const size_t smem = (S4G_PAD_CODE + 1) * 8 * 32 * 4 + (S4G_PAD_CODE + 1) * 32 + kWarps * kStripWarpBytes;
+        S4G_CUDA(ctx, cudaFuncSetAttribute(sw_score_striped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        S4G_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw_score_striped_kernel, kWarps * 32, smem));
+        if (per_sm < 1) per_sm = 1;
+        const int grid = ctx->sm_count * per_sm;
+        unsigned* d_strip = (unsigned*)s4g_scratch(ctx, SLOT_SW_STRIP, sizeof(unsigned) * (size_t)grid * kTilePairs * 2 * kStripCols);
+        if (!d_strip) return S4G_ERR_NOMEM;
+        P.strip_bound = d_strip;
+        sw_score_striped_kernel<<<grid, kWarps * 32, smem, st>>>(P);
+        S4G_CHECK_LAUNCH(ctx);
+    }
+    S4G_CUDA(ctx, cudaEventRecord(ctx->ev_sw1, st));      // s4g_last_sw_kernel_ms: packed + striped kernels
+    ctx->sw_timed = true;
+    // 5. exact 32-bit kernel for what the 16-bit kernels could not settle (scores near 32767, targets longer than the
+    //    striped kernel's boundary buffer)
     {
-        bool any_long = q->max_len > 32 * kMaxK;
-        if (any_long) {
-            // number of long-query candidates is data dependent but bounded by n_pairs; the kernel reads
-            // the true count from d_long_start[nq]
-            gather_long_kernel<<<nq, 128, 0, st>>>(P, d_long_start, d_vals2, d_long_idx);
-            S4G_CHECK_LAUNCH(ctx);
-            int64_t h_long = 0;
-            S4G_CUDA(ctx, cudaMemcpyAsync(&h_long, d_long_start + nq, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-            S4G_CUDA(ctx, cudaStreamSynchronize(st));
-            GenericWork W; W.list = nullptr; W.n_list = nullptr; W.long_idx = d_long_idx; W.n_long = h_long;
-            sw_score_generic_kernel<<<gen_blocks, kWarps * 32, 0, st>>>(P, W);
-            S4G_CHECK_LAUNCH(ctx);
-            S4G_CUDA(ctx, cudaMemsetAsync(d_counters + 2, 0, 8, st));
-        }
         GenericWork W; W.list = d_ovf; W.n_list = d_counters + 1; W.long_idx = nullptr; W.n_long = 0;
         sw_score_generic_kernel<<<gen_blocks, kWarps * 32, 0, st>>>(P, W);
         S4G_CHECK_LAUNCH(ctx);

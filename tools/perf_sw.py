@@ -7,12 +7,14 @@ from oracle import oracle as O
 
 nq = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 ncand = int(sys.argv[2]) if len(sys.argv) > 2 else 5000
+qlo = int(sys.argv[3]) if len(sys.argv) > 3 else 100
+qhi = int(sys.argv[4]) if len(sys.argv) > 4 else 1000
 ndb = 200000
 rng = np.random.default_rng(1)
 lens = np.clip(np.exp(rng.normal(5.6, 0.6, size=ndb)), 30, 35000).astype(np.int64)
 off = np.zeros(ndb + 1, dtype=np.int64); off[1:] = np.cumsum(lens)
 codes = rng.integers(0, 20, size=int(off[-1]), dtype=np.uint8)
-qlens = rng.integers(100, 1001, size=nq)
+qlens = rng.integers(qlo, qhi + 1, size=nq)
 qoff = np.zeros(nq + 1, dtype=np.int64); qoff[1:] = np.cumsum(qlens)
 qcodes = rng.integers(0, 20, size=int(qoff[-1]), dtype=np.uint8)
 ctx = capi.Context(0)
