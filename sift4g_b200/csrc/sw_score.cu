@@ -206,6 +206,154 @@ __device__ __forceinline__ unsigned score_pair_packed(const unsigned* __restrict
     return best;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// streaming form of the packed sweep (score mode): the pairs a warp takes from its tile are laid end to end as ONE
+// stream of target columns, so the 31-step fill/drain of the systolic wavefront is paid once per warp and tile instead
+// of once per pair (candidate lists of random data are dominated by ~100-residue targets, where the drain is 29 % of the
+// steps).  The first column of every pair carries a flag (bit 15 of its ring entry); a lane that reaches it
+//   * hands its running maximum of the finished pair down the lanes (a third SHFL.UP rides the wavefront: lane L gets
+//     lane L-1's merged maximum exactly when it crosses the same boundary one step later; lane 31 writes the score),
+//   * clears its H / E rows, diagonal input and maximum.
+// The flag block is the only divergent code and runs once per lane and pair.  After the last pair a flagged sentinel
+// column and 31 pad columns flush the wavefront.
+constexpr int kDescRing = 16;             // output positions of the pairs in flight
+constexpr int kMinCols = 8;               // pairs are padded to this many columns (bounds the pairs in flight)
+constexpr int kStreamTilePairs = 256;     // pairs per (query, tile) of the streaming score kernel
+constexpr unsigned kNoTarget = 0xffffffffu;
+
+template <int K>
+__device__ __forceinline__ void stream_pairs_packed(const ScoreParams& P, const unsigned* __restrict__ prof_lane, unsigned short* ring1,
+                                                    unsigned short* ring2, uint2* desc, int* s_next, int64_t cbeg, int64_t cend,
+                                                    int pair_end, unsigned negQ, unsigned negR, int lane) {
+    constexpr int KW = (K + 3) / 4;
+    constexpr unsigned kRowBytes = KW * 128;
+    constexpr unsigned kPadOff = S4G_PAD_CODE * kRowBytes;
+    constexpr unsigned kFlag = 0x8000u;
+    constexpr int kRingMask = 2 * kRing - 1;
+    constexpr int kOpen = 0x7fffffff;
+    const unsigned FULL = 0xffffffffu;
+    static_assert(kPadOff < kFlag, "profile offsets must leave bit 15 free");
+
+    unsigned H[K], E[K];
+#pragma unroll
+    for (int r = 0; r < K; ++r) { H[r] = 0; E[r] = 0; }
+    unsigned best = 0, h_last = 0, f_out = 0, diag_in = 0, b_out = 0;
+    int n31 = 0;                          // boundaries this lane has crossed (used by lane 31)
+
+    // fill state (warp uniform): current pair and the next column of it to be staged
+    const uint8_t *t1 = nullptr, *t2 = nullptr;
+    int len1 = 0, len2 = 0, L = 0, pos = 0, n_pulled = 0, end_col = kOpen;
+
+    for (int c = lane; c < kRing; c += 32) { ring1[kRing + c] = kPadOff; ring2[kRing + c] = kPadOff; }
+    const char* prof_bytes = reinterpret_cast<const char*>(prof_lane);
+
+    for (int s0 = 0;; s0 += kRing) {
+        // ---- stage stream columns s0 .. s0+kRing-1
+        int col = s0;
+        while (col < s0 + kRing) {
+            if (pos >= L && end_col == kOpen) {
+                int p = 0;
+                if (lane == 0) p = atomicAdd(s_next, 1);
+                p = __shfl_sync(FULL, p, 0);
+                if (p < pair_end) {
+                    const int64_t i1 = cbeg + 2 * (int64_t)p, i2 = i1 + 1;
+                    const uint32_t c1 = P.sorted_idx[i1];
+                    const bool has2 = i2 < cend;
+                    const uint32_t c2 = has2 ? P.sorted_idx[i2] : c1;
+                    const uint32_t g1 = P.cand_ids[c1] - P.id_base, g2 = P.cand_ids[c2] - P.id_base;
+                    const int64_t a1 = P.db_off[g1], b1 = P.db_off[g1 + 1];
+                    const int64_t a2 = P.db_off[g2], b2 = P.db_off[g2 + 1];
+                    t1 = P.db_codes + a1; len1 = (int)(b1 - a1);
+                    t2 = P.db_codes + a2; len2 = has2 ? (int)(b2 - a2) : 0;
+                    L = len1 > len2 ? len1 : len2;
+                    if (L < kMinCols) L = kMinCols;
+                    pos = 0;
+                    if (lane == 0) desc[n_pulled & (kDescRing - 1)] = make_uint2(c1, has2 ? c2 : kNoTarget);
+                    ++n_pulled;
+                } else {
+                    end_col = col;                                   // the sentinel boundary sits here
+                }
+            }
+            if (end_col != kOpen) {
+                for (int c = col + lane; c < s0 + kRing; c += 32) {
+                    ring1[c & kRingMask] = (unsigned short)(c == end_col ? (kPadOff | kFlag) : kPadOff);
+                    ring2[c & kRingMask] = (unsigned short)kPadOff;
+                }
+                break;
+            }
+            const int n = min(L - pos, s0 + kRing - col);
+            for (int i = lane; i < n; i += 32) {
+                const int j = pos + i;
+                unsigned o1 = j < len1 ? (unsigned)t1[j] * kRowBytes : kPadOff;
+                const unsigned o2 = j < len2 ? (unsigned)t2[j] * kRowBytes : kPadOff;
+                if (j == 0) o1 |= kFlag;
+                ring1[(col + i) & kRingMask] = (unsigned short)o1;
+                ring2[(col + i) & kRingMask] = (unsigned short)o2;
+            }
+            col += n; pos += n;
+        }
+        if (n_pulled == 0) return;                                   // the tile was empty for this warp
+        __syncwarp();
+        // lane 31 crosses the sentinel at step end_col + 31
+        const int send = end_col == kOpen ? kRing : min(kRing, end_col + 32 - s0);
+#pragma unroll 1
+        for (int ss = 0; ss < send; ++ss) {
+            const int j = (s0 + ss - lane) & kRingMask;
+            int o1 = (short)ring1[j];
+            const unsigned o2 = ring2[j];
+            unsigned h_up = __shfl_up_sync(FULL, h_last, 1);
+            unsigned f = __shfl_up_sync(FULL, f_out, 1);
+            unsigned b_in = __shfl_up_sync(FULL, b_out, 1);
+            if (lane == 0) { h_up = 0; f = 0; b_in = 0; }
+            if (o1 < 0) {                                            // first column of a pair (or the sentinel)
+                o1 &= 0x7fff;
+                b_out = __vmaxs2(best, b_in);
+                if (lane == 31) {
+                    if (n31 > 0) {
+                        const uint2 d = desc[(n31 - 1) & (kDescRing - 1)];
+                        const int s1 = (int)(b_out & 0xffffu), s2 = (int)(b_out >> 16);
+                        if (s1 > P.ovf_limit) P.overflow[atomicAdd(&P.counters[1], 1ull)] = d.x; else P.out[d.x] = s1;
+                        if (d.y != kNoTarget) { if (s2 > P.ovf_limit) P.overflow[atomicAdd(&P.counters[1], 1ull)] = d.y; else P.out[d.y] = s2; }
+                    }
+                    ++n31;
+                }
+                best = 0; diag_in = 0;
+#pragma unroll
+                for (int r = 0; r < K; ++r) { H[r] = 0; E[r] = 0; }
+            }
+            unsigned w1[KW], w2[KW];
+#pragma unroll
+            for (int m = 0; m < KW; ++m) {
+                w1[m] = *reinterpret_cast<const unsigned*>(prof_bytes + o1 + m * 128);
+                w2[m] = *reinterpret_cast<const unsigned*>(prof_bytes + o2 + m * 128);
+            }
+            unsigned t = __vadd2(diag_in, prmt(w1[0], w2[0], 0xC480u)), t_prev = 0;
+            diag_in = h_up;
+#pragma unroll
+            for (int r = 0; r < K; ++r) {                            // cell update: see score_pair_packed
+                unsigned t_next = 0;
+                if (r + 1 < K) {
+                    const unsigned sel = ((r + 1) & 3) == 0 ? 0xC480u : ((r + 1) & 3) == 1 ? 0xD591u : ((r + 1) & 3) == 2 ? 0xE6A2u : 0xF7B3u;
+                    t_next = __vadd2(H[r], prmt(w1[(r + 1) >> 2], w2[(r + 1) >> 2], sel));
+                }
+                const unsigned h = __vimax3_s16x2_relu(t, E[r], f);
+                H[r] = h;
+                const unsigned hq = __vadd2(h, negQ);
+                E[r] = __viaddmax_s16x2(E[r], negR, hq);
+                f = __viaddmax_s16x2(f, negR, hq);
+                if (r & 1) best = __vimax3_s16x2(best, t_prev, t);
+                else if (r == K - 1) best = __vmaxs2(best, t);
+                t_prev = t;
+                t = t_next;
+            }
+            h_last = H[K - 1];
+            f_out = f;
+        }
+        __syncwarp();
+        if (end_col != kOpen && s0 + kRing >= end_col + 32) break;
+    }
+}
+
 // Build the int8 profile of one query into shared memory: prof[letter][m][lane] words, byte b of word
 // (m, lane) = S[q[lane*K + 4m + b]][letter]; rows beyond the query read 0; pad letter row reads mat8 row 26.
 template <int K>
@@ -240,6 +388,12 @@ __device__ void run_tile(const ScoreParams& P, unsigned* prof, const int8_t* sma
     unsigned short* ring2 = ring1 + 2 * kRing;
     const unsigned negQ = ((unsigned)(-P.gap_open) & 0xffffu) * 0x10001u;
     const unsigned negR = ((unsigned)(-P.gap_extend) & 0xffffu) * 0x10001u;
+    if (!TRACK) {
+        uint2* desc = reinterpret_cast<uint2*>(rings + kWarps * (4 * kRing)) + warp * kDescRing;
+        stream_pairs_packed<K>(P, prof + lane, ring1, ring2, desc, s_next, cbeg, cend, pair_end, negQ, negR, lane);
+        __syncthreads();
+        return;
+    }
     while (true) {
         int p = 0;
         if (lane == 0) p = atomicAdd(s_next, 1);
@@ -303,8 +457,9 @@ __device__ __forceinline__ void packed_kernel_body(const ScoreParams& P) {
         const int qlen = (int)(P.q_off[q + 1] - P.q_off[q]);
         const long long n_c = P.cand_off[q + 1] - P.cand_off[q];
         const int n_pairs = (int)((n_c + 1) >> 1);
-        const int pb = (int)(tile - P.tile_start[q]) * kTilePairs;
-        const int pe = pb + kTilePairs < n_pairs ? pb + kTilePairs : n_pairs;
+        constexpr int TP = TRACK ? kTilePairs : kStreamTilePairs;
+        const int pb = (int)(tile - P.tile_start[q]) * TP;
+        const int pe = pb + TP < n_pairs ? pb + TP : n_pairs;
         const int K = (qlen + 31) >> 5;
         switch ((K + 1) >> 1) {
             case 0: case 1: run_tile<2, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
@@ -606,14 +761,14 @@ __global__ void make_keys_kernel(ScoreParams P, int64_t n_pairs, unsigned long l
 }
 
 // tiles per query for the packed kernel (0 for long queries) and for the striped kernel (0 for short ones)
-__global__ void count_tiles_kernel(ScoreParams P, int64_t* tiles, int64_t* long_cands) {
+__global__ void count_tiles_kernel(ScoreParams P, int64_t* tiles, int64_t* long_cands, int packed_tile_pairs) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q > P.nq) return;
     int64_t t = 0, l = 0;
     if (q < P.nq) {
         const int64_t n_c = P.cand_off[q + 1] - P.cand_off[q];
         const int qlen = (int)(P.q_off[q + 1] - P.q_off[q]);
-        if (qlen <= 32 * kMaxK) t = ((n_c + 1) / 2 + kTilePairs - 1) / kTilePairs;
+        if (qlen <= 32 * kMaxK) t = ((n_c + 1) / 2 + packed_tile_pairs - 1) / packed_tile_pairs;
         else l = ((n_c + 1) / 2 + kTilePairs - 1) / kTilePairs;      // tiles of the striped kernel
     }
     tiles[q] = t;
@@ -709,7 +864,7 @@ int s4g_sw_score_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, const uint32_t
     }
     // 2. tile table
     {
-        count_tiles_kernel<<<(nq + 1 + 255) / 256, 256, 0, st>>>(P, d_tile_cnt, d_long_cnt);
+        count_tiles_kernel<<<(nq + 1 + 255) / 256, 256, 0, st>>>(P, d_tile_cnt, d_long_cnt, kStreamTilePairs);
         S4G_CHECK_LAUNCH(ctx);
         size_t tmp_bytes = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_tile_cnt, d_tile_start, nq + 1, st);
@@ -721,7 +876,8 @@ int s4g_sw_score_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, const uint32_t
     }
     // 3. packed kernel (persistent grid)
     {
-        const size_t smem = (S4G_PAD_CODE + 1) * 8 * 32 * 4 + (S4G_PAD_CODE + 1) * 32 + kWarps * 4 * kRing * sizeof(unsigned short);
+        const size_t smem = (S4G_PAD_CODE + 1) * 8 * 32 * 4 + (S4G_PAD_CODE + 1) * 32 + kWarps * 4 * kRing * sizeof(unsigned short) +
+                            kWarps * kDescRing * sizeof(uint2);
         S4G_CUDA(ctx, cudaFuncSetAttribute(sw_score_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
         S4G_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw_score_packed_kernel, kWarps * 32, smem));
@@ -796,7 +952,7 @@ int s4g_sw_forward_ends_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t
     }
     hit_qstart_kernel<<<(nq + 1 + 255) / 256, 256, 0, st>>>(d_keys2, n, nq, d_qstart);
     S4G_CHECK_LAUNCH(ctx);
-    count_tiles_kernel<<<(nq + 1 + 255) / 256, 256, 0, st>>>(P, d_tile_cnt, d_long_cnt);
+    count_tiles_kernel<<<(nq + 1 + 255) / 256, 256, 0, st>>>(P, d_tile_cnt, d_long_cnt, kTilePairs);
     S4G_CHECK_LAUNCH(ctx);
     {
         size_t tmp_bytes = 0;
