@@ -194,10 +194,12 @@ class DevicePipeline:
             seg = cs[cand_off[1:]] - cs[cand_off[:-1]]
             cells_dev = (seg * self.t_q_lens).sum()
         n_s = int(self._scr_cnt.item())
-        h_q = s_q[:n_s].cpu().numpy().view(np.uint32)
-        h_ids = s_id[:n_s].cpu().numpy().view(np.uint32)
-        h_scores = s_sc[:n_s].cpu().numpy()
-        h_lens = s_tl[:n_s].cpu().numpy()
+        surv = [self._to_host(nm, t[:n_s]) for nm, t in (("s_q", s_q), ("s_id", s_id), ("s_sc", s_sc), ("s_tl", s_tl))]
+        torch.cuda.current_stream(self.dev).synchronize()
+        h_q = surv[0].numpy().view(np.uint32)
+        h_ids = surv[1].numpy().view(np.uint32)
+        h_scores = surv[2].numpy()
+        h_lens = surv[3].numpy()
         h_off = np.searchsorted(h_q, np.arange(nq + 1), side="left").astype(np.int64)
         r.n_pairs = n_pairs
         r.sw_cells = int(cells_dev.item()) if n_pairs else 0
@@ -226,15 +228,34 @@ class DevicePipeline:
         if trace and self.rank == 0:
             print("[s4g trace] step: " + " ".join(marks), file=sys.stderr)
         if e2e:
-            host = [ids.cpu(), cnt.cpu()]
+            # results to the host through grow-only pinned buffers: async copies on the stream, one synchronise
+            host = [self._to_host("ids", ids), self._to_host("cnt", cnt)]
             r.d2h_bytes = ids.numel() * 4 + cnt.numel() * 4 + n_s * 16 + 4
             r.h2d_bytes += 3 * 4 * len(pq)
             if r.coords is not None:
-                n_path = int(r.path_off[-1].item())
-                host += [r.coords.cpu(), r.paths[:n_path].cpu(), r.path_off.cpu()]
+                host += [self._to_host("coords", r.coords), self._to_host("poff", r.path_off)]
+                # every path byte the capacity bound allows is at most 2x the real total; copy only the real ones
+                torch.cuda.current_stream(self.dev).synchronize()
+                n_path = int(host[-1][-1])
+                host.append(self._to_host("paths", r.paths[:n_path]))
                 r.d2h_bytes += r.coords.numel() * 4 + n_path + r.path_off.numel() * 8
+            torch.cuda.current_stream(self.dev).synchronize()
             r.timings = host
         return r
+
+    def _to_host(self, name, t):
+        """Asynchronous device-to-host copy of `t` into a pinned buffer owned by the pipeline (valid until the next
+        step); the caller synchronises the stream."""
+        torch = self.torch
+        t = t.reshape(-1)
+        pool = self.__dict__.setdefault("_pinned", {})
+        buf = pool.get(name)
+        if buf is None or buf.dtype != t.dtype or buf.numel() < t.numel():
+            buf = torch.empty(max(int(t.numel() * 1.25), 1), dtype=t.dtype, pin_memory=True)
+            pool[name] = buf
+        out = buf[:t.numel()]
+        out.copy_(t, non_blocking=True)
+        return out
 
     def _merge_hits(self, pq, pt, ps, ev, hoff, lo, hi):
         return merge_hits(self.torch, self.dist, self.dev, self.nq, self.max_alignments, pq, pt, ps, ev, hoff, lo, hi, ctx=self.ctx)
