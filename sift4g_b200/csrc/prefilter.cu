@@ -501,18 +501,103 @@ __global__ void cb_init_kernel(unsigned long long* thr, uint32_t* count, int nq)
     if (q < nq) { thr[q] = kNoThr; count[q] = 0; }
 }
 
-// list the queries whose buffer could overflow during the next chunk (or all non-empty ones when `all`)
+// list the queries whose buffer could overflow during the next chunk (or all non-empty ones when `all`).
+// sel_cap > 0: buffers holding at most sel_cap keys go to a second list (n_seg[1], filled from the end of the arrays)
+// that cb_topn_kernel reduces by selection in shared memory; the rest is sorted.
 __global__ void cb_select_kernel(const uint32_t* count, int nq, uint32_t cap, uint32_t limit, int all, int64_t* seg_begin,
-                                 int64_t* seg_end, uint32_t* seg_q, unsigned long long* n_seg) {
+                                 int64_t* seg_end, uint32_t* seg_q, unsigned long long* n_seg, uint32_t sel_cap) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
     const uint32_t c = count[q] < cap ? count[q] : cap;
     if ((all && c > 0) || c > limit) {
+        if (c <= sel_cap) {
+            const unsigned long long s = atomicAdd(n_seg + 1, 1ull);
+            seg_q[nq - 1 - s] = (uint32_t)q;
+            return;
+        }
         const unsigned long long s = atomicAdd(n_seg, 1ull);
         seg_begin[s] = (int64_t)q * cap;
         seg_end[s] = (int64_t)q * cap + c;
         seg_q[s] = (uint32_t)q;
     }
+}
+
+// Keep the best N keys of a buffer WITHOUT sorting it (the scan only needs the set and the cut-off): one CTA per listed
+// query, keys in shared memory, MSB-first radix select (8 passes of 8 bits, warp-aggregated histogram updates because
+// score bytes are heavily repeated), then the keys <= the N-th smallest are written back in arbitrary order.
+constexpr int kSelCap = 12288;           // keys per CTA (96 KB)
+constexpr int kSelThreads = 512;
+
+__global__ void __launch_bounds__(kSelThreads) cb_topn_kernel(unsigned long long* cand, uint32_t* count, unsigned long long* thr,
+                                                               uint32_t cap, uint32_t N, const uint32_t* seg_q_end) {
+    extern __shared__ unsigned long long sel_keys[];
+    __shared__ uint32_t hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ uint32_t s_remaining, s_out;
+    const unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t q = seg_q_end[-(int)blockIdx.x];
+    const uint32_t c = count[q] < cap ? count[q] : cap;
+    unsigned long long* src = cand + (size_t)q * cap;
+    if (c <= N) {                                    // nothing to drop
+        if (tid == 0) count[q] = c;
+        return;
+    }
+    for (uint32_t i = tid; i < c; i += kSelThreads) sel_keys[i] = src[i];
+    if (tid == 0) { s_prefix = 0; s_remaining = N; s_out = 0; }
+    __syncthreads();
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        if (tid < 256) hist[tid] = 0;
+        __syncthreads();
+        const unsigned long long prefix = s_prefix;
+        const unsigned long long himask = shift == 56 ? 0ull : (~0ull << (shift + 8));
+        for (uint32_t i0 = 0; i0 < c; i0 += kSelThreads) {
+            const uint32_t i = i0 + tid;
+            unsigned long long k = 0;
+            bool act = i < c;
+            if (act) { k = sel_keys[i]; act = (k & himask) == prefix; }
+            const unsigned m = __ballot_sync(FULL, act);
+            if (act) {
+                const uint32_t d = (uint32_t)(k >> shift) & 255u;
+                const unsigned peers = __match_any_sync(m, d);
+                if ((peers & ((1u << lane) - 1u)) == 0) atomicAdd(&hist[d], (uint32_t)__popc(peers));
+            }
+        }
+        __syncthreads();
+        if (tid < 32) {
+            uint32_t loc[8], sum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { loc[j] = hist[tid * 8 + j]; sum += loc[j]; }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += y; }
+            const uint32_t excl = incl - sum;
+            const uint32_t rem = s_remaining;
+            __syncwarp();
+            if (excl < rem && rem <= incl) {
+                uint32_t r = rem - excl;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (r <= loc[j]) { s_prefix = prefix | ((unsigned long long)(tid * 8 + j) << shift); s_remaining = r; break; }
+                    r -= loc[j];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const unsigned long long kth = s_prefix;
+    for (uint32_t i0 = 0; i0 < c; i0 += kSelThreads) {
+        const uint32_t i = i0 + tid;
+        unsigned long long k = 0;
+        bool keep = false;
+        if (i < c) { k = sel_keys[i]; keep = k <= kth; }
+        const unsigned m = __ballot_sync(FULL, keep);
+        uint32_t base = 0;
+        if (lane == 0 && m) base = atomicAdd(&s_out, (uint32_t)__popc(m));
+        base = __shfl_sync(FULL, base, 0);
+        if (keep) src[base + __popc(m & ((1u << lane) - 1u))] = k;
+    }
+    if (tid == 0) { count[q] = N; thr[q] = kth; }
 }
 
 // one CTA per compacted query: copy the best min(count, N) keys back from the sort output, set count and cut-off
@@ -593,17 +678,27 @@ int segmented_sort(s4g_ctx* ctx, const unsigned long long* keys_in, unsigned lon
 }  // namespace
 
 // Compact (sort + keep best N) the listed queries.  `all` = every non-empty query (final pass).
+// `select` = the order inside the buffers does not matter afterwards (intermediate compactions, and the final one
+// when the output is re-sorted by id): buffers that fit in shared memory are reduced by cb_topn_kernel.
 static int compact(s4g_ctx* ctx, int nq, uint32_t cap, uint32_t N, uint32_t limit, int all, unsigned long long* d_cand,
                    unsigned long long* d_cand_alt, uint32_t* d_count, unsigned long long* d_thr, int64_t* d_seg, uint32_t* d_seg_q,
-                   unsigned long long* d_nseg, bool* did) {
+                   unsigned long long* d_nseg, bool* did, bool select = false) {
     cudaStream_t st = ctx->stream;
-    S4G_CUDA(ctx, cudaMemsetAsync(d_nseg, 0, 8, st));
-    cb_select_kernel<<<(nq + 255) / 256, 256, 0, st>>>(d_count, nq, cap, limit, all, d_seg, d_seg + nq, d_seg_q, d_nseg);
+    S4G_CUDA(ctx, cudaMemsetAsync(d_nseg, 0, 16, st));
+    cb_select_kernel<<<(nq + 255) / 256, 256, 0, st>>>(d_count, nq, cap, limit, all, d_seg, d_seg + nq, d_seg_q, d_nseg,
+                                                       select ? (uint32_t)kSelCap : 0u);
     S4G_CHECK_LAUNCH(ctx);
-    unsigned long long h_nseg = 0;
-    S4G_CUDA(ctx, cudaMemcpyAsync(&h_nseg, d_nseg, 8, cudaMemcpyDeviceToHost, st));
+    unsigned long long h_n[2] = {0, 0};
+    S4G_CUDA(ctx, cudaMemcpyAsync(h_n, d_nseg, 16, cudaMemcpyDeviceToHost, st));
     S4G_CUDA(ctx, cudaStreamSynchronize(st));
-    if (did) *did = h_nseg > 0;
+    const unsigned long long h_nseg = h_n[0];
+    if (did) *did = h_nseg + h_n[1] > 0;
+    if (h_n[1] > 0) {
+        const size_t smem = sizeof(unsigned long long) * kSelCap;
+        S4G_CUDA(ctx, cudaFuncSetAttribute(cb_topn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cb_topn_kernel<<<(unsigned)h_n[1], kSelThreads, smem, st>>>(d_cand, d_count, d_thr, cap, N, d_seg_q + nq - 1);
+        S4G_CHECK_LAUNCH(ctx);
+    }
     if (h_nseg == 0) return S4G_OK;
     int rc = segmented_sort(ctx, d_cand, d_cand_alt, (int64_t)nq * cap, (int)h_nseg, d_seg, d_seg + nq);
     if (rc != S4G_OK) return rc;
@@ -817,7 +912,7 @@ int s4g_prefilter_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int ma
         // compact buffers that could overflow in the next chunk
         const bool last = P.seq_end >= db->n;
         if (!last) {
-            int rc = compact(ctx, nq, cap, N, N + slack, 0, d_cand, d_cand_alt, d_count, d_thr, d_seg, d_seg_q, d_nseg, nullptr);
+            int rc = compact(ctx, nq, cap, N, N + slack, 0, d_cand, d_cand_alt, d_count, d_thr, d_seg, d_seg_q, d_nseg, nullptr, true);
             if (rc != S4G_OK) return rc;
         }
         s4g_trace_mark(ctx, "compact");
@@ -834,7 +929,7 @@ int s4g_prefilter_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int ma
     }
     // ---- final top-N, output ----
     {
-        int rc = compact(ctx, nq, cap, N, 0, 1, d_cand, d_cand_alt, d_count, d_thr, d_seg, d_seg_q, d_nseg, nullptr);
+        int rc = compact(ctx, nq, cap, N, 0, 1, d_cand, d_cand_alt, d_count, d_thr, d_seg, d_seg_q, d_nseg, nullptr, sorted_by_id != 0);
         if (rc != S4G_OK) return rc;
     }
     if (!sorted_by_id) {
