@@ -4,7 +4,10 @@
 A step = one pass of the whole hot path (k-mer prefilter -> Smith-Waterman scores -> E-value selection ->
 traceback of kept hits) over one batch of synthetic queries against a synthetic, HBM-resident database of
 BASELINE.json configs[1]'s shape: 1,000 queries (len 100-1,000) vs 10 M sequences / ~3.5 B residues.
-At N GPUs the SAME workload is sharded (one resident database shard per rank): "scaling": "strong".
+At N GPUs the database is sharded (one resident shard per rank) and the query batch grows with N (1,000 x N queries per
+step): every GPU then scans 1/N of the database for N times the queries and scores/aligns 1/N of every candidate list,
+i.e. per-GPU work is fixed -- "scaling": "weak" (towards configs[2]'s 20,000-query batch).  --scaling strong keeps the
+1,000-query batch and only shards the database.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
@@ -229,7 +232,7 @@ def reference_arm(args):
     gcups = cells * len(times) / tot / 1e9
     sample = "%d queries (len 100-1000) x %d-sequence database (same generator as the GPU arm), max_candidates 5000, %d threads; whole reference path (searchDatabase + alignDatabase) per step" % (args.ref_queries, args.ref_db_seqs, cores)
     line = {"impl": "reference", "metric": "sw_gcups", "value": round(gcups, 4), "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(tot / len(times) * 1e3, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int8/int16/int32 SIMD (swimd AVX2)",
+            "ms_per_step": round(tot / len(times) * 1e3, 3), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "int8/int16/int32 SIMD (swimd AVX2)",
             "data": "synthetic", "config": {"workload": "configs[1] bounded sample: " + sample},
             "queries_per_sec": round(args.ref_queries * len(times) / tot, 4),
             "stages_s": {"search": round(sum(s for s, _ in times) / len(times), 4), "align": round(sum(a for _, a in times) / len(times), 4)},
@@ -261,7 +264,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--queries", type=int, default=1000)
+    ap.add_argument("--queries", type=int, default=1000, help="queries per step and GPU (weak) / per step (strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--db-seqs", type=int, default=10_000_000)
     ap.add_argument("--max-candidates", type=int, default=5000)
     ap.add_argument("--ref-queries", type=int, default=16)
@@ -291,7 +295,8 @@ def main():
     ctx = capi.Context(local)
     mat = np.array(BLOSUM62_A_TO_Z, dtype=np.int32)
 
-    q_codes, q_off = make_queries(args.queries)
+    n_queries = args.queries * world if args.scaling == "weak" else args.queries
+    q_codes, q_off = make_queries(n_queries)
     n_db = args.db_seqs
     lo, hi = n_db * rank // world, n_db * (rank + 1) // world
     t0 = time.time()
@@ -347,7 +352,7 @@ def main():
     # e2e through the host-buffer API
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(torch, ctx, db, pipe, q_codes, q_off, mat, lens, total_res, args, use_dist, dist, dev)
+        e2e = run_e2e(torch, ctx, db, pipe, q_codes, q_off, mat, lens, total_res, args, use_dist, dist, dev, n_queries)
 
     base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -357,21 +362,22 @@ def main():
         kern_gcups = cells_local / (sw_kernel_ms * 1e-3) / 1e9 if sw_kernel_ms > 0 else None
         line = {
             "metric": "sw_gcups", "value": round(gcups, 2), "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "s16x2 (DPX), s32 re-run on overflow",
+            "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "s16x2 (DPX), s32 re-run on overflow",
             "data": "synthetic",
             "config": {"workload": "configs[1]: %d queries (len 100-1000) vs %d-sequence / %.2f B-residue synthetic database, whole hot path per step (prefilter k=5, top %d; SW BLOSUM62 10/1; E<=1e-4, top 400; traceback)" % (
-                args.queries, n_db, total_res / 1e9, args.max_candidates),
-                "sharding": "database split in %d contiguous shards, one resident per GPU" % world,
+                n_queries, n_db, total_res / 1e9, args.max_candidates),
+                "sharding": "database split in %d contiguous shards, one resident per GPU; %d queries per step (%s scaling: %s)" % (
+                    world, n_queries, args.scaling, "1000 queries per GPU and step" if args.scaling == "weak" else "same batch at every N"),
                 "l2": "inputs (%.2f GB database shard per GPU) exceed the 126 MB L2; no explicit flush" % ((hi - lo) / n_db * total_res / 1e9),
                 "db_generation_s": round(gen_s, 2)},
-            "queries_per_sec": round(args.queries / (ms_per_step * 1e-3), 2),
+            "queries_per_sec": round(n_queries / (ms_per_step * 1e-3), 2),
             "sw_cells_per_step": cells, "pairs_per_step": pairs, "kept_hits_per_step": hits,
             "stages_ms": split,
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
             "roofline": {"bound": "int_dpx", "kernel": "sw_score_packed_kernel", "achieved": round(kern_gcups, 2) if kern_gcups else None, "peak": round(roof_gcups, 2),
                          "unit": "GCUPS", "frac": round(kern_gcups / roof_gcups, 4) if kern_gcups else None,
-                         "traffic": NCU_TRAFFIC_C2 if (world == 1 and args.queries == 1000 and n_db == 10_000_000 and args.max_candidates == 5000) else None,
+                         "traffic": NCU_TRAFFIC_C2 if (world == 1 and n_queries == 1000 and n_db == 10_000_000 and args.max_candidates == 5000) else None,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this command (profiles/r01i_sw_digest.md)",
                          "kernel_ms": round(sw_kernel_ms, 3),
                          "peak_source": "measured live on this GPU (no DPX figure in MEASURED_PEAKS.json): %.4e VIADDMNMX.S16x2 lane-ops/s sustained over 300 ms x 2 cells per op / 6 instructions per cell (BASELINE.md)" % peak},
@@ -428,7 +434,7 @@ def stage_split(torch, ctx, pipe):
     return out
 
 
-def run_e2e(torch, ctx, db, pipe, q_codes, q_off, mat, lens, total_res, args, use_dist, dist, dev):
+def run_e2e(torch, ctx, db, pipe, q_codes, q_off, mat, lens, total_res, args, use_dist, dist, dev, n_queries):
     """Same step through the public pipeline API with HOST buffers: the query batch is uploaded every step and the
     candidate lists, survivor scores and alignments are copied back to the host inside the timed region."""
     pipe.step(e2e=True)
@@ -449,7 +455,7 @@ def run_e2e(torch, ctx, db, pipe, q_codes, q_off, mat, lens, total_res, args, us
         ts = t.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
         dt, cells, h2d, d2h = float(tm[0]), float(ts[1]), float(ts[2]), float(ts[3])
     return {"value": round(cells / dt / 1e9, 2), "unit": "GCUPS", "ms_per_step": round(dt * 1e3, 3), "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "queries_per_sec": round(args.queries / dt, 2),
+            "queries_per_sec": round(n_queries / dt, 2),
             "timed": "host wall clock around pipeline.DevicePipeline.step(e2e=True): queries H2D, candidate lists + survivor scores + alignments D2H every step; max over ranks"}
 
 

@@ -104,6 +104,21 @@ int s4g_merge_candidates(s4g_ctx* ctx, int n_ranks, int n_queries, int max_candi
                          const uint32_t* gathered_counts, uint32_t* out_ids, float* out_scores,
                          uint32_t* out_counts);
 
+/* Multi-GPU, query-owner protocol (what the pipeline uses; no row is copied or re-sorted).  The merge of
+ * per-thread lists in searchDatabase() (sift4g/src/database_search.cpp:132-154) keeps, per query, the rows up
+ * to the max_candidates-th best (score desc, id asc) key of the union -- so the shards only have to agree on
+ * that key.  After an all-to-all every rank holds the best-first rows of all n_ranks shards for the
+ * n_queries queries it owns (same layout as for s4g_merge_candidates); s4g_topn_cutoff writes their cut-off
+ * keys ((~score bits) << 32 | id; all ones when the union has at most max_candidates rows).  After an
+ * all-gather of the cut-offs, s4g_cutoff_counts tells a shard how long the prefix of each of its own
+ * best-first rows is that survives (out_counts[q] <= counts[q]).  Device pointers only, n_ranks <= 32. */
+int s4g_topn_cutoff(s4g_ctx* ctx, int n_ranks, int n_queries, int max_candidates,
+                    const uint32_t* gathered_ids, const float* gathered_scores,
+                    const uint32_t* gathered_counts, uint64_t* out_cutoff);
+int s4g_cutoff_counts(s4g_ctx* ctx, int n_queries, int max_candidates, const uint32_t* ids,
+                      const float* scores, const uint32_t* counts, const uint64_t* cutoff,
+                      uint32_t* out_counts);
+
 /* ---- stage 2: Smith-Waterman affine-gap scores ------------------------------------------------ */
 /* cand_ids: concatenated per-query candidate ids (global ids inside this shard's range),
  * cand_offsets[n_queries+1].  matrix: 26x26 int32 row-major (sw/scorer.c:206-208).

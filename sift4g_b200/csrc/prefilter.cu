@@ -980,3 +980,83 @@ extern "C" int s4g_merge_candidates(s4g_ctx* ctx, int n_ranks, int n_queries, in
     S4G_CHECK_LAUNCH(ctx);
     return S4G_OK;
 }
+
+// ---- multi-GPU, query-owner protocol ------------------------------------------------------------------------
+// Every rank owns a slice of the queries.  After an all-to-all the owner holds, for each of its queries, the
+// best-first rows of all shards; it only has to find the global cut-off key (the max_candidates-th smallest
+// (score desc, id asc) key of the union) -- database_search.cpp:132-154 keeps exactly the rows up to it.  Rows stay
+// where they are: each shard then keeps the prefix of its own row that lies within the cut-off.
+namespace {
+
+__device__ __forceinline__ uint32_t rows_upper_bound(const uint32_t* ids, const float* sc, uint32_t a, uint32_t b, unsigned long long key) {
+    while (a < b) {
+        const uint32_t m = (a + b) >> 1;
+        if (cand_key(sc[m], ids[m]) <= key) a = m + 1; else b = m;
+    }
+    return a;
+}
+
+// one warp per query, lane r walks shard r's row.  Bisection on the key value; every lane keeps the window of its
+// row that can still contain the boundary, so the searches shrink with the key range.
+__global__ void __launch_bounds__(kWarps * 32) mg_cutoff_kernel(int n_ranks, int nq, uint32_t N, const uint32_t* ids, const float* scores,
+                                                                const uint32_t* counts, unsigned long long* cutoff) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const unsigned FULL = 0xffffffffu;
+    uint32_t c = 0;
+    const uint32_t* my_ids = ids;
+    const float* my_sc = scores;
+    if (lane < n_ranks) {
+        c = counts[(size_t)lane * nq + q];
+        if (c > N) c = N;
+        my_ids = ids + ((size_t)lane * nq + q) * N;
+        my_sc = scores + ((size_t)lane * nq + q) * N;
+    }
+    if (__reduce_add_sync(FULL, c) <= N) {                 // nothing to drop
+        if (lane == 0) cutoff[q] = ~0ull;
+        return;
+    }
+    unsigned long long lo = 0, hi = ~0ull;
+    uint32_t a = 0, b = c;
+    while (lo < hi) {
+        const unsigned long long mid = lo + ((hi - lo) >> 1);
+        const uint32_t p = rows_upper_bound(my_ids, my_sc, a, b, mid);
+        if (__reduce_add_sync(FULL, p) >= N) { hi = mid; b = p; } else { lo = mid + 1; a = p; }
+    }
+    if (lane == 0) cutoff[q] = lo;
+}
+
+__global__ void mg_within_kernel(int nq, uint32_t N, const uint32_t* ids, const float* scores, const uint32_t* counts,
+                                 const unsigned long long* cutoff, uint32_t* out_counts) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    uint32_t c = counts[q];
+    if (c > N) c = N;
+    out_counts[q] = rows_upper_bound(ids + (size_t)q * N, scores + (size_t)q * N, 0, c, cutoff[q]);
+}
+
+}  // namespace
+
+extern "C" int s4g_topn_cutoff(s4g_ctx* ctx, int n_ranks, int n_queries, int max_candidates, const uint32_t* gathered_ids,
+                               const float* gathered_scores, const uint32_t* gathered_counts, uint64_t* out_cutoff) {
+    if (!ctx || n_ranks < 1 || n_ranks > 32 || n_queries < 0 || max_candidates < 1 || !gathered_ids || !gathered_scores || !gathered_counts || !out_cutoff)
+        return S4G_ERR_ARG;
+    if (n_queries == 0) return S4G_OK;
+    S4G_CUDA(ctx, cudaSetDevice(ctx->device));
+    mg_cutoff_kernel<<<(n_queries + kWarps - 1) / kWarps, kWarps * 32, 0, ctx->stream>>>(
+        n_ranks, n_queries, (uint32_t)max_candidates, gathered_ids, gathered_scores, gathered_counts, (unsigned long long*)out_cutoff);
+    S4G_CHECK_LAUNCH(ctx);
+    return S4G_OK;
+}
+
+extern "C" int s4g_cutoff_counts(s4g_ctx* ctx, int n_queries, int max_candidates, const uint32_t* ids, const float* scores,
+                                 const uint32_t* counts, const uint64_t* cutoff, uint32_t* out_counts) {
+    if (!ctx || n_queries < 0 || max_candidates < 1 || !ids || !scores || !counts || !cutoff || !out_counts) return S4G_ERR_ARG;
+    if (n_queries == 0) return S4G_OK;
+    S4G_CUDA(ctx, cudaSetDevice(ctx->device));
+    mg_within_kernel<<<(n_queries + 127) / 128, 128, 0, ctx->stream>>>(n_queries, (uint32_t)max_candidates, ids, scores, counts,
+                                                                      (const unsigned long long*)cutoff, out_counts);
+    S4G_CHECK_LAUNCH(ctx);
+    return S4G_OK;
+}

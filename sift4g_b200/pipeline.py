@@ -104,16 +104,20 @@ class DevicePipeline:
         self.total_residues = int(total_residues)   # whole database (E-value length)
         self.Q = ctx.queries(q_codes, q_off)
         nq, N = self.nq, self.N
-        self.t_ids = torch.zeros((nq, N), dtype=torch.int32, device=self.dev)
-        self.t_sc = torch.zeros((nq, N), dtype=torch.float32, device=self.dev)
-        self.t_cnt = torch.zeros(nq, dtype=torch.int32, device=self.dev)
+        # multi-GPU: rank r owns the queries [r * S, (r + 1) * S) for the cut-off exchange (rows padded to W * S)
+        self.slice = (nq + self.world - 1) // self.world
+        rows = self.slice * self.world
+        self.t_ids = torch.zeros((rows, N), dtype=torch.int32, device=self.dev)
+        self.t_sc = torch.zeros((rows, N), dtype=torch.float32, device=self.dev)
+        self.t_cnt = torch.zeros(rows, dtype=torch.int32, device=self.dev)
         if self.world > 1:
-            self.g_ids = torch.zeros((self.world, nq, N), dtype=torch.int32, device=self.dev)
-            self.g_sc = torch.zeros((self.world, nq, N), dtype=torch.float32, device=self.dev)
-            self.g_cnt = torch.zeros((self.world, nq), dtype=torch.int32, device=self.dev)
-            self.m_ids = torch.zeros((nq, N), dtype=torch.int32, device=self.dev)
-            self.m_sc = torch.zeros((nq, N), dtype=torch.float32, device=self.dev)
-            self.m_cnt = torch.zeros(nq, dtype=torch.int32, device=self.dev)
+            self.g_ids = torch.zeros((self.world, self.slice, N), dtype=torch.int32, device=self.dev)
+            self.g_sc = torch.zeros((self.world, self.slice, N), dtype=torch.float32, device=self.dev)
+            self.g_cnt = torch.zeros((self.world, self.slice), dtype=torch.int32, device=self.dev)
+            self.cut_own = torch.zeros(self.slice, dtype=torch.int64, device=self.dev)
+            self.cut_all = torch.zeros(rows, dtype=torch.int64, device=self.dev)
+            self.own_cnt = torch.zeros(nq, dtype=torch.int32, device=self.dev)
+        self.col = torch.arange(N, device=self.dev, dtype=torch.int32)[None, :]
         self.t_db_lens = torch.from_numpy(np.ascontiguousarray(db_lens, dtype=np.int64)).to(self.dev)
         self.t_q_lens = torch.from_numpy(self.q_lens.astype(np.int64)).to(self.dev)
         self.q_host = (q_codes, q_off)
@@ -151,24 +155,26 @@ class DevicePipeline:
             ids, cnt = self.t_ids, self.t_cnt
             mark("prefilter")
         else:
+            # best-first rows of this shard; the owners of the queries find the global cut-off keys, every shard keeps
+            # the prefix of its own rows inside the cut-off (no row leaves its GPU except for the owner's search)
+            W, S = self.world, self.slice
             capi.prefilter(ctx, db, self.Q, self.k, N, False, out=(self.t_ids, self.t_sc, self.t_cnt), where=capi.S4G_DEVICE)
             mark("prefilter")
-            self.dist.all_gather_into_tensor(self.g_ids.view(-1), self.t_ids.view(-1))
-            self.dist.all_gather_into_tensor(self.g_sc.view(-1), self.t_sc.view(-1))
-            self.dist.all_gather_into_tensor(self.g_cnt.view(-1), self.t_cnt)
-            mark("gather_candidates")
-            ctx.check(ctx.lib.s4g_merge_candidates(ctx.h, self.world, nq, N, self.g_ids.data_ptr(), self.g_sc.data_ptr(), self.g_cnt.data_ptr(),
-                                                   self.m_ids.data_ptr(), self.m_sc.data_ptr(), self.m_cnt.data_ptr()))
-            ids, cnt = self.m_ids, self.m_cnt
-            mark("merge_candidates")
-        # candidates owned by this rank (ids are uint32 bit patterns in int32 tensors)
-        col = torch.arange(N, device=self.dev, dtype=torch.int32)[None, :]
-        ids64 = ids.to(torch.int64) & 0xffffffff
-        own = (col < cnt[:, None]) & (ids64 >= lo) & (ids64 < hi)
+            self.dist.all_to_all_single(self.g_ids.view(-1), self.t_ids.view(-1))
+            self.dist.all_to_all_single(self.g_sc.view(-1), self.t_sc.view(-1))
+            self.dist.all_to_all_single(self.g_cnt.view(-1), self.t_cnt)
+            mark("exchange_rows")
+            ctx.check(ctx.lib.s4g_topn_cutoff(ctx.h, W, S, N, self.g_ids.data_ptr(), self.g_sc.data_ptr(), self.g_cnt.data_ptr(), self.cut_own.data_ptr()))
+            self.dist.all_gather_into_tensor(self.cut_all, self.cut_own)
+            ctx.check(ctx.lib.s4g_cutoff_counts(ctx.h, nq, N, self.t_ids.data_ptr(), self.t_sc.data_ptr(), self.t_cnt.data_ptr(), self.cut_all.data_ptr(),
+                                                self.own_cnt.data_ptr()))
+            ids, cnt = self.t_ids[:nq], self.own_cnt
+            mark("cutoff")
+        # this rank's candidates (ids are uint32 bit patterns in int32 tensors)
+        own = self.col < cnt[:, None]
         cand_ids = ids[own].contiguous()
-        cand_cnt = own.sum(dim=1)
         cand_off = torch.zeros(nq + 1, dtype=torch.int64, device=self.dev)
-        cand_off[1:] = torch.cumsum(cand_cnt, 0)
+        cand_off[1:] = torch.cumsum(cnt, 0)
         n_pairs = int(cand_ids.numel())
         scores = torch.empty(max(n_pairs, 1), dtype=torch.int32, device=self.dev)
         mark("own_candidates")
@@ -229,8 +235,9 @@ class DevicePipeline:
             print("[s4g trace] step: " + " ".join(marks), file=sys.stderr)
         if e2e:
             # results to the host through grow-only pinned buffers: async copies on the stream, one synchronise
-            host = [self._to_host("ids", ids), self._to_host("cnt", cnt)]
-            r.d2h_bytes = ids.numel() * 4 + cnt.numel() * 4 + n_s * 16 + 4
+            out_ids = ids if self.world == 1 else cand_ids          # sharded: this rank's share of every candidate list
+            host = [self._to_host("ids", out_ids), self._to_host("cnt", cnt)]
+            r.d2h_bytes = out_ids.numel() * 4 + cnt.numel() * 4 + n_s * 16 + 4
             r.h2d_bytes += 3 * 4 * len(pq)
             if r.coords is not None:
                 host += [self._to_host("coords", r.coords), self._to_host("poff", r.path_off)]
@@ -262,36 +269,47 @@ class DevicePipeline:
 
 
 def merge_hits(torch, dist, dev, nq, M, pq, pt, ps, ev, hoff, lo, hi, ctx=None):
-    """Global top M hits per query over all ranks under (E asc, score desc, id asc); every rank keeps the hits
-    whose targets it owns ([lo, hi)), so the traceback needs no further exchange.  Two small all-gathers (per-query
-    counts, then the {E, score, id} rows padded to the largest rank), then s4g_merge_hits (threaded C++) everywhere."""
+    """Global top M hits per query over all ranks under (E asc, score desc, id asc) -- dbAlignmentsMerge's order and
+    truncation (sw/post_proc.c:299-339,432-456); every rank keeps the hits whose targets it owns ([lo, hi)), so the
+    traceback needs no further exchange.  One small all-gather of the per-query counts tells every rank which queries
+    have more than M hits over all shards; only their {E, score, id} rows are exchanged (a second all-gather, padded to
+    the largest rank) and cut by s4g_merge_hits.  Queries with at most M hits in total keep their local lists as is."""
     W = dist.get_world_size()
     cuda = dev.type == "cuda"
-    cnt = torch.from_numpy(np.diff(hoff).astype(np.int64))
-    rows = np.empty((len(pq), 3), dtype=np.float64)
-    rows[:, 0] = ev; rows[:, 1] = ps; rows[:, 2] = pt
-    if cuda:
-        cnt = cnt.to(dev)
-        all_cnt = torch.empty((W, nq), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(all_cnt.view(-1), cnt)
-        all_cnt = all_cnt.cpu()
-    else:
-        parts = [torch.empty_like(cnt) for _ in range(W)]
-        dist.all_gather(parts, cnt)
-        all_cnt = torch.stack(parts)
-    stride = max(int(all_cnt.sum(dim=1).max()), 1)
-    loc = torch.zeros((stride, 3), dtype=torch.float64)
-    loc[:len(pq)] = torch.from_numpy(rows)
-    if cuda:
-        loc = loc.to(dev)
-        allh = torch.empty((W, stride, 3), dtype=torch.float64, device=dev)
-        dist.all_gather_into_tensor(allh.view(-1), loc.view(-1))
-        allh = allh.cpu()
-    else:
-        parts = [torch.empty_like(loc) for _ in range(W)]
-        dist.all_gather(parts, loc)
-        allh = torch.stack(parts)
-    return capi.merge_hits(ctx, allh.numpy(), all_cnt.numpy(), nq, M, lo, hi)
+
+    def gather(t):
+        if cuda:
+            out = torch.empty((W,) + tuple(t.shape), dtype=t.dtype, device=dev)
+            dist.all_gather_into_tensor(out.view(-1), t.to(dev).view(-1))
+            return out.cpu().numpy()
+        parts = [torch.empty_like(t) for _ in range(W)]
+        dist.all_gather(parts, t)
+        return torch.stack(parts).numpy()
+
+    cnt = np.diff(hoff).astype(np.int64)
+    all_cnt = gather(torch.from_numpy(cnt))                                   # [W, nq]
+    over = np.nonzero(all_cnt.sum(axis=0) > M)[0]
+    if len(over) == 0:
+        return pq, pt, ps, ev, hoff
+    is_over = np.zeros(nq, dtype=bool)
+    is_over[over] = True
+    mine = is_over[pq]
+    sub_cnt = np.ascontiguousarray(all_cnt[:, over])                          # [W, n_over]
+    stride = max(int(sub_cnt.sum(axis=1).max()), 1)
+    loc = np.zeros((stride, 3), dtype=np.float64)
+    n_mine = int(mine.sum())
+    loc[:n_mine, 0] = ev[mine]; loc[:n_mine, 1] = ps[mine]; loc[:n_mine, 2] = pt[mine]
+    allh = gather(torch.from_numpy(loc))                                      # [W, stride, 3]
+    oq, ot, osc, oev, _ = capi.merge_hits(ctx, allh, sub_cnt, len(over), M, lo, hi)
+    keep = ~mine
+    nq_ = np.concatenate([pq[keep], over[oq].astype(np.uint32)])
+    order = np.argsort(nq_, kind="stable")
+    pq2 = nq_[order]
+    pt2 = np.concatenate([pt[keep], ot])[order]
+    ps2 = np.concatenate([ps[keep], osc])[order]
+    ev2 = np.concatenate([ev[keep], oev])[order]
+    hoff2 = np.searchsorted(pq2, np.arange(nq + 1), side="left").astype(np.int64)
+    return pq2, pt2, ps2, ev2, hoff2
 
 
 def merge_hits_numpy(allh, counts, nq, M, lo, hi):

@@ -69,6 +69,58 @@ def test_sharded_prefilter_merge_equals_single_shard(ctx):
     Q.close()
 
 
+def test_query_owner_cutoff_protocol_equals_single_shard(ctx):
+    """Multi-GPU stage-1 exchange on one device: rows of 3 shards -> (simulated all-to-all) -> s4g_topn_cutoff per owner ->
+    (simulated all-gather) -> s4g_cutoff_counts per shard; the union of the surviving prefixes is the single-shard set."""
+    import torch
+    queries, db = synth.make_dataset(43, 7, 5000, q_len=(50, 400), homologs=(5, 20))
+    qc, qo = synth.pack(queries); dc, do = synth.pack(db)
+    nq, W = len(queries), 3
+    S = (nq + W - 1) // W
+    rows = S * W
+    dev = torch.device("cuda:0")
+    Q = ctx.queries(qc, qo)
+    for N in (40, 200, 6000):                              # heavy cut-off ties / typical / union smaller than N
+        D = ctx.database(dc, do)
+        ids1, sc1, cnt1 = capi.prefilter(ctx, D, Q, 5, N, sorted_by_id=True)
+        D.close()
+        bounds = [0, 1700, 3100, 5000]
+        loc = []
+        for r in range(W):
+            lo, hi = bounds[r], bounds[r + 1]
+            Dr = ctx.database(dc[do[lo]:do[hi]], do[lo:hi + 1] - do[lo], id_base=lo)
+            t_ids = torch.zeros((rows, N), dtype=torch.int32, device=dev)
+            t_sc = torch.zeros((rows, N), dtype=torch.float32, device=dev)
+            t_cnt = torch.zeros(rows, dtype=torch.int32, device=dev)
+            capi.prefilter(ctx, Dr, Q, 5, N, False, out=(t_ids, t_sc, t_cnt), where=capi.S4G_DEVICE)
+            ctx.sync()
+            loc.append((t_ids, t_sc, t_cnt))
+            Dr.close()
+        cut_all = torch.zeros(rows, dtype=torch.int64, device=dev)
+        for owner in range(W):                             # what all_to_all_single delivers to `owner`
+            g_ids = torch.stack([loc[r][0][owner * S:(owner + 1) * S] for r in range(W)]).contiguous()
+            g_sc = torch.stack([loc[r][1][owner * S:(owner + 1) * S] for r in range(W)]).contiguous()
+            g_cnt = torch.stack([loc[r][2][owner * S:(owner + 1) * S] for r in range(W)]).contiguous()
+            cut = torch.zeros(S, dtype=torch.int64, device=dev)
+            ctx.check(ctx.lib.s4g_topn_cutoff(ctx.h, W, S, N, g_ids.data_ptr(), g_sc.data_ptr(), g_cnt.data_ptr(), cut.data_ptr()))
+            ctx.sync()
+            cut_all[owner * S:(owner + 1) * S] = cut
+        got = [[] for _ in range(nq)]
+        for r in range(W):
+            t_ids, t_sc, t_cnt = loc[r]
+            own = torch.zeros(nq, dtype=torch.int32, device=dev)
+            ctx.check(ctx.lib.s4g_cutoff_counts(ctx.h, nq, N, t_ids.data_ptr(), t_sc.data_ptr(), t_cnt.data_ptr(), cut_all.data_ptr(), own.data_ptr()))
+            ctx.sync()
+            own = own.cpu().numpy(); h_ids = t_ids.cpu().numpy().view(np.uint32)
+            assert (own <= t_cnt[:nq].cpu().numpy()).all()
+            for q in range(nq):
+                got[q].append(h_ids[q, :own[q]])
+        for q in range(nq):
+            g = np.sort(np.concatenate(got[q]))
+            assert np.array_equal(g, ids1[q, :cnt1[q]]), "query %d, N %d" % (q, N)
+    Q.close()
+
+
 def test_fasta_reader_quirks(ctx, tmp_path):
     # sw/pre_proc.c:437-538: names trimmed, non-letters dropped, case folded, last byte of a file without trailing
     # newline is consumed as terminator
