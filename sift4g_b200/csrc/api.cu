@@ -264,6 +264,7 @@ void s4g_db_close(s4g_db* db) {
     cudaStreamSynchronize(db->ctx->stream);
     if (db->d_codes) cudaFree(db->d_codes);
     if (db->d_off) cudaFree(db->d_off);
+    if (db->d_order) cudaFree(db->d_order);
     delete db;
 }
 

@@ -39,6 +39,7 @@ struct s4g_db {
     s4g_ctx* ctx = nullptr;
     uint8_t* d_codes = nullptr;     // concatenated codes, FASTA order, + S4G_DB_TAIL_PAD
     int64_t* d_off = nullptr;       // n+1
+    uint32_t* d_order = nullptr;    // local sequence indices by ascending length (built by the first prefilter call)
     int64_t n = 0;
     uint64_t residues = 0;
     uint32_t id_base = 0;

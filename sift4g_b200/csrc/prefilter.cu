@@ -19,6 +19,7 @@
 // candidate buffer; buffers are compacted (segmented sort, keep the best N, raise the cut-off) whenever
 // they could overflow during the next chunk of sequences.
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <cub/cub.cuh>
 
@@ -35,6 +36,7 @@ constexpr unsigned long long kNoThr = ~0ull;
 struct PfParams {
     const uint8_t* db_codes;
     const int64_t* db_off;
+    const uint32_t* order;            // scan order: local sequence indices by ascending length
     uint32_t id_base;
     int64_t seq_begin, seq_end;
     int k;
@@ -48,7 +50,7 @@ struct PfParams {
     unsigned long long* cand;
     uint32_t cap;
     unsigned long long* counters;     // [0] sequence cursor [1] deferred sequences [2] pool cursor [3] error flags
-    uint32_t* def_seq;                // deferred: local sequence index
+    uint32_t* def_seq;                // deferred: local sequence index (in the shard, not in the scan order)
     unsigned long long* def_off;      // deferred: offset into the pool
     uint32_t max_deferred;
     unsigned long long* pool_keys;    // (slot << 48 | q << 28 | order)
@@ -228,19 +230,24 @@ __global__ void __launch_bounds__(kMaxWarps * 32) pf_scan_kernel(PfParams P, int
         if (lane == 0) s0 = (long long)atomicAdd(P.counters + 0, (unsigned long long)kSeqBatch);
         s0 = __shfl_sync(FULL, s0, 0) + P.seq_begin;
         if (s0 >= P.seq_end) break;
-        // offsets of the batch (lanes 0..kSeqBatch), and an L2 prefetch of its residues (contiguous in memory)
-        long long my_off = 0;
-        if (lane <= kSeqBatch && s0 + lane <= P.seq_end) my_off = P.db_off[s0 + lane];
-        {
-            const long long b0 = __shfl_sync(FULL, my_off, 0);
-            const int nb = (int)min((long long)kSeqBatch, P.seq_end - s0);
-            const long long b1 = __shfl_sync(FULL, my_off, nb);
+        // the batch: positions s0 .. s0+kSeqBatch-1 of the scan order (lane bi holds sequence bi: index, begin, end), and an
+        // L2 prefetch of their residues
+        long long my_a = 0, my_e = 0;
+        uint32_t my_idx = 0;
+        if (lane < kSeqBatch && s0 + lane < P.seq_end) {
+            my_idx = __ldg(P.order + s0 + lane);
+            my_a = P.db_off[my_idx];
+            my_e = P.db_off[my_idx + 1];
+        }
+#pragma unroll
+        for (int bi = 0; bi < kSeqBatch; ++bi) {
+            const long long b0 = __shfl_sync(FULL, my_a, bi), b1 = __shfl_sync(FULL, my_e, bi);
             for (long long a = b0 + 128ll * lane; a < b1; a += 128 * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.db_codes + a));
         }
         for (int bi = 0; bi < kSeqBatch && s0 + bi < P.seq_end; ++bi) {
-            const long long s = s0 + bi;
-            const int64_t a = __shfl_sync(FULL, my_off, bi);
-            const int len = (int)(__shfl_sync(FULL, my_off, bi + 1) - a);
+            const long long s = (long long)__shfl_sync(FULL, my_idx, bi);
+            const int64_t a = __shfl_sync(FULL, my_a, bi);
+            const int len = (int)(__shfl_sync(FULL, my_e, bi) - a);
             if (len < k) continue;
             const uint8_t* seq = P.db_codes + a;
             const int npos = len - k + 1;
@@ -331,7 +338,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) pf_scan_kernel(PfParams P, int
                 if (lane == 0) {
                     const unsigned long long slot = atomicAdd(P.counters + 1, 1ull);
                     const unsigned long long off = atomicAdd(P.counters + 2, (unsigned long long)T);
-                    if (slot < P.max_deferred && off + T <= P.pool_cap) { P.def_seq[slot] = (uint32_t)(s - P.seq_begin); P.def_off[slot] = off; }
+                    if (slot < P.max_deferred && off + T <= P.pool_cap) { P.def_seq[slot] = (uint32_t)s; P.def_off[slot] = off; }
                     else atomicOr(P.counters + 3, 2ull);
                 }
                 continue;
@@ -392,7 +399,7 @@ __global__ void __launch_bounds__(kWarps * 32) pf_fill_deferred_kernel(PfParams 
     const unsigned FULL = 0xffffffffu;
     const int k = P.k;
     for (uint32_t slot = blockIdx.x * kWarps + (threadIdx.x >> 5); slot < n_def; slot += gridDim.x * kWarps) {
-        const long long s = P.seq_begin + P.def_seq[slot];
+        const long long s = P.def_seq[slot];
         const int64_t a = P.db_off[s];
         const int len = (int)(P.db_off[s + 1] - a);
         const uint8_t* seq = P.db_codes + a;
@@ -442,7 +449,7 @@ __global__ void pf_lis_deferred_kernel(PfParams P, const unsigned long long* key
     }
     (void)e;
     const uint32_t slot = (uint32_t)(g >> 20), q = (uint32_t)(g & 0xfffffu);
-    const long long s = P.seq_begin + P.def_seq[slot];
+    const long long s = P.def_seq[slot];
     const int slen = (int)(P.db_off[s + 1] - P.db_off[s]);
     emit(P, q, len, slen, P.id_base + (uint32_t)s);
 }
@@ -505,11 +512,13 @@ __global__ void cb_init_kernel(unsigned long long* thr, uint32_t* count, int nq)
 // sel_cap > 0: buffers holding at most sel_cap keys go to a second list (n_seg[1], filled from the end of the arrays)
 // that cb_topn_kernel reduces by selection in shared memory; the rest is sorted.
 __global__ void cb_select_kernel(const uint32_t* count, int nq, uint32_t cap, uint32_t limit, int all, int64_t* seg_begin,
-                                 int64_t* seg_end, uint32_t* seg_q, unsigned long long* n_seg, uint32_t sel_cap) {
+                                 int64_t* seg_end, uint32_t* seg_q, unsigned long long* n_seg, uint32_t sel_cap,
+                                 const unsigned long long* thr, uint32_t N) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
     const uint32_t c = count[q] < cap ? count[q] : cap;
-    if ((all && c > 0) || c > limit) {
+    // a query without a cut-off gets its first one as soon as it holds more than N candidates
+    if ((all && c > 0) || c > limit || (thr && c > N && thr[q] == kNoThr)) {
         if (c <= sel_cap) {
             const unsigned long long s = atomicAdd(n_seg + 1, 1ull);
             seg_q[nq - 1 - s] = (uint32_t)q;
@@ -686,7 +695,7 @@ static int compact(s4g_ctx* ctx, int nq, uint32_t cap, uint32_t N, uint32_t limi
     cudaStream_t st = ctx->stream;
     S4G_CUDA(ctx, cudaMemsetAsync(d_nseg, 0, 16, st));
     cb_select_kernel<<<(nq + 255) / 256, 256, 0, st>>>(d_count, nq, cap, limit, all, d_seg, d_seg + nq, d_seg_q, d_nseg,
-                                                       select ? (uint32_t)kSelCap : 0u);
+                                                       select ? (uint32_t)kSelCap : 0u, (select && !all) ? d_thr : nullptr, N);
     S4G_CHECK_LAUNCH(ctx);
     unsigned long long h_n[2] = {0, 0};
     S4G_CUDA(ctx, cudaMemcpyAsync(h_n, d_nseg, 16, cudaMemcpyDeviceToHost, st));
@@ -707,6 +716,36 @@ static int compact(s4g_ctx* ctx, int nq, uint32_t cap, uint32_t N, uint32_t limi
     return S4G_OK;
 }
 
+namespace {
+__global__ void ord_keys_kernel(const int64_t* off, int64_t n, uint32_t* keys, uint32_t* vals) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { keys[i] = (uint32_t)(off[i + 1] - off[i]); vals[i] = (uint32_t)i; }
+}
+}  // namespace
+
+// Scan order of a shard: sequences by ascending length (stable).  score = LIS / len, so the short sequences hold the best
+// candidates of every query: scanning them first settles the cut-offs after a few percent of the residues, and the count
+// filter then removes nearly every hit of the long sequences.  Built once per database (it is resident).
+static int build_scan_order(s4g_ctx* ctx, s4g_db* db) {
+    if (db->d_order || db->n == 0) return S4G_OK;
+    const int64_t n = db->n;
+    S4G_CUDA(ctx, cudaMalloc(&db->d_order, sizeof(uint32_t) * (size_t)n));
+    uint32_t* tmp = (uint32_t*)s4g_scratch(ctx, SLOT_PF_TMP2, sizeof(uint32_t) * 3 * (size_t)n);
+    if (!tmp) return S4G_ERR_NOMEM;
+    uint32_t* keys = tmp, *keys2 = tmp + n, *vals = tmp + 2 * n;
+    ord_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(db->d_off, n, keys, vals);
+    S4G_CHECK_LAUNCH(ctx);
+    int bits = 1;
+    while (bits < 32 && (1ll << bits) <= (long long)db->max_len) ++bits;
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys, keys2, vals, db->d_order, n, 0, bits, ctx->stream);
+    void* d_tmp = s4g_scratch(ctx, SLOT_PF_CUB, bytes);
+    if (!d_tmp) return S4G_ERR_NOMEM;
+    S4G_CUDA(ctx, cub::DeviceRadixSort::SortPairs(d_tmp, bytes, keys, keys2, vals, db->d_order, n, 0, bits, ctx->stream));
+    ctx->launches += 3;
+    return S4G_OK;
+}
+
 int s4g_prefilter_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int max_candidates, int sorted_by_id,
                          uint32_t* d_ids, float* d_scores, uint32_t* d_counts) {
     cudaStream_t st = ctx->stream;
@@ -715,6 +754,10 @@ int s4g_prefilter_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int ma
     if (nq >= (1 << 20)) { s4g_set_error(ctx, "at most 2^20-1 queries per batch"); return S4G_ERR_ARG; }
     if (q->max_len >= (1 << 22)) { s4g_set_error(ctx, "query longer than 2^22"); return S4G_ERR_ARG; }
 
+    {
+        int rc = build_scan_order(ctx, db);
+        if (rc != S4G_OK) return rc;
+    }
     s4g_trace_start(ctx);
     // ---- index over all queries ----
     int64_t n_hits = 0;
@@ -823,7 +866,7 @@ int s4g_prefilter_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int ma
     S4G_CHECK_LAUNCH(ctx);
 
     PfParams P;
-    P.db_codes = db->d_codes; P.db_off = db->d_off; P.id_base = db->id_base;
+    P.db_codes = db->d_codes; P.db_off = db->d_off; P.order = db->d_order; P.id_base = db->id_base;
     P.k = k; P.mask = mask; P.bitrank = d_bitrank; P.bucket_start = d_bucket; P.hits = d_vals2; P.nq = nq;
     P.thr = d_thr; P.count = d_count; P.cand = d_cand; P.cap = cap; P.counters = d_counters;
     P.def_seq = d_def_seq; P.def_off = d_def_off; P.max_deferred = max_deferred;
@@ -867,13 +910,15 @@ int s4g_prefilter_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int ma
         S4G_CUDA(ctx, cudaMemcpyAsync(d_count_saved, d_count, sizeof(uint32_t) * nq, cudaMemcpyDeviceToDevice, st));
         // the pool is only allocated once a chunk needs it (first pass counts; see below)
         P.pool_keys = (unsigned long long*)ctx->slot_ptr[SLOT_PF_HITS];
+        const auto t_chunk = std::chrono::steady_clock::now();
         pf_scan_kernel<<<grid, scan_warps * 32, scan_smem, st>>>(P, scap, cslots, qthr_in_smem);
         S4G_CHECK_LAUNCH(ctx);
         unsigned long long h_c[4];
         S4G_CUDA(ctx, cudaMemcpyAsync(h_c, d_counters, 32, cudaMemcpyDeviceToHost, st));
         S4G_CUDA(ctx, cudaStreamSynchronize(st));
         s4g_trace_mark(ctx, "scan");
-        if (ctx->trace) fprintf(stderr, "[s4g trace] chunk [%lld,%lld): deferred %llu sequences, %llu hits\n", (long long)P.seq_begin, (long long)P.seq_end, h_c[1], h_c[2]);
+        if (ctx->trace) fprintf(stderr, "[s4g trace] chunk [%lld,%lld): scan %.3f ms, deferred %llu sequences, %llu hits\n", (long long)P.seq_begin, (long long)P.seq_end,
+                                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_chunk).count(), h_c[1], h_c[2]);
         if (h_c[3] & 1ull) { s4g_set_error(ctx, "prefilter: candidate buffer overflow (internal)"); return S4G_ERR_INTERNAL; }
         if (h_c[3] & 2ull) {
             if (P.seq_end - P.seq_begin <= 256) { s4g_set_error(ctx, "prefilter: more than %u deferred sequences or %llu deferred hits in a chunk of %lld sequences", max_deferred, pool_cap, (long long)(P.seq_end - P.seq_begin)); return S4G_ERR_CAPACITY; }
