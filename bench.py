@@ -155,21 +155,52 @@ def write_fasta(path, codes, off, prefix):
 # clocks
 
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region.  NVML is queried in-process (pynvml, ~50 us per
+    sample, no fork): spawning nvidia-smi from a process with a large address space stalled the timed steps by tens of
+    milliseconds.  nvidia-smi is only the fallback when pynvml is unusable."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index):
-        self.index, self.samples, self.stop, self.th = index, [], False, None
+    def __init__(self, index, period=0.05):
+        self.index, self.samples, self.stop, self.th, self.period = index, [], False, None, period
+        self.nvml = self.handle = None
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            idx = index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                ent = vis.split(",")[index].strip()
+                idx = int(ent) if ent.isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        mhz = int(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        r = int(get(self.handle))
+        bits = [0x8, 0x40, 0x20, 0x4]      # HwSlowdown, HwThermalSlowdown, SwThermalSlowdown, SwPowerCap (nvml.h)
+        return [str(mhz), str(self.max_mhz)] + ["Active" if r & b else "Not Active" for b in bits]
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        return [x.strip() for x in out.split(",")] if out else None
 
     def _run(self):
         while not self.stop:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                s = self._sample_nvml() if self.nvml else self._sample_smi()
+                if s:
+                    self.samples.append(s)
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(self.period if self.nvml else 0.5)
 
     def __enter__(self):
         self.th = threading.Thread(target=self._run, daemon=True)
@@ -182,12 +213,11 @@ class ClockSampler:
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML and nvidia-smi unavailable"]}
         sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        reasons = [n for i, n in enumerate(self.NAMES) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.samples)}
+                "reasons": reasons, "samples": len(self.samples), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -411,26 +441,24 @@ def hbm_peak():
         return 6650.0   # fallback stated in B200_PROFILING.md
 
 
-def stage_split(torch, ctx, pipe):
-    """Per-stage device+host time of one step (synchronised between stages; explains `value`)."""
-    from sift4g_b200 import capi
-    out = {}
-    torch.cuda.synchronize()
-    t0 = time.time()
-    capi.prefilter(ctx, pipe.db, pipe.Q, pipe.k, pipe.N, True, out=(pipe.t_ids, pipe.t_sc, pipe.t_cnt), where=capi.S4G_DEVICE)
-    torch.cuda.synchronize()
-    out["prefilter"] = round((time.time() - t0) * 1e3, 3)
-    t0 = time.time()
-    r = pipe.step(align=False)
-    torch.cuda.synchronize()
-    t_noalign = (time.time() - t0) * 1e3
-    t0 = time.time()
-    r = pipe.step(align=True)
-    torch.cuda.synchronize()
-    t_full = (time.time() - t0) * 1e3
-    out["score_kernel"] = round(ctx.last_sw_kernel_ms(), 3)
-    out["score_select_other"] = round(t_noalign - out["prefilter"] - out["score_kernel"], 3)
-    out["align"] = round(t_full - t_noalign, 3)
+def stage_split(torch, ctx, pipe, reps=3):
+    """Per-stage device+host time of a step (stream synchronised after every stage, median of `reps` untimed steps;
+    explains `value`).  score_kernel is the dominant kernel alone (CUDA events inside the library);
+    score_select_other = candidate gathering, sort of the pairs, re-runs, E-value screen, D2H of the survivors,
+    exact host selection and (N > 1) the hit merge."""
+    runs = []
+    for _ in range(reps):
+        st = {}
+        pipe.step(stages=st)
+        runs.append(st)
+    med = lambda k: sorted(r.get(k, 0.0) for r in runs)[len(runs) // 2]
+    pre = med("prefilter") + med("exchange_rows") + med("cutoff")
+    kern = med("sw_kernel")
+    other = med("own_candidates") + med("sw_score") - kern + med("screen_d2h") + med("select_hits") + med("merge_hits")
+    out = {"prefilter": round(pre, 3), "score_kernel": round(kern, 3), "score_select_other": round(other, 3), "align": round(med("align"), 3)}
+    if "exchange_rows" in runs[0]:
+        out["prefilter_scan_only"] = round(med("prefilter"), 3)
+        out["exchange"] = round(med("exchange_rows") + med("cutoff") + med("merge_hits"), 3)
     return out
 
 

@@ -17,6 +17,8 @@
  *                         alignScoredPairCpu()         sw/cpu_module.h:67-68
  *   s4g_db_* / s4g_queries_*  <- chainDatabaseGpuCreate/Delete()  sw/gpu_module.h:210-240
  *   s4g_db_open_fasta  <- readFastaChainsPart()       sw/pre_proc.h:76-81 (reader quirks kept)
+ *   s4g_db_pack_fasta / s4g_db_open_packed  <- dumpFastaChains()/readFastaChains() ".swsharp" cache
+ *                         sw/pre_proc.c:309-374,540-595 (record layout sw/chain.c:225-250)
  *
  * Pointer arguments marked [io] live on the host when `where == S4G_HOST` (the call copies in and
  * out and returns when results are on the host) or on the device of the context when
@@ -71,14 +73,30 @@ int s4g_db_create(s4g_ctx* ctx, const uint8_t* codes, const int64_t* offsets, in
 /* Parse a FASTA file like the reference reader (sw/pre_proc.c:437-538) and keep shard
  * `shard` of `n_shards` (contiguous ranges of FASTA order).  Names are kept on the host. */
 int s4g_db_open_fasta(s4g_ctx* ctx, const char* path, int shard, int n_shards, s4g_db** out);
+/* Packed on-disk database (".s4gdb"): what the FASTA reader produces (names, lengths, codes in FASTA order),
+ * written once so that later runs skip the parse -- the role of the reference's ".swsharp" cache
+ * (sw/pre_proc.c:309-374,540-595), in the layout the shard has in HBM.  Little endian:
+ *   64-byte header {char magic[8] = "S4GDB\0\0\1"; u64 n_seqs, n_residues, names_bytes, codes_pos; u64 reserved[3]}
+ *   i64 offsets[n_seqs+1] | i64 name_offsets[n_seqs+1] | names (NUL terminated) | zero pad | at codes_pos:
+ *   u8 codes[n_residues] (0..25).
+ * s4g_db_pack_fasta needs no GPU and no context (errors: s4g_last_error(NULL)); s4g_db_open_packed reads only the
+ * byte ranges of shard `shard` of `n_shards`; s4g_db_open picks the reader by the file's magic. */
+int s4g_db_pack_fasta(const char* fasta_path, const char* out_path);
+int s4g_db_file_info(const char* packed_path, int64_t* n_seqs, uint64_t* n_residues);
+int s4g_db_open_packed(s4g_ctx* ctx, const char* path, int shard, int n_shards, s4g_db** out);
+int s4g_db_open(s4g_ctx* ctx, const char* path, int shard, int n_shards, s4g_db** out);
 void s4g_db_close(s4g_db* db);
 int64_t s4g_db_num_seqs(const s4g_db* db);
 uint64_t s4g_db_num_residues(const s4g_db* db);   /* = `cells` returned by searchDatabase() */
 uint32_t s4g_db_id_base(const s4g_db* db);
+/* the whole file when the shard was opened from a file (the E-value's database length with n_shards > 1);
+ * equal to num_seqs / num_residues otherwise */
+int64_t s4g_db_total_seqs(const s4g_db* db);
+uint64_t s4g_db_total_residues(const s4g_db* db);
 /* host-side metadata (valid until s4g_db_close) */
 const int64_t* s4g_db_host_offsets(const s4g_db* db);
 const uint8_t* s4g_db_host_codes(const s4g_db* db);      /* NULL for device-created shards */
-const char* s4g_db_name(const s4g_db* db, int64_t local_index); /* NULL unless opened from FASTA */
+const char* s4g_db_name(const s4g_db* db, int64_t local_index); /* NULL unless opened from a file */
 
 /* ---- query batch -------------------------------------------------------------------------- */
 int s4g_queries_create(s4g_ctx* ctx, const uint8_t* codes, const int64_t* offsets, int32_t n_queries,

@@ -15,6 +15,8 @@
 //        -> searchDatabase() + alignDatabase()    sift4g/src/main.cpp:203-220
 //   ref_dump matrix
 //        -> scorerCreateMatrix("BLOSUM_62") table   vendor/swsharp/swsharp/src/pre_proc.c:399, constants.c:87-114
+//   ref_dump fasta FILE.fa
+//        -> readFastaChains(): per record "name<TAB>residues" (what the reader kept)   vendor/swsharp/swsharp/src/pre_proc.c:437-538
 //   ref_dump scorebench Q.fa DB.fa CANDS.txt threads
 //        -> the reference's threaded scoring loop (tasks of 1000 targets, database.c:896-996) timed
 //
@@ -260,8 +262,23 @@ static int cmd_matrix(int argc, char** argv) {
     return 0;
 }
 
+static int cmd_fasta(int argc, char** argv) {
+    if (argc < 3) return 2;
+    Chain** chains = NULL;
+    int n = 0;
+    readFastaChains(&chains, &n, argv[2]);
+    printf("%d\n", n);
+    for (int i = 0; i < n; ++i) {
+        printf("%s\t", chainGetName(chains[i]));
+        for (int j = 0; j < chainGetLength(chains[i]); ++j) putchar(chainGetChar(chains[i], j));
+        putchar('\n');
+    }
+    deleteFastaChains(chains, n);
+    return 0;
+}
+
 int main(int argc, char** argv) {
-    if (argc < 2) { fprintf(stderr, "usage: ref_dump <candidates|scores|align|pipeline|scorebench> ...\n"); return 2; }
+    if (argc < 2) { fprintf(stderr, "usage: ref_dump <candidates|scores|align|pipeline|scorebench|matrix|fasta> ...\n"); return 2; }
     std::string c = argv[1];
     if (c == "candidates") return cmd_candidates(argc, argv);
     if (c == "scores") return cmd_scores(argc, argv);
@@ -269,6 +286,7 @@ int main(int argc, char** argv) {
     if (c == "pipeline") return cmd_pipeline(argc, argv);
     if (c == "scorebench") return cmd_scorebench(argc, argv);
     if (c == "matrix") return cmd_matrix(argc, argv);
+    if (c == "fasta") return cmd_fasta(argc, argv);
     fprintf(stderr, "unknown command %s\n", argv[1]);
     return 2;
 }

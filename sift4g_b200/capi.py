@@ -28,6 +28,12 @@ SIGNATURES = {
     "s4g_launch_count_reset": (None, [_vp]),
     "s4g_db_create": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_uint32, C.c_int, C.POINTER(_vp)]),
     "s4g_db_open_fasta": (C.c_int, [_vp, C.c_char_p, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "s4g_db_pack_fasta": (C.c_int, [C.c_char_p, C.c_char_p]),
+    "s4g_db_file_info": (C.c_int, [C.c_char_p, _i64p, C.POINTER(C.c_uint64)]),
+    "s4g_db_open_packed": (C.c_int, [_vp, C.c_char_p, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "s4g_db_open": (C.c_int, [_vp, C.c_char_p, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "s4g_db_total_seqs": (C.c_int64, [_vp]),
+    "s4g_db_total_residues": (C.c_uint64, [_vp]),
     "s4g_db_close": (None, [_vp]),
     "s4g_db_num_seqs": (C.c_int64, [_vp]),
     "s4g_db_num_residues": (C.c_uint64, [_vp]),
@@ -71,6 +77,37 @@ def load():
 
 class S4GError(RuntimeError):
     pass
+
+
+def pack_fasta(fasta_path, out_path):
+    """FASTA -> packed database file (host only: needs neither a GPU nor a context)."""
+    lib = load()
+    rc = lib.s4g_db_pack_fasta(fasta_path.encode(), out_path.encode())
+    if rc != 0:
+        raise S4GError("s4g_db_pack_fasta failed (%d): %s" % (rc, lib.s4g_last_error(None).decode()))
+
+
+def packed_info(path):
+    lib = load()
+    n, r = C.c_int64(0), C.c_uint64(0)
+    rc = lib.s4g_db_file_info(path.encode(), C.byref(n), C.byref(r))
+    if rc != 0:
+        raise S4GError("s4g_db_file_info failed (%d): %s" % (rc, lib.s4g_last_error(None).decode()))
+    return n.value, r.value
+
+
+def read_packed(path):
+    """numpy reader of the packed layout documented in include/sift4g_b200.h (tests; independent of the library)."""
+    raw = np.fromfile(path, dtype=np.uint8)
+    assert raw[:8].tobytes() == b"S4GDB\0\0\1", "bad magic"
+    n, n_res, names_bytes, codes_pos = (int(x) for x in raw[8:40].view(np.uint64))
+    p = 64
+    off = raw[p:p + 8 * (n + 1)].view(np.int64).copy(); p += 8 * (n + 1)
+    name_off = raw[p:p + 8 * (n + 1)].view(np.int64).copy(); p += 8 * (n + 1)
+    blob = raw[p:p + names_bytes].tobytes()
+    names = [blob[name_off[i]:name_off[i + 1] - 1].decode() for i in range(n)]
+    codes = raw[codes_pos:codes_pos + n_res].copy()
+    return names, off, codes
 
 
 def _ptr(a):
@@ -131,10 +168,20 @@ class Context:
         return Database(self, codes, offsets, id_base, where)
 
     def database_from_fasta(self, path, shard=0, n_shards=1):
+        return self._open(self.lib.s4g_db_open_fasta, path, shard, n_shards)
+
+    def database_from_packed(self, path, shard=0, n_shards=1):
+        return self._open(self.lib.s4g_db_open_packed, path, shard, n_shards)
+
+    def database_from_file(self, path, shard=0, n_shards=1):
+        """FASTA or packed (.s4gdb) file, told apart by the magic."""
+        return self._open(self.lib.s4g_db_open, path, shard, n_shards)
+
+    def _open(self, fn, path, shard, n_shards):
         db = Database.__new__(Database)
         db.ctx = self
         h = _vp()
-        self.check(self.lib.s4g_db_open_fasta(self.h, path.encode(), shard, n_shards, C.byref(h)))
+        self.check(fn(self.h, path.encode(), shard, n_shards, C.byref(h)))
         db.h = h
         return db
 
@@ -164,6 +211,14 @@ class Database:
     @property
     def id_base(self):
         return int(self.ctx.lib.s4g_db_id_base(self.h))
+
+    @property
+    def total_seqs(self):
+        return int(self.ctx.lib.s4g_db_total_seqs(self.h))
+
+    @property
+    def total_residues(self):
+        return int(self.ctx.lib.s4g_db_total_residues(self.h))
 
     def host_offsets(self):
         p = self.ctx.lib.s4g_db_host_offsets(self.h)

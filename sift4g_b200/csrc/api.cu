@@ -192,72 +192,6 @@ int s4g_db_create(s4g_ctx* ctx, const uint8_t* codes, const int64_t* offsets, in
     return S4G_OK;
 }
 
-// FASTA reader with the observable behaviour of sw/pre_proc.c:437-538 + sw/chain.c:59-105:
-//  * a record ends at the next '>' that follows a sequence line, or at the LAST BYTE of the file
-//    (that byte is consumed as a terminator, so a file without trailing newline loses it);
-//  * name = header line without leading '>'/whitespace, without '\r', without trailing whitespace;
-//  * residues: letters only, case folded to 0..25; everything else is dropped;
-//  * a record that encodes to zero residues is an error (the reference aborts).
-int s4g_db_open_fasta(s4g_ctx* ctx, const char* path, int shard, int n_shards, s4g_db** out) {
-    if (!ctx || !path || !out || n_shards < 1 || shard < 0 || shard >= n_shards) return S4G_ERR_ARG;
-    *out = nullptr;
-    FILE* f = fopen(path, "rb");
-    if (!f) { s4g_set_error(ctx, "cannot open '%s'", path); return S4G_ERR_IO; }
-    std::vector<uint8_t> codes;
-    std::vector<int64_t> off(1, 0);
-    std::vector<std::string> names;
-    std::string name;
-    bool in_name = true;
-    int64_t cur_len = 0;
-    std::vector<char> buf(1 << 20);
-    // total size to detect the final byte
-    fseek(f, 0, SEEK_END);
-    long long total = ftell(f);
-    fseek(f, 0, SEEK_SET);
-    long long pos = 0;
-    int rc = S4G_OK;
-    auto close_record = [&]() -> bool {
-        while (!name.empty() && isspace((unsigned char)name.back())) name.pop_back();
-        if (name.empty() || cur_len == 0) return false;
-        names.push_back(name);
-        off.push_back((int64_t)codes.size());
-        name.clear();
-        cur_len = 0;
-        return true;
-    };
-    while (rc == S4G_OK) {
-        size_t got = fread(buf.data(), 1, buf.size(), f);
-        if (got == 0) break;
-        for (size_t i = 0; i < got && rc == S4G_OK; ++i, ++pos) {
-            char c = buf[i];
-            // the reference only sees "end of file" on a short fread (1 MiB buffer): a file whose size is an
-            // exact multiple of 1 MiB never closes its last record (sw/pre_proc.c:465-488)
-            bool last_byte = (pos == total - 1) && (total % (1 << 20) != 0);
-            if (!in_name && (c == '>' || last_byte)) {
-                if (!close_record()) { s4g_set_error(ctx, "'%s': empty record near byte %lld", path, pos); rc = S4G_ERR_IO; break; }
-                in_name = true;
-            }
-            if (in_name) {
-                if (c == '\n') in_name = false;
-                else if (!(name.empty() && (c == '>' || isspace((unsigned char)c))) && c != '\r') name.push_back(c);
-            } else {
-                unsigned char u = (unsigned char)c;
-                if (u >= 'A' && u <= 'Z') { codes.push_back((uint8_t)(u - 'A')); ++cur_len; }
-                else if (u >= 'a' && u <= 'z') { codes.push_back((uint8_t)(u - 'a')); ++cur_len; }
-            }
-        }
-    }
-    fclose(f);
-    if (rc != S4G_OK) return rc;
-    int64_t n_all = (int64_t)names.size();
-    int64_t lo = n_all * shard / n_shards, hi = n_all * (shard + 1) / n_shards;
-    std::vector<int64_t> soff(hi - lo + 1);
-    for (int64_t i = lo; i <= hi; ++i) soff[i - lo] = off[i] - off[lo];
-    rc = s4g_db_create(ctx, codes.data() + off[lo], soff.data(), hi - lo, (uint32_t)lo, S4G_HOST, out);
-    if (rc == S4G_OK) (*out)->names.assign(names.begin() + lo, names.begin() + hi);
-    return rc;
-}
-
 void s4g_db_close(s4g_db* db) {
     if (!db) return;
     cudaSetDevice(db->ctx->device);
@@ -271,6 +205,8 @@ void s4g_db_close(s4g_db* db) {
 int64_t s4g_db_num_seqs(const s4g_db* db) { return db ? db->n : 0; }
 uint64_t s4g_db_num_residues(const s4g_db* db) { return db ? db->residues : 0; }
 uint32_t s4g_db_id_base(const s4g_db* db) { return db ? db->id_base : 0; }
+int64_t s4g_db_total_seqs(const s4g_db* db) { return db ? (db->total_seqs ? db->total_seqs : db->n) : 0; }
+uint64_t s4g_db_total_residues(const s4g_db* db) { return db ? (db->total_residues ? db->total_residues : db->residues) : 0; }
 const int64_t* s4g_db_host_offsets(const s4g_db* db) { return db ? db->h_off.data() : nullptr; }
 const uint8_t* s4g_db_host_codes(const s4g_db* db) { return (db && !db->h_codes.empty()) ? db->h_codes.data() : nullptr; }
 const char* s4g_db_name(const s4g_db* db, int64_t i) {

@@ -29,6 +29,10 @@ struct s4g_ctx {
     // pinned host staging, grow-only
     void* pin_ptr[8] = {nullptr};
     size_t pin_bytes[8] = {0};
+    // candidate-buffer budget of the prefilter, remembered per batch shape (see s4g_prefilter_device)
+    size_t pf_budget = 0;
+    int pf_budget_nq = -1;
+    uint32_t pf_budget_n = 0;
     // S4G_TRACE=1: per-phase wall times (stream synchronised at every mark) printed to stderr
     bool trace = false;
     double trace_last = 0.0;
@@ -46,7 +50,9 @@ struct s4g_db {
     int32_t max_len = 0;
     std::vector<int64_t> h_off;     // always kept (metadata for the host shims)
     std::vector<uint8_t> h_codes;   // kept when created from host memory
-    std::vector<std::string> names; // kept when opened from FASTA
+    std::vector<std::string> names; // kept when opened from FASTA / a packed file
+    int64_t total_seqs = 0;         // whole file (all shards) when opened from a file, else 0
+    uint64_t total_residues = 0;
 };
 
 struct s4g_queries {

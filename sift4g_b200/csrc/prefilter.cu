@@ -834,14 +834,21 @@ int s4g_prefilter_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int ma
     // the scan runs in chunks of sequences; chunk sizes grow geometrically (cut-offs settle on the first small
     // chunks, later chunks append little) up to what the candidate-buffer budget allows
     int64_t chunk = 1 << 20;
-    size_t budget = (size_t)12 << 30;         // bytes for both candidate buffers: a third of the free HBM, 12 .. 48 GiB
-    {
+    // bytes for both candidate buffers: a third of the free HBM, 12 .. 48 GiB.  The driver is only asked when the
+    // buffers this context already holds cannot take full-size chunks (cudaMemGetInfo is a device-wide query that
+    // can stall for milliseconds; a steady-state call must not pay for it).
+    size_t budget = ctx->slot_bytes[SLOT_PF_CAND] + ctx->slot_bytes[SLOT_PF_TMP];
+    if ((size_t)nq * (size_t)(N + slack + chunk) * 16 > budget && !(ctx->pf_budget_nq == nq && ctx->pf_budget_n == N)) {
+        budget = (size_t)12 << 30;
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
             free_b += ctx->slot_bytes[SLOT_PF_CAND] + ctx->slot_bytes[SLOT_PF_TMP];      // what this call may reuse
             budget = std::min<size_t>(std::max<size_t>(free_b / 3, (size_t)12 << 30), (size_t)48 << 30);
             if (budget > free_b / 2) budget = free_b / 2;
         }
+        ctx->pf_budget = budget; ctx->pf_budget_nq = nq; ctx->pf_budget_n = N;
+    } else if (ctx->pf_budget_nq == nq && ctx->pf_budget_n == N) {
+        budget = std::max(budget, ctx->pf_budget);     // same batch shape as the last query of the driver: same answer
     }
     while (chunk > 4096 && (size_t)nq * (size_t)(N + slack + chunk) * 16 > budget) chunk >>= 1;
     if (chunk > db->n) chunk = db->n > 0 ? db->n : 1;
@@ -900,6 +907,7 @@ int s4g_prefilter_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int ma
     P.gbuf = (unsigned long long*)s4g_scratch(ctx, SLOT_PF_GBUF, sizeof(unsigned long long) * (size_t)grid * scan_warps * kGCap);
     if (!P.gbuf) return S4G_ERR_NOMEM;
 
+    s4g_trace_mark(ctx, "setup");
     int64_t this_chunk = chunk < 16384 ? chunk : 16384;
     int64_t ceiling = chunk;
     int ceiling_hold = 0;

@@ -27,7 +27,8 @@ void s4gOpenDatabase(const std::string& path) {
     S4gSession& s = s4gSession();
     if (s.db && s.db_path == path) return;
     if (s.db) { s4g_db_close(s.db); s.db = nullptr; }
-    s4gCheck(s4g_db_open_fasta(s.ctx, path.c_str(), 0, 1, &s.db), "s4g_db_open_fasta");
+    // FASTA, or a packed .s4gdb written by bin/s4g_pack (told apart by the magic)
+    s4gCheck(s4g_db_open(s.ctx, path.c_str(), 0, 1, &s.db), "s4g_db_open");
     s.db_path = path;
 }
 

@@ -126,22 +126,32 @@ class DevicePipeline:
     def close(self):
         self.Q.close()
 
-    def step(self, align=True, e2e=False):
+    def step(self, align=True, e2e=False, stages=None):
         """One pass of the hot path.  e2e=True: the query batch is uploaded from host memory first and every
-        result (candidate lists, survivor scores, alignments) is copied back to the host at the end."""
+        result (candidate lists, survivor scores, alignments) is copied back to the host at the end.
+        stages: optional dict; when given, the stream is synchronised after every stage and the stage's wall time
+        (ms) is added under its name (a diagnostic mode: the timed bench steps run without it)."""
         torch, ctx, db = self.torch, self.ctx, self.db
         r = Result()
         trace = os.environ.get("S4G_TRACE", "") not in ("", "0")
+        timed = trace or stages is not None
         marks = []
-        if trace:
+        if timed:
             torch.cuda.synchronize()
             t_last = [time.time()]
 
         def mark(name):
-            if trace:
+            if timed:
                 torch.cuda.synchronize()
                 now = time.time()
                 marks.append("%s=%.3fms" % (name, (now - t_last[0]) * 1e3))
+                if stages is not None:
+                    stages[name] = stages.get(name, 0.0) + (now - t_last[0]) * 1e3
+                    if name == "sw_score":
+                        try:
+                            stages["sw_kernel"] = self.ctx.last_sw_kernel_ms()
+                        except capi.S4GError:
+                            pass                      # no pair was scored on this rank
                 t_last[0] = now
         if e2e:
             self.Q.close()

@@ -56,3 +56,16 @@ def test_synthetic_database_with_candidate_cutoff_and_fewer_alignments():
     sd = os.path.join(util.GOLDEN, "synth_e2e")
     got = _run(["-q", sd + "/q.fa", "-d", sd + "/d.fa", "--sub-results", "--max-candidates", "200", "--max-aligns", "50"])
     assert got == _expected("synth_C200_M50")
+
+
+def test_packed_database_gives_the_same_files(tmp_path):
+    # the CLI takes a packed .s4gdb database in place of the FASTA (no parse at all) -- same bytes out
+    from sift4g_b200 import capi
+    sd = os.path.join(util.GOLDEN, "synth_e2e")
+    packed = str(tmp_path / "d.s4gdb")
+    capi.pack_fasta(sd + "/d.fa", packed)
+    assert _run(["-q", sd + "/q.fa", "-d", packed, "--sub-results"]) == _expected("synth_default")
+    pack_tool = os.path.join(ROOT, "sift4g_b200", "bin", "s4g_pack")
+    packed2 = str(tmp_path / "d2.s4gdb")
+    subprocess.run([pack_tool, sd + "/d.fa", packed2], check=True)
+    assert open(packed, "rb").read() == open(packed2, "rb").read()

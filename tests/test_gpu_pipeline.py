@@ -1,10 +1,13 @@
 """GPU: the device-resident pipeline (GPU E-value screen + host exact selection) returns exactly what the
 host-buffer path returns, and the multi-shard candidate merge equals the single-shard prefilter."""
+import os
+
 import numpy as np
 import pytest
 
 from oracle import oracle as O
 from sift4g_b200 import capi, pipeline, synth
+from tests.util import GOLDEN
 
 pytestmark = pytest.mark.gpu
 
@@ -139,3 +142,23 @@ def test_fasta_reader_quirks(ctx, tmp_path):
     A = ctx.database_from_fasta(str(p2), 0, 2); B = ctx.database_from_fasta(str(p2), 1, 2)
     assert A.n_seqs == 5 and B.n_seqs == 5 and A.id_base == 0 and B.id_base == 5 and B.name(0) == "s5"
     A.close(); B.close()
+
+
+def test_packed_database_opens_like_the_fasta(ctx, tmp_path):
+    # s4g_db_open_packed reads only the shard's byte ranges of the packed file; the resident shard must equal the one
+    # s4g_db_open_fasta builds (ids, names, offsets, codes), for one shard and for three
+    src = os.path.join(GOLDEN, "synth_e2e", "d.fa")
+    packed = str(tmp_path / "d.s4gdb")
+    capi.pack_fasta(src, packed)
+    for n_shards in (1, 3):
+        for s in range(n_shards):
+            A = ctx.database_from_fasta(src, s, n_shards)
+            B = ctx.database_from_file(packed, s, n_shards)
+            assert (A.n_seqs, A.n_residues, A.id_base) == (B.n_seqs, B.n_residues, B.id_base)
+            assert A.total_seqs == B.total_seqs and A.total_residues == B.total_residues
+            assert np.array_equal(A.host_offsets(), B.host_offsets()) and np.array_equal(A.host_codes(), B.host_codes())
+            assert all(A.name(i) == B.name(i) for i in range(A.n_seqs))
+            A.close(); B.close()
+    D = ctx.database_from_file(src)          # s4g_db_open on a FASTA falls through to the FASTA reader
+    assert D.n_seqs == D.total_seqs > 0
+    D.close()
