@@ -321,6 +321,7 @@ def main():
     dev = torch.device("cuda", local)
     use_dist = world > 1
     if use_dist:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner must not share stdout with the JSON line
         dist.init_process_group("nccl", device_id=dev)
     ctx = capi.Context(local)
     mat = np.array(BLOSUM62_A_TO_Z, dtype=np.int32)

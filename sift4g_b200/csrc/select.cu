@@ -119,7 +119,7 @@ extern "C" int s4g_select_hits(s4g_ctx* ctx, int32_t nq, const int32_t* query_le
     if (cand_offsets[nq] > 0 && (!cand_ids || !cand_scores || !cand_lens || !out_q || !out_t || !out_score || !out_evalue)) return S4G_ERR_ARG;
     (void)ctx;
     const EvParams P = make_params(db_residues, gap_open, gap_extend);
-    if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
+    if (n_threads <= 0) n_threads = std::min(32, (int)std::thread::hardware_concurrency());   // more threads cost more to start than they save
     if (n_threads < 1) n_threads = 1;
     if (n_threads > nq) n_threads = nq > 0 ? nq : 1;
     std::vector<int32_t> kept(nq, 0);

@@ -121,6 +121,10 @@ class DevicePipeline:
         self.t_db_lens = torch.from_numpy(np.ascontiguousarray(db_lens, dtype=np.int64)).to(self.dev)
         self.t_q_lens = torch.from_numpy(self.q_lens.astype(np.int64)).to(self.dev)
         self.q_host = (q_codes, q_off)
+        # host threads of the exact selection: this rank's share of the cores (one process per GPU on the box), at most
+        # 16 -- spawning a thread per core of a large host costs more than the selection itself
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(self.world)) or 1)
+        self.host_threads = max(1, min(16, (os.cpu_count() or 1) // max(1, local_world)))
         ctx.set_stream(torch.cuda.current_stream(self.dev).cuda_stream)
 
     def close(self):
@@ -221,7 +225,7 @@ class DevicePipeline:
         r.sw_cells = int(cells_dev.item()) if n_pairs else 0
         mark("screen_d2h")
         pq, pt, ps, ev, hoff = capi.select_hits(ctx, self.q_lens, h_ids, h_off, h_scores, h_lens, self.total_residues, self.go, self.ge,
-                                                self.max_evalue, self.max_alignments)
+                                                self.max_evalue, self.max_alignments, n_threads=self.host_threads)
         mark("select_hits")
         if self.world > 1:
             pq, pt, ps, ev, hoff = self._merge_hits(pq, pt, ps, ev, hoff, lo, hi)
