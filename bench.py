@@ -38,10 +38,17 @@ SEED = 20240002           # 20240001 + config id
 # ------------------------------------------------------------------------------------------------------------
 # synthetic workload (same recipe on host and device; see sift4g_b200/synth.py)
 
-def make_queries(n, lo=100, hi=1000, seed=SEED):
+def make_queries(n, lo=100, hi=1000, seed=SEED, shape="uniform"):
+    """uniform: lengths U[lo, hi] (configs[1]).  human: human-proteome-shaped log-normal lengths (median ~415, mean ~560,
+    clipped to [50, 35000]) for the configs[2]-shaped batch -- queries beyond 1024 aa take the
+    striped kernel."""
     from sift4g_b200 import synth
     rng = np.random.default_rng(seed)
-    qs = [synth.random_codes(rng, rng.integers(lo, hi + 1), 0.001) for _ in range(n)]
+    if shape == "human":
+        lens = np.clip(np.exp(rng.normal(6.03, 0.775, size=n)), 50, 35000).astype(np.int64)
+        qs = [synth.random_codes(rng, int(l), 0.001) for l in lens]
+    else:
+        qs = [synth.random_codes(rng, rng.integers(lo, hi + 1), 0.001) for _ in range(n)]
     return synth.pack(qs)
 
 
@@ -296,6 +303,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--queries", type=int, default=1000, help="queries per step and GPU (weak) / per step (strong)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--query-shape", default="uniform", choices=["uniform", "human"], help="query length distribution (human: configs[2])")
     ap.add_argument("--db-seqs", type=int, default=10_000_000)
     ap.add_argument("--max-candidates", type=int, default=5000)
     ap.add_argument("--ref-queries", type=int, default=16)
@@ -327,7 +335,7 @@ def main():
     mat = np.array(BLOSUM62_A_TO_Z, dtype=np.int32)
 
     n_queries = args.queries * world if args.scaling == "weak" else args.queries
-    q_codes, q_off = make_queries(n_queries)
+    q_codes, q_off = make_queries(n_queries, shape=args.query_shape)
     n_db = args.db_seqs
     lo, hi = n_db * rank // world, n_db * (rank + 1) // world
     t0 = time.time()
@@ -395,8 +403,10 @@ def main():
             "metric": "sw_gcups", "value": round(gcups, 2), "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "s16x2 (DPX), s32 re-run on overflow",
             "data": "synthetic",
-            "config": {"workload": "configs[1]: %d queries (len 100-1000) vs %d-sequence / %.2f B-residue synthetic database, whole hot path per step (prefilter k=5, top %d; SW BLOSUM62 10/1; E<=1e-4, top 400; traceback)" % (
-                n_queries, n_db, total_res / 1e9, args.max_candidates),
+            "config": {"workload": "%s: %d queries (%s) vs %d-sequence / %.2f B-residue synthetic database, whole hot path per step (prefilter k=5, top %d; SW BLOSUM62 10/1; E<=1e-4, top 400; traceback)" % (
+                "configs[1]" if n_db == 10_000_000 and args.query_shape == "uniform" else ("configs[2]-shaped" if n_db >= 40_000_000 else "custom"),
+                n_queries, "len 100-1000" if args.query_shape == "uniform" else "human-proteome-shaped log-normal lengths, median %d, max %d" % (
+                    int(np.median(np.diff(q_off))), int(np.diff(q_off).max())), n_db, total_res / 1e9, args.max_candidates),
                 "sharding": "database split in %d contiguous shards, one resident per GPU; %d queries per step (%s scaling: %s)" % (
                     world, n_queries, args.scaling, "1000 queries per GPU and step" if args.scaling == "weak" else "same batch at every N"),
                 "l2": "inputs (%.2f GB database shard per GPU) exceed the 126 MB L2; no explicit flush" % ((hi - lo) / n_db * total_res / 1e9),

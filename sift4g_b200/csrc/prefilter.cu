@@ -676,6 +676,7 @@ __global__ void mg_keys_kernel(int n_ranks, int nq, uint32_t N, const uint32_t* 
 int segmented_sort(s4g_ctx* ctx, const unsigned long long* keys_in, unsigned long long* keys_out, int64_t n_items_bound, int n_seg,
                    const int64_t* d_begin, const int64_t* d_end) {
     size_t tmp = 0;
+    if (n_items_bound >= ((int64_t)1 << 31)) { s4g_set_error(ctx, "segmented sort over %lld items (>= 2^31)", (long long)n_items_bound); return S4G_ERR_CAPACITY; }
     cub::DeviceSegmentedSort::SortKeys(nullptr, tmp, keys_in, keys_out, n_items_bound, (int64_t)n_seg, d_begin, d_end, ctx->stream);
     void* d_tmp = s4g_scratch(ctx, SLOT_PF_CUB, tmp);
     if (!d_tmp) return S4G_ERR_NOMEM;
@@ -850,7 +851,13 @@ int s4g_prefilter_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int ma
     } else if (ctx->pf_budget_nq == nq && ctx->pf_budget_n == N) {
         budget = std::max(budget, ctx->pf_budget);     // same batch shape as the last query of the driver: same answer
     }
-    while (chunk > 4096 && (size_t)nq * (size_t)(N + slack + chunk) * 16 > budget) chunk >>= 1;
+    // (nq x cap keys must also stay below 2^31: the segmented sort of the compactions counts items in 32 bits)
+    const size_t max_items = ((size_t)1 << 31) - 1;
+    while (chunk > 4096 && ((size_t)nq * (size_t)(N + slack + chunk) * 16 > budget || (size_t)nq * (size_t)(N + slack + chunk) > max_items)) chunk >>= 1;
+    if ((size_t)nq * (size_t)(N + slack + chunk) > max_items) {
+        s4g_set_error(ctx, "prefilter: %d queries x %u candidates exceed 2^31 candidate-buffer entries; split the query batch", nq, N);
+        return S4G_ERR_CAPACITY;
+    }
     if (chunk > db->n) chunk = db->n > 0 ? db->n : 1;
     const uint32_t cap = (uint32_t)(N + slack + chunk);
     unsigned long long* d_cand = (unsigned long long*)s4g_scratch(ctx, SLOT_PF_CAND, sizeof(unsigned long long) * (size_t)nq * cap);
