@@ -249,13 +249,13 @@ def run_reference_once(qf, df, threads):
     raise RuntimeError("reference produced no timing line:\n" + out[-500:])
 
 
-def reference_arm(args):
+def reference_arm(args, out=sys.stdout):
     from oracle import oracle as O
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     if not O.have_ref():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref binaries missing (built by oracle/Makefile in the build container)"}))
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref binaries missing (built by oracle/Makefile in the build container)"}), file=out, flush=True)
         return
     cores = os.cpu_count() or 1
     tmp = tempfile.mkdtemp()
@@ -275,7 +275,7 @@ def reference_arm(args):
             "stages_s": {"search": round(sum(s for s, _ in times) / len(times), 4), "align": round(sum(a for _, a in times) / len(times), 4)},
             "cpu_baseline": {"value": round(gcups, 4), "unit": "GCUPS", "cores": cores, "kind": "reference", "sample": sample},
             "e2e": {"value": round(gcups, 4), "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line))
+    print(json.dumps(line), file=out, flush=True)
 
 
 def cpu_baseline(args):
@@ -295,7 +295,17 @@ def cpu_baseline(args):
 
 # ------------------------------------------------------------------------------------------------------------
 
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner under NCCL_DEBUG), so the
+    real stdout is kept aside for the JSON line and file descriptor 1 is pointed at stderr for everybody else."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -315,7 +325,7 @@ def main():
         args.warmup = 3 if args.impl == "ours" else max(args.warmup, 1)
 
     if args.impl == "reference":
-        reference_arm(args)
+        reference_arm(args, out)
         return
 
     import torch
@@ -329,7 +339,6 @@ def main():
     dev = torch.device("cuda", local)
     use_dist = world > 1
     if use_dist:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner must not share stdout with the JSON line
         dist.init_process_group("nccl", device_id=dev)
     ctx = capi.Context(local)
     mat = np.array(BLOSUM62_A_TO_Z, dtype=np.int32)
@@ -368,12 +377,12 @@ def main():
         for _ in range(args.steps):
             r = pipe.step()
             cells_local = r.sw_cells
-            sw_ms.append(None)
+            sw_ms.append(r.sw_kernel_ms)
         e1.record()
         barrier()
     ms = e0.elapsed_time(e1)
     launches = ctx.launch_count()
-    sw_kernel_ms = ctx.last_sw_kernel_ms()
+    sw_kernel_ms = sw_ms[-1]                 # SW score kernel launches of the last step (one per half of the query batch), CUDA events inside the library
     t = torch.tensor([ms, float(cells_local), float(sw_kernel_ms), float(r.n_pairs), float(len(r.pair_q))], dtype=torch.float64, device=dev)
     if use_dist:
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -431,7 +440,7 @@ def main():
             line["e2e"] = e2e
         if base is not None:
             line["cpu_baseline"] = base
-        print(json.dumps(line))
+        print(json.dumps(line), file=out, flush=True)
     pipe.close()
     db.close()
     if use_dist:

@@ -318,9 +318,12 @@ def select_hits(ctx, query_lens, cand_ids, cand_offsets, cand_scores, cand_lens,
     name_arr = None
     if names is not None:
         name_arr = (C.c_char_p * max(len(names), 1))(*[n.encode() if isinstance(n, str) else n for n in names])
-    ctx.check(ctx.lib.s4g_select_hits(ctx.h, nq, _ptr(query_lens), _ptr(cand_ids), _ptr(cand_offsets), _ptr(cand_scores), _ptr(cand_lens),
-                                      C.cast(name_arr, _vp) if name_arr is not None else None, int(db_residues), gap_open, gap_extend,
-                                      max_evalue, max_alignments, n_threads, _ptr(oq), _ptr(ot), _ptr(osc), _ptr(oe), _ptr(off)))
+    lib = ctx.lib if ctx is not None else load()        # pure host code: usable without a context (CPU tests)
+    rc = lib.s4g_select_hits(ctx.h if ctx is not None else None, nq, _ptr(query_lens), _ptr(cand_ids), _ptr(cand_offsets), _ptr(cand_scores),
+                             _ptr(cand_lens), C.cast(name_arr, _vp) if name_arr is not None else None, int(db_residues), gap_open, gap_extend,
+                             max_evalue, max_alignments, n_threads, _ptr(oq), _ptr(ot), _ptr(osc), _ptr(oe), _ptr(off))
+    if rc != 0:
+        raise S4GError("s4g_select_hits failed (%d)" % rc)
     n = int(off[-1])
     return oq[:n], ot[:n], osc[:n], oe[:n], off
 

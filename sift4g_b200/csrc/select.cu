@@ -69,6 +69,38 @@ inline double evalue(const EvParams& p, int score, int qlen, int tlen) {
     return area * p.K * exp(-p.lambda * y) * scale;
 }
 
+// The factors of evalue() that depend on the score and the query length only, memoised per (query, score): a query's
+// survivors share few distinct scores, and the m-side costs one erf, one sqrt and two exp of the formula's 2 + 2 + 3.
+// Same operations in the same order as evalue() -> the same doubles bit for bit.
+struct EvMemo { int gen; double ab, sm, pm, p1, cpm, ex; };
+
+inline void evalue_query_side(const EvParams& p, int score, int qlen, EvMemo& o) {
+    const double y = score, m = qlen;
+    const double c0 = 0.39894228040143267793994605993438;
+    o.ab = p.a * y + p.b;
+    double lm = m - o.ab;
+    double vm = std::max(2.0 * p.alpha / p.lambda, p.alpha * y + p.beta);
+    o.sm = sqrt(vm);
+    double fm = lm / o.sm;
+    o.pm = 0.5 + 0.5 * erf(fm);
+    o.p1 = lm * o.pm + o.sm * c0 * exp(-0.5 * fm * fm);
+    double c = std::max(2.0 * p.sigma / p.lambda, p.sigma * y + p.tau);
+    o.cpm = c * o.pm;
+    o.ex = exp(-p.lambda * y);
+}
+
+inline double evalue_target_side(const EvParams& p, const EvMemo& o, int tlen) {
+    const double n = tlen;
+    const double scale = p.length / (double)tlen;
+    const double c0 = 0.39894228040143267793994605993438;
+    double ln = n - o.ab;
+    double fn = ln / o.sm;                       // vn == vm, so sn == sm
+    double pn = 0.5 + 0.5 * erf(fn);
+    double p2 = ln * pn + o.sm * c0 * exp(-0.5 * fn * fn);
+    double area = o.p1 * p2 + o.cpm * pn;
+    return area * p.K * o.ex * scale;
+}
+
 struct Row { int64_t i; int score; double value; };
 
 __global__ void ev_flag_kernel(EvParams P, const uint32_t* cand_ids, const int64_t* cand_off, int nq, int64_t n, const int32_t* scores,
@@ -125,13 +157,24 @@ extern "C" int s4g_select_hits(s4g_ctx* ctx, int32_t nq, const int32_t* query_le
     std::vector<int32_t> kept(nq, 0);
     auto work = [&](int tid) {
         std::vector<Row> rows;
+        std::vector<EvMemo> memo;
         for (int q = tid; q < nq; q += n_threads) {
             const int64_t b = cand_offsets[q], e = cand_offsets[q + 1];
             rows.resize(e - b);
             int pass = 0;
             for (int64_t i = b; i < e; ++i) {
-                rows[i - b] = {i, cand_scores[i], evalue(P, cand_scores[i], query_lens[q], cand_lens[i])};
-                if (rows[i - b].value <= max_evalue) ++pass;
+                const int sc = cand_scores[i];
+                double v;
+                if (sc >= 0 && sc < (1 << 20)) {
+                    if ((size_t)sc >= memo.size()) memo.resize((size_t)sc + 256, EvMemo{-1, 0, 0, 0, 0, 0, 0});
+                    EvMemo& mm = memo[sc];
+                    if (mm.gen != q) { evalue_query_side(P, sc, query_lens[q], mm); mm.gen = q; }
+                    v = evalue_target_side(P, mm, cand_lens[i]);
+                } else {
+                    v = evalue(P, sc, query_lens[q], cand_lens[i]);
+                }
+                rows[i - b] = {i, sc, v};
+                if (v <= max_evalue) ++pass;
             }
             const int k = std::min<int64_t>(std::min(pass, max_alignments), e - b);
             auto less = [&](const Row& x, const Row& y) {

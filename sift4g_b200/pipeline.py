@@ -12,6 +12,7 @@ torch is plumbing here (device buffers, streams, NCCL); all compute is in libsif
 """
 import os
 import sys
+import threading
 import time
 
 import numpy as np
@@ -21,7 +22,7 @@ from . import capi
 
 class Result:
     __slots__ = ("cand_ids", "cand_off", "scores", "pair_q", "pair_t", "pair_score", "evalue", "hit_off", "coords", "paths",
-                 "path_off", "sw_cells", "n_pairs", "timings", "h2d_bytes", "d2h_bytes")
+                 "path_off", "sw_cells", "n_pairs", "timings", "h2d_bytes", "d2h_bytes", "sw_kernel_ms")
 
     def __init__(self):
         for s in self.__slots__:
@@ -153,7 +154,7 @@ class DevicePipeline:
                     stages[name] = stages.get(name, 0.0) + (now - t_last[0]) * 1e3
                     if name == "sw_score":
                         try:
-                            stages["sw_kernel"] = self.ctx.last_sw_kernel_ms()
+                            stages["sw_kernel"] = stages.get("sw_kernel", 0.0) + self.ctx.last_sw_kernel_ms()
                         except capi.S4GError:
                             pass                      # no pair was scored on this rank
                 t_last[0] = now
@@ -192,58 +193,136 @@ class DevicePipeline:
         n_pairs = int(cand_ids.numel())
         scores = torch.empty(max(n_pairs, 1), dtype=torch.int32, device=self.dev)
         mark("own_candidates")
-        # ---- stage 2 ----
-        if n_pairs:
-            capi.sw_score(ctx, db, self.Q, cand_ids, cand_off, self.matrix, self.go, self.ge, out=scores, where=capi.S4G_DEVICE)
-        mark("sw_score")
-        # ---- E-value screen on the device, exact selection of the survivors on the host ----
+        # ---- stages 2 + 3, in two halves of the query batch: while the host selects the hits of one half (exact libm
+        # E-values, a few ms on a few cores) the GPU scores or aligns the other half
+        r.n_pairs = n_pairs
+        r.cand_ids, r.cand_off, r.scores = cand_ids, cand_off, scores     # device tensors (all candidates)
+        overlap = nq >= 2 and stages is None and os.environ.get("S4G_NO_OVERLAP", "") in ("", "0")
+        mid = nq // 2 if nq >= 2 else nq
+        p_mid = int(cand_off[mid].item()) if 0 < mid < nq else n_pairs
+        halves = [(0, mid, 0, p_mid), (mid, nq, p_mid, n_pairs)] if mid < nq else [(0, nq, 0, n_pairs)]
         cap = max(n_pairs, 1)
         if getattr(self, "_scr_cap", 0) < cap:
             self._scr = [torch.empty(cap, dtype=torch.int32, device=self.dev) for _ in range(4)]
             self._scr_cnt = torch.zeros(1, dtype=torch.int32, device=self.dev)
             self._scr_cap = cap
-        s_q, s_id, s_sc, s_tl = self._scr
-        ctx.check(ctx.lib.s4g_evalue_screen(ctx.h, db.h, self.Q.h, cand_ids.data_ptr(), cand_off.data_ptr(), n_pairs, scores.data_ptr(),
-                                            self.total_residues, self.go, self.ge, self.max_evalue, s_q.data_ptr(), s_id.data_ptr(),
-                                            s_sc.data_ptr(), s_tl.data_ptr(), self._scr_cnt.data_ptr()))
-        # algorithmic SW cells of this step (statistic): sum_q len(q) * sum_{t in cand(q)} len(t)
+        cells_dev = None
         if n_pairs:
+            # algorithmic SW cells of this step (statistic): sum_q len(q) * sum_{t in cand(q)} len(t)
             lens_dev = self.t_db_lens[(cand_ids.to(torch.int64) & 0xffffffff) - lo]
             cs = torch.zeros(n_pairs + 1, dtype=torch.int64, device=self.dev)
             cs[1:] = torch.cumsum(lens_dev, 0)
             seg = cs[cand_off[1:]] - cs[cand_off[:-1]]
             cells_dev = (seg * self.t_q_lens).sum()
-        n_s = int(self._scr_cnt.item())
-        surv = [self._to_host(nm, t[:n_s]) for nm, t in (("s_q", s_q), ("s_id", s_id), ("s_sc", s_sc), ("s_tl", s_tl))]
-        torch.cuda.current_stream(self.dev).synchronize()
-        h_q = surv[0].numpy().view(np.uint32)
-        h_ids = surv[1].numpy().view(np.uint32)
-        h_scores = surv[2].numpy()
-        h_lens = surv[3].numpy()
-        h_off = np.searchsorted(h_q, np.arange(nq + 1), side="left").astype(np.int64)
-        r.n_pairs = n_pairs
-        r.sw_cells = int(cells_dev.item()) if n_pairs else 0
-        mark("screen_d2h")
-        pq, pt, ps, ev, hoff = capi.select_hits(ctx, self.q_lens, h_ids, h_off, h_scores, h_lens, self.total_residues, self.go, self.ge,
-                                                self.max_evalue, self.max_alignments, n_threads=self.host_threads)
-        mark("select_hits")
-        if self.world > 1:
-            pq, pt, ps, ev, hoff = self._merge_hits(pq, pt, ps, ev, hoff, lo, hi)
-            mark("merge_hits")
-        r.pair_q, r.pair_t, r.pair_score, r.evalue, r.hit_off = pq, pt, ps, ev, hoff
-        r.cand_ids, r.cand_off, r.scores = cand_ids, cand_off, scores     # device tensors (all candidates)
-        # ---- stage 3 ----
-        if align and len(pq):
+        sw_ms = [0.0]
+        n_surv = [0]
+
+        def score_half(hx, qa, qb, pa, pb):
+            """SW scores + E-value screen of the queries [qa, qb); survivors to pinned host arrays"""
+            n = pb - pa
+            off = (cand_off.clamp(min=pa, max=pb) - pa).contiguous()              # other half's queries: empty lists
+            ids_h, sc_h = cand_ids[pa:pb], scores[pa:pb]
+            if n:
+                capi.sw_score(ctx, db, self.Q, ids_h, off, self.matrix, self.go, self.ge, out=sc_h, where=capi.S4G_DEVICE)
+                try:
+                    sw_ms[0] += ctx.last_sw_kernel_ms()
+                except capi.S4GError:
+                    pass
+            mark("sw_score")
+            s_q, s_id, s_sc, s_tl = self._scr
+            ctx.check(ctx.lib.s4g_evalue_screen(ctx.h, db.h, self.Q.h, ids_h.data_ptr(), off.data_ptr(), n, sc_h.data_ptr(),
+                                                self.total_residues, self.go, self.ge, self.max_evalue, s_q.data_ptr(), s_id.data_ptr(),
+                                                s_sc.data_ptr(), s_tl.data_ptr(), self._scr_cnt.data_ptr()))
+            n_s = int(self._scr_cnt.item())
+            n_surv[0] += n_s
+            surv = [self._to_host("%s%d" % (nm, hx), t[:n_s]) for nm, t in (("s_q", s_q), ("s_id", s_id), ("s_sc", s_sc), ("s_tl", s_tl))]
+            torch.cuda.current_stream(self.dev).synchronize()
+            mark("screen_d2h")
+            return surv
+
+        def select_half(surv, box):
+            h_q = surv[0].numpy().view(np.uint32)
+            h_off = np.searchsorted(h_q, np.arange(nq + 1), side="left").astype(np.int64)
+            box.append(capi.select_hits(ctx, self.q_lens, surv[1].numpy().view(np.uint32), h_off, surv[2].numpy(), surv[3].numpy(),
+                                        self.total_residues, self.go, self.ge, self.max_evalue, self.max_alignments, n_threads=self.host_threads))
+
+        def finish_half(box):
+            pq, pt, ps, ev, hoff = box[0]
+            mark("select_hits")
+            if self.world > 1:
+                pq, pt, ps, ev, hoff = self._merge_hits(pq, pt, ps, ev, hoff, lo, hi)
+                mark("merge_hits")
+            return pq, pt, ps, ev, hoff
+
+        def start_select(surv):
+            box = []
+            if not overlap:
+                select_half(surv, box)
+                return None, box
+            th = threading.Thread(target=select_half, args=(surv, box))
+            th.start()
+            return th, box
+
+        parts = []            # per half: (pq, pt, ps, ev, hoff)
+        aligned = []          # per half: (coords, poff, n_path)
+        path_buf = [None, 0]  # shared path buffer, bytes used
+
+        def align_half(hits):
+            pq, pt, ps = hits[0], hits[1], hits[2]
+            if not (align and len(pq)):
+                mark("align")
+                return
             d_pq = torch.from_numpy(pq.view(np.int32)).to(self.dev)
             d_pt = torch.from_numpy(pt.view(np.int32)).to(self.dev)
             d_ps = torch.from_numpy(ps).to(self.dev)
-            cap = int(self.q_lens[pq].astype(np.int64).sum() + self.db_lens[pt - lo].astype(np.int64).sum()) + 16
+            cap_h = int(self.q_lens[pq].astype(np.int64).sum() + self.db_lens[pt - lo].astype(np.int64).sum()) + 16
+            if path_buf[0] is None:
+                path_buf[0] = torch.empty(cap_h * (2 if len(halves) > 1 else 1) + 1024, dtype=torch.uint8, device=self.dev)
+            elif path_buf[0].numel() < path_buf[1] + cap_h:
+                grown = torch.empty(path_buf[1] + cap_h, dtype=torch.uint8, device=self.dev)
+                grown[:path_buf[1]] = path_buf[0][:path_buf[1]]
+                path_buf[0] = grown
             d_coords = torch.empty((len(pq), 4), dtype=torch.int32, device=self.dev)
-            d_paths = torch.empty(cap, dtype=torch.uint8, device=self.dev)
             d_poff = torch.empty(len(pq) + 1, dtype=torch.int64, device=self.dev)
+            out = path_buf[0][path_buf[1]:]
             ctx.check(ctx.lib.s4g_sw_align(ctx.h, db.h, self.Q.h, len(pq), d_pq.data_ptr(), d_pt.data_ptr(), d_ps.data_ptr(), self.matrix.ctypes.data,
-                                           self.go, self.ge, d_coords.data_ptr(), d_paths.data_ptr(), cap, d_poff.data_ptr(), capi.S4G_DEVICE))
-            r.coords, r.paths, r.path_off = d_coords, d_paths, d_poff
+                                           self.go, self.ge, d_coords.data_ptr(), out.data_ptr(), cap_h, d_poff.data_ptr(), capi.S4G_DEVICE))
+            n_path = int(d_poff[-1].item())
+            aligned.append((d_coords, d_poff[:-1] + path_buf[1], n_path))
+            path_buf[1] += n_path
+            mark("align")
+
+        pending = None        # (thread, box) of the half whose hits are being selected
+        for hx, (qa, qb, pa, pb) in enumerate(halves):
+            surv = score_half(hx, qa, qb, pa, pb)
+            if pending is not None:
+                # the previous half was selected while this half was scored; align it while this half is selected
+                if pending[0] is not None:
+                    pending[0].join()
+                prev = finish_half(pending[1])
+                pending = start_select(surv)
+                parts.append(prev)
+                align_half(prev)
+            else:
+                pending = start_select(surv)
+        if pending[0] is not None:
+            pending[0].join()
+        last = finish_half(pending[1])
+        parts.append(last)
+        align_half(last)
+        r.sw_cells = int(cells_dev.item()) if cells_dev is not None else 0
+        r.sw_kernel_ms = sw_ms[0]
+        n_s = n_surv[0]
+        pq = np.concatenate([x[0] for x in parts]); pt = np.concatenate([x[1] for x in parts])
+        ps = np.concatenate([x[2] for x in parts]); ev = np.concatenate([x[3] for x in parts])
+        hoff = parts[0][4].copy()
+        for x in parts[1:]:
+            hoff += x[4]
+        r.pair_q, r.pair_t, r.pair_score, r.evalue, r.hit_off = pq, pt, ps, ev, hoff
+        if aligned:
+            r.coords = torch.cat([a_[0] for a_ in aligned]) if len(aligned) > 1 else aligned[0][0]
+            r.path_off = torch.cat([a_[1] for a_ in aligned] + [torch.tensor([path_buf[1]], dtype=torch.int64, device=self.dev)])
+            r.paths = path_buf[0]
         mark("align")
         if trace and self.rank == 0:
             print("[s4g trace] step: " + " ".join(marks), file=sys.stderr)
