@@ -183,12 +183,29 @@ __device__ __forceinline__ void publish_step(uint32_t* off_s, uint32_t* hb_s, in
     __syncwarp();
 }
 
-__device__ __forceinline__ unsigned long long step_hit(const PfParams& P, const uint32_t* off_s, const uint32_t* hb_s, uint32_t x) {
+__device__ __forceinline__ uint32_t step_hit_index(const uint32_t* off_s, const uint32_t* hb_s, uint32_t x) {
     int p = 0;
 #pragma unroll
     for (int b = 64; b > 0; b >>= 1) if (off_s[p + b] <= x) p += b;
-    return __ldg(P.hits + hb_s[p] + (x - off_s[p]));
+    return hb_s[p] + (x - off_s[p]);
 }
+
+// Lane-owned enumeration: hit j of the lane's own (up to four) buckets, in emission order.  No table, no search: used
+// whenever the buckets of a step are spread evenly enough over the lanes (see lane_owned()).
+__device__ __forceinline__ uint32_t lane_hit_index(const uint32_t (&hb)[4], const uint32_t (&hc)[4], uint32_t j) {
+    const uint32_t p1 = hc[0], p2 = p1 + hc[1], p3 = p2 + hc[2];
+    uint32_t base = hb[0], pre = 0;
+    if (j >= p1) { base = hb[1]; pre = p1; }
+    if (j >= p2) { base = hb[2]; pre = p2; }
+    if (j >= p3) { base = hb[3]; pre = p3; }
+    return base + (j - pre);
+}
+
+// The warp walks max-over-lanes(c) rounds when every lane enumerates its own hits; the load-balanced enumeration walks
+// total/32 rounds but pays a 7-level table search per hit.  Lane-owned only for sparse steps (small query batches: a
+// step holds a few dozen hits in buckets of one or two): measured 1 % faster there, but 30 % slower on dense steps
+// (20 000 queries, ~435 hits per step), where every lane reading its own bucket turns one coalesced request into 32.
+__device__ __forceinline__ bool lane_owned(uint32_t cmax, uint32_t total) { return total <= 64u && cmax <= 6u; }
 
 // Can a (query, sequence) pair still beat the query's cut-off?  cnt16 = hashed per-sequence hit counters (they only
 // over-estimate a query's hits); the query's cut-off score comes from the CTA's shared table (upper 16 bits of the
@@ -208,7 +225,8 @@ __device__ __forceinline__ bool may_pass(const PfParams& P, const unsigned short
 //   rest    survivors are bitonic-sorted by (query, emission order), each query's run reduced by the in-place LIS.
 // Shared memory per warp: hit buffer scap x 8 B, counters cslots x 2 B (cslots = 1024 .. 4096 by batch size: the
 // fewer queries share a counter, the sharper the filter), step tables 2 x 128 x 4 B.
-__global__ void __launch_bounds__(kMaxWarps * 32) pf_scan_kernel(PfParams P, int scap, int cslots, int qthr_in_smem) {
+template <int kHitUnroll>
+__device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cslots, int qthr_in_smem) {
     extern __shared__ unsigned long long sbuf[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     unsigned long long* buf = sbuf + (size_t)warp * scap;
@@ -262,19 +280,56 @@ __global__ void __launch_bounds__(kMaxWarps * 32) pf_scan_kernel(PfParams P, int
                 const uint32_t excl = warp_excl_scan(c, lane, total);
                 if (total == 0) continue;
                 if (buffered && T + total > (uint32_t)scap) buffered = false;
+                const uint32_t cmax = __reduce_max_sync(FULL, c);
+                if (lane_owned(cmax, total)) {
+                    for (uint32_t j0 = 0; j0 < cmax; j0 += kHitUnroll) {
+                        unsigned long long h[kHitUnroll];
+#pragma unroll
+                        for (int u = 0; u < kHitUnroll; ++u) h[u] = j0 + u < c ? __ldg(P.hits + lane_hit_index(hb, hc, j0 + u)) : 0ull;
+#pragma unroll
+                        for (int u = 0; u < kHitUnroll; ++u) {
+                            if (j0 + u < c) {
+                                const uint32_t q = (uint32_t)(h[u] >> 32), slot = q & cmask;
+                                atomicAdd(cnt + (slot >> 1), (slot & 1u) ? 0x10000u : 1u);
+                                const uint32_t ord = T + excl + j0 + u;
+                                if (buffered) buf[ord] = ((unsigned long long)q << 44) | ((unsigned long long)ord << 22) | (h[u] & 0x3fffffu);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    T += total;
+                    continue;
+                }
                 publish_step(off_s, hb_s, lane, excl, hb, hc);
-                for (uint32_t x = lane; x < total; x += 32) {
-                    const unsigned long long h = step_hit(P, off_s, hb_s, x);
-                    const uint32_t q = (uint32_t)(h >> 32), slot = q & cmask;
-                    atomicAdd(cnt + (slot >> 1), (slot & 1u) ? 0x10000u : 1u);
-                    const uint32_t ord = T + x;
-                    if (buffered) buf[ord] = ((unsigned long long)q << 44) | ((unsigned long long)ord << 22) | (h & 0x3fffffu);
+                // kHitUnroll hits per lane in flight: with a large query batch a step holds hundreds of hits and the loop is
+                // bound by the latency of the hit loads (the index no longer fits L2 next to the streaming database)
+                for (uint32_t x0 = 0; x0 < total; x0 += 32 * kHitUnroll) {
+                    unsigned long long h[kHitUnroll];
+#pragma unroll
+                    for (int u = 0; u < kHitUnroll; ++u) {
+                        h[u] = 0;
+                        if (x0 + 32 * u < total) {                                  // warp-uniform
+                            const uint32_t x = x0 + 32 * u + lane;
+                            if (x < total) h[u] = __ldg(P.hits + step_hit_index(off_s, hb_s, x));
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < kHitUnroll; ++u) {
+                        const uint32_t x = x0 + 32 * u + lane;
+                        if (x < total) {
+                            const uint32_t q = (uint32_t)(h[u] >> 32), slot = q & cmask;
+                            atomicAdd(cnt + (slot >> 1), (slot & 1u) ? 0x10000u : 1u);
+                            const uint32_t ord = T + x;
+                            if (buffered) buf[ord] = ((unsigned long long)q << 44) | ((unsigned long long)ord << 22) | (h[u] & 0x3fffffu);
+                        }
+                    }
                 }
                 __syncwarp();
                 T += total;
             }
             if (T == 0) continue;
             const float flen = (float)len * 0.99999f;      // margin >> float rounding: dropping stays exact
+            const uint32_t id = P.id_base + (uint32_t)s;
             uint32_t nsurv = 0;
             bool defer = false;
             unsigned long long* wb = buf;        // where the survivors are: shared buffer or global scratch
@@ -285,7 +340,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32) pf_scan_kernel(PfParams P, int
                     bool keep = false;
                     if (i < (int)T) {
                         e = buf[i];
-                        keep = may_pass(P, qthr, cnt16, cmask, (uint32_t)(e >> 44), flen);
+                        const uint32_t q = (uint32_t)(e >> 44);
+                        keep = may_pass(P, qthr, cnt16, cmask, q, flen);
+                        if (keep && cnt16[q & cmask] == 1) { emit(P, q, 1, len, id); keep = false; }     // the query's only hit: LIS = 1, nothing to sort
                     }
                     const uint32_t bal = __ballot_sync(FULL, keep);
                     if (keep) buf[nsurv + __popc(bal & ((1u << lane) - 1u))] = e;      // nsurv + rank <= i: never ahead of the reads
@@ -298,6 +355,16 @@ __global__ void __launch_bounds__(kMaxWarps * 32) pf_scan_kernel(PfParams P, int
                 // re-walk, keep the survivors only (any order: the sort key carries the emission order); they go to the
                 // warp's global scratch, which holds what a strong homolog of a long query produces
                 wb = P.gbuf + (size_t)(blockIdx.x * nwarps + warp) * kGCap;
+                // Queries whose counter holds exactly one hit have LIS = 1 and are emitted straight from the walk -- but only
+                // when the other survivors are sure to fit the scratch (bound: all hits in counters >= 2), because a sequence
+                // that overflows it is handed to the deferred path as a whole and must not have emitted anything yet.
+                uint32_t m2 = 0;
+                for (int i = lane; i < cslots / 2; i += 32) {
+                    const uint32_t w = cnt[i], c0 = w & 0xffffu, c1 = w >> 16;
+                    m2 += (c0 >= 2u ? c0 : 0u) + (c1 >= 2u ? c1 : 0u);
+                }
+                m2 = __reduce_add_sync(FULL, m2);
+                const bool direct = m2 <= (uint32_t)kGCap;
                 uint32_t ordbase = 0;
                 carry = 0xffffffffu;
                 for (int base = 0; base < npos && !defer; base += 128) {
@@ -307,21 +374,61 @@ __global__ void __launch_bounds__(kMaxWarps * 32) pf_scan_kernel(PfParams P, int
                     uint32_t total;
                     const uint32_t excl = warp_excl_scan(c, lane, total);
                     if (total == 0) continue;
-                    publish_step(off_s, hb_s, lane, excl, hb, hc);
-                    for (uint32_t x0 = 0; x0 < total; x0 += 32) {
-                        const uint32_t x = x0 + lane;
-                        unsigned long long e = 0;
-                        bool keep = false;
-                        if (x < total) {
-                            const unsigned long long h = step_hit(P, off_s, hb_s, x);
-                            const uint32_t q = (uint32_t)(h >> 32);
-                            keep = may_pass(P, qthr, cnt16, cmask, q, flen);
-                            e = ((unsigned long long)q << 44) | ((unsigned long long)(ordbase + x) << 22) | (h & 0x3fffffu);
+                    const uint32_t cmax = __reduce_max_sync(FULL, c);
+                    if (lane_owned(cmax, total)) {
+                        for (uint32_t j0 = 0; j0 < cmax && !defer; j0 += kHitUnroll) {
+                            unsigned long long h[kHitUnroll];
+#pragma unroll
+                            for (int u = 0; u < kHitUnroll; ++u) h[u] = j0 + u < c ? __ldg(P.hits + lane_hit_index(hb, hc, j0 + u)) : 0ull;
+#pragma unroll
+                            for (int u = 0; u < kHitUnroll; ++u) {
+                                if (defer || j0 + u >= cmax) continue;                  // warp-uniform
+                                unsigned long long e = 0;
+                                bool keep = false;
+                                if (j0 + u < c) {
+                                    const uint32_t q = (uint32_t)(h[u] >> 32);
+                                    keep = may_pass(P, qthr, cnt16, cmask, q, flen);
+                                    if (direct && keep && cnt16[q & cmask] == 1) { emit(P, q, 1, len, id); keep = false; }
+                                    e = ((unsigned long long)q << 44) | ((unsigned long long)(ordbase + excl + j0 + u) << 22) | (h[u] & 0x3fffffu);
+                                }
+                                const uint32_t bal = __ballot_sync(FULL, keep);
+                                if (nsurv + __popc(bal) > (uint32_t)kGCap) { defer = true; continue; }
+                                if (keep) wb[nsurv + __popc(bal & ((1u << lane) - 1u))] = e;
+                                nsurv += __popc(bal);
+                            }
                         }
-                        const uint32_t bal = __ballot_sync(FULL, keep);
-                        if (nsurv + __popc(bal) > (uint32_t)kGCap) { defer = true; break; }
-                        if (keep) wb[nsurv + __popc(bal & ((1u << lane) - 1u))] = e;
-                        nsurv += __popc(bal);
+                        __syncwarp();
+                        ordbase += total;
+                        continue;
+                    }
+                    publish_step(off_s, hb_s, lane, excl, hb, hc);
+                    for (uint32_t x0 = 0; x0 < total && !defer; x0 += 32 * kHitUnroll) {
+                        unsigned long long h[kHitUnroll];
+#pragma unroll
+                        for (int u = 0; u < kHitUnroll; ++u) {
+                            h[u] = 0;
+                            if (x0 + 32 * u < total) {                              // warp-uniform
+                                const uint32_t x = x0 + 32 * u + lane;
+                                if (x < total) h[u] = __ldg(P.hits + step_hit_index(off_s, hb_s, x));
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < kHitUnroll; ++u) {
+                            if (defer || x0 + 32 * u >= total) continue;                // warp-uniform
+                            const uint32_t x = x0 + 32 * u + lane;
+                            unsigned long long e = 0;
+                            bool keep = false;
+                            if (x < total) {
+                                const uint32_t q = (uint32_t)(h[u] >> 32);
+                                keep = may_pass(P, qthr, cnt16, cmask, q, flen);
+                                if (direct && keep && cnt16[q & cmask] == 1) { emit(P, q, 1, len, id); keep = false; }
+                                e = ((unsigned long long)q << 44) | ((unsigned long long)(ordbase + x) << 22) | (h[u] & 0x3fffffu);
+                            }
+                            const uint32_t bal = __ballot_sync(FULL, keep);
+                            if (nsurv + __popc(bal) > (uint32_t)kGCap) { defer = true; continue; }
+                            if (keep) wb[nsurv + __popc(bal & ((1u << lane) - 1u))] = e;
+                            nsurv += __popc(bal);
+                        }
                     }
                     __syncwarp();
                     ordbase += total;
@@ -372,7 +479,6 @@ __global__ void __launch_bounds__(kMaxWarps * 32) pf_scan_kernel(PfParams P, int
                 if (lane == (base >> 5)) my_starts = bal;
             }
             __syncwarp();
-            const uint32_t id = P.id_base + (uint32_t)s;
             for (int base = 0; base < S; base += 32) {
                 const uint32_t bal = __shfl_sync(FULL, my_starts, base >> 5);
                 const bool st = (bal >> lane) & 1u;
@@ -391,6 +497,16 @@ __global__ void __launch_bounds__(kMaxWarps * 32) pf_scan_kernel(PfParams P, int
             }
         }
     }
+}
+
+// Two builds of the scan.  Small query batches (a step of 128 positions holds a few dozen hits) run 8-warp CTAs, four per
+// SM, within 64 registers, two hits of a step in flight per lane.  Batches whose shared-memory tables leave room for at most
+// two CTAs per SM are bound by the latency of the index loads at few resident warps: four hits in flight per lane, 96 registers.
+__global__ void __launch_bounds__(kWarps * 32, 4) pf_scan_kernel(PfParams P, int scap, int cslots, int qthr_in_smem) {
+    pf_scan_body<2>(P, scap, cslots, qthr_in_smem);
+}
+__global__ void __launch_bounds__(kMaxWarps * 32, 1) pf_scan_dense_kernel(PfParams P, int scap, int cslots, int qthr_in_smem) {
+    pf_scan_body<4>(P, scap, cslots, qthr_in_smem);
 }
 
 // deferred path, step 1: re-walk the sequence and write its hits into the pool
@@ -899,16 +1015,23 @@ int s4g_prefilter_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int ma
         if (4.0 * per_res * avg_len > 1024.0) scap = 512;
     }
     // per-query cut-off table in shared memory (2 B per query) when it fits beside the per-warp buffers
-    const int qthr_in_smem = nq <= 32768 ? 1 : 0;
-    const size_t qthr_bytes = qthr_in_smem ? (((size_t)nq * 2 + 15) / 16) * 16 : 0;
+    int qthr_in_smem = nq <= 32768 ? 1 : 0;
+    size_t qthr_bytes = qthr_in_smem ? (((size_t)nq * 2 + 15) / 16) * 16 : 0;
     const int cslots = nq <= 1024 ? 1024 : (nq <= 8192 ? 2048 : 4096);
     if (cslots == 4096) scap = 256;
-    const size_t per_warp_smem = sizeof(unsigned long long) * scap + sizeof(uint32_t) * (cslots / 2) + sizeof(uint32_t) * 256;
     // small tables: 8-warp CTAs, several per SM; a large cut-off table is shared by 16 warps
     const int scan_warps = qthr_bytes > 16384 ? kMaxWarps : kWarps;
+    const size_t per_warp_smem = sizeof(unsigned long long) * scap + sizeof(uint32_t) * (cslots / 2) + sizeof(uint32_t) * 256;
+    if (per_warp_smem * scan_warps + qthr_bytes > (size_t)227 * 1024) { qthr_in_smem = 0; qthr_bytes = 0; }   // cut-offs from global memory
     const size_t scan_smem = per_warp_smem * scan_warps + qthr_bytes;
-    S4G_CUDA(ctx, cudaFuncSetAttribute(pf_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
-    S4G_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pf_scan_kernel, scan_warps * 32, scan_smem));
+    auto scan_kernel = pf_scan_kernel;
+    S4G_CUDA(ctx, cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<size_t>(scan_smem, (size_t)227 * 1024)));
+    if (scan_warps == kWarps) S4G_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel, scan_warps * 32, scan_smem));
+    if (scan_warps == kMaxWarps || per_sm <= 2) {
+        scan_kernel = pf_scan_dense_kernel;
+        S4G_CUDA(ctx, cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
+        S4G_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel, scan_warps * 32, scan_smem));
+    }
     if (per_sm < 1) per_sm = 1;
     const int grid = ctx->sm_count * per_sm;
     P.gbuf = (unsigned long long*)s4g_scratch(ctx, SLOT_PF_GBUF, sizeof(unsigned long long) * (size_t)grid * scan_warps * kGCap);
@@ -926,7 +1049,7 @@ int s4g_prefilter_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int ma
         // the pool is only allocated once a chunk needs it (first pass counts; see below)
         P.pool_keys = (unsigned long long*)ctx->slot_ptr[SLOT_PF_HITS];
         const auto t_chunk = std::chrono::steady_clock::now();
-        pf_scan_kernel<<<grid, scan_warps * 32, scan_smem, st>>>(P, scap, cslots, qthr_in_smem);
+        scan_kernel<<<grid, scan_warps * 32, scan_smem, st>>>(P, scap, cslots, qthr_in_smem);
         S4G_CHECK_LAUNCH(ctx);
         unsigned long long h_c[4];
         S4G_CUDA(ctx, cudaMemcpyAsync(h_c, d_counters, 32, cudaMemcpyDeviceToHost, st));

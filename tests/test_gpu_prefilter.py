@@ -92,3 +92,36 @@ def test_multi_chunk_database(ctx):
     db = [codes[off[i]:off[i + 1]] for i in range(n)]
     db[5] = queries[0][:59].copy(); db[250000] = queries[0][100:150].copy(); db[299999] = queries[1][:40].copy()
     _compare(ctx, queries, db, 5, 200)
+
+
+def _reduced(rng, n, letters):
+    return rng.integers(0, letters, size=n).astype(np.uint8)
+
+
+def test_large_batch_takes_the_dense_scan(ctx):
+    # > 8192 queries: 16-warp CTAs around the shared cut-off table, four hits per lane in flight.  A 12-letter alphabet
+    # makes the steps dense (~2 index entries per k-mer position, a few hundred hits per 128 positions).
+    rng = np.random.default_rng(29)
+    queries = [_reduced(rng, n, 12) for n in rng.integers(40, 90, size=9000)]
+    db = [_reduced(rng, n, 12) for n in rng.integers(30, 700, size=1200)]
+    for i in range(0, 300, 7):                      # planted: mutated copies of queries inside random flanks
+        db[i] = np.concatenate([_reduced(rng, 20, 12), synth.mutate(rng, queries[i * 13], 0.85), _reduced(rng, 15, 12)])
+    _compare(ctx, queries, db, 5, 40)
+
+
+def test_large_batch_with_thousands_of_hits_per_step(ctx):
+    # 6-letter alphabet: thousands of hits per step and several thousand per sequence (counted first, re-walked for the survivors)
+    rng = np.random.default_rng(30)
+    queries = [_reduced(rng, n, 6) for n in rng.integers(40, 70, size=8500)]
+    db = [_reduced(rng, n, 6) for n in rng.integers(30, 110, size=160)]
+    db[3] = queries[17].copy(); db[90] = np.tile(queries[4000][:25], 3)
+    _compare(ctx, queries, db, 5, 12)
+
+
+def test_batch_too_large_for_the_shared_cutoff_table(ctx):
+    # 27 000 queries: the 2-byte cut-off table no longer fits beside the per-warp buffers -> cut-offs read from global memory
+    rng = np.random.default_rng(31)
+    queries = [synth.random_codes(rng, n) for n in rng.integers(6, 14, size=27000)]
+    db = [synth.random_codes(rng, n) for n in rng.integers(30, 300, size=800)]
+    db[11] = np.concatenate([queries[5], queries[26999], queries[13000]])
+    _compare(ctx, queries, db, 5, 6)
