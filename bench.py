@@ -428,7 +428,7 @@ def main():
             "roofline": {"bound": "int_dpx", "kernel": "sw_score_packed_kernel", "achieved": round(kern_gcups, 2) if kern_gcups else None, "peak": round(roof_gcups, 2),
                          "unit": "GCUPS", "frac": round(kern_gcups / roof_gcups, 4) if kern_gcups else None,
                          "traffic": NCU_TRAFFIC_C2 if (world == 1 and n_queries == 1000 and n_db == 10_000_000 and args.max_candidates == 5000) else None,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this command (profiles/r01i_sw_digest.md)",
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this command (profiles/r01i_sw_digest.md; re-captured as two half-batch launches, 0.728 GB each, in profiles/r01t_sw_digest.md)",
                          "kernel_ms": round(sw_kernel_ms, 3),
                          "peak_source": "measured live on this GPU (no DPX figure in MEASURED_PEAKS.json): %.4e VIADDMNMX.S16x2 lane-ops/s sustained over 300 ms x 2 cells per op / 6 instructions per cell (BASELINE.md)" % peak},
             "roofline_prefilter": {"bound": "hbm", "achieved": round(((hi - lo) / n_db * total_res + 8 * (hi - lo)) / (split["prefilter"] * 1e-3) / 1e9, 2) if split["prefilter"] else None,

@@ -126,6 +126,10 @@ class DevicePipeline:
         # 16 -- spawning a thread per core of a large host costs more than the selection itself
         local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(self.world)) or 1)
         self.host_threads = max(1, min(16, (os.cpu_count() or 1) // max(1, local_world)))
+        # 1: score, select and align the whole batch in turn; 2: in two halves of the query batch, the exact host selection of
+        # one half running beside the GPU work of the other.  Two launches per stage cost ~10 ms of GPU time at configs[1]
+        # (tails, per-call sorts), so halves only pay when the ranks of a box leave each other few host cores.
+        self.parts = 2 if self.host_threads < 8 else 1
         ctx.set_stream(torch.cuda.current_stream(self.dev).cuda_stream)
 
     def close(self):
@@ -197,8 +201,9 @@ class DevicePipeline:
         # E-values, a few ms on a few cores) the GPU scores or aligns the other half
         r.n_pairs = n_pairs
         r.cand_ids, r.cand_off, r.scores = cand_ids, cand_off, scores     # device tensors (all candidates)
-        overlap = nq >= 2 and stages is None and os.environ.get("S4G_NO_OVERLAP", "") in ("", "0")
-        mid = nq // 2 if nq >= 2 else nq
+        n_parts = int(os.environ.get("S4G_PARTS", "0")) or self.parts
+        overlap = n_parts > 1 and nq >= 2 and stages is None and os.environ.get("S4G_NO_OVERLAP", "") in ("", "0")
+        mid = nq // 2 if (nq >= 2 and n_parts > 1) else nq
         p_mid = int(cand_off[mid].item()) if 0 < mid < nq else n_pairs
         halves = [(0, mid, 0, p_mid), (mid, nq, p_mid, n_pairs)] if mid < nq else [(0, nq, 0, n_pairs)]
         cap = max(n_pairs, 1)
