@@ -210,9 +210,32 @@ __device__ __forceinline__ bool lane_owned(uint32_t cmax, uint32_t total) { retu
 // Can a (query, sequence) pair still beat the query's cut-off?  cnt16 = hashed per-sequence hit counters (they only
 // over-estimate a query's hits); the query's cut-off score comes from the CTA's shared table (upper 16 bits of the
 // float, i.e. rounded down -- conservative) or, for batches too large for it, from global memory.
-__device__ __forceinline__ bool may_pass(const PfParams& P, const unsigned short* qthr, const unsigned short* cnt16, uint32_t cmask, uint32_t q, float flen) {
+// Hashed per-sequence hit counters.  One hash: slot = q & cmask over all `cslots` counters.  Two hashes (batches with several
+// queries per counter): the array is split in two halves, a hit is counted in slot q & cmask of the first and in a
+// multiplicative-hash slot of the second; both over-estimate the query's hits, so their minimum does too -- and two
+// queries rarely collide in both halves, which makes the filter several times sharper at the same shared memory.
+struct Counters {
+    uint32_t* cnt;                 // 2 x 16 bit per word
+    const unsigned short* cnt16;
+    uint32_t cmask;                // slots per half - 1
+    uint32_t half;                 // 0: one hash; else slots per half
+    uint32_t hshift;
+    __device__ __forceinline__ uint32_t slot2(uint32_t q) const { return half + ((q * 0x9E3779B1u) >> hshift); }
+    __device__ __forceinline__ void add(uint32_t q) const {
+        const uint32_t s1 = q & cmask;
+        atomicAdd(cnt + (s1 >> 1), (s1 & 1u) ? 0x10000u : 1u);
+        if (half) { const uint32_t s2 = slot2(q); atomicAdd(cnt + (s2 >> 1), (s2 & 1u) ? 0x10000u : 1u); }
+    }
+    __device__ __forceinline__ uint32_t count(uint32_t q) const {      // >= the query's hits in this sequence; 1 = exactly one
+        uint32_t c = cnt16[q & cmask];
+        if (half) c = min(c, (uint32_t)cnt16[slot2(q)]);
+        return c;
+    }
+};
+
+__device__ __forceinline__ bool may_pass(const PfParams& P, const unsigned short* qthr, uint32_t count, uint32_t q, float flen) {
     const float th = qthr ? __uint_as_float((uint32_t)qthr[q] << 16) : __uint_as_float(~(uint32_t)(__ldcg(P.thr + q) >> 32));
-    return !((float)cnt16[q & cmask] < th * flen);
+    return !((float)count < th * flen);
 }
 
 // The scan kernel.  Per sequence (one warp):
@@ -226,16 +249,17 @@ __device__ __forceinline__ bool may_pass(const PfParams& P, const unsigned short
 // Shared memory per warp: hit buffer scap x 8 B, counters cslots x 2 B (cslots = 1024 .. 4096 by batch size: the
 // fewer queries share a counter, the sharper the filter), step tables 2 x 128 x 4 B.
 template <int kHitUnroll>
-__device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cslots, int qthr_in_smem) {
+__device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cslots, int qthr_in_smem, int hash2) {
     extern __shared__ unsigned long long sbuf[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     unsigned long long* buf = sbuf + (size_t)warp * scap;
     uint32_t* cnt_all = reinterpret_cast<uint32_t*>(sbuf + (size_t)nwarps * scap);
-    const uint32_t cmask = (uint32_t)cslots - 1u;
+    const uint32_t chalf = hash2 ? (uint32_t)cslots / 2u : 0u;
     uint32_t* step_all = cnt_all + nwarps * (cslots / 2);
     unsigned short* qthr = qthr_in_smem ? reinterpret_cast<unsigned short*>(step_all + nwarps * 256) : nullptr;
     uint32_t* cnt = cnt_all + warp * (cslots / 2);
     unsigned short* cnt16 = reinterpret_cast<unsigned short*>(cnt);
+    const Counters C{cnt, cnt16, (chalf ? chalf : (uint32_t)cslots) - 1u, chalf, chalf ? (uint32_t)__clz(chalf) + 1u : 0u};
     uint32_t* off_s = step_all + warp * 256;
     uint32_t* hb_s = off_s + 128;
     const unsigned FULL = 0xffffffffu;
@@ -289,8 +313,8 @@ __device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cs
 #pragma unroll
                         for (int u = 0; u < kHitUnroll; ++u) {
                             if (j0 + u < c) {
-                                const uint32_t q = (uint32_t)(h[u] >> 32), slot = q & cmask;
-                                atomicAdd(cnt + (slot >> 1), (slot & 1u) ? 0x10000u : 1u);
+                                const uint32_t q = (uint32_t)(h[u] >> 32);
+                                C.add(q);
                                 const uint32_t ord = T + excl + j0 + u;
                                 if (buffered) buf[ord] = ((unsigned long long)q << 44) | ((unsigned long long)ord << 22) | (h[u] & 0x3fffffu);
                             }
@@ -317,8 +341,8 @@ __device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cs
                     for (int u = 0; u < kHitUnroll; ++u) {
                         const uint32_t x = x0 + 32 * u + lane;
                         if (x < total) {
-                            const uint32_t q = (uint32_t)(h[u] >> 32), slot = q & cmask;
-                            atomicAdd(cnt + (slot >> 1), (slot & 1u) ? 0x10000u : 1u);
+                            const uint32_t q = (uint32_t)(h[u] >> 32);
+                            C.add(q);
                             const uint32_t ord = T + x;
                             if (buffered) buf[ord] = ((unsigned long long)q << 44) | ((unsigned long long)ord << 22) | (h[u] & 0x3fffffu);
                         }
@@ -341,8 +365,9 @@ __device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cs
                     if (i < (int)T) {
                         e = buf[i];
                         const uint32_t q = (uint32_t)(e >> 44);
-                        keep = may_pass(P, qthr, cnt16, cmask, q, flen);
-                        if (keep && cnt16[q & cmask] == 1) { emit(P, q, 1, len, id); keep = false; }     // the query's only hit: LIS = 1, nothing to sort
+                        const uint32_t c = C.count(q);
+                        keep = may_pass(P, qthr, c, q, flen);
+                        if (keep && c == 1) { emit(P, q, 1, len, id); keep = false; }     // the query's only hit: LIS = 1, nothing to sort
                     }
                     const uint32_t bal = __ballot_sync(FULL, keep);
                     if (keep) buf[nsurv + __popc(bal & ((1u << lane) - 1u))] = e;      // nsurv + rank <= i: never ahead of the reads
@@ -359,7 +384,7 @@ __device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cs
                 // when the other survivors are sure to fit the scratch (bound: all hits in counters >= 2), because a sequence
                 // that overflows it is handed to the deferred path as a whole and must not have emitted anything yet.
                 uint32_t m2 = 0;
-                for (int i = lane; i < cslots / 2; i += 32) {
+                for (int i = lane; i < (chalf ? cslots / 4 : cslots / 2); i += 32) {       // every hit sits in the first half exactly once
                     const uint32_t w = cnt[i], c0 = w & 0xffffu, c1 = w >> 16;
                     m2 += (c0 >= 2u ? c0 : 0u) + (c1 >= 2u ? c1 : 0u);
                 }
@@ -387,8 +412,9 @@ __device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cs
                                 bool keep = false;
                                 if (j0 + u < c) {
                                     const uint32_t q = (uint32_t)(h[u] >> 32);
-                                    keep = may_pass(P, qthr, cnt16, cmask, q, flen);
-                                    if (direct && keep && cnt16[q & cmask] == 1) { emit(P, q, 1, len, id); keep = false; }
+                                    const uint32_t c = C.count(q);
+                                    keep = may_pass(P, qthr, c, q, flen);
+                                    if (direct && keep && c == 1) { emit(P, q, 1, len, id); keep = false; }
                                     e = ((unsigned long long)q << 44) | ((unsigned long long)(ordbase + excl + j0 + u) << 22) | (h[u] & 0x3fffffu);
                                 }
                                 const uint32_t bal = __ballot_sync(FULL, keep);
@@ -420,8 +446,9 @@ __device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cs
                             bool keep = false;
                             if (x < total) {
                                 const uint32_t q = (uint32_t)(h[u] >> 32);
-                                keep = may_pass(P, qthr, cnt16, cmask, q, flen);
-                                if (direct && keep && cnt16[q & cmask] == 1) { emit(P, q, 1, len, id); keep = false; }
+                                const uint32_t c = C.count(q);
+                                keep = may_pass(P, qthr, c, q, flen);
+                                if (direct && keep && c == 1) { emit(P, q, 1, len, id); keep = false; }
                                 e = ((unsigned long long)q << 44) | ((unsigned long long)(ordbase + x) << 22) | (h[u] & 0x3fffffu);
                             }
                             const uint32_t bal = __ballot_sync(FULL, keep);
@@ -502,11 +529,11 @@ __device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cs
 // Two builds of the scan.  Small query batches (a step of 128 positions holds a few dozen hits) run 8-warp CTAs, four per
 // SM, within 64 registers, two hits of a step in flight per lane.  Batches whose shared-memory tables leave room for at most
 // two CTAs per SM are bound by the latency of the index loads at few resident warps: four hits in flight per lane, 96 registers.
-__global__ void __launch_bounds__(kWarps * 32, 4) pf_scan_kernel(PfParams P, int scap, int cslots, int qthr_in_smem) {
-    pf_scan_body<2>(P, scap, cslots, qthr_in_smem);
+__global__ void __launch_bounds__(kWarps * 32, 4) pf_scan_kernel(PfParams P, int scap, int cslots, int qthr_in_smem, int hash2) {
+    pf_scan_body<2>(P, scap, cslots, qthr_in_smem, hash2);
 }
-__global__ void __launch_bounds__(kMaxWarps * 32, 1) pf_scan_dense_kernel(PfParams P, int scap, int cslots, int qthr_in_smem) {
-    pf_scan_body<4>(P, scap, cslots, qthr_in_smem);
+__global__ void __launch_bounds__(kMaxWarps * 32, 1) pf_scan_dense_kernel(PfParams P, int scap, int cslots, int qthr_in_smem, int hash2) {
+    pf_scan_body<4>(P, scap, cslots, qthr_in_smem, hash2);
 }
 
 // deferred path, step 1: re-walk the sequence and write its hits into the pool
@@ -1017,10 +1044,14 @@ int s4g_prefilter_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int ma
     // per-query cut-off table in shared memory (2 B per query) when it fits beside the per-warp buffers
     int qthr_in_smem = nq <= 32768 ? 1 : 0;
     size_t qthr_bytes = qthr_in_smem ? (((size_t)nq * 2 + 15) / 16) * 16 : 0;
+    // counters per warp: measured (profiles/r01s_c3_prefilter.md) -- fewer slots per query cost more in false survivors
+    // than the extra resident warps win, more slots than these cost residency
     const int cslots = nq <= 1024 ? 1024 : (nq <= 8192 ? 2048 : 4096);
     if (cslots == 4096) scap = 256;
     // small tables: 8-warp CTAs, several per SM; a large cut-off table is shared by 16 warps
     const int scan_warps = qthr_bytes > 16384 ? kMaxWarps : kWarps;
+    // two-hash counters for the large batches (~5 queries per counter): -4.5 % there, nothing at 4 queries per counter
+    const int hash2 = scan_warps == kMaxWarps ? 1 : 0;
     const size_t per_warp_smem = sizeof(unsigned long long) * scap + sizeof(uint32_t) * (cslots / 2) + sizeof(uint32_t) * 256;
     if (per_warp_smem * scan_warps + qthr_bytes > (size_t)227 * 1024) { qthr_in_smem = 0; qthr_bytes = 0; }   // cut-offs from global memory
     const size_t scan_smem = per_warp_smem * scan_warps + qthr_bytes;
@@ -1049,7 +1080,7 @@ int s4g_prefilter_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int ma
         // the pool is only allocated once a chunk needs it (first pass counts; see below)
         P.pool_keys = (unsigned long long*)ctx->slot_ptr[SLOT_PF_HITS];
         const auto t_chunk = std::chrono::steady_clock::now();
-        scan_kernel<<<grid, scan_warps * 32, scan_smem, st>>>(P, scap, cslots, qthr_in_smem);
+        scan_kernel<<<grid, scan_warps * 32, scan_smem, st>>>(P, scap, cslots, qthr_in_smem, hash2);
         S4G_CHECK_LAUNCH(ctx);
         unsigned long long h_c[4];
         S4G_CUDA(ctx, cudaMemcpyAsync(h_c, d_counters, 32, cudaMemcpyDeviceToHost, st));
