@@ -519,7 +519,9 @@ __device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cs
                     n = e - i;
                 }
                 __syncwarp();          // all run lengths of this block are known before any of its runs is overwritten
-                if (st) emit(P, q, n == 1 ? 1 : lis_inplace(wb, i, n), len, id);
+                // the run length is the query's exact hit count and bounds its LIS: runs that cannot reach the cut-off (survivors
+                // of counter collisions) are dropped before the LIS and the global cut-off load
+                if (st && may_pass(P, qthr, (uint32_t)n, q, flen)) emit(P, q, n == 1 ? 1 : lis_inplace(wb, i, n), len, id);
                 __syncwarp();
             }
         }
