@@ -128,8 +128,9 @@ class DevicePipeline:
         self.host_threads = max(1, min(16, (os.cpu_count() or 1) // max(1, local_world)))
         # 1: score, select and align the whole batch in turn; 2: in two halves of the query batch, the exact host selection of
         # one half running beside the GPU work of the other.  Two launches per stage cost ~10 ms of GPU time at configs[1]
-        # (tails, per-call sorts), so halves only pay when the ranks of a box leave each other few host cores.
-        self.parts = 2 if self.host_threads < 8 else 1
+        # (tails, per-call sorts; 133.3 vs 136.5 ms per step on one GPU), so halves only pay where the ranks of a box leave
+        # each other so few host cores that the selection takes longer than that (8 ranks on 16 cores: ~12 ms, 154 -> 151 ms).
+        self.parts = 2 if self.host_threads <= 2 else 1
         ctx.set_stream(torch.cuda.current_stream(self.dev).cuda_stream)
 
     def close(self):
