@@ -908,6 +908,10 @@ int s4g_prefilter_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int ma
     // ---- index over all queries ----
     int64_t n_hits = 0;
     for (int i = 0; i < nq; ++i) { int64_t len = q->h_off[i + 1] - q->h_off[i]; if (len >= k) n_hits += len - k + 1; }
+    if (n_hits >= ((int64_t)1 << 31)) {      // index entries are addressed in 32 bits (bucket starts, cub item counts)
+        s4g_set_error(ctx, "prefilter: %lld query k-mers exceed 2^31 index entries; split the query batch", (long long)n_hits);
+        return S4G_ERR_CAPACITY;
+    }
     const uint32_t n_kmer_space = 1u << (5 * k);
     const uint32_t n_words = n_kmer_space / 32;
     const uint32_t mask = n_kmer_space - 1;
