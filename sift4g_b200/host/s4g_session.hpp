@@ -1,20 +1,37 @@
 // Process-wide session shared by the two reference seams (searchDatabase / alignDatabase):
-// one C-ABI context per process, the database shard opened once and kept resident in HBM between the
-// prefilter and the alignment stage (the reference parses the FASTA twice:
+// one C-ABI context per GPU, the database opened once -- one resident shard per GPU (contiguous FASTA ranges) --
+// and kept in HBM between the prefilter and the alignment stage (the reference parses the FASTA twice:
 // sift4g/src/database_search.cpp:81-97, database_alignment.cpp:36-48).
+// Devices: S4G_DEVICES="0,1,2,3" (one host thread per GPU inside the seams, lists merged on the host), else
+// S4G_DEVICE=<n>, else device 0.  The reference's own multi-card analogue is `cards` + one host thread per card
+// (sw/database.c:497-532).
 #pragma once
 
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "sift4g_b200.h"
 
-struct S4gSession {
+struct S4gShard {
     s4g_ctx* ctx = nullptr;
     s4g_db* db = nullptr;
-    std::string db_path;
     s4g_queries* queries = nullptr;
+    uint32_t lo = 0, hi = 0;             // FASTA indices [lo, hi) resident on this GPU
+};
+
+struct S4gSession {
+    std::vector<S4gShard> shards;
+    std::string db_path;
     const void* queries_key = nullptr;   // Chain** the batch was built from
     int queries_n = 0;
+    int64_t total_seqs = 0;
+    uint64_t total_residues = 0;
+    int shardOf(uint32_t id) const {     // shards are contiguous and ascending
+        int d = 0;
+        while (d + 1 < (int)shards.size() && id >= shards[d].hi) ++d;
+        return d;
+    }
 };
 
 S4gSession& s4gSession();
@@ -23,3 +40,14 @@ void s4gCheck(int rc, const char* what);
 void s4gOpenDatabase(const std::string& path);
 struct Chain;
 void s4gUploadQueries(Chain** queries, int queries_length);
+
+// f(shard index) on one host thread per GPU (inline when there is a single GPU)
+template <class F>
+void s4gForEachShard(F f) {
+    S4gSession& s = s4gSession();
+    const int n = (int)s.shards.size();
+    if (n == 1) { f(0); return; }
+    std::vector<std::thread> th;
+    for (int d = 0; d < n; ++d) th.emplace_back([&f, d] { f(d); });
+    for (auto& t : th) t.join();
+}

@@ -17,9 +17,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "sift4g_b200", "bin", "sift4g_b200")
 
 
-def _run(args):
+def _run(args, env=None):
     out = tempfile.mkdtemp()
-    r = subprocess.run([BIN] + args + ["--out", out], capture_output=True, text=True)
+    r = subprocess.run([BIN] + args + ["--out", out], capture_output=True, text=True, env=dict(os.environ, **(env or {})))
     assert r.returncode == 0, r.stderr[-2000:]
     return {f: hashlib.sha256(open(os.path.join(out, f), "rb").read()).hexdigest() for f in sorted(os.listdir(out))}
 
@@ -69,3 +69,21 @@ def test_packed_database_gives_the_same_files(tmp_path):
     packed2 = str(tmp_path / "d2.s4gdb")
     subprocess.run([pack_tool, sd + "/d.fa", packed2], check=True)
     assert open(packed, "rb").read() == open(packed2, "rb").read()
+
+
+def test_cli_with_one_shard_per_device_writes_the_same_files(tmp_path):
+    # S4G_DEVICES: one resident database shard per listed device inside the CLI (one host thread each, host merge of the
+    # candidate lists) -- every output file equals the single-shard / reference bytes, for the FASTA and the packed
+    # database.  Listing a device twice gives it two shards, so the 2- and 3-shard (uneven) splits also run on one GPU.
+    import torch
+    n = torch.cuda.device_count()
+    from sift4g_b200 import capi
+    sd = os.path.join(util.GOLDEN, "synth_e2e")
+    tf = os.path.join(util.GOLDEN, "test_files")
+    packed = str(tmp_path / "d.s4gdb")
+    capi.pack_fasta(sd + "/d.fa", packed)
+    for devs in ["0,0", "0,0,0"] + (["0,1"] if n >= 2 else []) + ([",".join(str(i) for i in range(n))] if n >= 3 else []):
+        env = {"S4G_DEVICES": devs}
+        assert _run(["-q", sd + "/q.fa", "-d", sd + "/d.fa", "--sub-results"], env) == _expected("synth_default"), devs
+        assert _run(["-q", sd + "/q.fa", "-d", packed, "--sub-results", "--max-candidates", "200", "--max-aligns", "50"], env) == _expected("synth_C200_M50"), devs
+        assert _run(["-q", tf + "/query.fasta", "-d", tf + "/sample_protein_database.fa", "--subst", tf + "/", "--sub-results"], env) == _expected("test_files_subst"), devs
