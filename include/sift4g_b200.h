@@ -122,6 +122,16 @@ int s4g_merge_candidates(s4g_ctx* ctx, int n_ranks, int n_queries, int max_candi
                          const uint32_t* gathered_counts, uint32_t* out_ids, float* out_scores,
                          uint32_t* out_counts);
 
+/* Host form of the same merge, for callers that drive several GPUs from one process without a collective (the CLI:
+ * sift4g_b200/host/database_search.cpp) -- it is the reference's merge of its per-thread lists
+ * (sift4g/src/database_search.cpp:132-154,173-180) under the deterministic tie rule.  ids/scores/counts[r] point to shard
+ * r's s4g_prefilter output with sorted_by_id = 0 (n_queries x max_candidates rows, counts per query); host pointers, no
+ * GPU and no context involved.  out_ids (n_queries x max_candidates): the global best max_candidates of every query by
+ * (score desc, id asc), written in ascending id; out_counts[q] of them.  n_threads <= 0: all host cores. */
+int s4g_merge_candidates_host(int n_ranks, int n_queries, int max_candidates, const uint32_t* const* ids,
+                              const float* const* scores, const uint32_t* const* counts, int n_threads,
+                              uint32_t* out_ids, uint32_t* out_counts);
+
 /* Multi-GPU, query-owner protocol (what the pipeline uses; no row is copied or re-sorted).  The merge of
  * per-thread lists in searchDatabase() (sift4g/src/database_search.cpp:132-154) keeps, per query, the rows up
  * to the max_candidates-th best (score desc, id asc) key of the union -- so the shards only have to agree on

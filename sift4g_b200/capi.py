@@ -50,6 +50,7 @@ SIGNATURES = {
     "s4g_sw_score": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int64, _vp, C.c_int, C.c_int, _vp, C.c_int]),
     "s4g_sw_align": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int64, _vp, C.c_int]),
     "s4g_merge_hits": (C.c_int, [_vp, C.c_int, C.c_int32, C.c_int, _vp, C.c_int64, _vp, C.c_uint32, C.c_uint32, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "s4g_merge_candidates_host": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp]),
     "s4g_select_hits": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, C.c_uint64, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "s4g_evalue_screen": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int64, _vp, C.c_uint64, C.c_int, C.c_int, C.c_double, _vp, _vp, _vp, _vp, _vp]),
     "s4g_measure_dpx_peak": (C.c_int, [_vp, C.c_int, _f64p]),
@@ -346,3 +347,22 @@ def merge_hits(ctx, gathered, counts, nq, max_alignments, own_lo=0, own_hi=0xfff
         raise S4GError("s4g_merge_hits failed (%d)" % rc)
     n = int(off[-1])
     return oq[:n], ot[:n], osc[:n], oe[:n], off
+
+
+def merge_candidates_host(ids, scores, counts, max_candidates, n_threads=0):
+    """Host merge of per-shard best-first prefilter rows (lists of (nq x N) uint32 / float32 arrays and (nq,) uint32 counts):
+    global top max_candidates per query by (score desc, id asc), returned in ascending id -- the CLI's multi-GPU path.
+    Pure host code: no context."""
+    lib = load()
+    n = len(ids)
+    nq = int(counts[0].shape[0])
+    ids = [np.ascontiguousarray(a, dtype=np.uint32) for a in ids]
+    scores = [np.ascontiguousarray(a, dtype=np.float32) for a in scores]
+    counts = [np.ascontiguousarray(a, dtype=np.uint32) for a in counts]
+    arr = lambda xs: (C.c_void_p * n)(*[x.ctypes.data for x in xs])
+    out = np.zeros((nq, max_candidates), dtype=np.uint32)
+    out_cnt = np.zeros(nq, dtype=np.uint32)
+    rc = lib.s4g_merge_candidates_host(n, nq, max_candidates, arr(ids), arr(scores), arr(counts), n_threads, _ptr(out), _ptr(out_cnt))
+    if rc != 0:
+        raise S4GError("s4g_merge_candidates_host failed (%d)" % rc)
+    return out, out_cnt

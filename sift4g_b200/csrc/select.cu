@@ -211,6 +211,43 @@ extern "C" int s4g_select_hits(s4g_ctx* ctx, int32_t nq, const int32_t* query_le
     return S4G_OK;
 }
 
+extern "C" int s4g_merge_candidates_host(int n_ranks, int n_queries, int max_candidates, const uint32_t* const* ids,
+                                         const float* const* scores, const uint32_t* const* counts, int n_threads,
+                                         uint32_t* out_ids, uint32_t* out_counts) {
+    if (n_ranks < 1 || n_queries < 0 || max_candidates < 1 || !ids || !scores || !counts || !out_ids || !out_counts) return S4G_ERR_ARG;
+    for (int r = 0; r < n_ranks; ++r) if (!ids[r] || !scores[r] || !counts[r]) return S4G_ERR_ARG;
+    if (n_threads <= 0) n_threads = std::min(32, (int)std::thread::hardware_concurrency());
+    n_threads = std::max(1, std::min(n_threads, std::max(n_queries, 1)));
+    const size_t row = (size_t)max_candidates;
+    auto work = [&](int tid) {
+        std::vector<unsigned long long> keys;
+        for (int q = tid; q < n_queries; q += n_threads) {
+            keys.clear();
+            for (int r = 0; r < n_ranks; ++r) {
+                const uint32_t* id = ids[r] + (size_t)q * row;
+                const float* sc = scores[r] + (size_t)q * row;
+                const uint32_t c = std::min<uint32_t>(counts[r][q], (uint32_t)max_candidates);
+                for (uint32_t j = 0; j < c; ++j) {
+                    uint32_t bits;
+                    memcpy(&bits, sc + j, 4);
+                    keys.push_back(((unsigned long long)(~bits) << 32) | id[j]);      // ascending = (score desc, id asc): the device's cand_key
+                }
+            }
+            const size_t keep = std::min(keys.size(), row);
+            if (keep < keys.size()) std::nth_element(keys.begin(), keys.begin() + keep, keys.end());
+            uint32_t* out = out_ids + (size_t)q * row;
+            for (size_t j = 0; j < keep; ++j) out[j] = (uint32_t)keys[j];
+            std::sort(out, out + keep);                                                // database_search.cpp:173-180
+            out_counts[q] = (uint32_t)keep;
+        }
+    };
+    if (n_threads == 1) { work(0); return S4G_OK; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t) th.emplace_back(work, t);
+    for (auto& t : th) t.join();
+    return S4G_OK;
+}
+
 extern "C" int s4g_merge_hits(s4g_ctx* ctx, int n_ranks, int32_t nq, int max_alignments, const double* gathered, int64_t rank_stride,
                               const int64_t* gathered_counts, uint32_t own_lo, uint32_t own_hi, int n_threads, uint32_t* out_q,
                               uint32_t* out_t, int32_t* out_score, double* out_evalue, int64_t* out_offsets) {

@@ -47,31 +47,14 @@ uint64_t searchDatabase(std::vector<std::vector<uint32_t>>& dst, const std::stri
             s4gCheck(s4g_prefilter(sh.ctx, sh.db, sh.queries, (int)kmer_length, (int)max_candidates, /*sorted_by_id=*/0, ids[d].data(),
                                    scores[d].data(), counts[d].data(), S4G_HOST), "s4g_prefilter");
         });
-        // host merge, queries dealt to the host threads: key = (~score bits, id) ascending = (score desc, id asc)
-        const int n_threads = std::max(1, std::min<int>(32, (int)std::thread::hardware_concurrency()));
-        std::vector<std::thread> th;
-        for (int t = 0; t < n_threads; ++t)
-            th.emplace_back([&, t] {
-                std::vector<unsigned long long> keys;
-                for (int32_t i = t; i < queries_length; i += n_threads) {
-                    keys.clear();
-                    for (int d = 0; d < n_shards; ++d) {
-                        const uint32_t* id = ids[d].data() + (size_t)i * row;
-                        const float* sc = scores[d].data() + (size_t)i * row;
-                        for (uint32_t j = 0; j < counts[d][i]; ++j) {
-                            uint32_t bits;
-                            memcpy(&bits, sc + j, 4);
-                            keys.push_back(((unsigned long long)(~bits) << 32) | id[j]);
-                        }
-                    }
-                    const size_t keep = std::min<size_t>(keys.size(), row);
-                    if (keep < keys.size()) std::nth_element(keys.begin(), keys.begin() + keep, keys.end());
-                    dst[i].resize(keep);
-                    for (size_t j = 0; j < keep; ++j) dst[i][j] = (uint32_t)keys[j];
-                    std::sort(dst[i].begin(), dst[i].end());          // output ids ascending (database_search.cpp:173-180)
-                }
-            });
-        for (auto& x : th) x.join();
+        // host merge (the reference's merge of its per-thread lists, database_search.cpp:132-154)
+        std::vector<const uint32_t*> p_ids(n_shards), p_counts(n_shards);
+        std::vector<const float*> p_scores(n_shards);
+        for (int d = 0; d < n_shards; ++d) { p_ids[d] = ids[d].data(); p_scores[d] = scores[d].data(); p_counts[d] = counts[d].data(); }
+        std::vector<uint32_t> merged((size_t)queries_length * row), merged_counts(queries_length);
+        s4gCheck(s4g_merge_candidates_host(n_shards, queries_length, (int)max_candidates, p_ids.data(), p_scores.data(), p_counts.data(), 0,
+                                           merged.data(), merged_counts.data()), "s4g_merge_candidates_host");
+        for (int32_t i = 0; i < queries_length; ++i) dst[i].assign(merged.begin() + (size_t)i * row, merged.begin() + (size_t)i * row + merged_counts[i]);
     }
     fprintf(stderr, "* processing database part 1 (size ~%.2f GB): 100.00/100.00%% *\n\n", s.total_residues / 1e9);
     return s.total_residues;
