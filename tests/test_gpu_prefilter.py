@@ -125,3 +125,15 @@ def test_batch_too_large_for_the_shared_cutoff_table(ctx):
     db = [synth.random_codes(rng, n) for n in rng.integers(30, 300, size=800)]
     db[11] = np.concatenate([queries[5], queries[26999], queries[13000]])
     _compare(ctx, queries, db, 5, 6)
+
+
+def test_mid_size_batch_takes_the_four_in_flight_build_with_8_warp_ctas(ctx):
+    # 5000 queries x ~200 residues: the hit buffer grows to 512 entries, only two 8-warp CTAs fit an SM and the scan runs
+    # the 4-hits-in-flight build with 8-warp CTAs and one hash -- the configuration of the 8-GPU weak-scaling bench
+    # (8000 queries per rank)
+    rng = np.random.default_rng(32)
+    queries = [synth.random_codes(rng, n) for n in rng.integers(150, 250, size=5000)]
+    db = [synth.random_codes(rng, n) for n in rng.integers(100, 500, size=500)]
+    for i in range(0, 120, 3):
+        db[i] = np.concatenate([synth.random_codes(rng, 30), synth.mutate(rng, queries[i * 40], 0.8), synth.random_codes(rng, 25)])
+    _compare(ctx, queries, db, 5, 25)
