@@ -74,19 +74,30 @@ inline double evalue(const EvParams& p, int score, int qlen, int tlen) {
 // Same operations in the same order as evalue() -> the same doubles bit for bit.
 struct EvMemo { int gen; double ab, sm, pm, p1, cpm, ex; };
 
-inline void evalue_query_side(const EvParams& p, int score, int qlen, EvMemo& o) {
-    const double y = score, m = qlen;
-    const double c0 = 0.39894228040143267793994605993438;
+// ... and the factors that depend on the score alone (one sqrt, one exp), computed once per score value and worker thread:
+// the survivors of a query mostly carry distinct scores, so this is the memo that is hit in practice.
+struct EvScore { int set; double ab, sm, c, ex; };
+
+inline void evalue_score_side(const EvParams& p, int score, EvScore& o) {
+    const double y = score;
     o.ab = p.a * y + p.b;
+    o.sm = sqrt(std::max(2.0 * p.alpha / p.lambda, p.alpha * y + p.beta));
+    o.c = std::max(2.0 * p.sigma / p.lambda, p.sigma * y + p.tau);
+    o.ex = exp(-p.lambda * y);
+    o.set = 1;
+}
+
+inline void evalue_query_side(const EvScore& s, int qlen, EvMemo& o) {
+    const double m = qlen;
+    const double c0 = 0.39894228040143267793994605993438;
+    o.ab = s.ab;
     double lm = m - o.ab;
-    double vm = std::max(2.0 * p.alpha / p.lambda, p.alpha * y + p.beta);
-    o.sm = sqrt(vm);
+    o.sm = s.sm;
     double fm = lm / o.sm;
     o.pm = 0.5 + 0.5 * erf(fm);
     o.p1 = lm * o.pm + o.sm * c0 * exp(-0.5 * fm * fm);
-    double c = std::max(2.0 * p.sigma / p.lambda, p.sigma * y + p.tau);
-    o.cpm = c * o.pm;
-    o.ex = exp(-p.lambda * y);
+    o.cpm = s.c * o.pm;
+    o.ex = s.ex;
 }
 
 inline double evalue_target_side(const EvParams& p, const EvMemo& o, int tlen) {
@@ -158,6 +169,7 @@ extern "C" int s4g_select_hits(s4g_ctx* ctx, int32_t nq, const int32_t* query_le
     auto work = [&](int tid) {
         std::vector<Row> rows;
         std::vector<EvMemo> memo;
+        std::vector<EvScore> by_score;
         for (int q = tid; q < nq; q += n_threads) {
             const int64_t b = cand_offsets[q], e = cand_offsets[q + 1];
             rows.resize(e - b);
@@ -166,9 +178,14 @@ extern "C" int s4g_select_hits(s4g_ctx* ctx, int32_t nq, const int32_t* query_le
                 const int sc = cand_scores[i];
                 double v;
                 if (sc >= 0 && sc < (1 << 20)) {
-                    if ((size_t)sc >= memo.size()) memo.resize((size_t)sc + 256, EvMemo{-1, 0, 0, 0, 0, 0, 0});
+                    if ((size_t)sc >= memo.size()) { memo.resize((size_t)sc + 256, EvMemo{-1, 0, 0, 0, 0, 0, 0}); by_score.resize(memo.size(), EvScore{0, 0, 0, 0, 0}); }
                     EvMemo& mm = memo[sc];
-                    if (mm.gen != q) { evalue_query_side(P, sc, query_lens[q], mm); mm.gen = q; }
+                    if (mm.gen != q) {
+                        EvScore& ss = by_score[sc];
+                        if (!ss.set) evalue_score_side(P, sc, ss);
+                        evalue_query_side(ss, query_lens[q], mm);
+                        mm.gen = q;
+                    }
                     v = evalue_target_side(P, mm, cand_lens[i]);
                 } else {
                     v = evalue(P, sc, query_lens[q], cand_lens[i]);
