@@ -54,6 +54,10 @@ typedef struct s4g_queries s4g_queries;
 
 /* ---- context ---------------------------------------------------------------------------- */
 int s4g_version(void);
+/* number of CUDA devices visible to the process (0 when there is none or the driver cannot be reached): what the CLI's
+ * --cards default ("all available CUDA cards", sift4g/src/main.cpp:329-332) enumerates -- replaces cudaGetCards /
+ * cudaCheckCards (sw/cuda_utils.h:73-83) */
+int s4g_device_count(void);
 int s4g_init(int device, s4g_ctx** out);
 void s4g_shutdown(s4g_ctx* ctx);
 /* last error text of this context (or of the calling thread when ctx == NULL) */
@@ -85,6 +89,11 @@ int s4g_db_pack_fasta(const char* fasta_path, const char* out_path);
 int s4g_db_file_info(const char* packed_path, int64_t* n_seqs, uint64_t* n_residues);
 int s4g_db_open_packed(s4g_ctx* ctx, const char* path, int shard, int n_shards, s4g_db** out);
 int s4g_db_open(s4g_ctx* ctx, const char* path, int shard, int n_shards, s4g_db** out);
+/* One process driving several GPUs (the CLI with --cards): reads / parses the file ONCE and leaves shard d of n_ctx
+ * (contiguous FASTA ranges) resident on the device of ctxs[d]; out[d] receives the shard.  With fewer sequences than
+ * contexts the trailing shards are empty (n_seqs = 0), which every stage accepts.  n_threads: host threads of the
+ * FASTA parse (<= 0: all cores; the CLI passes -t). */
+int s4g_db_open_sharded(s4g_ctx* const* ctxs, int n_ctx, const char* path, int n_threads, s4g_db** out);
 void s4g_db_close(s4g_db* db);
 int64_t s4g_db_num_seqs(const s4g_db* db);
 uint64_t s4g_db_num_residues(const s4g_db* db);   /* = `cells` returned by searchDatabase() */
@@ -177,13 +186,16 @@ int s4g_sw_align(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_pairs, cons
  * (E asc, score desc, name asc).  `names` may be NULL: ties then fall back to ascending target id
  * (equal to name order for zero-padded numeric names).  Runs on `n_threads` host threads (0 = all).
  * Inputs are host pointers.  out_* arrays need capacity n_queries * max_alignments; hits of query q are
- * written contiguously, out_offsets[n_queries+1] delimits them.  matrix_name: only "BLOSUM_62" rows are
- * built in (other matrices use the reference's fallback row). */
+ * written contiguously, out_offsets[n_queries+1] delimits them.
+ * matrix_name (NULL = "BLOSUM_62") picks the constants like createEValueParams (sw/evalue.cu:148-220): the reference's
+ * table (:73-88) has protein rows for BLOSUM_62 only, so BLOSUM_62 with listed gap penalties takes its row and every
+ * other case -- unlisted penalties, any other protein matrix -- the reference's fallback, row 0 (:178-191).
+ * "EDNA_FULL" would select the DNA formula, which is not on this path: S4G_ERR_ARG. */
 int s4g_select_hits(s4g_ctx* ctx, int32_t n_queries, const int32_t* query_lens, const uint32_t* cand_ids,
                     const int64_t* cand_offsets, const int32_t* cand_scores, const int32_t* cand_lens,
-                    const char* const* cand_names, uint64_t db_residues, int gap_open, int gap_extend,
-                    double max_evalue, int max_alignments, int n_threads, uint32_t* out_q, uint32_t* out_t,
-                    int32_t* out_score, double* out_evalue, int64_t* out_offsets);
+                    const char* const* cand_names, const char* matrix_name, uint64_t db_residues, int gap_open,
+                    int gap_extend, double max_evalue, int max_alignments, int n_threads, uint32_t* out_q,
+                    uint32_t* out_t, int32_t* out_score, double* out_evalue, int64_t* out_offsets);
 
 /* Multi-GPU (one database shard per GPU): the global `max_alignments` best hits of every query out of the per-shard
  * selections.  gathered: n_ranks blocks of rank_stride rows of 3 doubles {E-value, score, target id}; block r holds rank
@@ -204,8 +216,8 @@ int s4g_merge_hits(s4g_ctx* ctx, int n_ranks, int32_t n_queries, int max_alignme
  * cand_ids / cand_offsets / scores: device pointers (as given to / produced by s4g_sw_score with S4G_DEVICE).
  * out_*: device arrays of capacity n_pairs; out_count: device uint32. */
 int s4g_evalue_screen(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, const uint32_t* cand_ids, const int64_t* cand_offsets,
-                      int64_t n_pairs, const int32_t* scores, uint64_t db_residues, int gap_open, int gap_extend,
-                      double max_evalue, uint32_t* out_query, uint32_t* out_id, int32_t* out_score, int32_t* out_tlen,
+                      int64_t n_pairs, const int32_t* scores, const char* matrix_name, uint64_t db_residues, int gap_open,
+                      int gap_extend, double max_evalue, uint32_t* out_query, uint32_t* out_id, int32_t* out_score, int32_t* out_tlen,
                       uint32_t* out_count);
 
 /* ---- measurement helpers ------------------------------------------------------------------------ */

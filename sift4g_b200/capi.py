@@ -19,6 +19,7 @@ _vp = C.c_void_p
 # name -> (restype, argtypes); must list every symbol include/sift4g_b200.h declares
 SIGNATURES = {
     "s4g_version": (C.c_int, []),
+    "s4g_device_count": (C.c_int, []),
     "s4g_init": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "s4g_shutdown": (None, [_vp]),
     "s4g_last_error": (C.c_char_p, [_vp]),
@@ -32,6 +33,7 @@ SIGNATURES = {
     "s4g_db_file_info": (C.c_int, [C.c_char_p, _i64p, C.POINTER(C.c_uint64)]),
     "s4g_db_open_packed": (C.c_int, [_vp, C.c_char_p, C.c_int, C.c_int, C.POINTER(_vp)]),
     "s4g_db_open": (C.c_int, [_vp, C.c_char_p, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "s4g_db_open_sharded": (C.c_int, [_vp, C.c_int, C.c_char_p, C.c_int, _vp]),
     "s4g_db_total_seqs": (C.c_int64, [_vp]),
     "s4g_db_total_residues": (C.c_uint64, [_vp]),
     "s4g_db_close": (None, [_vp]),
@@ -51,8 +53,8 @@ SIGNATURES = {
     "s4g_sw_align": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int64, _vp, C.c_int]),
     "s4g_merge_hits": (C.c_int, [_vp, C.c_int, C.c_int32, C.c_int, _vp, C.c_int64, _vp, C.c_uint32, C.c_uint32, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "s4g_merge_candidates_host": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp]),
-    "s4g_select_hits": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, C.c_uint64, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
-    "s4g_evalue_screen": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int64, _vp, C.c_uint64, C.c_int, C.c_int, C.c_double, _vp, _vp, _vp, _vp, _vp]),
+    "s4g_select_hits": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, C.c_char_p, C.c_uint64, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "s4g_evalue_screen": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int64, _vp, C.c_char_p, C.c_uint64, C.c_int, C.c_int, C.c_double, _vp, _vp, _vp, _vp, _vp]),
     "s4g_measure_dpx_peak": (C.c_int, [_vp, C.c_int, _f64p]),
     "s4g_last_sw_kernel_ms": (C.c_int, [_vp, _f32p]),
 }
@@ -304,7 +306,7 @@ def sw_align(ctx, db, q, pair_q, pair_t, pair_score, matrix, gap_open=10, gap_ex
 
 
 def select_hits(ctx, query_lens, cand_ids, cand_offsets, cand_scores, cand_lens, db_residues, gap_open=10, gap_extend=1,
-                max_evalue=1e-4, max_alignments=400, names=None, n_threads=0):
+                max_evalue=1e-4, max_alignments=400, names=None, n_threads=0, matrix_name=b"BLOSUM_62"):
     """host: -> (pair_q, pair_t, pair_score, evalues, offsets[nq+1])"""
     query_lens = np.ascontiguousarray(query_lens, dtype=np.int32)
     cand_ids = np.ascontiguousarray(cand_ids, dtype=np.uint32)
@@ -321,10 +323,10 @@ def select_hits(ctx, query_lens, cand_ids, cand_offsets, cand_scores, cand_lens,
         name_arr = (C.c_char_p * max(len(names), 1))(*[n.encode() if isinstance(n, str) else n for n in names])
     lib = ctx.lib if ctx is not None else load()        # pure host code: usable without a context (CPU tests)
     rc = lib.s4g_select_hits(ctx.h if ctx is not None else None, nq, _ptr(query_lens), _ptr(cand_ids), _ptr(cand_offsets), _ptr(cand_scores),
-                             _ptr(cand_lens), C.cast(name_arr, _vp) if name_arr is not None else None, int(db_residues), gap_open, gap_extend,
+                             _ptr(cand_lens), C.cast(name_arr, _vp) if name_arr is not None else None, matrix_name, int(db_residues), gap_open, gap_extend,
                              max_evalue, max_alignments, n_threads, _ptr(oq), _ptr(ot), _ptr(osc), _ptr(oe), _ptr(off))
     if rc != 0:
-        raise S4GError("s4g_select_hits failed (%d)" % rc)
+        raise S4GError("s4g_select_hits failed (%d): %s" % (rc, lib.s4g_last_error(ctx.h if ctx is not None else None).decode()))
     n = int(off[-1])
     return oq[:n], ot[:n], osc[:n], oe[:n], off
 

@@ -10,10 +10,14 @@
 //                   first column holding `score`, smallest reversed row (ssw.c:296,500,827-838);
 //   3. path       : banded_sw on the sub-rectangle, band |dt - dq| + 1 doubled until the banded maximum
 //                   reaches the score; direction rules and band-edge behaviour of ssw.c:549-727.
-// Steps 1+2: one warp per hit, 32-bit systolic sweep (lanes own 8 query rows each, the anti-diagonal moves
-// by shuffles, any query length through 256-row passes).  Step 3: one thread per hit with its three band
-// rows in shared memory and one packed direction byte per band cell in HBM; hits are batched by band width.
-// The host only sequences the band-doubling rounds (it needs the end/begin cells anyway to size buffers).
+// Step 1 (end cells): packed s16x2 systolic sweep, two hits of a query per warp (al_forward_packed_kernel, sw_score.cu);
+// the 32-bit sweep below (al_sweep32_kernel, one hit per warp, lanes own 8 query rows, 256-row passes) takes the hits of
+// queries beyond the packed kernel's reach and the swAlign-rule hits.  Step 2 (begin cells): packed reverse sweep, two
+// hits of a query per warp sharing one profile (al_reverse_packed_kernel); al_sweep32_kernel for what it cannot take.
+// Step 3 (path): al_band_persistent_kernel -- one warp takes a hit through all its band-doubling attempts, rows
+// warp-parallel (max-plus prefix scan for F), direction bytes in a per-warp scratch region; bands that outgrow its
+// shared-memory rows go to the host-sequenced rounds (al_band_warp_kernel; al_band_kernel, one thread per hit, for
+// gap_extend > gap_open, where the scan does not apply).  Score > 32767 or gap penalties beyond 8 bits: al_swalign_kernel.
 #include <algorithm>
 #include <cub/cub.cuh>
 
@@ -786,6 +790,7 @@ extern "C" int s4g_sw_align(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_
                             int64_t* out_path_offsets, int where) {
     if (!ctx || !db || !q || n_pairs < 0 || !matrix || !out_path_offsets) return S4G_ERR_ARG;
     if (n_pairs > 0 && (!pair_q || !pair_t || !pair_score || !out_coords || !out_paths)) return S4G_ERR_ARG;
+    if (n_pairs >= ((int64_t)1 << 31)) { s4g_set_error(ctx, "s4g_sw_align: %lld hits in one call (limit 2^31 - 1); split the batch", (long long)n_pairs); return S4G_ERR_CAPACITY; }
     S4G_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     if (n_pairs == 0) {

@@ -105,27 +105,38 @@ int s4g_init(int device, s4g_ctx** out) {
     if (device < 0 || device >= n) { s4g_set_error(nullptr, "device %d out of range (0..%d)", device, n - 1); return S4G_ERR_ARG; }
     s4g_ctx* ctx = new s4g_ctx();
     ctx->device = device;
-    S4G_CUDA(ctx, cudaSetDevice(device));
-    cudaDeviceProp prop;
-    S4G_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10) {
-        s4g_set_error(nullptr, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
-        delete ctx;
-        return S4G_ERR_CUDA;
-    }
-    ctx->sm_count = prop.multiProcessorCount;
-    { const char* t = getenv("S4G_TRACE"); ctx->trace = t && t[0] && t[0] != '0'; }
-    S4G_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    S4G_CUDA(ctx, cudaEventCreate(&ctx->ev_sw0));
-    S4G_CUDA(ctx, cudaEventCreate(&ctx->ev_sw1));
+    // every failure below releases the context (s4g_shutdown destroys what was created so far) and leaves its text in the
+    // calling thread's error slot, which is what s4g_last_error(NULL) reads
+    const int rc = [&]() -> int {
+        S4G_CUDA(ctx, cudaSetDevice(device));
+        cudaDeviceProp prop;
+        S4G_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10) {
+            s4g_set_error(nullptr, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+            return S4G_ERR_CUDA;
+        }
+        ctx->sm_count = prop.multiProcessorCount;
+        { const char* t = getenv("S4G_TRACE"); ctx->trace = t && t[0] && t[0] != '0'; }
+        S4G_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        S4G_CUDA(ctx, cudaEventCreate(&ctx->ev_sw0));
+        S4G_CUDA(ctx, cudaEventCreate(&ctx->ev_sw1));
+        return S4G_OK;
+    }();
+    if (rc != S4G_OK) { s4g_shutdown(ctx); return rc; }
     *out = ctx;
     return S4G_OK;
+}
+
+int s4g_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
 }
 
 void s4g_shutdown(s4g_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < s4g_ctx::kSlots; ++i) if (ctx->slot_ptr[i]) cudaFree(ctx->slot_ptr[i]);
     for (int i = 0; i < 8; ++i) if (ctx->pin_ptr[i]) cudaFreeHost(ctx->pin_ptr[i]);
     if (ctx->ev_sw0) cudaEventDestroy(ctx->ev_sw0);
@@ -264,6 +275,8 @@ int s4g_sw_score(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, const uint32_t* cand_
                  int64_t n_pairs, const int32_t* matrix, int gap_open, int gap_extend, int32_t* out_scores, int where) {
     if (!ctx || !db || !q || !cand_offsets || !matrix || n_pairs < 0 || (n_pairs > 0 && (!cand_ids || !out_scores))) return S4G_ERR_ARG;
     if (gap_open < 0 || gap_extend < 0 || gap_open > 4096 || gap_extend > 4096) { s4g_set_error(ctx, "gap penalties out of range"); return S4G_ERR_ARG; }
+    // pair positions travel as uint32 (sort values, overflow list) and cub counts items in int
+    if (n_pairs >= ((int64_t)1 << 31)) { s4g_set_error(ctx, "s4g_sw_score: %lld pairs in one call (limit 2^31 - 1); split the batch", (long long)n_pairs); return S4G_ERR_CAPACITY; }
     S4G_CUDA(ctx, cudaSetDevice(ctx->device));
     if (n_pairs == 0) return S4G_OK;
     if (where == S4G_DEVICE)

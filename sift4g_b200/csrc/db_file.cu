@@ -77,13 +77,15 @@ void parse_piece(const char* data, size_t total, Piece& pc, bool last_piece, uin
         const char c = data[pos];
         if (!in_name) {
             const unsigned char u = (unsigned char)c;
-            if ((unsigned)((u | 32) - 'a') < 26u) {           // the common case first
+            // the file's last byte is a terminator, not a residue: it is neither stored nor counted (the count pass
+            // sized `codes` without it)
+            const bool term = last_piece && pos == total - 1 && eof_closes;
+            if (!term && (unsigned)((u | 32) - 'a') < 26u) {   // the common case first
                 if (EMIT) codes[n_res] = (uint8_t)((u | 32) - 'a');
                 ++n_res; ++cur_len;
-                if (!(last_piece && pos == total - 1 && eof_closes)) continue;
-                --n_res; --cur_len;                            // the file's last byte is a terminator, not a residue
+                continue;
             }
-            if (c == '>' || (last_piece && pos == total - 1 && eof_closes)) {
+            if (c == '>' || term) {
                 if (!close_record(pos)) return;
                 in_name = true;
             } else {
@@ -105,12 +107,12 @@ struct Parsed {
     std::vector<std::string> names;
 };
 
-int parse_fasta(s4g_ctx* ctx, const char* path, Parsed& out) {
+int parse_fasta(s4g_ctx* ctx, const char* path, Parsed& out, int want_threads = 0) {
     MappedFile f;
     if (!f.open(path)) { s4g_set_error(ctx, "cannot open '%s'", path); return S4G_ERR_IO; }
     const char* data = f.p;
     const size_t total = f.size;
-    unsigned hw = std::thread::hardware_concurrency();
+    unsigned hw = want_threads > 0 ? (unsigned)want_threads : std::thread::hardware_concurrency();
     if (const char* t = getenv("S4G_HOST_THREADS")) hw = (unsigned)atoi(t);
     const size_t n_threads = std::max<size_t>(1, std::min<size_t>(hw ? hw : 1, 64));
     // cut points: a '>' that directly follows a '\n' is always met outside a header line, i.e. always starts a record
@@ -198,6 +200,7 @@ extern "C" {
 int s4g_db_open_fasta(s4g_ctx* ctx, const char* path, int shard, int n_shards, s4g_db** out) {
     if (!ctx || !path || !out || n_shards < 1 || shard < 0 || shard >= n_shards) return S4G_ERR_ARG;
     *out = nullptr;
+    try {
     Parsed p;
     int rc = parse_fasta(ctx, path, p);
     if (rc != S4G_OK) return rc;
@@ -213,10 +216,16 @@ int s4g_db_open_fasta(s4g_ctx* ctx, const char* path, int shard, int n_shards, s
         (*out)->total_residues = (uint64_t)p.off[n_all];
     }
     return rc;
+    } catch (const std::exception& e) {          // nothing is thrown across the C ABI
+        if (*out) { s4g_db_close(*out); *out = nullptr; }
+        s4g_set_error(ctx, "'%s': %s while reading the FASTA file", path, e.what());
+        return S4G_ERR_NOMEM;
+    }
 }
 
 int s4g_db_pack_fasta(const char* fasta_path, const char* out_path) {
     if (!fasta_path || !out_path) return S4G_ERR_ARG;
+    try {
     Parsed p;
     int rc = parse_fasta(nullptr, fasta_path, p);
     if (rc != S4G_OK) return rc;
@@ -241,6 +250,10 @@ int s4g_db_pack_fasta(const char* fasta_path, const char* out_path) {
     ok = (fclose(f) == 0) && ok;
     if (!ok) { s4g_set_error(nullptr, "write to '%s' failed", out_path); return S4G_ERR_IO; }
     return S4G_OK;
+    } catch (const std::exception& e) {
+        s4g_set_error(nullptr, "'%s': %s while packing", fasta_path, e.what());
+        return S4G_ERR_NOMEM;
+    }
 }
 
 int s4g_db_file_info(const char* path, int64_t* n_seqs, uint64_t* n_residues) {
@@ -263,34 +276,113 @@ int s4g_db_open_packed(s4g_ctx* ctx, const char* path, int shard, int n_shards, 
     if (fd < 0) { s4g_set_error(ctx, "cannot open '%s'", path); return S4G_ERR_IO; }
     DbFileHeader h;
     if (!read_header(fd, h)) { ::close(fd); s4g_set_error(ctx, "'%s' is not a packed sift4g_b200 database", path); return S4G_ERR_IO; }
+    // Nothing of the header is trusted before it is checked against the size of the file: the tables, the names and the
+    // codes must all lie inside it (a corrupt n_seqs would otherwise size the vectors below).
+    struct stat fst;
+    const bool have_size = fstat(fd, &fst) == 0;
+    const uint64_t fsize = have_size ? (uint64_t)fst.st_size : 0;
+    const uint64_t tables = sizeof(h) + 2 * sizeof(int64_t) * (h.n_seqs + 1);
+    const bool header_ok = have_size && h.n_seqs < ((uint64_t)1 << 32) && tables <= fsize && h.names_bytes <= fsize - tables &&
+                           h.codes_pos >= tables + h.names_bytes && h.codes_pos <= fsize && h.n_residues <= fsize - h.codes_pos;
+    if (!header_ok) { ::close(fd); s4g_set_error(ctx, "'%s': corrupt packed database header", path); return S4G_ERR_IO; }
     const int64_t n_all = (int64_t)h.n_seqs;
     const int64_t lo = n_all * shard / n_shards, hi = n_all * (shard + 1) / n_shards, n = hi - lo;
-    std::vector<int64_t> off(n + 1), name_off(n + 1);
-    const uint64_t off_pos = sizeof(h), name_off_pos = off_pos + sizeof(int64_t) * (n_all + 1), names_pos = name_off_pos + sizeof(int64_t) * (n_all + 1);
-    bool ok = read_at(fd, off.data(), sizeof(int64_t) * (n + 1), off_pos + sizeof(int64_t) * lo) &&
-              read_at(fd, name_off.data(), sizeof(int64_t) * (n + 1), name_off_pos + sizeof(int64_t) * lo);
-    std::vector<char> names;
-    std::vector<uint8_t> codes;
-    if (ok) {
-        ok = off[0] >= 0 && off[n] >= off[0] && (uint64_t)off[n] <= h.n_residues && name_off[n] >= name_off[0] && (uint64_t)name_off[n] <= h.names_bytes;
+    try {
+        std::vector<int64_t> off(n + 1), name_off(n + 1);
+        const uint64_t off_pos = sizeof(h), name_off_pos = off_pos + sizeof(int64_t) * (n_all + 1), names_pos = name_off_pos + sizeof(int64_t) * (n_all + 1);
+        bool ok = read_at(fd, off.data(), sizeof(int64_t) * (n + 1), off_pos + sizeof(int64_t) * lo) &&
+                  read_at(fd, name_off.data(), sizeof(int64_t) * (n + 1), name_off_pos + sizeof(int64_t) * lo);
+        std::vector<char> names;
+        std::vector<uint8_t> codes;
         if (ok) {
-            names.resize((size_t)(name_off[n] - name_off[0]));
-            codes.resize((size_t)(off[n] - off[0]));
-            ok = (names.empty() || read_at(fd, names.data(), names.size(), names_pos + (uint64_t)name_off[0])) &&
-                 (codes.empty() || read_at(fd, codes.data(), codes.size(), h.codes_pos + (uint64_t)off[0]));
+            ok = off[0] >= 0 && (uint64_t)off[n] <= h.n_residues && name_off[0] >= 0 && (uint64_t)name_off[n] <= h.names_bytes;
+            // every entry, not only the ends: sequences are non-empty, a name holds at least its NUL
+            for (int64_t i = 0; ok && i < n; ++i) ok = off[i + 1] > off[i] && name_off[i + 1] > name_off[i];
+            if (ok) {
+                names.resize((size_t)(name_off[n] - name_off[0]));
+                codes.resize((size_t)(off[n] - off[0]));
+                ok = (names.empty() || read_at(fd, names.data(), names.size(), names_pos + (uint64_t)name_off[0])) &&
+                     (codes.empty() || read_at(fd, codes.data(), codes.size(), h.codes_pos + (uint64_t)off[0]));
+                // name i ends with the NUL in front of name i + 1
+                for (int64_t i = 0; ok && i < n; ++i) ok = names[(size_t)(name_off[i + 1] - name_off[0]) - 1] == 0;
+            }
         }
+        ::close(fd);
+        fd = -1;
+        if (!ok) { s4g_set_error(ctx, "'%s': truncated or corrupt packed database", path); return S4G_ERR_IO; }
+        for (size_t i = 0; i < codes.size(); ++i) if (codes[i] >= S4G_NLET) { s4g_set_error(ctx, "'%s': residue code out of range", path); return S4G_ERR_IO; }
+        const int64_t base = off[0];
+        for (auto& o : off) o -= base;
+        int rc = s4g_db_create(ctx, codes.data(), off.data(), n, (uint32_t)lo, S4G_HOST, out);
+        if (rc != S4G_OK) return rc;
+        (*out)->names.resize(n);
+        for (int64_t i = 0; i < n; ++i) (*out)->names[i].assign(names.data() + (name_off[i] - name_off[0]));
+        (*out)->total_seqs = n_all;
+        (*out)->total_residues = h.n_residues;
+        return S4G_OK;
+    } catch (const std::exception& e) {          // nothing is thrown across the C ABI
+        if (fd >= 0) ::close(fd);
+        if (*out) { s4g_db_close(*out); *out = nullptr; }
+        s4g_set_error(ctx, "'%s': %s while reading the packed database", path, e.what());
+        return S4G_ERR_NOMEM;
     }
-    ::close(fd);
-    if (!ok) { s4g_set_error(ctx, "'%s': truncated or corrupt packed database", path); return S4G_ERR_IO; }
-    for (size_t i = 0; i < codes.size(); ++i) if (codes[i] >= S4G_NLET) { s4g_set_error(ctx, "'%s': residue code out of range", path); return S4G_ERR_IO; }
-    const int64_t base = off[0];
-    for (auto& o : off) o -= base;
-    int rc = s4g_db_create(ctx, codes.data(), off.data(), n, (uint32_t)lo, S4G_HOST, out);
-    if (rc != S4G_OK) return rc;
-    (*out)->names.resize(n);
-    for (int64_t i = 0; i < n; ++i) (*out)->names[i].assign(names.data() + (name_off[i] - name_off[0]));
-    (*out)->total_seqs = n_all;
-    (*out)->total_residues = h.n_residues;
+}
+
+static bool is_packed_file(const char* path, bool* opened) {
+    char magic[8] = {0};
+    FILE* f = fopen(path, "rb");
+    *opened = f != nullptr;
+    if (!f) return false;
+    const size_t got = fread(magic, 1, 8, f);
+    fclose(f);
+    return got == 8 && memcmp(magic, kMagic, 8) == 0;
+}
+
+int s4g_db_open_sharded(s4g_ctx* const* ctxs, int n_ctx, const char* path, int n_threads, s4g_db** out) {
+    if (!ctxs || n_ctx < 1 || !path || !out) return S4G_ERR_ARG;
+    for (int d = 0; d < n_ctx; ++d) { if (!ctxs[d]) return S4G_ERR_ARG; out[d] = nullptr; }
+    bool opened = false;
+    const bool packed = is_packed_file(path, &opened);
+    if (!opened) { s4g_set_error(ctxs[0], "cannot open '%s'", path); return S4G_ERR_IO; }
+    std::vector<int> rcs(n_ctx, S4G_OK);
+    try {
+        Parsed p;
+        int64_t n_all = 0;
+        if (!packed) {
+            const int rc = parse_fasta(ctxs[0], path, p, n_threads);
+            if (rc != S4G_OK) return rc;
+            n_all = (int64_t)p.names.size();
+        }
+        // one host thread per GPU: the H2D copies of the shards (and, for a packed file, the reads of their byte ranges) overlap
+        auto open_one = [&](int d) {
+            if (packed) { rcs[d] = s4g_db_open_packed(ctxs[d], path, d, n_ctx, &out[d]); return; }
+            const int64_t lo = n_all * d / n_ctx, hi = n_all * (d + 1) / n_ctx;
+            std::vector<int64_t> soff(hi - lo + 1);
+            for (int64_t i = lo; i <= hi; ++i) soff[i - lo] = p.off[i] - p.off[lo];
+            rcs[d] = s4g_db_create(ctxs[d], p.codes.data() + p.off[lo], soff.data(), hi - lo, (uint32_t)lo, S4G_HOST, &out[d]);
+            if (rcs[d] != S4G_OK) return;
+            out[d]->names.resize(hi - lo);
+            for (int64_t i = lo; i < hi; ++i) out[d]->names[i - lo].swap(p.names[i]);
+            out[d]->total_seqs = n_all;
+            out[d]->total_residues = (uint64_t)p.off[n_all];
+        };
+        if (n_ctx == 1) open_one(0);
+        else {
+            std::vector<std::thread> th;
+            for (int d = 0; d < n_ctx; ++d) th.emplace_back(open_one, d);
+            for (auto& t : th) t.join();
+        }
+    } catch (const std::exception& e) {
+        s4g_set_error(ctxs[0], "'%s': %s while opening the database", path, e.what());
+        rcs[0] = S4G_ERR_NOMEM;
+    }
+    for (int d = 0; d < n_ctx; ++d)
+        if (rcs[d] != S4G_OK) {
+            const std::string msg = ctxs[d]->err;           // closing the other shards must not lose the text
+            for (int x = 0; x < n_ctx; ++x) if (out[x]) { s4g_db_close(out[x]); out[x] = nullptr; }
+            s4g_set_error(ctxs[0], "%s", msg.c_str());
+            return rcs[d];
+        }
     return S4G_OK;
 }
 

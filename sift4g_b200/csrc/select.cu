@@ -33,10 +33,17 @@ const EvRow kB62[] = {
 
 struct EvParams { double lambda, K, a, b, alpha, beta, sigma, tau; double length; };
 
-EvParams make_params(uint64_t db_residues, int go, int ge) {
+// createEValueParams (sw/evalue.cu:148-220): the table holds rows for BLOSUM_62 (protein) and EDNA_FULL (DNA) only.  BLOSUM_62
+// with listed gap penalties takes its row; BLOSUM_62 with other penalties and EVERY other protein matrix fall back to
+// row 0 (the ungapped BLOSUM_62 constants, with a warning) -- so row 0 is what any name but "BLOSUM_62" selects here.
+// EDNA_FULL selects the DNA formula (calculateEValueDna), which is not on this path: rejected by the callers.
+bool matrix_supported(const char* matrix_name) { return !(matrix_name && strcmp(matrix_name, "EDNA_FULL") == 0); }
+
+EvParams make_params(const char* matrix_name, uint64_t db_residues, int go, int ge) {
     int idx = 0;
-    for (int i = 0; i < (int)(sizeof(kB62) / sizeof(kB62[0])); ++i)
-        if (kB62[i].go == go && kB62[i].ge == ge) { idx = i; break; }
+    if (!matrix_name || strcmp(matrix_name, "BLOSUM_62") == 0)
+        for (int i = 0; i < (int)(sizeof(kB62) / sizeof(kB62[0])); ++i)
+            if (kB62[i].go == go && kB62[i].ge == ge) { idx = i; break; }
     const EvRow& r = kB62[idx];
     const double G = go + ge;
     EvParams p;
@@ -155,13 +162,13 @@ __global__ void ev_gather_kernel(const uint32_t* sel, const uint32_t* n_sel, con
 
 extern "C" int s4g_select_hits(s4g_ctx* ctx, int32_t nq, const int32_t* query_lens, const uint32_t* cand_ids,
                                const int64_t* cand_offsets, const int32_t* cand_scores, const int32_t* cand_lens,
-                               const char* const* cand_names, uint64_t db_residues, int gap_open, int gap_extend,
-                               double max_evalue, int max_alignments, int n_threads, uint32_t* out_q, uint32_t* out_t,
-                               int32_t* out_score, double* out_evalue, int64_t* out_offsets) {
+                               const char* const* cand_names, const char* matrix_name, uint64_t db_residues, int gap_open,
+                               int gap_extend, double max_evalue, int max_alignments, int n_threads, uint32_t* out_q,
+                               uint32_t* out_t, int32_t* out_score, double* out_evalue, int64_t* out_offsets) {
     if (nq < 0 || !query_lens || !cand_offsets || !out_offsets || max_alignments < 0) return S4G_ERR_ARG;
+    if (!matrix_supported(matrix_name)) { s4g_set_error(ctx, "s4g_select_hits: %s selects the DNA E-value formula, which this path does not provide", matrix_name); return S4G_ERR_ARG; }
     if (cand_offsets[nq] > 0 && (!cand_ids || !cand_scores || !cand_lens || !out_q || !out_t || !out_score || !out_evalue)) return S4G_ERR_ARG;
-    (void)ctx;
-    const EvParams P = make_params(db_residues, gap_open, gap_extend);
+    const EvParams P = make_params(matrix_name, db_residues, gap_open, gap_extend);
     if (n_threads <= 0) n_threads = std::min(32, (int)std::thread::hardware_concurrency());   // more threads cost more to start than they save
     if (n_threads < 1) n_threads = 1;
     if (n_threads > nq) n_threads = nq > 0 ? nq : 1;
@@ -327,15 +334,16 @@ extern "C" int s4g_merge_hits(s4g_ctx* ctx, int n_ranks, int32_t nq, int max_ali
 }
 
 extern "C" int s4g_evalue_screen(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, const uint32_t* cand_ids, const int64_t* cand_offsets,
-                                 int64_t n_pairs, const int32_t* scores, uint64_t db_residues, int gap_open, int gap_extend,
-                                 double max_evalue, uint32_t* out_query, uint32_t* out_id, int32_t* out_score, int32_t* out_tlen,
+                                 int64_t n_pairs, const int32_t* scores, const char* matrix_name, uint64_t db_residues, int gap_open,
+                                 int gap_extend, double max_evalue, uint32_t* out_query, uint32_t* out_id, int32_t* out_score, int32_t* out_tlen,
                                  uint32_t* out_count) {
     if (!ctx || !db || !q || !cand_offsets || !out_count || n_pairs < 0) return S4G_ERR_ARG;
     S4G_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     if (n_pairs == 0) { S4G_CUDA(ctx, cudaMemsetAsync(out_count, 0, 4, st)); return S4G_OK; }
-    if (n_pairs >= (1ll << 31)) { s4g_set_error(ctx, "s4g_evalue_screen: more than 2^31 pairs"); return S4G_ERR_ARG; }
-    const EvParams P = make_params(db_residues, gap_open, gap_extend);
+    if (n_pairs >= (1ll << 31)) { s4g_set_error(ctx, "s4g_evalue_screen: more than 2^31 pairs"); return S4G_ERR_CAPACITY; }
+    if (!matrix_supported(matrix_name)) { s4g_set_error(ctx, "s4g_evalue_screen: %s selects the DNA E-value formula, which this path does not provide", matrix_name); return S4G_ERR_ARG; }
+    const EvParams P = make_params(matrix_name, db_residues, gap_open, gap_extend);
     char* buf = (char*)s4g_scratch(ctx, SLOT_AL_WORK, (size_t)n_pairs * (1 + 4 + 4 + 4) + 256);
     if (!buf) return S4G_ERR_NOMEM;
     uint32_t* qidx = (uint32_t*)buf;

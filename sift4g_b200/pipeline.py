@@ -237,7 +237,7 @@ class DevicePipeline:
             mark("sw_score")
             s_q, s_id, s_sc, s_tl = self._scr
             ctx.check(ctx.lib.s4g_evalue_screen(ctx.h, db.h, self.Q.h, ids_h.data_ptr(), off.data_ptr(), n, sc_h.data_ptr(),
-                                                self.total_residues, self.go, self.ge, self.max_evalue, s_q.data_ptr(), s_id.data_ptr(),
+                                                b"BLOSUM_62", self.total_residues, self.go, self.ge, self.max_evalue, s_q.data_ptr(), s_id.data_ptr(),
                                                 s_sc.data_ptr(), s_tl.data_ptr(), self._scr_cnt.data_ptr()))
             n_s = int(self._scr_cnt.item())
             n_surv[0] += n_s

@@ -116,3 +116,16 @@ def test_errors(tmp_path):
     q.write_bytes(b">a\nACD\n")
     with pytest.raises(capi.S4GError):
         capi.packed_info(str(q))
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("n_last", [1, 2, 7, 8, 12, 13, 24, 25, 40, 56, 57, 120])
+def test_last_byte_is_a_residue_letter(tmp_path, n_last):
+    # no trailing newline and the file ends in a residue letter: the reader consumes that byte as the record terminator
+    # (sw/pre_proc.c:488).  The EMIT pass must not store it either: the code vector was sized without it (round-1 advisor
+    # finding: a one-byte heap overflow that aborted in free() when the residue count filled its malloc chunk exactly).
+    p = tmp_path / "t.fa"
+    p.write_bytes(b">a\nAAAAAAAAAAAA\n>b\n" + b"C" * n_last + b"D")
+    got = packed_records(p, tmp_path)
+    assert got == ref_records(p)
+    assert got[-1] == ("b", "C" * n_last)
