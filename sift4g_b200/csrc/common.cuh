@@ -100,7 +100,7 @@ enum {
     SLOT_SW_MISC, SLOT_SW_OVF, SLOT_SW_BOUND, SLOT_SW_MAT,
     SLOT_PF_INDEX, SLOT_PF_BITMAP, SLOT_PF_RANK, SLOT_PF_BUCKET, SLOT_PF_HITS, SLOT_PF_CAND,
     SLOT_PF_COUNT, SLOT_PF_THR, SLOT_PF_CUB, SLOT_PF_TMP, SLOT_PF_TMP2, SLOT_PF_SPILL, SLOT_PF_GBUF, SLOT_SW_STRIP,
-    SLOT_AL_WORK, SLOT_AL_DIR, SLOT_AL_MISC, SLOT_AL_OUT
+    SLOT_AL_WORK, SLOT_AL_DIR, SLOT_AL_MISC, SLOT_AL_OUT, SLOT_PF_ENTRY
 };
 
 // ---- stage launchers (device pointers, enqueue on ctx->stream) ----------------------------------

@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstring>
+#include <type_traits>
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -28,7 +29,6 @@
 namespace {
 
 constexpr int kWarps = 8;
-constexpr int kMaxWarps = 16;            // scan kernel: warps per CTA when its shared-memory tables are large
 constexpr int kSeqBatch = 4;           // sequences claimed per atomic
 constexpr int kGCap = 1024;             // surviving hits per sequence handled in the per-warp global scratch
 constexpr unsigned long long kNoThr = ~0ull;
@@ -44,6 +44,8 @@ struct PfParams {
     const uint2* bitrank;
     const uint32_t* bucket_start;
     const unsigned long long* hits;
+    const unsigned long long* entry;  // per index k-mer: bit 63 set -> its only hit, else (bucket size << 32 | first entry in `hits`)
+    const int64_t* q_hit_start;       // first index entry of every query (nq + 1): equal neighbours = a query without k-mers
     int nq;
     unsigned long long* thr;
     uint32_t* count;
@@ -113,12 +115,11 @@ __device__ int lis_inplace(unsigned long long* buf, int a, int n) {
     return len;
 }
 
-// One scan step of a warp: 128 k-mer positions starting at `base`, 4 consecutive positions per lane (the 4 index
-// probes of a lane are independent loads -> memory-level parallelism; emission order = position order).
-// Returns the lane's buckets: first entry hb[i] and size hc[i] for each of its positions (0 when the k-mer is absent
-// from the index, is a consecutive duplicate (database_search.cpp:212-214) or lies beyond the sequence).
-__device__ __forceinline__ void scan_step(const PfParams& P, const uint8_t* seq, int npos, int base, int lane, uint32_t& carry,
-                                          uint32_t (&hb)[4], uint32_t (&hc)[4]) {
+// k-mers of one scan step of a warp: 128 positions starting at `base`, 4 consecutive positions per lane.  probe[i] says
+// whether position j0 + i takes part at all: inside the sequence and not a consecutive duplicate of the k-mer in front of it
+// (database_search.cpp:212-214).
+__device__ __forceinline__ void step_kmers(const PfParams& P, const uint8_t* seq, int npos, int base, int lane, uint32_t& carry,
+                                           uint32_t (&km)[4], bool (&probe)[4]) {
     const unsigned FULL = 0xffffffffu;
     const int k = P.k;
     const int j0 = base + 4 * lane;
@@ -136,7 +137,6 @@ __device__ __forceinline__ void scan_step(const PfParams& P, const uint8_t* seq,
     uint32_t by[8];
 #pragma unroll
     for (int x = 0; x < 4; ++x) { by[x] = (lo >> (8 * x)) & 0x1fu; by[x + 4] = (hi >> (8 * x)) & 0x1fu; }
-    uint32_t km[4];
     {
         uint32_t v = (((by[0] << 5) | by[1]) << 5) | by[2];
         if (k >= 4) v = (v << 5) | by[3];
@@ -153,10 +153,18 @@ __device__ __forceinline__ void scan_step(const PfParams& P, const uint8_t* seq,
     uint32_t prev0 = __shfl_up_sync(FULL, km[3], 1);
     if (lane == 0) prev0 = carry;
     carry = __shfl_sync(FULL, km[3], 31);
-    bool probe[4];
     probe[0] = j0 < npos && !(j0 > 0 && km[0] == prev0);
 #pragma unroll
     for (int i = 1; i < 4; ++i) probe[i] = (j0 + i < npos) && km[i] != km[i - 1];
+}
+
+// One scan step of a warp (the re-walk and the deferred path): the lane's buckets -- first entry hb[i] and size hc[i] for
+// each of its positions (0 when the k-mer is absent from the index, is a consecutive duplicate or lies beyond the sequence).
+__device__ __forceinline__ void scan_step(const PfParams& P, const uint8_t* seq, int npos, int base, int lane, uint32_t& carry,
+                                          uint32_t (&hb)[4], uint32_t (&hc)[4]) {
+    uint32_t km[4];
+    bool probe[4];
+    step_kmers(P, seq, npos, base, lane, carry, km, probe);
     uint2 br[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) br[i] = probe[i] ? __ldg(P.bitrank + (km[i] >> 5)) : make_uint2(0u, 0u);
@@ -207,66 +215,60 @@ __device__ __forceinline__ uint32_t lane_hit_index(const uint32_t (&hb)[4], cons
 // (20 000 queries, ~435 hits per step), where every lane reading its own bucket turns one coalesced request into 32.
 __device__ __forceinline__ bool lane_owned(uint32_t cmax, uint32_t total) { return total <= 64u && cmax <= 6u; }
 
-// Can a (query, sequence) pair still beat the query's cut-off?  cnt16 = hashed per-sequence hit counters (they only
-// over-estimate a query's hits); the query's cut-off score comes from the CTA's shared table (upper 16 bits of the
-// float, i.e. rounded down -- conservative) or, for batches too large for it, from global memory.
-// Hashed per-sequence hit counters.  One hash: slot = q & cmask over all `cslots` counters.  Two hashes (batches with several
-// queries per counter): the array is split in two halves, a hit is counted in slot q & cmask of the first and in a
-// multiplicative-hash slot of the second; both over-estimate the query's hits, so their minimum does too -- and two
-// queries rarely collide in both halves, which makes the filter several times sharper at the same shared memory.
-struct Counters {
-    uint32_t* cnt;                 // 2 x 16 bit per word
-    const unsigned short* cnt16;
-    uint32_t cmask;                // slots per half - 1
-    uint32_t half;                 // 0: one hash; else slots per half
-    uint32_t hshift;
-    __device__ __forceinline__ uint32_t slot2(uint32_t q) const { return half + ((q * 0x9E3779B1u) >> hshift); }
-    __device__ __forceinline__ void add(uint32_t q) const {
-        const uint32_t s1 = q & cmask;
-        atomicAdd(cnt + (s1 >> 1), (s1 & 1u) ? 0x10000u : 1u);
-        if (half) { const uint32_t s2 = slot2(q); atomicAdd(cnt + (s2 >> 1), (s2 & 1u) ? 0x10000u : 1u); }
-    }
-    __device__ __forceinline__ uint32_t count(uint32_t q) const {      // >= the query's hits in this sequence; 1 = exactly one
-        uint32_t c = cnt16[q & cmask];
-        if (half) c = min(c, (uint32_t)cnt16[slot2(q)]);
-        return c;
-    }
-};
+// Exact per-sequence hit counters: one 16-bit counter per query of the batch (two per 32-bit word), private to the warp.
+__device__ __forceinline__ uint32_t count_of(const uint32_t* cnt, uint32_t q) { return reinterpret_cast<const unsigned short*>(cnt)[q]; }
 
-__device__ __forceinline__ bool may_pass(const PfParams& P, const unsigned short* qthr, uint32_t count, uint32_t q, float flen) {
-    const float th = qthr ? __uint_as_float((uint32_t)qthr[q] << 16) : __uint_as_float(~(uint32_t)(__ldcg(P.thr + q) >> 32));
+// Can a (query, sequence) pair still beat the query's cut-off?  LIS <= number of hits, so a pair whose hit COUNT cannot reach
+// cut-off x length is no candidate.  The cut-off comes from the CTA's shared table: upper 16 bits of the float score, i.e.
+// rounded down -- conservative; 0 while the query has no cut-off yet.
+__device__ __forceinline__ bool may_pass(const unsigned short* qthr, uint32_t count, uint32_t q, float flen) {
+    const float th = __uint_as_float((uint32_t)qthr[q] << 16);
     return !((float)count < th * flen);
 }
 
+constexpr uint32_t kRankRing = 256, kBucketRing = 64;      // entries of the two per-warp queues of pass A (1 KB + 512 B)
+constexpr uint32_t kLaneBucket = 24;      // index buckets up to this size are walked by one lane, larger ones by the warp
+
 // The scan kernel.  Per sequence (one warp):
-//   pass A  walks the k-mer positions, counts the hits of every query in per-warp hashed 16-bit counters and buffers
-//           the hits in shared memory while they fit;
-//   filter  a (query, sequence) pair can only become a candidate when LIS/len beats the query's cut-off, and
-//           LIS <= number of hits, so hits of queries whose COUNT cannot beat the cut-off are dropped (exact: the
-//           counters only over-estimate).  Once the cut-offs have settled this removes practically every random hit
-//           before any sorting;  sequences whose hits did not fit are re-walked keeping only the survivors;
-//   rest    survivors are bitonic-sorted by (query, emission order), each query's run reduced by the in-place LIS.
-// Shared memory per warp: hit buffer scap x 8 B, counters cslots x 2 B (cslots = 1024 .. 4096 by batch size: the
-// fewer queries share a counter, the sharper the filter), step tables 2 x 128 x 4 B.
-template <int kHitUnroll>
-__device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cslots, int qthr_in_smem, int hash2) {
+//   pass A  walks the k-mer positions (4 per lane and step) and COUNTS the hits of every query in the warp's exact counters.
+//           Nothing is stored: a shared-memory atomic returns the previous count, and the one hit that takes a query's count
+//           across  cut-off x length  raises a flag.  The presence/rank probe is a random 32-byte sector access, of which an
+//           SM completes one per clock (tools/gather_microbench.cu: 290 G/s whole GPU); k-mers of the index with a single
+//           hit carry it in their bucket entry (one access instead of two).  A Bloom filter in shared memory in front of the
+//           probe was built and measured: it halves the probes and makes the scan slower (the kernel is bound by issued
+//           instructions, not by the L1 wavefront rate -- profiles/r02_prefilter.md).
+//   no flag -> the sequence holds no candidate for any query: clear the counters, next sequence (practically every
+//           sequence once the cut-offs have settled).
+//   pass B  re-walks the sequence and keeps the hits of the queries whose exact count reaches their cut-off; a query with
+//           exactly one hit has LIS = 1 and is emitted straight away, the other survivors are bitonic-sorted by
+//           (query, emission order) and each query's run is reduced by the in-place LIS.
+// Shared memory: per warp  scap x 8 B (sort buffer; the step tables of pass B alias it) + cnt_words x 4 B counters;
+// per CTA  the 2-byte cut-off table.
+__device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cnt_words) {
     extern __shared__ unsigned long long sbuf[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     unsigned long long* buf = sbuf + (size_t)warp * scap;
     uint32_t* cnt_all = reinterpret_cast<uint32_t*>(sbuf + (size_t)nwarps * scap);
-    const uint32_t chalf = hash2 ? (uint32_t)cslots / 2u : 0u;
-    uint32_t* step_all = cnt_all + nwarps * (cslots / 2);
-    unsigned short* qthr = qthr_in_smem ? reinterpret_cast<unsigned short*>(step_all + nwarps * 256) : nullptr;
-    uint32_t* cnt = cnt_all + warp * (cslots / 2);
-    unsigned short* cnt16 = reinterpret_cast<unsigned short*>(cnt);
-    const Counters C{cnt, cnt16, (chalf ? chalf : (uint32_t)cslots) - 1u, chalf, chalf ? (uint32_t)__clz(chalf) + 1u : 0u};
-    uint32_t* off_s = step_all + warp * 256;
+    uint32_t* cnt = cnt_all + (size_t)warp * cnt_words;
+    unsigned short* qthr = reinterpret_cast<unsigned short*>(cnt_all + (size_t)nwarps * cnt_words);
+    uint32_t* off_s = reinterpret_cast<uint32_t*>(buf);      // pass B only (step tables); its survivors go to the global scratch
     uint32_t* hb_s = off_s + 128;
+    uint32_t* ring_r = reinterpret_cast<uint32_t*>(buf);     // pass A only: queue of index ranks (31 left over + 128 of a step)
+    unsigned long long* ring_m = buf + kRankRing / 2;        // pass A only: queue of buckets (31 left over + 32 of a take)
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    constexpr int kHitUnroll = 2;
     const unsigned FULL = 0xffffffffu;
     const int k = P.k;
-    for (int i = threadIdx.x; i < nwarps * (cslots / 2); i += blockDim.x) cnt_all[i] = 0;
-    if (qthr) for (int q = threadIdx.x; q < P.nq; q += blockDim.x) qthr[q] = (unsigned short)((~(uint32_t)(__ldcg(P.thr + q) >> 32)) >> 16);   // no cut-off yet -> 0
+    for (int i = threadIdx.x; i < nwarps * cnt_words; i += blockDim.x) cnt_all[i] = 0;
+    for (int q = threadIdx.x; q < P.nq; q += blockDim.x) qthr[q] = (unsigned short)((~(uint32_t)(__ldcg(P.thr + q) >> 32)) >> 16);   // no cut-off yet -> 0
     __syncthreads();
+    // smallest cut-off score of the batch (0 while some query has none)
+    float thr_min;
+    {
+        uint32_t m = 0xffffu;
+        for (int q = lane; q < P.nq; q += 32) if (P.q_hit_start[q + 1] > P.q_hit_start[q]) m = min(m, (uint32_t)qthr[q]);   // queries shorter than k never get one
+        thr_min = __uint_as_float(__reduce_min_sync(FULL, m) << 16);
+    }
     while (true) {
         long long s0 = 0;
         if (lane == 0) s0 = (long long)atomicAdd(P.counters + 0, (unsigned long long)kSeqBatch);
@@ -293,103 +295,118 @@ __device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cs
             if (len < k) continue;
             const uint8_t* seq = P.db_codes + a;
             const int npos = len - k + 1;
-            // ---- pass A: count (and buffer while it fits)
-            uint32_t T = 0, carry = 0xffffffffu;
-            bool buffered = true;
-            for (int base = 0; base < npos; base += 128) {
-                uint32_t hb[4], hc[4];
-                scan_step(P, seq, npos, base, lane, carry, hb, hc);
-                const uint32_t c = hc[0] + hc[1] + hc[2] + hc[3];
-                uint32_t total;
-                const uint32_t excl = warp_excl_scan(c, lane, total);
-                if (total == 0) continue;
-                if (buffered && T + total > (uint32_t)scap) buffered = false;
-                const uint32_t cmax = __reduce_max_sync(FULL, c);
-                if (lane_owned(cmax, total)) {
-                    for (uint32_t j0 = 0; j0 < cmax; j0 += kHitUnroll) {
-                        unsigned long long h[kHitUnroll];
-#pragma unroll
-                        for (int u = 0; u < kHitUnroll; ++u) h[u] = j0 + u < c ? __ldg(P.hits + lane_hit_index(hb, hc, j0 + u)) : 0ull;
-#pragma unroll
-                        for (int u = 0; u < kHitUnroll; ++u) {
-                            if (j0 + u < c) {
-                                const uint32_t q = (uint32_t)(h[u] >> 32);
-                                C.add(q);
-                                const uint32_t ord = T + excl + j0 + u;
-                                if (buffered) buf[ord] = ((unsigned long long)q << 44) | ((unsigned long long)ord << 22) | (h[u] & 0x3fffffu);
-                            }
-                        }
-                    }
-                    __syncwarp();
-                    T += total;
-                    continue;
+            const float flen = (float)len * 0.99999f;      // margin >> float rounding: dropping stays exact
+            // ---- pass A: count; `crossed` = one of this lane's hits took a query across its cut-off.
+            // need_min: no query can reach its cut-off in this sequence with fewer hits (from the smallest cut-off of the batch;
+            // 1 while some query has none), so the exact per-query test only runs for the rare counts that get that far.
+            const uint32_t need_min = max(1u, (uint32_t)ceilf(thr_min * flen));
+            uint32_t nh = 0, carry = 0xffffffffu;            // nh: hits counted by this lane
+            bool crossed = false;
+            auto count_hit = [&](uint32_t q) {
+                const uint32_t old = atomicAdd(cnt + (q >> 1), (q & 1u) ? 0x10000u : 1u);
+                const uint32_t oc = (q & 1u) ? (old >> 16) : (old & 0xffffu);
+                if (oc + 1u >= need_min) {
+                    // count oc -> oc + 1 crosses the query's own threshold (a query without cut-off crosses with its first hit)
+                    const float need = fmaxf(__uint_as_float((uint32_t)qthr[q] << 16) * flen, 0.5f);
+                    crossed |= ((float)(oc + 1u) >= need) && ((float)oc < need);
                 }
-                publish_step(off_s, hb_s, lane, excl, hb, hc);
-                // kHitUnroll hits per lane in flight: with a large query batch a step holds hundreds of hits and the loop is
-                // bound by the latency of the hit loads (the index no longer fits L2 next to the streaming database)
-                for (uint32_t x0 = 0; x0 < total; x0 += 32 * kHitUnroll) {
-                    unsigned long long h[kHitUnroll];
-#pragma unroll
-                    for (int u = 0; u < kHitUnroll; ++u) {
-                        h[u] = 0;
-                        if (x0 + 32 * u < total) {                                  // warp-uniform
-                            const uint32_t x = x0 + 32 * u + lane;
-                            if (x < total) h[u] = __ldg(P.hits + step_hit_index(off_s, hb_s, x));
-                        }
+            };
+            // Only ~1 position in 6 of a 1 000-query batch meets a k-mer of the index, so the lanes do not chase their own
+            // positions any further than the presence bit: the index ranks of the k-mers found are queued in the warp's ring and
+            // taken out 32 at a time -- entry load and counting run with full warps.  An entry is either the k-mer's only hit
+            // (counted at once) or a bucket; buckets are queued once more and walked 32 at a time, one lane each (the buckets of
+            // a batch of a few thousand queries are small), the rare large ones by the whole warp.
+            uint32_t r_head = 0, r_n = 0, m_head = 0, m_n = 0;        // both rings: first item, items queued (warp-uniform)
+            auto flush_buckets = [&](uint32_t n) {                  // n <= 32
+                unsigned long long e = 0ull;
+                if ((uint32_t)lane < n) e = ring_m[(m_head + lane) & (kBucketRing - 1u)];
+                m_head += n; m_n -= n;
+                const uint32_t st = (uint32_t)e, c = (uint32_t)(e >> 32);
+                nh += c;
+                const bool big = c > kLaneBucket;
+                if (!big) {
+                    for (uint32_t j = 0; j < c; j += 2) {
+                        const unsigned long long h0 = __ldg(P.hits + st + j);
+                        const unsigned long long h1 = j + 1 < c ? __ldg(P.hits + st + j + 1) : 0ull;
+                        count_hit((uint32_t)(h0 >> 32));
+                        if (j + 1 < c) count_hit((uint32_t)(h1 >> 32));
                     }
-#pragma unroll
-                    for (int u = 0; u < kHitUnroll; ++u) {
-                        const uint32_t x = x0 + 32 * u + lane;
-                        if (x < total) {
-                            const uint32_t q = (uint32_t)(h[u] >> 32);
-                            C.add(q);
-                            const uint32_t ord = T + x;
-                            if (buffered) buf[ord] = ((unsigned long long)q << 44) | ((unsigned long long)ord << 22) | (h[u] & 0x3fffffu);
-                        }
-                    }
+                }
+                unsigned m = __ballot_sync(FULL, big);
+                while (m) {                                          // a frequent k-mer: the whole warp walks its bucket
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint32_t bs = __shfl_sync(FULL, st, src), bc = __shfl_sync(FULL, c, src);
+                    for (uint32_t x = lane; x < bc; x += 32) count_hit((uint32_t)(__ldg(P.hits + bs + x) >> 32));
                 }
                 __syncwarp();
-                T += total;
+            };
+            auto take = [&](uint32_t n) {                           // n <= 32
+                unsigned long long e = 0ull;
+                if ((uint32_t)lane < n) e = __ldg(P.entry + ring_r[(r_head + lane) & (kRankRing - 1u)]);
+                r_head += n; r_n -= n;
+                const bool single = e >> 63;
+                if (single) { count_hit((uint32_t)(e >> 32) & 0x7fffffffu); ++nh; }
+                const bool bucket = e != 0ull && !single;
+                const unsigned m = __ballot_sync(FULL, bucket);
+                if (m) {
+                    if (bucket) ring_m[(m_head + m_n + __popc(m & lt_mask)) & (kBucketRing - 1u)] = e;
+                    m_n += __popc(m);
+                    __syncwarp();
+                    if (m_n >= 32u) flush_buckets(32u);
+                }
+            };
+            for (int base = 0;; base += 128) {
+                const bool drain = base >= npos;
+                if (!drain) {
+                    uint32_t km[4];
+                    bool probe[4];
+                    step_kmers(P, seq, npos, base, lane, carry, km, probe);
+                    uint2 br[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) br[i] = probe[i] ? __ldg(P.bitrank + (km[i] >> 5)) : make_uint2(0u, 0u);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t bit = km[i] & 31u;
+                        const bool has = (br[i].x >> bit) & 1u;      // br is zero where the position does not take part
+                        const unsigned m = __ballot_sync(FULL, has);
+                        if (has) ring_r[(r_head + r_n + __popc(m & lt_mask)) & (kRankRing - 1u)] = br[i].y + __popc(br[i].x & ((1u << bit) - 1u));
+                        r_n += __popc(m);
+                    }
+                    __syncwarp();
+                }
+                while (r_n >= 32u || (drain && r_n > 0u)) take(r_n < 32u ? r_n : 32u);
+                if (drain) {
+                    if (m_n > 0u) flush_buckets(m_n);
+                    break;
+                }
             }
+            const uint32_t T = __reduce_add_sync(FULL, nh);
             if (T == 0) continue;
-            const float flen = (float)len * 0.99999f;      // margin >> float rounding: dropping stays exact
+            const bool any_crossed = __any_sync(FULL, crossed);
             const uint32_t id = P.id_base + (uint32_t)s;
             uint32_t nsurv = 0;
             bool defer = false;
             unsigned long long* wb = buf;        // where the survivors are: shared buffer or global scratch
-            if (buffered) {
-                for (int base = 0; base < (int)T; base += 32) {
-                    const int i = base + lane;
-                    unsigned long long e = 0;
-                    bool keep = false;
-                    if (i < (int)T) {
-                        e = buf[i];
-                        const uint32_t q = (uint32_t)(e >> 44);
-                        const uint32_t c = C.count(q);
-                        keep = may_pass(P, qthr, c, q, flen);
-                        if (keep && c == 1) { emit(P, q, 1, len, id); keep = false; }     // the query's only hit: LIS = 1, nothing to sort
-                    }
-                    const uint32_t bal = __ballot_sync(FULL, keep);
-                    if (keep) buf[nsurv + __popc(bal & ((1u << lane) - 1u))] = e;      // nsurv + rank <= i: never ahead of the reads
-                    nsurv += __popc(bal);
-                    __syncwarp();
-                }
-            } else if (T >= 65536u || T >= (1u << 22)) {
-                defer = true;                                 // a 16-bit counter may have wrapped: no filtering
-            } else {
-                // re-walk, keep the survivors only (any order: the sort key carries the emission order); they go to the
-                // warp's global scratch, which holds what a strong homolog of a long query produces
+            if (T >= 65536u) {
+                defer = true;                                 // a 16-bit counter may have wrapped (and the order field holds 22 bits): no filtering
+            } else if (any_crossed) {
+                // ---- pass B: re-walk, keep the survivors only (any order: the sort key carries the emission order); they go to
+                // the warp's global scratch, which holds what a strong homolog of a long query produces
+                __syncwarp();
                 wb = P.gbuf + (size_t)(blockIdx.x * nwarps + warp) * kGCap;
                 // Queries whose counter holds exactly one hit have LIS = 1 and are emitted straight from the walk -- but only
-                // when the other survivors are sure to fit the scratch (bound: all hits in counters >= 2), because a sequence
-                // that overflows it is handed to the deferred path as a whole and must not have emitted anything yet.
-                uint32_t m2 = 0;
-                for (int i = lane; i < (chalf ? cslots / 4 : cslots / 2); i += 32) {       // every hit sits in the first half exactly once
-                    const uint32_t w = cnt[i], c0 = w & 0xffffu, c1 = w >> 16;
-                    m2 += (c0 >= 2u ? c0 : 0u) + (c1 >= 2u ? c1 : 0u);
+                // when the other survivors are sure to fit the scratch (all hits do, or all hits in counters >= 2), because a
+                // sequence that overflows it is handed to the deferred path as a whole and must not have emitted anything yet.
+                bool direct = T <= (uint32_t)kGCap;
+                if (!direct) {
+                    uint32_t m2 = 0;
+                    for (int i = lane; i < cnt_words; i += 32) {
+                        const uint32_t w = cnt[i], c0 = w & 0xffffu, c1 = w >> 16;
+                        m2 += (c0 >= 2u ? c0 : 0u) + (c1 >= 2u ? c1 : 0u);
+                    }
+                    direct = __reduce_add_sync(FULL, m2) <= (uint32_t)kGCap;
                 }
-                m2 = __reduce_add_sync(FULL, m2);
-                const bool direct = m2 <= (uint32_t)kGCap;
                 uint32_t ordbase = 0;
                 carry = 0xffffffffu;
                 for (int base = 0; base < npos && !defer; base += 128) {
@@ -412,9 +429,9 @@ __device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cs
                                 bool keep = false;
                                 if (j0 + u < c) {
                                     const uint32_t q = (uint32_t)(h[u] >> 32);
-                                    const uint32_t c = C.count(q);
-                                    keep = may_pass(P, qthr, c, q, flen);
-                                    if (direct && keep && c == 1) { emit(P, q, 1, len, id); keep = false; }
+                                    const uint32_t cq = count_of(cnt, q);
+                                    keep = may_pass(qthr, cq, q, flen);
+                                    if (direct && keep && cq == 1) { emit(P, q, 1, len, id); keep = false; }
                                     e = ((unsigned long long)q << 44) | ((unsigned long long)(ordbase + excl + j0 + u) << 22) | (h[u] & 0x3fffffu);
                                 }
                                 const uint32_t bal = __ballot_sync(FULL, keep);
@@ -446,9 +463,9 @@ __device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cs
                             bool keep = false;
                             if (x < total) {
                                 const uint32_t q = (uint32_t)(h[u] >> 32);
-                                const uint32_t c = C.count(q);
-                                keep = may_pass(P, qthr, c, q, flen);
-                                if (direct && keep && c == 1) { emit(P, q, 1, len, id); keep = false; }
+                                const uint32_t cq = count_of(cnt, q);
+                                keep = may_pass(qthr, cq, q, flen);
+                                if (direct && keep && cq == 1) { emit(P, q, 1, len, id); keep = false; }
                                 e = ((unsigned long long)q << 44) | ((unsigned long long)(ordbase + x) << 22) | (h[u] & 0x3fffffu);
                             }
                             const uint32_t bal = __ballot_sync(FULL, keep);
@@ -462,7 +479,7 @@ __device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cs
                 }
             }
             __syncwarp();
-            for (int i = lane; i < cslots / 2; i += 32) cnt[i] = 0;
+            for (int i = 4 * lane; i < cnt_words; i += 128) *reinterpret_cast<uint4*>(cnt + i) = make_uint4(0u, 0u, 0u, 0u);
             if (!defer && wb != buf && nsurv <= (uint32_t)scap) {       // few survivors: sort them in shared memory
                 for (int i = lane; i < (int)nsurv; i += 32) buf[i] = wb[i];
                 wb = buf;
@@ -496,7 +513,7 @@ __device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cs
                     __syncwarp();
                 }
             }
-            // run starts first (one ballot word per 32 entries, kept by lane i / 32; scap <= 1024), because the in-place
+            // run starts first (one ballot word per 32 entries, kept by lane i / 32; kGCap <= 1024), because the in-place
             // LIS below overwrites the entries of finished runs
             uint32_t my_starts = 0;
             for (int base = 0; base < S; base += 32) {
@@ -519,23 +536,17 @@ __device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cs
                     n = e - i;
                 }
                 __syncwarp();          // all run lengths of this block are known before any of its runs is overwritten
-                // the run length is the query's exact hit count and bounds its LIS: runs that cannot reach the cut-off (survivors
-                // of counter collisions) are dropped before the LIS and the global cut-off load
-                if (st && may_pass(P, qthr, (uint32_t)n, q, flen)) emit(P, q, n == 1 ? 1 : lis_inplace(wb, i, n), len, id);
+                if (st) emit(P, q, n == 1 ? 1 : lis_inplace(wb, i, n), len, id);
                 __syncwarp();
             }
         }
     }
 }
 
-// Two builds of the scan.  Small query batches (a step of 128 positions holds a few dozen hits) run 8-warp CTAs, four per
-// SM, within 64 registers, two hits of a step in flight per lane.  Batches whose shared-memory tables leave room for at most
-// two CTAs per SM are bound by the latency of the index loads at few resident warps: four hits in flight per lane, 96 registers.
-__global__ void __launch_bounds__(kWarps * 32, 4) pf_scan_kernel(PfParams P, int scap, int cslots, int qthr_in_smem, int hash2) {
-    pf_scan_body<2>(P, scap, cslots, qthr_in_smem, hash2);
-}
-__global__ void __launch_bounds__(kMaxWarps * 32, 1) pf_scan_dense_kernel(PfParams P, int scap, int cslots, int qthr_in_smem, int hash2) {
-    pf_scan_body<4>(P, scap, cslots, qthr_in_smem, hash2);
+// Builds of the scan by CTA size (the register budget follows the resident warps).
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads, 1) pf_scan_kernel(PfParams P, int scap, int cnt_words) {
+    pf_scan_body(P, scap, cnt_words);
 }
 
 // deferred path, step 1: re-walk the sequence and write its hits into the pool
@@ -644,6 +655,15 @@ __global__ void ix_bucket_kernel(const uint32_t* sorted_keys, int64_t n, const u
         const uint32_t r = br.y + __popc(br.x & ((1u << (kmer & 31u)) - 1u));
         bucket_start[r] = (uint32_t)i;
     }
+}
+
+// bucket entries of the scan's pass A: a k-mer with a single hit carries it (bit 63 set; query ids stay below 2^20),
+// the others their bucket (size << 32 | first entry)
+__global__ void ix_entry_kernel(const uint32_t* bucket_start, const unsigned long long* hits, uint32_t n_distinct, unsigned long long* entry) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_distinct) return;
+    const uint32_t b = bucket_start[r], c = bucket_start[r + 1] - b;
+    entry[r] = c == 1 ? ((1ull << 63) | hits[b]) : (((unsigned long long)c << 32) | b);
 }
 
 // ---- candidate buffers -------------------------------------------------------------------------------------
@@ -892,13 +912,57 @@ static int build_scan_order(s4g_ctx* ctx, s4g_db* db) {
     return S4G_OK;
 }
 
+// Shared memory of the scan kernel: what a CTA may use, the per-warp part for `nq` queries, and the largest batch that still
+// leaves kMinScanWarps warps per SM beside the 2-byte cut-off table (larger batches are scanned in groups of queries: the
+// candidate lists of different queries are independent, the database streams once per group).
+constexpr size_t kScanSmemCap = 227 * 1024;
+constexpr int kScanSortCap = 256;          // 8-byte entries of a warp's buffer: hit queue of pass A (twice as many 32-bit items), sort buffer of pass B
+constexpr int kMinScanWarps = 4;
+static int scan_cnt_words(int nq) { return ((nq + 1) / 2 + 127) / 128 * 128; }
+static int scan_sort_cap(int) { return kScanSortCap; }
+static size_t scan_warp_smem(int nq) { return sizeof(uint32_t) * (size_t)scan_cnt_words(nq) + sizeof(unsigned long long) * scan_sort_cap(nq); }
+static size_t scan_qthr_smem(int nq) { return sizeof(unsigned short) * (size_t)((nq + 7) & ~7); }
+// Queries per scan: the exact counters cost 2 B per query and warp, and the scan lives on resident warps (one random index
+// probe per position and warp instruction: it is bound by issue and latency, not by bandwidth).  Large batches are therefore
+// scanned in groups of queries -- the candidate lists of different queries are independent, and one more pass over the
+// resident database costs far less than running the whole batch at a few warps per SM.
+static int scan_max_queries() {
+    int group = 4096;
+    if (const char* e = getenv("S4G_PF_GROUP")) group = atoi(e);
+    int cap = 1024;
+    while (scan_qthr_smem(cap + 1024) + kMinScanWarps * scan_warp_smem(cap + 1024) <= kScanSmemCap) cap += 1024;
+    return std::max(256, std::min(group, cap));
+}
+
+static int prefilter_group(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int max_candidates, int sorted_by_id,
+                           uint32_t* d_ids, float* d_scores, uint32_t* d_counts);
+
 int s4g_prefilter_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int max_candidates, int sorted_by_id,
                          uint32_t* d_ids, float* d_scores, uint32_t* d_counts) {
+    const int nq = q->n;
+    if (nq >= (1 << 20)) { s4g_set_error(ctx, "at most 2^20-1 queries per batch"); return S4G_ERR_ARG; }
+    if (q->max_len >= (1 << 22)) { s4g_set_error(ctx, "query longer than 2^22"); return S4G_ERR_ARG; }
+    const int group = scan_max_queries();
+    if (nq <= group) return prefilter_group(ctx, db, q, k, max_candidates, sorted_by_id, d_ids, d_scores, d_counts);
+    // equal groups of queries, each a view of the resident batch
+    const int n_groups = (nq + group - 1) / group;
+    for (int g = 0; g < n_groups; ++g) {
+        const int g0 = (int)((int64_t)nq * g / n_groups), g1 = (int)((int64_t)nq * (g + 1) / n_groups);
+        s4g_queries view;
+        view.ctx = q->ctx; view.d_codes = q->d_codes; view.d_off = q->d_off + g0; view.n = g1 - g0; view.max_len = q->max_len;
+        view.h_off.assign(q->h_off.begin() + g0, q->h_off.begin() + g1 + 1);
+        const int rc = prefilter_group(ctx, db, &view, k, max_candidates, sorted_by_id, d_ids + (size_t)g0 * max_candidates,
+                                       d_scores ? d_scores + (size_t)g0 * max_candidates : nullptr, d_counts + g0);
+        if (rc != S4G_OK) return rc;
+    }
+    return S4G_OK;
+}
+
+static int prefilter_group(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int max_candidates, int sorted_by_id,
+                           uint32_t* d_ids, float* d_scores, uint32_t* d_counts) {
     cudaStream_t st = ctx->stream;
     const int nq = q->n;
     const uint32_t N = (uint32_t)max_candidates;
-    if (nq >= (1 << 20)) { s4g_set_error(ctx, "at most 2^20-1 queries per batch"); return S4G_ERR_ARG; }
-    if (q->max_len >= (1 << 22)) { s4g_set_error(ctx, "query longer than 2^22"); return S4G_ERR_ARG; }
 
     {
         int rc = build_scan_order(ctx, db);
@@ -976,6 +1040,18 @@ int s4g_prefilter_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int ma
         ix_bucket_kernel<<<(unsigned)((n_hits + 255) / 256), 256, 0, st>>>(d_keys2, n_hits, d_bitrank, d_bucket, n_distinct);
         S4G_CHECK_LAUNCH(ctx);
     }
+    // ---- scan configuration: warps per SM from the exact counters (2 B per query and warp) ----
+    const int cnt_words = scan_cnt_words(nq);
+    const int scap = scan_sort_cap(nq);
+    const size_t per_warp_smem = scan_warp_smem(nq), qthr_bytes = scan_qthr_smem(nq);
+    int scan_warps = (int)std::min<size_t>(32, (kScanSmemCap - qthr_bytes) / per_warp_smem);
+    if (const char* e = getenv("S4G_PF_WARPS")) scan_warps = std::max(1, std::min(scan_warps, atoi(e)));
+    unsigned long long* d_entry = (unsigned long long*)s4g_scratch(ctx, SLOT_PF_ENTRY, sizeof(unsigned long long) * ((size_t)n_distinct + 1));
+    if (!d_entry) return S4G_ERR_NOMEM;
+    if (n_distinct > 0) {
+        ix_entry_kernel<<<(n_distinct + 255) / 256, 256, 0, st>>>(d_bucket, d_vals2, n_distinct, d_entry);
+        S4G_CHECK_LAUNCH(ctx);
+    }
 
     s4g_trace_mark(ctx, "index");
     // ---- candidate buffers ----
@@ -1035,44 +1111,17 @@ int s4g_prefilter_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int ma
     P.def_seq = d_def_seq; P.def_off = d_def_off; P.max_deferred = max_deferred;
     P.pool_keys = nullptr; P.pool_vals = nullptr; P.pool_cap = pool_cap;
 
-    int per_sm = 0;
-    // hit buffer per warp: room for the hits of a typical sequence (hits per residue = index size / k-mer space, times
-    // 4 average lengths), within 256 .. 1024 entries
-    int scap = 256;
-    {
-        const double per_res = (double)n_hits / (double)n_kmer_space * 8.0;        // frequent letters dominate: x8 over uniform
-        const double avg_len = db->n > 0 ? (double)db->residues / (double)db->n : 1.0;
-        while (scap < 1024 && (double)scap < 4.0 * per_res * avg_len) scap <<= 1;
-        // batches so large that a typical sequence cannot be buffered anyway are counted first and re-walked;
-        // the buffer then only holds the survivors of the filter
-        if (4.0 * per_res * avg_len > 1024.0) scap = 512;
-    }
-    // per-query cut-off table in shared memory (2 B per query) when it fits beside the per-warp buffers
-    int qthr_in_smem = nq <= 32768 ? 1 : 0;
-    size_t qthr_bytes = qthr_in_smem ? (((size_t)nq * 2 + 15) / 16) * 16 : 0;
-    // counters per warp: measured (profiles/r01s_c3_prefilter.md) -- fewer slots per query cost more in false survivors
-    // than the extra resident warps win, more slots than these cost residency
-    const int cslots = nq <= 1024 ? 1024 : (nq <= 8192 ? 2048 : 4096);
-    if (cslots == 4096) scap = 256;
-    // small tables: 8-warp CTAs, several per SM; a large cut-off table is shared by 16 warps
-    const int scan_warps = qthr_bytes > 16384 ? kMaxWarps : kWarps;
-    // two-hash counters for the large batches (~5 queries per counter): -4.5 % there, nothing at 4 queries per counter
-    const int hash2 = scan_warps == kMaxWarps ? 1 : 0;
-    const size_t per_warp_smem = sizeof(unsigned long long) * scap + sizeof(uint32_t) * (cslots / 2) + sizeof(uint32_t) * 256;
-    if (per_warp_smem * scan_warps + qthr_bytes > (size_t)227 * 1024) { qthr_in_smem = 0; qthr_bytes = 0; }   // cut-offs from global memory
+    P.entry = d_entry; P.q_hit_start = d_start;
+    // one CTA per SM: its warps share the cut-off table and the filter; the build follows the CTA size (register budget)
     const size_t scan_smem = per_warp_smem * scan_warps + qthr_bytes;
-    auto scan_kernel = pf_scan_kernel;
-    S4G_CUDA(ctx, cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<size_t>(scan_smem, (size_t)227 * 1024)));
-    if (scan_warps == kWarps) S4G_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel, scan_warps * 32, scan_smem));
-    if (scan_warps == kMaxWarps || per_sm <= 2) {
-        scan_kernel = pf_scan_dense_kernel;
-        S4G_CUDA(ctx, cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
-        S4G_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel, scan_warps * 32, scan_smem));
-    }
-    if (per_sm < 1) per_sm = 1;
-    const int grid = ctx->sm_count * per_sm;
+    void (*scan_kernel)(PfParams, int, int) = nullptr;
+    scan_kernel = scan_warps > 24 ? pf_scan_kernel<1024> : (scan_warps > 16 ? pf_scan_kernel<768> : (scan_warps > 8 ? pf_scan_kernel<512> : pf_scan_kernel<256>));
+    S4G_CUDA(ctx, cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
+    const int grid = ctx->sm_count;
     P.gbuf = (unsigned long long*)s4g_scratch(ctx, SLOT_PF_GBUF, sizeof(unsigned long long) * (size_t)grid * scan_warps * kGCap);
     if (!P.gbuf) return S4G_ERR_NOMEM;
+    if (ctx->trace) fprintf(stderr, "[s4g trace] scan: %d queries, %u index k-mers (%lld hits), %d warps per SM, counters %d B per warp, %zu B of shared memory\n",
+                            nq, n_distinct, (long long)n_hits, scan_warps, cnt_words * 4, scan_smem);
 
     s4g_trace_mark(ctx, "setup");
     int64_t this_chunk = chunk < 16384 ? chunk : 16384;
@@ -1086,7 +1135,7 @@ int s4g_prefilter_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int ma
         // the pool is only allocated once a chunk needs it (first pass counts; see below)
         P.pool_keys = (unsigned long long*)ctx->slot_ptr[SLOT_PF_HITS];
         const auto t_chunk = std::chrono::steady_clock::now();
-        scan_kernel<<<grid, scan_warps * 32, scan_smem, st>>>(P, scap, cslots, qthr_in_smem, hash2);
+        scan_kernel<<<grid, scan_warps * 32, scan_smem, st>>>(P, scap, cnt_words);
         S4G_CHECK_LAUNCH(ctx);
         unsigned long long h_c[4];
         S4G_CUDA(ctx, cudaMemcpyAsync(h_c, d_counters, 32, cudaMemcpyDeviceToHost, st));
