@@ -132,7 +132,9 @@ def build_db_host(n_db, q_codes, q_off, seed=SEED, plant_scale=1.0):
     off = np.zeros(n_db + 1, dtype=np.int64)
     np.cumsum(lens, out=off[1:])
     rng = np.random.default_rng(seed + 3)
-    codes = rng.choice(26, size=int(off[-1]), p=synth.letter_table(0.001)).astype(np.uint8)
+    # letters through a 65 536-entry quantile table of the background distribution (rng.choice takes ~15 s for 3e8 residues)
+    table = np.searchsorted(np.cumsum(synth.letter_table(0.001)), (np.arange(65536) + 0.5) / 65536.0).clip(max=25).astype(np.uint8)
+    codes = table[rng.integers(0, 65536, size=int(off[-1]), dtype=np.uint16)]
     plan = plant_plan(n_db, lens, q_off, seed, scale=plant_scale)
     qlen = np.diff(q_off)
     for p in range(len(plan["seq"])):
@@ -150,12 +152,25 @@ def build_db_host(n_db, q_codes, q_off, seed=SEED, plant_scale=1.0):
 
 
 def write_fasta(path, codes, off, prefix):
-    txt = (codes + 65).astype(np.uint8).tobytes()
+    """>P%08d records, one line per sequence; assembled with numpy in blocks of sequences (a Python loop over a million
+    records would take longer than the reference run the file is for)."""
+    n = len(off) - 1
     with open(path, "wb") as f:
-        for i in range(len(off) - 1):
-            f.write(b">%s%08d\n" % (prefix, i))
-            f.write(txt[off[i]:off[i + 1]])
-            f.write(b"\n")
+        for a in range(0, n, 200_000):
+            b = min(n, a + 200_000)
+            m = b - a
+            lens = np.diff(off[a:b + 1])
+            hdr = np.frombuffer(b"".join(b">%s%08d\n" % (prefix, i) for i in range(a, b)), dtype=np.uint8).reshape(m, -1)
+            h = hdr.shape[1]
+            start = (off[a:b] - off[a]) + (h + 1) * np.arange(m)                  # first byte of every record in this block
+            out = np.empty(int(off[b] - off[a]) + (h + 1) * m, dtype=np.uint8)
+            out[(start[:, None] + np.arange(h)[None, :]).reshape(-1)] = hdr.reshape(-1)
+            out[start + h + lens] = 10
+            res = np.ones(len(out), dtype=bool)
+            res[(start[:, None] + np.arange(h)[None, :]).reshape(-1)] = False
+            res[start + h + lens] = False
+            out[res] = codes[off[a]:off[b]] + 65
+            f.write(out.tobytes())
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -250,8 +265,12 @@ def run_reference_once(qf, df, threads):
 
 
 def reference_arm(args, out=sys.stdout):
+    """`--impl reference`: the UNMODIFIED reference (oracle/_ref: swimd AVX2 scoring, SSW traceback, its own prefilter) on all
+    host cores, quoted on our arm's config; every step is one run of its whole database-search path (searchDatabase +
+    alignDatabase through the seam harness, FASTA parses included as in the reference) over a bounded sample of the workload."""
     from oracle import oracle as O
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     if not O.have_ref():
@@ -260,20 +279,23 @@ def reference_arm(args, out=sys.stdout):
     cores = os.cpu_count() or 1
     tmp = tempfile.mkdtemp()
     qf, df = reference_sample(tmp, args.ref_queries, args.ref_db_seqs)
-    times, cells = [], 0
-    for i in range(args.warmup + args.steps):
+    times, cells, pairs = [], 0, 0
+    warm = min(args.warmup, 1)                      # a warm-up run only warms the page cache
+    for i in range(warm + args.steps):
         s, a, cells, pairs = run_reference_once(qf, df, cores)
-        if i >= args.warmup:
+        if i >= warm:
             times.append((s, a))
     tot = sum(s + a for s, a in times)
     gcups = cells * len(times) / tot / 1e9
-    sample = "%d queries (len 100-1000) x %d-sequence database (same generator as the GPU arm), max_candidates 5000, %d threads; whole reference path (searchDatabase + alignDatabase) per step" % (args.ref_queries, args.ref_db_seqs, cores)
+    sample = "%d queries (len 100-1000) x %d-sequence database of the same generator (%d pairs, %.3e SW cells per step), max_candidates 5000, %d threads; whole reference path (searchDatabase + alignDatabase, both FASTA parses) per step" % (
+        args.ref_queries, args.ref_db_seqs, pairs, cells, cores)
     line = {"impl": "reference", "metric": "sw_gcups", "value": round(gcups, 4), "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(tot / len(times) * 1e3, 3), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "int8/int16/int32 SIMD (swimd AVX2)",
-            "data": "synthetic", "config": {"workload": "configs[1] bounded sample: " + sample},
+            "data": "synthetic", "config": workload_config(args, world),
             "queries_per_sec": round(args.ref_queries * len(times) / tot, 4),
             "stages_s": {"search": round(sum(s for s, _ in times) / len(times), 4), "align": round(sum(a for _, a in times) / len(times), 4)},
-            "cpu_baseline": {"value": round(gcups, 4), "unit": "GCUPS", "cores": cores, "kind": "reference", "sample": sample},
+            "cpu_baseline": {"value": round(gcups, 4), "unit": "GCUPS", "cores": cores, "kind": "reference", "sample": sample,
+                             "sw_stage_gcups": round(cells * len(times) / sum(a for _, a in times) / 1e9, 4)},
             "e2e": {"value": round(gcups, 4), "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), file=out, flush=True)
 
@@ -294,6 +316,87 @@ def cpu_baseline(args):
 
 
 # ------------------------------------------------------------------------------------------------------------
+# result digest of a FIXED verification workload, computed in the warm-up of every run (any N): the database is sharded
+# over the ranks like the bench workload; rank 0 also runs it unsharded.  Equal digests across the N = 1, 2, 4, 8 lines of a
+# scaling run mean the sharded path returns the single-GPU results bit for bit (candidate sets, kept hits with their
+# E-values as hex doubles, alignment cells, path bytes).
+
+PARITY_CASES = ((51, 13, 6000, 200, 400), (52, 9, 4000, 300, 6), (53, 5, 900, 2000, 400), (54, 48, 40000, 500, 400))
+
+
+def _collect(r, nq):
+    """host view of one rank's step result: per query candidate ids, hits as tuples incl. cells and path bytes"""
+    cand_ids = r.cand_ids.cpu().numpy().view(np.uint32)
+    cand_off = r.cand_off.cpu().numpy()
+    cands = [cand_ids[cand_off[q]:cand_off[q + 1]] for q in range(nq)]
+    hits = []
+    if r.coords is not None:
+        coords = r.coords.cpu().numpy(); poff = r.path_off.cpu().numpy(); paths = r.paths[:int(poff[-1])].cpu().numpy()
+    for h in range(len(r.pair_q)):
+        hits.append((int(r.pair_q[h]), float(r.evalue[h]).hex(), int(r.pair_score[h]), int(r.pair_t[h]), tuple(coords[h].tolist()),
+                     paths[poff[h]:poff[h + 1]].tobytes()))
+    return cands, hits
+
+
+def parity_digest(ctx, mat, dist=None, log=None):
+    """-> {"digest": sha256 of the order-normalised results of PARITY_CASES through the (sharded) device pipeline,
+           "sharded_equals_single": bool (rank 0 re-runs every case on one unsharded database), "cases": n}"""
+    import hashlib
+    from sift4g_b200 import pipeline, synth
+    world = dist.get_world_size() if dist is not None else 1
+    rank = dist.get_rank() if dist is not None else 0
+    sha = hashlib.sha256()
+    same = True
+    for seed, nq, n_db, N, M in PARITY_CASES:
+        queries, db = synth.make_dataset(seed, nq, n_db, q_len=(50, 400), homologs=(8, 25), rare_fraction=0.005)
+        qc, qo = synth.pack(queries); dc, do = synth.pack(db)
+        lens = np.diff(do)
+        lo, hi = n_db * rank // world, n_db * (rank + 1) // world
+        D = ctx.database(dc[do[lo]:do[hi]], do[lo:hi + 1] - do[lo], id_base=lo)
+        pipe = pipeline.DevicePipeline(ctx, D, qc, qo, mat, lens[lo:hi], int(do[-1]), max_candidates=N, max_alignments=M, dist=dist)
+        mine = _collect(pipe.step(), nq)
+        pipe.close(); D.close()
+        parts = [mine]
+        if dist is not None:
+            parts = [None] * world
+            dist.all_gather_object(parts, mine)
+        if rank == 0:
+            cands = [np.sort(np.concatenate([p[0][q] for p in parts])) for q in range(nq)]
+            hits = sorted(h for p in parts for h in p[1])
+            for q in range(nq):
+                sha.update(cands[q].astype("<u4").tobytes())
+            for h in hits:
+                sha.update(repr(h[:5]).encode()); sha.update(h[5])
+            if world > 1:
+                D1 = ctx.database(dc, do)
+                p1 = pipeline.DevicePipeline(ctx, D1, qc, qo, mat, lens, int(do[-1]), max_candidates=N, max_alignments=M)
+                c1, h1 = _collect(p1.step(), nq)
+                p1.close(); D1.close()
+                ok = all(np.array_equal(cands[q], np.sort(c1[q])) for q in range(nq)) and hits == sorted(h1)
+                same = same and ok
+                if log:
+                    log("parity case seed %d: %d queries, %d candidates, %d hits over %d shards: %s" % (
+                        seed, nq, sum(len(c) for c in c1), len(h1), world, "equal to one GPU" if ok else "DIFFERENT from one GPU"))
+    return {"digest": sha.hexdigest() if rank == 0 else None, "sharded_equals_single": bool(same), "cases": len(PARITY_CASES),
+            "what": "sha256 over candidate id sets, kept hits (query, E as hex double, score, target, cells) and path bytes of %d fixed small workloads run through the %d-shard pipeline in the warm-up; the same at every N" % (len(PARITY_CASES), world)}
+
+
+def workload_config(args, world):
+    """`config` of the JSON line: the workload both arms are quoted on (the reference arm times bounded samples of it)."""
+    n_queries = args.queries * world if args.scaling == "weak" else args.queries
+    n_db = args.db_seqs
+    total_res = int(db_lengths(n_db).sum())
+    qdesc = "len 100-1000"
+    if args.query_shape == "human":
+        ql = np.diff(make_queries(n_queries, shape="human")[1])
+        qdesc = "human-proteome-shaped log-normal lengths, median %d, max %d" % (int(np.median(ql)), int(ql.max()))
+    name = "configs[1]" if n_db == 10_000_000 and args.query_shape == "uniform" else ("configs[2]-shaped" if n_db >= 40_000_000 else "custom")
+    return {"workload": "%s: %d queries (%s) vs %d-sequence / %.2f B-residue synthetic database, whole hot path per step (prefilter k=5, top %d; SW BLOSUM62 10/1; E<=1e-4, top 400; traceback)" % (
+                name, n_queries, qdesc, n_db, total_res / 1e9, args.max_candidates),
+            "sharding": "database split in %d contiguous shards, one resident per GPU; %d queries per step (%s scaling: %s)" % (
+                world, n_queries, args.scaling, "%d queries per GPU and step" % args.queries if args.scaling == "weak" else "same batch at every N"),
+            "l2": "inputs (%.2f GB database shard per GPU) exceed the 126 MB L2; no explicit flush" % (total_res / world / 1e9)}
+
 
 def _claim_stdout():
     """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner under NCCL_DEBUG), so the
@@ -316,13 +419,14 @@ def main():
     ap.add_argument("--query-shape", default="uniform", choices=["uniform", "human"], help="query length distribution (human: configs[2])")
     ap.add_argument("--db-seqs", type=int, default=10_000_000)
     ap.add_argument("--max-candidates", type=int, default=5000)
-    ap.add_argument("--ref-queries", type=int, default=16)
-    ap.add_argument("--ref-db-seqs", type=int, default=100_000)
+    ap.add_argument("--ref-queries", type=int, default=256, help="queries of the bounded sample the reference CPU build is timed on")
+    ap.add_argument("--ref-db-seqs", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the result digest of the fixed verification workload in the warm-up")
     args = ap.parse_args()
-    if args.warmup < 3:
-        args.warmup = 3 if args.impl == "ours" else max(args.warmup, 1)
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
 
     if args.impl == "reference":
         reference_arm(args, out)
@@ -365,6 +469,11 @@ def main():
 
     for _ in range(args.warmup):
         r = pipe.step()
+    barrier()
+    parity = parity_digest(ctx, mat, dist if use_dist else None, log=lambda m: print(m, file=sys.stderr)) if not args.no_parity else None
+    if parity is not None and not parity["sharded_equals_single"]:
+        raise SystemExit("bench: the sharded pipeline does not reproduce the single-GPU results (see stderr)")
+    ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
     barrier()
     ctx.reset_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -412,14 +521,7 @@ def main():
             "metric": "sw_gcups", "value": round(gcups, 2), "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "s16x2 (DPX), s32 re-run on overflow",
             "data": "synthetic",
-            "config": {"workload": "%s: %d queries (%s) vs %d-sequence / %.2f B-residue synthetic database, whole hot path per step (prefilter k=5, top %d; SW BLOSUM62 10/1; E<=1e-4, top 400; traceback)" % (
-                "configs[1]" if n_db == 10_000_000 and args.query_shape == "uniform" else ("configs[2]-shaped" if n_db >= 40_000_000 else "custom"),
-                n_queries, "len 100-1000" if args.query_shape == "uniform" else "human-proteome-shaped log-normal lengths, median %d, max %d" % (
-                    int(np.median(np.diff(q_off))), int(np.diff(q_off).max())), n_db, total_res / 1e9, args.max_candidates),
-                "sharding": "database split in %d contiguous shards, one resident per GPU; %d queries per step (%s scaling: %s)" % (
-                    world, n_queries, args.scaling, "1000 queries per GPU and step" if args.scaling == "weak" else "same batch at every N"),
-                "l2": "inputs (%.2f GB database shard per GPU) exceed the 126 MB L2; no explicit flush" % ((hi - lo) / n_db * total_res / 1e9),
-                "db_generation_s": round(gen_s, 2)},
+            "config": workload_config(args, world), "db_generation_s": round(gen_s, 2),
             "queries_per_sec": round(n_queries / (ms_per_step * 1e-3), 2),
             "sw_cells_per_step": cells, "pairs_per_step": pairs, "kept_hits_per_step": hits,
             "stages_ms": split,
@@ -436,6 +538,8 @@ def main():
         }
         if line["roofline_prefilter"]["achieved"]:
             line["roofline_prefilter"]["frac"] = round(line["roofline_prefilter"]["achieved"] / line["roofline_prefilter"]["peak"], 4)
+        if parity is not None:
+            line["parity"] = parity
         if e2e is not None:
             line["e2e"] = e2e
         if base is not None:
@@ -483,28 +587,44 @@ def stage_split(torch, ctx, pipe, reps=3):
 
 
 def run_e2e(torch, ctx, db, pipe, q_codes, q_off, mat, lens, total_res, args, use_dist, dist, dev, n_queries):
-    """Same step through the public pipeline API with HOST buffers: the query batch is uploaded every step and the
-    candidate lists, survivor scores and alignments are copied back to the host inside the timed region."""
+    """Same step end to end with HOST buffers, host<->device copies inside the timed region.
+    One GPU: the product boundary itself -- the query batch is uploaded (s4g_queries_create) and ONE C-ABI call, s4g_search,
+    returns candidate lists, kept hits with E-values and alignments in host memory (pipeline.search_host; no torch, no
+    Python between the stages).  N > 1 (one process per GPU under torchrun): the sharded pipeline with its NCCL exchanges,
+    queries uploaded and every result copied back each step (DevicePipeline.step(e2e=True))."""
+    from sift4g_b200 import pipeline
+    n = max(1, min(args.steps, 3))
+    if not use_dist:
+        ctx.sync()
+        run = lambda: pipeline.search_host(ctx, db, q_codes, q_off, mat, max_candidates=args.max_candidates, want_candidates=True, align=True)
+        out = run()
+        t0 = time.time()
+        for _ in range(n):
+            out = run()
+            checksum = int(out.path_off[-1]) + int(out.hit_off[-1]) + int(out.cand_off[-1])       # results are on the host
+        dt = (time.time() - t0) / n
+        ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+        return {"value": round(out.sw_cells / dt / 1e9, 2), "unit": "GCUPS", "ms_per_step": round(dt * 1e3, 3), "h2d_bytes_per_step": int(out.h2d_bytes),
+                "d2h_bytes_per_step": int(out.d2h_bytes), "queries_per_sec": round(n_queries / dt, 2),
+                "stages_ms": {k: round(float(v), 3) for k, v in out.stage_ms.items()}, "kept_hits": int(out.n_hits), "result_checksum": checksum,
+                "timed": "host wall clock around s4g_queries_create + s4g_search (C ABI, host buffers): queries H2D; candidate lists, kept hits, E-values, alignment cells and paths D2H every step"}
     pipe.step(e2e=True)
-    if use_dist:
-        dist.barrier()
+    dist.barrier()
     torch.cuda.synchronize()
     t0 = time.time()
     cells = h2d = d2h = 0
-    n = max(1, min(args.steps, 3))
     for _ in range(n):
         r = pipe.step(e2e=True)
         cells, h2d, d2h = r.sw_cells, r.h2d_bytes, r.d2h_bytes
     torch.cuda.synchronize()
     dt = (time.time() - t0) / n
     t = torch.tensor([dt, float(cells), float(h2d), float(d2h)], dtype=torch.float64, device=dev)
-    if use_dist:
-        tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        ts = t.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
-        dt, cells, h2d, d2h = float(tm[0]), float(ts[1]), float(ts[2]), float(ts[3])
+    tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ts = t.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+    dt, cells, h2d, d2h = float(tm[0]), float(ts[1]), float(ts[2]), float(ts[3])
     return {"value": round(cells / dt / 1e9, 2), "unit": "GCUPS", "ms_per_step": round(dt * 1e3, 3), "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "queries_per_sec": round(n_queries / dt, 2),
-            "timed": "host wall clock around pipeline.DevicePipeline.step(e2e=True): queries H2D, candidate lists + survivor scores + alignments D2H every step; max over ranks"}
+            "timed": "host wall clock around pipeline.DevicePipeline.step(e2e=True): queries H2D, this rank's share of the candidate lists + survivor scores + alignments D2H every step; max over ranks"}
 
 
 # BLOSUM62 over 'A'..'Z' exactly as the reference's scorer hands it to the GPU seam (sw/constants.c:87-114);

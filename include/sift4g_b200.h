@@ -15,6 +15,7 @@
  *                         scoreDatabaseCpu()           sw/cpu_module.h:143-144
  *   s4g_sw_align       <- alignScoredPair()           sw/align.h (sw/align.c:235-255) ->
  *                         alignScoredPairCpu()         sw/cpu_module.h:67-68
+ *   s4g_search         <- searchDatabase() + alignDatabase() as called by sift4g/src/main.cpp:203-220
  *   s4g_db_* / s4g_queries_*  <- chainDatabaseGpuCreate/Delete()  sw/gpu_module.h:210-240
  *   s4g_db_open_fasta  <- readFastaChainsPart()       sw/pre_proc.h:76-81 (reader quirks kept)
  *   s4g_db_pack_fasta / s4g_db_open_packed  <- dumpFastaChains()/readFastaChains() ".swsharp" cache
@@ -219,6 +220,65 @@ int s4g_evalue_screen(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, const uint32_t* 
                       int64_t n_pairs, const int32_t* scores, const char* matrix_name, uint64_t db_residues, int gap_open,
                       int gap_extend, double max_evalue, uint32_t* out_query, uint32_t* out_id, int32_t* out_score, int32_t* out_tlen,
                       uint32_t* out_count);
+
+/* ---- the stages as one call ------------------------------------------------------------------------ */
+/* Stage 2 + E-value pre-screen for callers that select over several shards (the CLI with --cards): scores every
+ * (query, candidate) pair like s4g_sw_score and returns only the pairs s4g_evalue_screen lets through -- the full score
+ * array never crosses the bus.  cand_ids / cand_offsets: host (where = S4G_HOST) or device pointers.  db_residues: the
+ * E-value's database length (0 = the whole file the shard was opened from).  The arrays of `out` are pinned host memory
+ * owned by the context, in candidate order (grouped by ascending query), valid until the next s4g_score_screen / s4g_search
+ * on this context.  Replaces the scoring + eValues sweep of scoreDatabase / extractThread (sw/database.c:402-646,821-875). */
+typedef struct s4g_survivors {
+    int64_t n;                  /* pairs that passed the screen */
+    const uint32_t* query;      /* query index */
+    const uint32_t* id;         /* target id */
+    const int32_t* score;       /* exact SW score */
+    const int32_t* tlen;        /* target length */
+    int64_t n_pairs;            /* pairs scored */
+    uint64_t sw_cells;          /* sum over the scored pairs of len(query) * len(target) */
+    float sw_kernel_ms;         /* device time of the dominant score kernel */
+} s4g_survivors;
+int s4g_score_screen(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, const uint32_t* cand_ids /*[io]*/, const int64_t* cand_offsets /*[io]*/,
+                     int64_t n_pairs, int where, const int32_t* matrix /*host*/, const char* matrix_name, uint64_t db_residues,
+                     int gap_open, int gap_extend, double max_evalue, s4g_survivors* out);
+
+/* The whole hot path for one resident shard and one query batch: k-mer prefilter -> SW scores -> E-value selection ->
+ * traceback, i.e. searchDatabase() followed by alignDatabase() (sift4g/src/main.cpp:203-220, database_search.hpp:17-19,
+ * database_alignment.hpp:18-23) behind one entry point.  Candidate lists, scores and survivors stay in HBM between the
+ * stages; the exact selection runs on host threads with the reference's libm arithmetic and order (ties by target name when
+ * the shard was opened from a file, else by id).  Result arrays are pinned host memory owned by the context, valid until the
+ * next s4g_search / s4g_score_screen on it. */
+typedef struct s4g_search_params {
+    int kmer_length, max_candidates;            /* prefilter: sift4g -k / --max-candidates (main.cpp:88-95) */
+    const int32_t* matrix;                      /* 26x26 scorer table */
+    const char* matrix_name;                    /* E-value constants; NULL = "BLOSUM_62" */
+    int gap_open, gap_extend;
+    double max_evalue;
+    int max_alignments;
+    int n_threads;                              /* host threads of the selection; <= 0: all cores (capped) */
+    int want_candidates;                        /* != 0: copy the candidate lists to the host as well */
+    int want_alignments;                        /* != 0: trace the kept hits back (stage 3) */
+} s4g_search_params;
+typedef struct s4g_search_result {
+    int32_t n_queries;
+    int64_t n_pairs;                            /* (query, candidate) pairs scored */
+    int64_t n_survivors;                        /* pairs that passed the device screen */
+    uint64_t sw_cells, db_residues;
+    const uint32_t* cand_ids;                   /* want_candidates: ascending ids per query ... */
+    const int64_t* cand_offsets;                /* ... delimited by cand_offsets[n_queries + 1] */
+    int64_t n_hits;                             /* kept hits, grouped by query in the reference's order (E asc, score desc, name asc) */
+    const uint32_t* hit_query;
+    const uint32_t* hit_target;
+    const int32_t* hit_score;
+    const double* hit_evalue;
+    const int64_t* hit_offsets;                 /* [n_queries + 1] */
+    const int32_t* coords;                      /* want_alignments: {qstart, qend, tstart, tend} per hit */
+    const uint8_t* paths;                       /* moves 1 = DIAG, 2 = LEFT, 3 = UP */
+    const int64_t* path_offsets;                /* [n_hits + 1] */
+    float ms_prefilter, ms_score, ms_select, ms_align, sw_kernel_ms;     /* wall time per stage, device time of the score kernel */
+    int64_t h2d_bytes, d2h_bytes;               /* bytes this call copied over the bus */
+} s4g_search_result;
+int s4g_search(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, const s4g_search_params* params, s4g_search_result* out);
 
 /* ---- measurement helpers ------------------------------------------------------------------------ */
 /* Sustained issue rate of the DPX / integer ALU pipe (lane-operations per second of

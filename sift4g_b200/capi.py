@@ -55,9 +55,35 @@ SIGNATURES = {
     "s4g_merge_candidates_host": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp]),
     "s4g_select_hits": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, C.c_char_p, C.c_uint64, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "s4g_evalue_screen": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int64, _vp, C.c_char_p, C.c_uint64, C.c_int, C.c_int, C.c_double, _vp, _vp, _vp, _vp, _vp]),
+    "s4g_score_screen": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, _vp, C.c_char_p, C.c_uint64, C.c_int, C.c_int, C.c_double, _vp]),
+    "s4g_search": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "s4g_measure_dpx_peak": (C.c_int, [_vp, C.c_int, _f64p]),
     "s4g_last_sw_kernel_ms": (C.c_int, [_vp, _f32p]),
 }
+
+
+
+class Survivors(C.Structure):
+    """s4g_survivors (include/sift4g_b200.h)"""
+    _fields_ = [("n", C.c_int64), ("query", _vp), ("id", _vp), ("score", _vp), ("tlen", _vp), ("n_pairs", C.c_int64),
+                ("sw_cells", C.c_uint64), ("sw_kernel_ms", C.c_float)]
+
+
+class SearchParams(C.Structure):
+    """s4g_search_params"""
+    _fields_ = [("kmer_length", C.c_int), ("max_candidates", C.c_int), ("matrix", _vp), ("matrix_name", C.c_char_p),
+                ("gap_open", C.c_int), ("gap_extend", C.c_int), ("max_evalue", C.c_double), ("max_alignments", C.c_int),
+                ("n_threads", C.c_int), ("want_candidates", C.c_int), ("want_alignments", C.c_int)]
+
+
+class SearchResult(C.Structure):
+    """s4g_search_result"""
+    _fields_ = [("n_queries", C.c_int32), ("n_pairs", C.c_int64), ("n_survivors", C.c_int64), ("sw_cells", C.c_uint64),
+                ("db_residues", C.c_uint64), ("cand_ids", _vp), ("cand_offsets", _vp), ("n_hits", C.c_int64), ("hit_query", _vp),
+                ("hit_target", _vp), ("hit_score", _vp), ("hit_evalue", _vp), ("hit_offsets", _vp), ("coords", _vp), ("paths", _vp),
+                ("path_offsets", _vp), ("ms_prefilter", C.c_float), ("ms_score", C.c_float), ("ms_select", C.c_float),
+                ("ms_align", C.c_float), ("sw_kernel_ms", C.c_float), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+
 
 _LIB = None
 
@@ -368,3 +394,60 @@ def merge_candidates_host(ids, scores, counts, max_candidates, n_threads=0):
     if rc != 0:
         raise S4GError("s4g_merge_candidates_host failed (%d)" % rc)
     return out, out_cnt
+
+
+def _view(ptr, n, dtype):
+    """numpy view of `n` items of library-owned host memory (valid until the next call on the context)"""
+    if not ptr or n == 0:
+        return np.zeros(0, dtype=dtype)
+    buf = (C.c_char * (int(n) * np.dtype(dtype).itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=int(n))
+
+
+def score_screen(ctx, db, q, cand_ids, cand_offsets, matrix, gap_open=10, gap_extend=1, max_evalue=1e-4, db_residues=0,
+                 matrix_name=b"BLOSUM_62", where=S4G_HOST):
+    """s4g_score_screen -> (query, id, score, tlen) views of the survivors, sw_cells"""
+    matrix = np.ascontiguousarray(matrix, dtype=np.int32)
+    if where == S4G_HOST:
+        cand_ids = np.ascontiguousarray(cand_ids, dtype=np.uint32)
+        cand_offsets = np.ascontiguousarray(cand_offsets, dtype=np.int64)
+        n = len(cand_ids)
+    else:
+        n = cand_ids.numel()
+    sv = Survivors()
+    ctx.check(ctx.lib.s4g_score_screen(ctx.h, db.h, q.h, _ptr(cand_ids), _ptr(cand_offsets), n, where, _ptr(matrix), matrix_name,
+                                       int(db_residues), gap_open, gap_extend, max_evalue, C.addressof(sv)))
+    return _view(sv.query, sv.n, np.uint32), _view(sv.id, sv.n, np.uint32), _view(sv.score, sv.n, np.int32), _view(sv.tlen, sv.n, np.int32), int(sv.sw_cells)
+
+
+class SearchOutput:
+    """numpy views of an s4g_search_result (library-owned pinned memory: copy what must outlive the next call)"""
+
+    def __init__(self, r):
+        nq = r.n_queries
+        self.n_queries, self.n_pairs, self.n_survivors, self.n_hits = nq, int(r.n_pairs), int(r.n_survivors), int(r.n_hits)
+        self.sw_cells, self.db_residues = int(r.sw_cells), int(r.db_residues)
+        self.cand_off = _view(r.cand_offsets, nq + 1, np.int64) if r.cand_offsets else None
+        self.cand_ids = _view(r.cand_ids, self.n_pairs, np.uint32) if r.cand_ids else None
+        self.pair_q = _view(r.hit_query, self.n_hits, np.uint32)
+        self.pair_t = _view(r.hit_target, self.n_hits, np.uint32)
+        self.pair_score = _view(r.hit_score, self.n_hits, np.int32)
+        self.evalue = _view(r.hit_evalue, self.n_hits, np.float64)
+        self.hit_off = _view(r.hit_offsets, nq + 1, np.int64)
+        self.coords = _view(r.coords, 4 * self.n_hits, np.int32).reshape(-1, 4) if r.coords else None
+        self.path_off = _view(r.path_offsets, self.n_hits + 1, np.int64) if r.path_offsets else None
+        self.paths = _view(r.paths, int(self.path_off[-1]) if self.path_off is not None and self.n_hits else 0, np.uint8) if r.paths else None
+        self.stage_ms = {"prefilter": r.ms_prefilter, "score": r.ms_score, "select": r.ms_select, "align": r.ms_align}
+        self.sw_kernel_ms = r.sw_kernel_ms
+        self.h2d_bytes, self.d2h_bytes = int(r.h2d_bytes), int(r.d2h_bytes)
+
+
+def search(ctx, db, q, matrix, k=5, max_candidates=5000, gap_open=10, gap_extend=1, max_evalue=1e-4, max_alignments=400, n_threads=0,
+           want_candidates=True, want_alignments=True, matrix_name=b"BLOSUM_62"):
+    """s4g_search: the whole hot path for one resident shard, host buffers out."""
+    matrix = np.ascontiguousarray(matrix, dtype=np.int32)
+    prm = SearchParams(k, max_candidates, matrix.ctypes.data, matrix_name, gap_open, gap_extend, max_evalue, max_alignments, n_threads,
+                       1 if want_candidates else 0, 1 if want_alignments else 0)
+    res = SearchResult()
+    ctx.check(ctx.lib.s4g_search(ctx.h, db.h, q.h, C.addressof(prm), C.addressof(res)))
+    return SearchOutput(res)

@@ -138,7 +138,7 @@ void s4g_shutdown(s4g_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < s4g_ctx::kSlots; ++i) if (ctx->slot_ptr[i]) cudaFree(ctx->slot_ptr[i]);
-    for (int i = 0; i < 8; ++i) if (ctx->pin_ptr[i]) cudaFreeHost(ctx->pin_ptr[i]);
+    for (int i = 0; i < s4g_ctx::kPins; ++i) if (ctx->pin_ptr[i]) cudaFreeHost(ctx->pin_ptr[i]);
     if (ctx->ev_sw0) cudaEventDestroy(ctx->ev_sw0);
     if (ctx->ev_sw1) cudaEventDestroy(ctx->ev_sw1);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);

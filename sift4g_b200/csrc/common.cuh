@@ -23,12 +23,13 @@ struct s4g_ctx {
     cudaEvent_t ev_sw0 = nullptr, ev_sw1 = nullptr;
     bool sw_timed = false;
     // grow-only scratch arena, one buffer per slot (device memory)
-    static const int kSlots = 40;
+    static const int kSlots = 48;
     void* slot_ptr[kSlots] = {nullptr};
     size_t slot_bytes[kSlots] = {0};
     // pinned host staging, grow-only
-    void* pin_ptr[8] = {nullptr};
-    size_t pin_bytes[8] = {0};
+    static const int kPins = 24;
+    void* pin_ptr[kPins] = {nullptr};
+    size_t pin_bytes[kPins] = {0};
     // candidate-buffer budget of the prefilter, remembered per batch shape (see s4g_prefilter_device)
     size_t pf_budget = 0;
     int pf_budget_nq = -1;
@@ -100,7 +101,8 @@ enum {
     SLOT_SW_MISC, SLOT_SW_OVF, SLOT_SW_BOUND, SLOT_SW_MAT,
     SLOT_PF_INDEX, SLOT_PF_BITMAP, SLOT_PF_RANK, SLOT_PF_BUCKET, SLOT_PF_HITS, SLOT_PF_CAND,
     SLOT_PF_COUNT, SLOT_PF_THR, SLOT_PF_CUB, SLOT_PF_TMP, SLOT_PF_TMP2, SLOT_PF_SPILL, SLOT_PF_GBUF, SLOT_SW_STRIP,
-    SLOT_AL_WORK, SLOT_AL_DIR, SLOT_AL_MISC, SLOT_AL_OUT, SLOT_PF_ENTRY
+    SLOT_AL_WORK, SLOT_AL_DIR, SLOT_AL_MISC, SLOT_AL_OUT, SLOT_PF_ENTRY,
+    SLOT_SR_ROWS, SLOT_SR_CNT, SLOT_SR_OFF, SLOT_SR_CAND, SLOT_SR_SCORES, SLOT_SR_SURV
 };
 
 // ---- stage launchers (device pointers, enqueue on ctx->stream) ----------------------------------

@@ -1,9 +1,11 @@
 // Drop-in body of sift4g's alignDatabase() (signature: sift4g/src/database_alignment.hpp:18-23).
 // What the reference did per query through swsharp (database.c:402-646: score every candidate, E-values,
 // keep the best <= max_alignments, trace them back) is done for the whole query batch at once:
-//   scores  : s4g_sw_score (GPU)
-//   E-values: the reference's own eValues() host routine, so the doubles are bit-identical to the CPU build
-//             (vendor/swsharp/swsharp/src/evalue.cu:227-273,436-489); ordering rule of database.c:1043-1059
+//   scores  : s4g_score_screen (GPU): scores + an E-value pre-screen on the device; only the few per cent of pairs that can
+//             pass max_evalue come back
+//   E-values: s4g_select_hits on `-t` host threads: the reference's formula in IEEE double with libm, evaluated in its
+//             operation order (vendor/swsharp/swsharp/src/evalue.cu:227-273,436-489) -- bit-identical doubles (pinned by the
+//             golden E-values of tests/golden) -- and the ordering rule of database.c:1043-1059 incl. the name tie key
 //   paths   : s4g_sw_align (GPU)
 // The results are handed over as the reference's own DbAlignment objects (malloc'ed paths, borrowed Chain
 // pointers into `database`), which is what selectAlignments / outputShotgunDatabase consume.
@@ -13,7 +15,6 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <map>
 #include <string>
 #include <vector>
 
@@ -26,16 +27,7 @@ struct Row {
     int idx;          // position in the query's candidate list
     int score;
     double value;
-    const char* name;
 };
-
-bool rowLess(const Row& a, const Row& b) {    // dbAlignmentDataCmp, database.c:1043-1059
-    if (a.value == b.value) {
-        if (a.score == b.score) return strcmp(a.name, b.name) < 0;
-        return a.score > b.score;
-    }
-    return a.value < b.value;
-}
 
 }  // namespace
 
@@ -43,13 +35,19 @@ void alignDatabase(DbAlignment**** alignments, int** alignments_lengths, Chain**
                    const std::string& database_path, Chain** queries, int32_t queries_length,
                    std::vector<std::vector<uint32_t>>& indices, int32_t algorithm, EValueParams* evalue_params, double max_evalue,
                    uint32_t max_alignments, Scorer* scorer, int32_t* cards, int32_t cards_length) {
-    (void)cards; (void)cards_length;      // GPUs are named by S4G_DEVICES / S4G_DEVICE (s4g_session.hpp)
+    (void)evalue_params;                  // the same constants are derived from (matrix name, gap penalties, database length) below
     fprintf(stderr, "** Aligning queries with candidate sequences **\n");
     if (algorithm != SW_ALIGN) {
         fprintf(stderr, "[ERROR:sift4g_b200] only the SW algorithm is provided by the B200 path\n");
         exit(-1);
     }
     S4gSession& s = s4gSession();
+    // `cards` reaches this seam only; the session (opened by searchDatabase) read the same flag from the command line
+    if (cards_length > 0 && !getenv("S4G_DEVICES") && !getenv("S4G_DEVICE")) {
+        bool same = (int)s.shards.size() == cards_length;
+        for (int d = 0; same && d < cards_length; ++d) same = s.shards[d].device == cards[d];
+        if (!same) { fprintf(stderr, "[ERROR:sift4g_b200] --cards does not match the GPUs the database shards are resident on\n"); exit(-1); }
+    }
     s4gOpenDatabase(database_path);
     s4gUploadQueries(queries, queries_length);
     const int n_shards = (int)s.shards.size();
@@ -58,91 +56,75 @@ void alignDatabase(DbAlignment**** alignments, int** alignments_lengths, Chain**
     struct Loc { const S4gShard* sh; int64_t local; };
     auto locate = [&](uint32_t id) { const S4gShard& sh = s.shards[s.shardOf(id)]; return Loc{&sh, (int64_t)id - sh.lo}; };
     auto length_of = [&](uint32_t id) { const Loc l = locate(id); const int64_t* off = s4g_db_host_offsets(l.sh->db); return (int)(off[l.local + 1] - off[l.local]); };
-    auto name_of = [&](uint32_t id) { const Loc l = locate(id); return s4g_db_name(l.sh->db, l.local); };
 
-    // ---- scores of every (query, candidate) ----
+    // ---- scores of every (query, candidate) + E-value pre-screen, on the GPU that holds the candidate ----
     std::vector<int64_t> cand_off(queries_length + 1, 0);
     for (int32_t i = 0; i < queries_length; ++i) cand_off[i + 1] = cand_off[i] + (int64_t)indices[i].size();
-    const int64_t n_pairs = cand_off[queries_length];
-    std::vector<uint32_t> cand_ids(n_pairs);
-    for (int32_t i = 0; i < queries_length; ++i) std::copy(indices[i].begin(), indices[i].end(), cand_ids.begin() + cand_off[i]);
-    std::vector<int32_t> scores(n_pairs);
     const int* table = scorerGetTable(scorer);
+    const int gap_open = scorerGetGapOpen(scorer), gap_extend = scorerGetGapExtend(scorer);
+    const char* matrix_name = scorerGetName(scorer);
     if (scorerGetMaxCode(scorer) != 26) { fprintf(stderr, "[ERROR:sift4g_b200] protein scorer expected\n"); exit(-1); }
-    if (n_shards == 1) {
-        S4gShard& sh = s.shards[0];
-        s4gCheck(s4g_sw_score(sh.ctx, sh.db, sh.queries, cand_ids.data(), cand_off.data(), n_pairs, table, scorerGetGapOpen(scorer),
-                              scorerGetGapExtend(scorer), scores.data(), S4G_HOST), "s4g_sw_score");
-    } else {
-        // candidate ids ascend within a query (database_search.cpp:173-180), shards are contiguous id ranges: the part of a
-        // query's list that a GPU owns is one sub-range, and the scores go back to the same positions
-        s4gForEachShard([&](int d) {
-            S4gShard& sh = s.shards[d];
-            std::vector<int64_t> off(queries_length + 1, 0), first(queries_length, 0);
-            for (int32_t i = 0; i < queries_length; ++i) {
-                const uint32_t* b = cand_ids.data() + cand_off[i];
-                const uint32_t* e = cand_ids.data() + cand_off[i + 1];
-                const uint32_t* lo = std::lower_bound(b, e, sh.lo);
-                const uint32_t* hi = std::lower_bound(lo, e, sh.hi);
-                first[i] = lo - cand_ids.data();
-                off[i + 1] = off[i] + (hi - lo);
+    // candidate ids ascend within a query (database_search.cpp:173-180) and shards are contiguous id ranges: the part of a
+    // query's list that a GPU owns is one sub-range
+    std::vector<s4g_survivors> surv(n_shards);
+    s4gForEachShard([&](int d) {
+        S4gShard& sh = s.shards[d];
+        std::vector<int64_t> off(queries_length + 1, 0);
+        std::vector<uint32_t> ids;
+        ids.reserve(n_shards == 1 ? (size_t)cand_off[queries_length] : (size_t)cand_off[queries_length] / n_shards * 2);
+        for (int32_t i = 0; i < queries_length; ++i) {
+            const auto lo = std::lower_bound(indices[i].begin(), indices[i].end(), sh.lo);
+            const auto hi = std::lower_bound(lo, indices[i].end(), sh.hi);
+            ids.insert(ids.end(), lo, hi);
+            off[i + 1] = (int64_t)ids.size();
+        }
+        s4gCheck(s4g_score_screen(sh.ctx, sh.db, sh.queries, ids.data(), off.data(), (int64_t)ids.size(), S4G_HOST, table, matrix_name, s.total_residues,
+                                  gap_open, gap_extend, max_evalue, &surv[d]), "s4g_score_screen", sh.ctx);
+    });
+
+    // ---- exact E-values + selection on host threads (reference arithmetic and order: sw/evalue.cu:436-489, database.c:1043-1059)
+    // survivors of a query from all shards, shard after shard (each shard lists its survivors by ascending query)
+    int64_t n_surv = 0;
+    for (int d = 0; d < n_shards; ++d) n_surv += surv[d].n;
+    std::vector<uint32_t> s_id(n_surv);
+    std::vector<int32_t> s_sc(n_surv), s_tl(n_surv), q_lens(queries_length);
+    std::vector<const char*> s_name(n_surv);
+    std::vector<int64_t> s_off(queries_length + 1, 0);
+    {
+        std::vector<int64_t> cur(n_shards, 0);
+        int64_t w = 0;
+        for (int32_t i = 0; i < queries_length; ++i) {
+            q_lens[i] = chainGetLength(queries[i]);
+            for (int d = 0; d < n_shards; ++d) {
+                const s4g_survivors& sv = surv[d];
+                int64_t& c = cur[d];
+                for (; c < sv.n && sv.query[c] == (uint32_t)i; ++c, ++w) {
+                    s_id[w] = sv.id[c]; s_sc[w] = sv.score[c]; s_tl[w] = sv.tlen[c];
+                    s_name[w] = s4g_db_name(s.shards[d].db, (int64_t)sv.id[c] - s.shards[d].lo);
+                }
             }
-            std::vector<uint32_t> ids(off[queries_length]);
-            for (int32_t i = 0; i < queries_length; ++i) std::copy(cand_ids.begin() + first[i], cand_ids.begin() + first[i] + (off[i + 1] - off[i]), ids.begin() + off[i]);
-            std::vector<int32_t> sc(ids.size());
-            s4gCheck(s4g_sw_score(sh.ctx, sh.db, sh.queries, ids.data(), off.data(), (int64_t)ids.size(), table, scorerGetGapOpen(scorer),
-                                  scorerGetGapExtend(scorer), sc.data(), S4G_HOST), "s4g_sw_score");
-            for (int32_t i = 0; i < queries_length; ++i) std::copy(sc.begin() + off[i], sc.begin() + off[i + 1], scores.begin() + first[i]);
-        });
+            s_off[i + 1] = w;
+        }
     }
-
-    // ---- E-values + selection (host, reference arithmetic) ----
-    // eValues() only reads chain lengths: serve it length-only views of one dummy chain
-    int max_len = 1;
-    for (const S4gShard& sh : s.shards) {
-        const int64_t* off = s4g_db_host_offsets(sh.db);
-        for (int64_t i = 0; i < (int64_t)(sh.hi - sh.lo); ++i) max_len = std::max<int>(max_len, (int)(off[i + 1] - off[i]));
-    }
-    std::string dummy((size_t)max_len, 'A');
-    Chain* dummy_chain = chainCreate((char*)"len", 3, (char*)dummy.c_str(), max_len);
-    std::map<int, Chain*> len_view;
-    auto view_of = [&](int len) {
-        auto it = len_view.find(len);
-        if (it != len_view.end()) return it->second;
-        Chain* v = chainCreateView(dummy_chain, 0, len - 1, 0);
-        len_view[len] = v;
-        return v;
-    };
-
+    const size_t hit_cap = (size_t)queries_length * max_alignments;
+    std::vector<uint32_t> pair_q(hit_cap), pair_t(hit_cap);
+    std::vector<int32_t> pair_s(hit_cap);
+    std::vector<double> pair_e(hit_cap);
+    std::vector<int64_t> hit_off(queries_length + 1, 0);
+    s4gCheck(s4g_select_hits(s.shards[0].ctx, queries_length, q_lens.data(), s_id.data(), s_off.data(), s_sc.data(), s_tl.data(), s_name.data(), matrix_name,
+                             s.total_residues, gap_open, gap_extend, max_evalue, (int)max_alignments, s.host_threads, pair_q.data(), pair_t.data(),
+                             pair_s.data(), pair_e.data(), hit_off.data()), "s4g_select_hits", s.shards[0].ctx);
+    const int64_t n_hits = hit_off[queries_length];
     std::vector<std::vector<Row>> kept(queries_length);
-    std::vector<uint32_t> pair_q, pair_t;
-    std::vector<int32_t> pair_s;
     for (int32_t i = 0; i < queries_length; ++i) {
-        const int n = (int)indices[i].size();
-        if (n == 0) continue;
-        std::vector<Chain*> views(n);
-        for (int j = 0; j < n; ++j) views[j] = view_of(length_of(indices[i][j]));
-        std::vector<double> values(n);
-        eValues(values.data(), scores.data() + cand_off[i], queries[i], views.data(), n, nullptr, 0, evalue_params);
-        std::vector<Row> rows(n);
-        int thresholded = 0;
-        for (int j = 0; j < n; ++j) {
-            rows[j] = {j, scores[cand_off[i] + j], values[j], name_of(indices[i][j])};
-            if (values[j] <= max_evalue) ++thresholded;
+        kept[i].resize(hit_off[i + 1] - hit_off[i]);
+        for (int64_t h = hit_off[i]; h < hit_off[i + 1]; ++h) {
+            const int idx = (int)(std::lower_bound(indices[i].begin(), indices[i].end(), pair_t[h]) - indices[i].begin());
+            kept[i][h - hit_off[i]] = {idx, pair_s[h], pair_e[h]};
         }
-        const int k = std::min<int>(thresholded, std::min<int>((int)max_alignments, n));   // database.c:347-349,866
-        std::partial_sort(rows.begin(), rows.begin() + k, rows.end(), rowLess);
-        rows.resize(k);
-        for (int j = 0; j < k; ++j) {
-            pair_q.push_back((uint32_t)i);
-            pair_t.push_back(indices[i][rows[j].idx]);
-            pair_s.push_back(rows[j].score);
-        }
-        kept[i].swap(rows);
     }
 
     // ---- paths of the kept hits ----
-    const int64_t n_hits = (int64_t)pair_q.size();
     std::vector<int32_t> coords(4 * n_hits);
     std::vector<int64_t> path_off(n_hits + 1, 0);       // single GPU: offsets into `paths`
     std::vector<uint8_t> paths;
@@ -155,8 +137,8 @@ void alignDatabase(DbAlignment**** alignments, int** alignments_lengths, Chain**
         int64_t cap = 16;
         for (int64_t h = 0; h < n_hits; ++h) cap += chainGetLength(queries[pair_q[h]]) + length_of(pair_t[h]);
         paths.resize(cap);
-        s4gCheck(s4g_sw_align(sh.ctx, sh.db, sh.queries, n_hits, pair_q.data(), pair_t.data(), pair_s.data(), table, scorerGetGapOpen(scorer),
-                              scorerGetGapExtend(scorer), coords.data(), paths.data(), cap, path_off.data(), S4G_HOST), "s4g_sw_align");
+        s4gCheck(s4g_sw_align(sh.ctx, sh.db, sh.queries, n_hits, pair_q.data(), pair_t.data(), pair_s.data(), table, gap_open, gap_extend, coords.data(),
+                              paths.data(), cap, path_off.data(), S4G_HOST), "s4g_sw_align", sh.ctx);
     } else {
         std::vector<std::vector<int64_t>> mine(n_shards);            // global hit numbers per shard, in order
         for (int64_t h = 0; h < n_hits; ++h) {
@@ -177,8 +159,8 @@ void alignDatabase(DbAlignment**** alignments, int** alignments_lengths, Chain**
             }
             sh_paths[d].resize(cap);
             sh_path_off[d].assign(n + 1, 0);
-            s4gCheck(s4g_sw_align(sh.ctx, sh.db, sh.queries, n, pq.data(), pt.data(), ps.data(), table, scorerGetGapOpen(scorer),
-                                  scorerGetGapExtend(scorer), co.data(), sh_paths[d].data(), cap, sh_path_off[d].data(), S4G_HOST), "s4g_sw_align");
+            s4gCheck(s4g_sw_align(sh.ctx, sh.db, sh.queries, n, pq.data(), pt.data(), ps.data(), table, gap_open, gap_extend, co.data(), sh_paths[d].data(),
+                                  cap, sh_path_off[d].data(), S4G_HOST), "s4g_sw_align", sh.ctx);
             for (int64_t x = 0; x < n; ++x) std::copy(co.begin() + 4 * x, co.begin() + 4 * x + 4, coords.begin() + 4 * mine[d][x]);
         });
     }
@@ -221,9 +203,6 @@ void alignDatabase(DbAlignment**** alignments, int** alignments_lengths, Chain**
         }
         indices[i].clear();   // the reference consumes the candidate lists (database_alignment.cpp:159-161)
     }
-    for (auto& kv : len_view) chainDelete(kv.second);
-    chainDelete(dummy_chain);
-
     fprintf(stderr, "* processing database part 1 (size ~%.2f GB): 100.00/100.00%% *\n\n", s.total_residues / 1e9);
     *alignments = out;
     *alignments_lengths = out_len;

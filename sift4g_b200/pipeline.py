@@ -1,13 +1,16 @@
 """Host-side orchestration of the hot path over the C ABI (Python mirror of what the C++ shims in
 sift4g_b200/host do for the CLI): prefilter -> SW scores -> E-value selection -> traceback.
 
-Two entry points, same results:
-  * run_host(...)    -- host (numpy) buffers in and out; every call copies H2D/D2H inside the C ABI.
-                        This is the call a user of the library makes (bench.py's `e2e`).
-  * run_device(...)  -- inputs and intermediate results stay in HBM as torch tensors (bench.py's `value`);
-                        with torch.distributed initialised the database is sharded, one resident shard per
-                        rank, and the per-query candidate lists / kept hits are merged with two NCCL
-                        all-gathers (the only exchanges on the path).
+Three entry points, same results:
+  * search_host(...)   -- ONE C-ABI call (s4g_search) with host buffers in and out; candidate lists, scores and survivors
+                          stay in HBM between the stages, the exact selection runs on C++ host threads.  This is the call a
+                          user of the library makes and what bench.py times as `e2e` on one GPU.
+  * run_host(...)      -- the same path stage by stage through the host-buffer form of every stage call (s4g_prefilter,
+                          s4g_sw_score, s4g_select_hits, s4g_sw_align): every intermediate result crosses the bus; kept for
+                          the parity tests, which look at every stage's output.
+  * DevicePipeline     -- inputs and intermediate results stay in HBM as torch tensors (bench.py's `value`); with
+                          torch.distributed initialised the database is sharded, one resident shard per rank, and the
+                          per-query cut-offs / kept hits are exchanged over NCCL (the only exchanges on the path).
 torch is plumbing here (device buffers, streams, NCCL); all compute is in libsift4g_b200.so.
 """
 import os
@@ -43,6 +46,20 @@ def _ragged(ids2d, cnt):
     off = np.zeros(nq + 1, dtype=np.int64)
     off[1:] = np.cumsum(cnt)
     return np.ascontiguousarray(ids2d[mask]), off
+
+
+def search_host(ctx, db, q_codes, q_off, matrix, k=5, max_candidates=5000, gap_open=10, gap_extend=1, max_evalue=1e-4, max_alignments=400,
+                n_threads=0, want_candidates=True, align=True):
+    """Whole hot path through s4g_search: query batch uploaded, one call, results as numpy views of the library's pinned
+    buffers (capi.SearchOutput; valid until the next call on the context)."""
+    Q = ctx.queries(q_codes, q_off)
+    try:
+        out = capi.search(ctx, db, Q, matrix, k, max_candidates, gap_open, gap_extend, max_evalue, max_alignments, n_threads,
+                          want_candidates=want_candidates, want_alignments=align)
+    finally:
+        Q.close()
+    out.h2d_bytes += q_codes.nbytes + q_off.nbytes
+    return out
 
 
 def run_host(ctx, db, q_codes, q_off, matrix, db_lens, k=5, max_candidates=5000, gap_open=10, gap_extend=1, max_evalue=1e-4,

@@ -87,3 +87,29 @@ def test_cli_with_one_shard_per_device_writes_the_same_files(tmp_path):
         assert _run(["-q", sd + "/q.fa", "-d", sd + "/d.fa", "--sub-results"], env) == _expected("synth_default"), devs
         assert _run(["-q", sd + "/q.fa", "-d", packed, "--sub-results", "--max-candidates", "200", "--max-aligns", "50"], env) == _expected("synth_C200_M50"), devs
         assert _run(["-q", tf + "/query.fasta", "-d", tf + "/sample_protein_database.fa", "--subst", tf + "/", "--sub-results"], env) == _expected("test_files_subst"), devs
+
+
+def test_cli_flags_cards_and_threads():
+    # --cards (sift4g/src/main.cpp:123-125: one card index per character) names the GPUs; -t the host threads of the FASTA
+    # parse and of the exact hit selection.  Neither changes a byte of the output; an unknown card is refused like the
+    # reference refuses it (main.cpp:186 "invalid cuda cards").
+    import torch
+    n = torch.cuda.device_count()
+    sd = os.path.join(util.GOLDEN, "synth_e2e")
+    for cards in ["0"] + (["01", "10"] if n >= 2 else []):
+        for t in ("1", "5"):
+            assert _run(["-q", sd + "/q.fa", "-d", sd + "/d.fa", "--sub-results", "--cards", cards, "-t", t]) == _expected("synth_default"), (cards, t)
+    out = tempfile.mkdtemp()
+    r = subprocess.run([BIN, "-q", sd + "/q.fa", "-d", sd + "/d.fa", "--out", out, "--cards", "9"], capture_output=True, text=True)
+    assert r.returncode != 0 and "invalid cuda cards" in r.stderr
+
+
+def test_cli_defaults_to_every_visible_gpu():
+    # help text of the reference: "--cards ... default: all available CUDA cards" (main.cpp:329-332)
+    sd = os.path.join(util.GOLDEN, "synth_e2e")
+    out = tempfile.mkdtemp()
+    env = {k: v for k, v in os.environ.items() if k not in ("S4G_DEVICES", "S4G_DEVICE")}
+    r = subprocess.run([BIN, "-q", sd + "/q.fa", "-d", sd + "/d.fa", "--out", out], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    import torch
+    assert "%d GPU" % torch.cuda.device_count() in r.stderr

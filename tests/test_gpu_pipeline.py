@@ -39,6 +39,74 @@ def test_device_pipeline_equals_host_pipeline(ctx, blosum):
     pipe.close(); D.close()
 
 
+def test_one_call_search_matches_the_oracle_stage_by_stage(ctx, blosum):
+    """s4g_search (prefilter -> scores -> selection -> traceback in one C-ABI call, host buffers out) against the oracle:
+    candidate sets, the kept hits of EVERY query (libm E-values, order of dbAlignmentDataCmp), cells and path bytes."""
+    queries, db = synth.make_dataset(43, 9, 2500, q_len=(50, 600), homologs=(8, 30), rare_fraction=0.005)
+    qc, qo = synth.pack(queries); dc, do = synth.pack(db)
+    lens = np.diff(do)
+    total = int(do[-1])
+    D = ctx.database(dc, do)
+    N, M = 250, 12                                  # M below the homolog count: the top-M truncation is exercised
+    out = pipeline.search_host(ctx, D, qc, qo, blosum, max_candidates=N, max_alignments=M)
+    cells, oids, osc, _ = O.prefilter(dc, do, qc, qo, 5, N)
+    assert cells == total == out.db_residues
+    n_hits = 0
+    for q in range(len(queries)):
+        got = out.cand_ids[out.cand_off[q]:out.cand_off[q + 1]]
+        assert np.array_equal(got, oids[q]), "candidate set of query %d" % q
+        # oracle selection over the oracle's scores of these candidates
+        sc = np.array([O.sw_score(queries[q], db[t], blosum) for t in oids[q]], dtype=np.int32)
+        ev = np.array([O.evalue(int(s), len(queries[q]), int(lens[t]), total) for s, t in zip(sc, oids[q])])
+        keep = O.select(ev, sc, ["D%08d" % t for t in oids[q]], 1e-4, M)
+        a, b = int(out.hit_off[q]), int(out.hit_off[q + 1])
+        assert np.array_equal(out.pair_t[a:b], oids[q][keep]), "kept hits of query %d" % q
+        assert np.array_equal(out.pair_score[a:b], sc[keep]) and np.array_equal(out.evalue[a:b], ev[keep])
+        assert (out.pair_q[a:b] == q).all()
+        for h in range(a, b):
+            coords, path = O.align(queries[q], db[int(out.pair_t[h])], int(out.pair_score[h]), blosum)
+            assert np.array_equal(coords, out.coords[h])
+            assert np.array_equal(path, out.paths[out.path_off[h]:out.path_off[h + 1]])
+        n_hits += b - a
+    assert n_hits == out.n_hits and n_hits > 40
+    assert out.sw_cells == sum(len(queries[q]) * int(lens[oids[q]].sum()) for q in range(len(queries)))
+    assert out.d2h_bytes > 0 and out.h2d_bytes > 0
+    # the stage-by-stage host path and the torch-resident pipeline return the same thing
+    hits = (out.pair_q.copy(), out.pair_t.copy(), out.pair_score.copy(), out.evalue.copy(), out.coords.copy(), out.paths.copy(), out.path_off.copy())
+    rh = pipeline.run_host(ctx, D, qc, qo, blosum, lens, max_candidates=N, max_alignments=M)
+    assert np.array_equal(rh.pair_q, hits[0]) and np.array_equal(rh.pair_t, hits[1]) and np.array_equal(rh.pair_score, hits[2])
+    assert np.array_equal(rh.evalue, hits[3]) and np.array_equal(rh.coords, hits[4]) and np.array_equal(rh.path_off, hits[6])
+    assert np.array_equal(rh.paths[:int(rh.path_off[-1])], hits[5])
+    D.close()
+
+
+def test_score_screen_returns_every_pair_that_can_pass(ctx, blosum):
+    """s4g_score_screen: the survivors are a superset of the pairs with E <= max_evalue (oracle doubles), in candidate order,
+    with exact scores and target lengths; sw_cells is the algorithmic count."""
+    queries, db = synth.make_dataset(44, 6, 1200, q_len=(50, 500), homologs=(5, 20), rare_fraction=0.005)
+    qc, qo = synth.pack(queries); dc, do = synth.pack(db)
+    lens = np.diff(do)
+    total = int(do[-1])
+    D = ctx.database(dc, do); Q = ctx.queries(qc, qo)
+    rng = np.random.default_rng(3)
+    cands = [np.sort(rng.choice(len(db), size=400, replace=False)).astype(np.uint32) for _ in queries]
+    ids = np.concatenate(cands); off = np.arange(len(queries) + 1, dtype=np.int64) * 400
+    s_q, s_id, s_sc, s_tl, cells = capi.score_screen(ctx, D, Q, ids, off, blosum)
+    assert cells == sum(len(queries[q]) * int(lens[cands[q]].sum()) for q in range(len(queries)))
+    want = []
+    for q in range(len(queries)):
+        for t in cands[q]:
+            s = O.sw_score(queries[q], db[t], blosum)
+            if O.evalue(s, len(queries[q]), int(lens[t]), total) <= 1e-4:
+                want.append((q, int(t), s, int(lens[t])))
+    got = list(zip(s_q.tolist(), s_id.tolist(), s_sc.tolist(), s_tl.tolist()))
+    assert got == sorted(got, key=lambda r: (r[0], r[1])) and set(want) <= set(got) and len(want) > 10
+    for q, t, s, tl in got:
+        assert s == O.sw_score(queries[q], db[t], blosum) and tl == lens[t]
+    assert len(got) <= len(want) + 5               # the screen's margin is 1e-6 relative: practically the same set
+    Q.close(); D.close()
+
+
 def test_sharded_prefilter_merge_equals_single_shard(ctx):
     import torch
     queries, db = synth.make_dataset(42, 6, 4000, q_len=(50, 400), homologs=(5, 20))
