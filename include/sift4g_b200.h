@@ -15,6 +15,8 @@
  *                         scoreDatabaseCpu()           sw/cpu_module.h:143-144
  *   s4g_sw_align       <- alignScoredPair()           sw/align.h (sw/align.c:235-255) ->
  *                         alignScoredPairCpu()         sw/cpu_module.h:67-68
+ *   s4g_alignment_strings / s4g_alignments_select  <- alignmentsExtract() / alignmentsSelect()
+ *                         sift4g/src/select_alignments.cpp:127-242
  *   s4g_search         <- searchDatabase() + alignDatabase() as called by sift4g/src/main.cpp:203-220
  *   s4g_db_* / s4g_queries_*  <- chainDatabaseGpuCreate/Delete()  sw/gpu_module.h:210-240
  *   s4g_db_open_fasta  <- readFastaChainsPart()       sw/pre_proc.h:76-81 (reader quirks kept)
@@ -279,6 +281,23 @@ typedef struct s4g_search_result {
     int64_t h2d_bytes, d2h_bytes;               /* bytes this call copied over the bus */
 } s4g_search_result;
 int s4g_search(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, const s4g_search_params* params, s4g_search_result* out);
+
+/* ---- behind the hot path: the alignments SIFT4G keeps for the prediction -------------------- */
+/* alignmentsExtract (sift4g/src/select_alignments.cpp:127-180 with aligmentStr :244-299): every hit as a string over its
+ * query's positions -- the target letter ('A'..'Z') aligned to each position, 'X' in front of / behind the alignment and
+ * where the query residue faces a gap.  Host arrays in the layout s4g_search / s4g_sw_align return them; the strings of hit h
+ * are written to out_strings[out_string_offsets[h] .. out_string_offsets[h + 1]) (length of its query); out_strings needs
+ * sum over hits of len(query) bytes, out_string_offsets n_hits + 1 entries.  The targets must lie in this shard. */
+int s4g_alignment_strings(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_hits, const uint32_t* hit_query, const uint32_t* hit_target,
+                          const int32_t* coords, const uint8_t* paths, const int64_t* path_offsets, uint8_t* out_strings,
+                          int64_t* out_string_offsets);
+/* alignmentsSelect (select_alignments.cpp:182-242, getMedian sift4g/src/constants.hpp:77-86): out_selected[q] = how many of
+ * query q's strings (hit_offsets[q] .. hit_offsets[q + 1], in the hit order) are kept: strings are added one at a time while
+ * the median over the query positions of  log2(20) + sum_a p_a log2 p_a  (float arithmetic of the reference, its
+ * all-but-the-last-element sort included) stays above `threshold` (the CLI's --median-threshold, default 2.75).  `strings`:
+ * the strings of all hits back to back (what s4g_alignment_strings wrote).  At most 2047 hits per query. */
+int s4g_alignments_select(s4g_ctx* ctx, int32_t n_queries, const int32_t* query_lens, const int64_t* hit_offsets, const uint8_t* strings,
+                          float threshold, int32_t* out_selected);
 
 /* ---- measurement helpers ------------------------------------------------------------------------ */
 /* Sustained issue rate of the DPX / integer ALU pipe (lane-operations per second of

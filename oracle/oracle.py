@@ -46,6 +46,9 @@ def lib():
         L.s4g_oracle_ssw_endpoints.argtypes = [u8p, C.c_int32, u8p, C.c_int32, i32p, C.c_int32, C.c_int32, i32p, i32p]
         L.s4g_oracle_ssw_banded.argtypes = [u8p, C.c_int32, u8p, C.c_int32, i32p, C.c_int32, C.c_int32, C.c_int32, u8p, C.c_int32]
         L.s4g_oracle_ssw_banded.restype = C.c_int32
+        L.s4g_oracle_alignment_string.argtypes = [u8p, C.c_int32, C.c_int32, C.c_int32, u8p, C.c_int32, C.c_char_p]
+        L.s4g_oracle_alignments_select.argtypes = [C.POINTER(C.c_char_p), C.c_int32, C.c_int32, C.c_float]
+        L.s4g_oracle_alignments_select.restype = C.c_int32
         _LIB = L
     return _LIB
 
@@ -126,6 +129,20 @@ def ssw_endpoints(q, t, mat=None, go=10, ge=1):
     coords = np.zeros(4, dtype=np.int32); s = C.c_int32(0)
     lib().s4g_oracle_ssw_endpoints(_p(q, C.c_uint8), len(q), _p(t, C.c_uint8), len(t), _p(mat, C.c_int32), go, ge, C.byref(s), _p(coords, C.c_int32))
     return s.value, coords
+
+
+def alignment_string(t, qlen, coords, path):
+    """alignmentsExtract: the hit as bytes over the query positions"""
+    t = np.ascontiguousarray(t, dtype=np.uint8); path = np.ascontiguousarray(path, dtype=np.uint8)
+    out = C.create_string_buffer(int(qlen) + 1)
+    lib().s4g_oracle_alignment_string(_p(t, C.c_uint8), int(qlen), int(coords[0]), int(coords[2]), _p(path, C.c_uint8), len(path), out)
+    return out.raw[:int(qlen)]
+
+
+def alignments_select(strings, qlen, threshold=2.75):
+    """alignmentsSelect: how many of the strings (in order) are kept"""
+    arr = (C.c_char_p * max(len(strings), 1))(*strings)
+    return lib().s4g_oracle_alignments_select(arr, len(strings), int(qlen), threshold)
 
 
 # ---- the real reference, when oracle/_ref was built (this container, or travelled to the GPU box) ----

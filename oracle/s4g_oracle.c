@@ -532,3 +532,58 @@ int32_t s4g_oracle_align(const uint8_t* q, int32_t qlen, const uint8_t* t, int32
     return s4g_oracle_ssw_banded(q + coords[0], coords[1] - coords[0] + 1, t + coords[2],
                                  coords[3] - coords[2] + 1, mat, go, ge, s1, path, path_cap);
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* SIFT4G's selection of the alignments a prediction is built from (the step right behind the hot path). */
+
+/* alignmentsExtract + aligmentStr, sift4g/src/select_alignments.cpp:127-180,244-299: the hit as a string over the query
+ * positions -- 'X' in front of qstart, then one character per path move that consumes a query residue (the aligned target
+ * letter for a DIAG move, 'X' for a gap in the target), 'X' behind the end of the path. */
+void s4g_oracle_alignment_string(const uint8_t* t, int32_t qlen, int32_t qstart, int32_t tstart, const uint8_t* path,
+                                 int32_t path_len, char* out) {
+    int32_t j = 0, ti = tstart;
+    for (; j < qstart; ++j) out[j] = 'X';
+    for (int32_t k = 0; k < path_len; ++k) {
+        if (path[k] == 1) { out[j++] = (char)('A' + t[ti]); ++ti; }         /* MOVE_DIAG */
+        else if (path[k] == 3) out[j++] = 'X';                              /* MOVE_UP: query residue against a gap */
+        else ++ti;                                                          /* MOVE_LEFT: target residue against a gap: no column */
+    }
+    for (; j < qlen; ++j) out[j] = 'X';
+}
+
+static int flt_cmp(const void* a, const void* b) { float x = *(const float*)a, y = *(const float*)b; return (x > y) - (x < y); }
+
+/* getMedian, sift4g/src/constants.hpp:77-86: std::sort(&a[0], &a[len - 1]) leaves the last element where it is */
+static float sift_median(float* a, int32_t len) {
+    if (len > 1) qsort(a, (size_t)(len - 1), sizeof(float), flt_cmp);
+    if (len % 2 == 0) return (float)((a[len / 2 - 1] + a[len / 2]) / 2.0);
+    return a[len / 2];
+}
+
+/* alignmentsSelect, select_alignments.cpp:182-242: strings[i] (qlen characters each) are added one at a time while the
+ * median conservation stays above the threshold; returns how many are kept. */
+int32_t s4g_oracle_alignments_select(const char* const* strings, int32_t n, int32_t qlen, float threshold) {
+    const double kLog_2_20 = 4.321928095;                                   /* constants.hpp:10 */
+    int nums[26];
+    float* pos_freq = (float*)calloc((size_t)(qlen > 0 ? qlen : 1), sizeof(float));
+    float median = (float)kLog_2_20;
+    int32_t i;
+    for (int k = 0; k < 26; ++k) nums[k] = 0;
+    for (i = 1; median > threshold && i <= n; ++i) {
+        for (int32_t j = 0; j < qlen; ++j) {
+            int valid = 0;
+            for (int32_t k = 0; k < i; ++k) {
+                const char c = strings[k][j];
+                if (c != 'X') { ++valid; nums[c - 'A']++; }
+            }
+            for (int k = 0; k < 26; ++k)
+                if (nums[k] != 0) pos_freq[j] += nums[k] / (float)valid * log2f(nums[k] / (float)valid);
+            pos_freq[j] += kLog_2_20;
+            for (int k = 0; k < 26; ++k) nums[k] = 0;
+        }
+        median = sift_median(pos_freq, qlen);
+        for (int32_t j = 0; j < qlen; ++j) pos_freq[j] = 0.0f;
+    }
+    free(pos_freq);
+    return i - 1;
+}

@@ -76,6 +76,13 @@ int32_t s4g_oracle_ssw_banded(const uint8_t* q, int32_t qlen, const uint8_t* t, 
                               const int32_t* mat676, int32_t gap_open, int32_t gap_extend,
                               int32_t score, uint8_t* path, int32_t path_cap);
 
+/* alignmentsExtract / alignmentsSelect of sift4g/src/select_alignments.cpp:127-242 (what SIFT4G does with the hot path's
+ * alignments before the prediction stage): the hit as a string over the query positions, and the number of leading
+ * hits kept under the median-conservation rule (getMedian's all-but-last sort included). */
+void s4g_oracle_alignment_string(const uint8_t* t, int32_t qlen, int32_t qstart, int32_t tstart, const uint8_t* path,
+                                 int32_t path_len, char* out);
+int32_t s4g_oracle_alignments_select(const char* const* strings, int32_t n, int32_t qlen, float threshold);
+
 #ifdef __cplusplus
 }
 #endif

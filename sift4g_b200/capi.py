@@ -57,6 +57,8 @@ SIGNATURES = {
     "s4g_evalue_screen": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int64, _vp, C.c_char_p, C.c_uint64, C.c_int, C.c_int, C.c_double, _vp, _vp, _vp, _vp, _vp]),
     "s4g_score_screen": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, _vp, C.c_char_p, C.c_uint64, C.c_int, C.c_int, C.c_double, _vp]),
     "s4g_search": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "s4g_alignment_strings": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "s4g_alignments_select": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, C.c_float, _vp]),
     "s4g_measure_dpx_peak": (C.c_int, [_vp, C.c_int, _f64p]),
     "s4g_last_sw_kernel_ms": (C.c_int, [_vp, _f32p]),
 }
@@ -276,6 +278,7 @@ class Queries:
             codes = np.ascontiguousarray(codes, dtype=np.uint8)
             offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         self.n = (len(offsets) if where == S4G_HOST else offsets.numel()) - 1
+        self.lens = np.diff(offsets).astype(np.int64) if where == S4G_HOST else None
         h = _vp()
         ctx.check(ctx.lib.s4g_queries_create(ctx.h, _ptr(codes), _ptr(offsets), self.n, where, C.byref(h)))
         self.h = h
@@ -451,3 +454,25 @@ def search(ctx, db, q, matrix, k=5, max_candidates=5000, gap_open=10, gap_extend
     res = SearchResult()
     ctx.check(ctx.lib.s4g_search(ctx.h, db.h, q.h, C.addressof(prm), C.addressof(res)))
     return SearchOutput(res)
+
+
+def alignment_strings(ctx, db, q, pair_q, pair_t, coords, paths, path_off):
+    """s4g_alignment_strings -> (strings uint8 back to back, offsets[n_hits + 1]); needs the query lengths via q"""
+    pair_q = np.ascontiguousarray(pair_q, dtype=np.uint32); pair_t = np.ascontiguousarray(pair_t, dtype=np.uint32)
+    coords = np.ascontiguousarray(coords, dtype=np.int32); paths = np.ascontiguousarray(paths, dtype=np.uint8)
+    path_off = np.ascontiguousarray(path_off, dtype=np.int64)
+    n = len(pair_q)
+    qlens = q.lens if hasattr(q, "lens") else None
+    cap = int(qlens[pair_q].sum()) if qlens is not None else 0
+    out = np.zeros(max(cap, 1), dtype=np.uint8)
+    off = np.zeros(n + 1, dtype=np.int64)
+    ctx.check(ctx.lib.s4g_alignment_strings(ctx.h, db.h, q.h, n, _ptr(pair_q), _ptr(pair_t), _ptr(coords), _ptr(paths), _ptr(path_off), _ptr(out), _ptr(off)))
+    return out[:int(off[-1])], off
+
+
+def alignments_select(ctx, query_lens, hit_off, strings, threshold=2.75):
+    query_lens = np.ascontiguousarray(query_lens, dtype=np.int32); hit_off = np.ascontiguousarray(hit_off, dtype=np.int64)
+    strings = np.ascontiguousarray(strings, dtype=np.uint8)
+    out = np.zeros(len(query_lens), dtype=np.int32)
+    ctx.check(ctx.lib.s4g_alignments_select(ctx.h, len(query_lens), _ptr(query_lens), _ptr(hit_off), _ptr(strings), threshold, _ptr(out)))
+    return out

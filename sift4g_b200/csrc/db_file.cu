@@ -7,6 +7,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cctype>
 #include <chrono>
@@ -193,6 +194,24 @@ bool read_header(int fd, DbFileHeader& h) {
     return read_at(fd, &h, sizeof(h), 0) && memcmp(h.magic, kMagic, 8) == 0;
 }
 
+// true when pred(i) holds for every i in [0, n): checked on several host threads
+template <class F>
+static bool parallel_all(int64_t n, F pred) {
+    const int n_threads = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>((int64_t)std::thread::hardware_concurrency(), 16), n / (1 << 20) + 1));
+    std::atomic<bool> ok(true);
+    auto work = [&](int t) {
+        const int64_t a = n * t / n_threads, b = n * (t + 1) / n_threads;
+        bool mine = true;
+        for (int64_t i = a; i < b && mine; ++i) mine = pred(i);
+        if (!mine) ok = false;
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_threads; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+    return ok;
+}
+
 }  // namespace
 
 extern "C" {
@@ -272,56 +291,57 @@ int s4g_db_file_info(const char* path, int64_t* n_seqs, uint64_t* n_residues) {
 int s4g_db_open_packed(s4g_ctx* ctx, const char* path, int shard, int n_shards, s4g_db** out) {
     if (!ctx || !path || !out || n_shards < 1 || shard < 0 || shard >= n_shards) return S4G_ERR_ARG;
     *out = nullptr;
-    int fd = ::open(path, O_RDONLY);
-    if (fd < 0) { s4g_set_error(ctx, "cannot open '%s'", path); return S4G_ERR_IO; }
-    DbFileHeader h;
-    if (!read_header(fd, h)) { ::close(fd); s4g_set_error(ctx, "'%s' is not a packed sift4g_b200 database", path); return S4G_ERR_IO; }
-    // Nothing of the header is trusted before it is checked against the size of the file: the tables, the names and the
-    // codes must all lie inside it (a corrupt n_seqs would otherwise size the vectors below).
-    struct stat fst;
-    const bool have_size = fstat(fd, &fst) == 0;
-    const uint64_t fsize = have_size ? (uint64_t)fst.st_size : 0;
-    const uint64_t tables = sizeof(h) + 2 * sizeof(int64_t) * (h.n_seqs + 1);
-    const bool header_ok = have_size && h.n_seqs < ((uint64_t)1 << 32) && tables <= fsize && h.names_bytes <= fsize - tables &&
-                           h.codes_pos >= tables + h.names_bytes && h.codes_pos <= fsize && h.n_residues <= fsize - h.codes_pos;
-    if (!header_ok) { ::close(fd); s4g_set_error(ctx, "'%s': corrupt packed database header", path); return S4G_ERR_IO; }
-    const int64_t n_all = (int64_t)h.n_seqs;
-    const int64_t lo = n_all * shard / n_shards, hi = n_all * (shard + 1) / n_shards, n = hi - lo;
     try {
-        std::vector<int64_t> off(n + 1), name_off(n + 1);
-        const uint64_t off_pos = sizeof(h), name_off_pos = off_pos + sizeof(int64_t) * (n_all + 1), names_pos = name_off_pos + sizeof(int64_t) * (n_all + 1);
-        bool ok = read_at(fd, off.data(), sizeof(int64_t) * (n + 1), off_pos + sizeof(int64_t) * lo) &&
-                  read_at(fd, name_off.data(), sizeof(int64_t) * (n + 1), name_off_pos + sizeof(int64_t) * lo);
-        std::vector<char> names;
-        std::vector<uint8_t> codes;
-        if (ok) {
-            ok = off[0] >= 0 && (uint64_t)off[n] <= h.n_residues && name_off[0] >= 0 && (uint64_t)name_off[n] <= h.names_bytes;
-            // every entry, not only the ends: sequences are non-empty, a name holds at least its NUL
-            for (int64_t i = 0; ok && i < n; ++i) ok = off[i + 1] > off[i] && name_off[i + 1] > name_off[i];
-            if (ok) {
-                names.resize((size_t)(name_off[n] - name_off[0]));
-                codes.resize((size_t)(off[n] - off[0]));
-                ok = (names.empty() || read_at(fd, names.data(), names.size(), names_pos + (uint64_t)name_off[0])) &&
-                     (codes.empty() || read_at(fd, codes.data(), codes.size(), h.codes_pos + (uint64_t)off[0]));
-                // name i ends with the NUL in front of name i + 1
-                for (int64_t i = 0; ok && i < n; ++i) ok = names[(size_t)(name_off[i + 1] - name_off[0]) - 1] == 0;
-            }
+        // the file is the HBM layout: it is mapped, checked in place on the host cores and copied once (H2D + the host mirror)
+        MappedFile f;
+        if (!f.open(path)) { s4g_set_error(ctx, "cannot open '%s'", path); return S4G_ERR_IO; }
+        DbFileHeader h;
+        if (f.size < sizeof(h) || (memcpy(&h, f.p, sizeof(h)), memcmp(h.magic, kMagic, 8) != 0)) {
+            s4g_set_error(ctx, "'%s' is not a packed sift4g_b200 database", path);
+            return S4G_ERR_IO;
         }
-        ::close(fd);
-        fd = -1;
+        // Nothing of the header is trusted before it is checked against the size of the file: the tables, the names and the
+        // codes must all lie inside it (a corrupt n_seqs would otherwise size the loops below).
+        const uint64_t fsize = f.size;
+        const uint64_t tables = sizeof(h) + 2 * sizeof(int64_t) * (h.n_seqs + 1);
+        const bool header_ok = h.n_seqs < ((uint64_t)1 << 32) && tables <= fsize && h.names_bytes <= fsize - tables &&
+                               h.codes_pos >= tables + h.names_bytes && h.codes_pos <= fsize && h.n_residues <= fsize - h.codes_pos;
+        if (!header_ok) { s4g_set_error(ctx, "'%s': corrupt packed database header", path); return S4G_ERR_IO; }
+        const int64_t n_all = (int64_t)h.n_seqs;
+        const int64_t lo = n_all * shard / n_shards, hi = n_all * (shard + 1) / n_shards, n = hi - lo;
+        const int64_t* off = reinterpret_cast<const int64_t*>(f.p + sizeof(h)) + lo;
+        const int64_t* name_off = reinterpret_cast<const int64_t*>(f.p + sizeof(h) + sizeof(int64_t) * (n_all + 1)) + lo;
+        const char* names = f.p + tables;
+        const uint8_t* codes = reinterpret_cast<const uint8_t*>(f.p + h.codes_pos);
+        bool ok = off[0] >= 0 && (uint64_t)off[n] <= h.n_residues && name_off[0] >= 0 && (uint64_t)name_off[n] <= h.names_bytes;
+        // every entry, not only the ends: sequences are non-empty, a name holds at least its NUL and ends with it
+        ok = ok && parallel_all(n, [&](int64_t i) { return off[i + 1] > off[i] && name_off[i + 1] > name_off[i] && (uint64_t)name_off[i + 1] <= h.names_bytes &&
+                                                           (uint64_t)off[i + 1] <= h.n_residues; });
+        ok = ok && parallel_all(n, [&](int64_t i) { return names[name_off[i + 1] - 1] == 0; });
         if (!ok) { s4g_set_error(ctx, "'%s': truncated or corrupt packed database", path); return S4G_ERR_IO; }
-        for (size_t i = 0; i < codes.size(); ++i) if (codes[i] >= S4G_NLET) { s4g_set_error(ctx, "'%s': residue code out of range", path); return S4G_ERR_IO; }
-        const int64_t base = off[0];
-        for (auto& o : off) o -= base;
-        int rc = s4g_db_create(ctx, codes.data(), off.data(), n, (uint32_t)lo, S4G_HOST, out);
+        const uint8_t* my_codes = codes + off[0];
+        const int64_t my_res = off[n] - off[0];
+        // 8 codes per step: any byte above 25 has bit 5, 6 or 7 set, or is 26..31 (bits 3+4 and one of bits 1, 2)
+        const int64_t words = my_res / 8;
+        bool codes_ok = parallel_all(words, [&](int64_t w) {
+            uint64_t x;
+            memcpy(&x, my_codes + 8 * w, 8);
+            const uint64_t hi3 = x & 0xE0E0E0E0E0E0E0E0ull;
+            const uint64_t big = (x & 0x1818181818181818ull) == 0 ? 0 : ((x >> 3) & (x >> 4) & ((x >> 1) | (x >> 2)) & 0x0101010101010101ull);
+            return (hi3 | big) == 0;
+        });
+        for (int64_t i = 8 * words; codes_ok && i < my_res; ++i) codes_ok = my_codes[i] < S4G_NLET;
+        if (!codes_ok) { s4g_set_error(ctx, "'%s': residue code out of range", path); return S4G_ERR_IO; }
+        std::vector<int64_t> loc(n + 1);
+        for (int64_t i = 0; i <= n; ++i) loc[i] = off[i] - off[0];
+        int rc = s4g_db_create(ctx, my_codes, loc.data(), n, (uint32_t)lo, S4G_HOST, out);
         if (rc != S4G_OK) return rc;
         (*out)->names.resize(n);
-        for (int64_t i = 0; i < n; ++i) (*out)->names[i].assign(names.data() + (name_off[i] - name_off[0]));
+        parallel_all(n, [&](int64_t i) { (*out)->names[i].assign(names + name_off[i]); return true; });
         (*out)->total_seqs = n_all;
         (*out)->total_residues = h.n_residues;
         return S4G_OK;
     } catch (const std::exception& e) {          // nothing is thrown across the C ABI
-        if (fd >= 0) ::close(fd);
         if (*out) { s4g_db_close(*out); *out = nullptr; }
         s4g_set_error(ctx, "'%s': %s while reading the packed database", path, e.what());
         return S4G_ERR_NOMEM;

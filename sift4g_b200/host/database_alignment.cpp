@@ -12,6 +12,7 @@
 // With several GPUs (S4G_DEVICES) every GPU scores and traces the candidates that lie in its resident shard; the
 // E-values and the selection see all scores of a query at once, as on one GPU.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -37,6 +38,8 @@ void alignDatabase(DbAlignment**** alignments, int** alignments_lengths, Chain**
                    uint32_t max_alignments, Scorer* scorer, int32_t* cards, int32_t cards_length) {
     (void)evalue_params;                  // the same constants are derived from (matrix name, gap penalties, database length) below
     fprintf(stderr, "** Aligning queries with candidate sequences **\n");
+    const auto t0 = std::chrono::steady_clock::now();
+    auto since = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
     if (algorithm != SW_ALIGN) {
         fprintf(stderr, "[ERROR:sift4g_b200] only the SW algorithm is provided by the B200 path\n");
         exit(-1);
@@ -82,6 +85,7 @@ void alignDatabase(DbAlignment**** alignments, int** alignments_lengths, Chain**
                                   gap_open, gap_extend, max_evalue, &surv[d]), "s4g_score_screen", sh.ctx);
     });
 
+    const double t_score = since();
     // ---- exact E-values + selection on host threads (reference arithmetic and order: sw/evalue.cu:436-489, database.c:1043-1059)
     // survivors of a query from all shards, shard after shard (each shard lists its survivors by ascending query)
     int64_t n_surv = 0;
@@ -125,6 +129,7 @@ void alignDatabase(DbAlignment**** alignments, int** alignments_lengths, Chain**
     }
 
     // ---- paths of the kept hits ----
+    const double t_select = since();
     std::vector<int32_t> coords(4 * n_hits);
     std::vector<int64_t> path_off(n_hits + 1, 0);       // single GPU: offsets into `paths`
     std::vector<uint8_t> paths;
@@ -172,6 +177,7 @@ void alignDatabase(DbAlignment**** alignments, int** alignments_lengths, Chain**
         return sh_paths[d].data() + sh_path_off[d][x];
     };
 
+    const double t_align = since();
     // ---- hand over as reference objects ----
     Chain** database = (Chain**)calloc((size_t)std::max<int64_t>(n_db, 1), sizeof(Chain*));
     DbAlignment*** out = (DbAlignment***)malloc(queries_length * sizeof(DbAlignment**));
@@ -203,6 +209,18 @@ void alignDatabase(DbAlignment**** alignments, int** alignments_lengths, Chain**
         }
         indices[i].clear();   // the reference consumes the candidate lists (database_alignment.cpp:159-161)
     }
+    // keep the hits in the C ABI's layout for the selection step (host/select_alignments.cpp)
+    s.hits_key = (const void*)out;
+    s.hit_q.assign(pair_q.begin(), pair_q.begin() + n_hits);
+    s.hit_t.assign(pair_t.begin(), pair_t.begin() + n_hits);
+    s.hit_coords = coords;
+    s.hit_off = hit_off;
+    s.hit_path_off.assign(n_hits + 1, 0);
+    for (int64_t x = 0; x < n_hits; ++x) { int plen = 0; path_of(x, plen); s.hit_path_off[x + 1] = s.hit_path_off[x] + plen; }
+    s.hit_paths.resize((size_t)s.hit_path_off[n_hits]);
+    for (int64_t x = 0; x < n_hits; ++x) { int plen = 0; const uint8_t* src = path_of(x, plen); memcpy(s.hit_paths.data() + s.hit_path_off[x], src, plen); }
+    fprintf(stderr, "* sift4g_b200: scores + screen %.3f s, selection %.3f s (%lld hits), paths %.3f s, result objects %.3f s *\n", t_score,
+            t_select - t_score, (long long)n_hits, t_align - t_select, since() - t_align);
     fprintf(stderr, "* processing database part 1 (size ~%.2f GB): 100.00/100.00%% *\n\n", s.total_residues / 1e9);
     *alignments = out;
     *alignments_lengths = out_len;

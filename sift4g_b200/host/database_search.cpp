@@ -6,6 +6,7 @@
 // host exactly like the reference merges its per-thread lists (database_search.cpp:132-154): best max_candidates
 // by (score desc, id asc) -- the same result as one GPU, whatever the number of shards.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -19,9 +20,13 @@
 uint64_t searchDatabase(std::vector<std::vector<uint32_t>>& dst, const std::string& database_path, Chain** queries,
                         int32_t queries_length, uint32_t kmer_length, uint32_t max_candidates, uint32_t num_threads) {
     fprintf(stderr, "** Searching database for candidate sequences **\n");
+    const auto t0 = std::chrono::steady_clock::now();
+    auto since = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
     S4gSession& s = s4gSession();
     s.host_threads = (int)num_threads;        // -t: host threads of the FASTA parse, the candidate merge and the hit selection
+    const double t_ctx = since();
     s4gOpenDatabase(database_path);
+    const double t_open = since();
     s4gUploadQueries(queries, queries_length);
     const int n_shards = (int)s.shards.size();
     const size_t row = max_candidates;
@@ -56,6 +61,8 @@ uint64_t searchDatabase(std::vector<std::vector<uint32_t>>& dst, const std::stri
                                            merged.data(), merged_counts.data()), "s4g_merge_candidates_host");
         for (int32_t i = 0; i < queries_length; ++i) dst[i].assign(merged.begin() + (size_t)i * row, merged.begin() + (size_t)i * row + merged_counts[i]);
     }
+    fprintf(stderr, "* sift4g_b200: GPU contexts %.3f s, database resident after %.3f s (%lld sequences), prefilter + candidate lists %.3f s *\n",
+            t_ctx, t_open - t_ctx, (long long)s.total_seqs, since() - t_open);
     fprintf(stderr, "* processing database part 1 (size ~%.2f GB): 100.00/100.00%% *\n\n", s.total_residues / 1e9);
     return s.total_residues;
 }

@@ -32,6 +32,13 @@ struct S4gSession {
     int64_t total_seqs = 0;
     uint64_t total_residues = 0;
     int host_threads = 0;                // -t of the CLI (0: all cores)
+    // the kept hits of the last alignDatabase() call in the C ABI's layout, for the selection step behind it
+    // (selectAlignments): valid while `hits_key` is the DbAlignment*** that call handed out
+    const void* hits_key = nullptr;
+    std::vector<uint32_t> hit_q, hit_t;
+    std::vector<int32_t> hit_coords;
+    std::vector<int64_t> hit_off, hit_path_off;
+    std::vector<uint8_t> hit_paths;
     int shardOf(uint32_t id) const {     // shards are contiguous and ascending
         int d = 0;
         while (d + 1 < (int)shards.size() && id >= shards[d].hi) ++d;

@@ -113,3 +113,17 @@ def test_cli_defaults_to_every_visible_gpu():
     assert r.returncode == 0, r.stderr[-2000:]
     import torch
     assert "%d GPU" % torch.cuda.device_count() in r.stderr
+
+
+def test_selection_step_on_the_gpu_and_in_reference_code_write_the_same_files():
+    # selectAlignments runs through s4g_alignment_strings / s4g_alignments_select by default (every other
+    # test of this module); S4G_SELECT=reference sends main.cpp's call to the reference's own code, still in the binary.
+    sd = os.path.join(util.GOLDEN, "synth_e2e")
+    tf = os.path.join(util.GOLDEN, "test_files")
+    for env in ({"S4G_SELECT": "reference"}, {"S4G_SELECT": "reference", "S4G_DEVICES": "0,0"}):
+        assert _run(["-q", sd + "/q.fa", "-d", sd + "/d.fa", "--sub-results"], env) == _expected("synth_default")
+        assert _run(["-q", tf + "/query.fasta", "-d", tf + "/sample_protein_database.fa", "--subst", tf + "/", "--sub-results"], env) == _expected("test_files_subst")
+    # another median threshold changes the selection: both paths must still agree with each other
+    a = _run(["-q", sd + "/q.fa", "-d", sd + "/d.fa", "--sub-results", "--median-threshold", "3.4"])
+    b = _run(["-q", sd + "/q.fa", "-d", sd + "/d.fa", "--sub-results", "--median-threshold", "3.4"], {"S4G_SELECT": "reference"})
+    assert a == b and a != _expected("synth_default")
