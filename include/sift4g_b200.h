@@ -299,6 +299,19 @@ int s4g_alignment_strings(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_hi
 int s4g_alignments_select(s4g_ctx* ctx, int32_t n_queries, const int32_t* query_lens, const int64_t* hit_offsets, const uint8_t* strings,
                           float threshold, int32_t* out_selected);
 
+/* ---- the --sub-results alignment table from the result buffers -------------------------------- */
+/* Per hit {identities, mismatches, gap openings, alignment length} as outputDatabaseBlastM8 counts them
+ * (sw/post_proc.c:962-1003), computed on the GPU from the path and the residues.  Host arrays in s4g_search's layout;
+ * out_stats: 4 int32 per hit.  The targets must lie in this shard. */
+int s4g_alignment_stats(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_hits, const uint32_t* hit_query, const uint32_t* hit_target,
+                        const int32_t* coords, const uint8_t* paths, const int64_t* path_offsets, int32_t* out_stats);
+/* outputShotgunDatabase() for SW_OUT_DB_BLASTM8 (with_header = 0) / SW_OUT_DB_BLASTM9 (with_header != 0: the "# Fields:" block
+ * in front of every query) -- sw/post_proc.c:253-266,962-1049 -- written straight from the buffers: one line per hit, names cut
+ * like the reference cuts them.  path NULL = stdout.  Needs no GPU and no context (errors: s4g_last_error(NULL)). */
+int s4g_write_blast_tab(const char* path, int with_header, int32_t n_queries, const int64_t* hit_offsets, const char* const* query_names,
+                        const char* const* target_names, const int32_t* stats, const int32_t* coords, const double* evalues,
+                        const int32_t* scores);
+
 /* ---- measurement helpers ------------------------------------------------------------------------ */
 /* Sustained issue rate of the DPX / integer ALU pipe (lane-operations per second of
  * VIADDMNMX.S16x2), measured for ~`millis` ms on the context's device: the denominator of the SW

@@ -49,6 +49,7 @@ def lib():
         L.s4g_oracle_alignment_string.argtypes = [u8p, C.c_int32, C.c_int32, C.c_int32, u8p, C.c_int32, C.c_char_p]
         L.s4g_oracle_alignments_select.argtypes = [C.POINTER(C.c_char_p), C.c_int32, C.c_int32, C.c_float]
         L.s4g_oracle_alignments_select.restype = C.c_int32
+        L.s4g_oracle_alignment_stats.argtypes = [u8p, u8p, C.c_int32, C.c_int32, u8p, C.c_int32, i32p]
         _LIB = L
     return _LIB
 
@@ -137,6 +138,14 @@ def alignment_string(t, qlen, coords, path):
     out = C.create_string_buffer(int(qlen) + 1)
     lib().s4g_oracle_alignment_string(_p(t, C.c_uint8), int(qlen), int(coords[0]), int(coords[2]), _p(path, C.c_uint8), len(path), out)
     return out.raw[:int(qlen)]
+
+
+def alignment_stats(q, t, coords, path):
+    """-> [identities, mismatches, gap openings, length] of the --sub-results table"""
+    q = np.ascontiguousarray(q, dtype=np.uint8); t = np.ascontiguousarray(t, dtype=np.uint8); path = np.ascontiguousarray(path, dtype=np.uint8)
+    out = np.zeros(4, dtype=np.int32)
+    lib().s4g_oracle_alignment_stats(_p(q, C.c_uint8), _p(t, C.c_uint8), int(coords[0]), int(coords[2]), _p(path, C.c_uint8), len(path), _p(out, C.c_int32))
+    return out
 
 
 def alignments_select(strings, qlen, threshold=2.75):

@@ -587,3 +587,24 @@ int32_t s4g_oracle_alignments_select(const char* const* strings, int32_t n, int3
     free(pos_freq);
     return i - 1;
 }
+
+/* outputDatabaseBlastM8's counts, sw/post_proc.c:962-1003: identities, mismatches and gap openings along the path, with its
+ * state machine as written (only an identical pair closes an open gap).  stats = {identity, mismatches, gap openings, length}. */
+void s4g_oracle_alignment_stats(const uint8_t* q, const uint8_t* t, int32_t qstart, int32_t tstart, const uint8_t* path,
+                                int32_t path_len, int32_t* stats) {
+    int identity = 0, mismatches = 0, openings = 0, openq = 0, opent = 0;
+    int32_t qi = qstart, ti = tstart;
+    for (int32_t k = 0; k < path_len; ++k) {
+        /* aligmentStr (post_proc.c, private copy of select_alignments.cpp:244-299): '-' in the query string for MOVE_LEFT,
+         * in the target string for MOVE_UP */
+        const int qgap = path[k] == 2, tgap = path[k] == 3;
+        const int qc = qgap ? -1 : q[qi], tc = tgap ? -1 : t[ti];
+        if (!qgap) ++qi;
+        if (!tgap) ++ti;
+        if (qc == tc) { ++identity; openq = 0; opent = 0; }
+        else if (qgap) { if (!openq) ++openings; openq = 1; opent = 0; }
+        else if (tgap) { if (!opent) ++openings; openq = 0; opent = 1; }
+        else ++mismatches;
+    }
+    stats[0] = identity; stats[1] = mismatches; stats[2] = openings; stats[3] = path_len;
+}

@@ -82,6 +82,9 @@ int32_t s4g_oracle_ssw_banded(const uint8_t* q, int32_t qlen, const uint8_t* t, 
 void s4g_oracle_alignment_string(const uint8_t* t, int32_t qlen, int32_t qstart, int32_t tstart, const uint8_t* path,
                                  int32_t path_len, char* out);
 int32_t s4g_oracle_alignments_select(const char* const* strings, int32_t n, int32_t qlen, float threshold);
+/* identities, mismatches, gap openings, length of an alignment as the --sub-results table counts them (sw/post_proc.c:962-1003) */
+void s4g_oracle_alignment_stats(const uint8_t* q, const uint8_t* t, int32_t qstart, int32_t tstart, const uint8_t* path,
+                                int32_t path_len, int32_t* stats);
 
 #ifdef __cplusplus
 }

@@ -59,6 +59,8 @@ SIGNATURES = {
     "s4g_search": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "s4g_alignment_strings": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "s4g_alignments_select": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, C.c_float, _vp]),
+    "s4g_alignment_stats": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "s4g_write_blast_tab": (C.c_int, [C.c_char_p, C.c_int, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "s4g_measure_dpx_peak": (C.c_int, [_vp, C.c_int, _f64p]),
     "s4g_last_sw_kernel_ms": (C.c_int, [_vp, _f32p]),
 }
@@ -476,3 +478,26 @@ def alignments_select(ctx, query_lens, hit_off, strings, threshold=2.75):
     out = np.zeros(len(query_lens), dtype=np.int32)
     ctx.check(ctx.lib.s4g_alignments_select(ctx.h, len(query_lens), _ptr(query_lens), _ptr(hit_off), _ptr(strings), threshold, _ptr(out)))
     return out
+
+
+def alignment_stats(ctx, db, q, pair_q, pair_t, coords, paths, path_off):
+    """s4g_alignment_stats -> int32 [n_hits, 4]: identities, mismatches, gap openings, alignment length"""
+    pair_q = np.ascontiguousarray(pair_q, dtype=np.uint32); pair_t = np.ascontiguousarray(pair_t, dtype=np.uint32)
+    coords = np.ascontiguousarray(coords, dtype=np.int32); paths = np.ascontiguousarray(paths, dtype=np.uint8)
+    path_off = np.ascontiguousarray(path_off, dtype=np.int64)
+    out = np.zeros((len(pair_q), 4), dtype=np.int32)
+    ctx.check(ctx.lib.s4g_alignment_stats(ctx.h, db.h, q.h, len(pair_q), _ptr(pair_q), _ptr(pair_t), _ptr(coords), _ptr(paths), _ptr(path_off), _ptr(out)))
+    return out
+
+
+def write_blast_tab(path, with_header, hit_off, query_names, target_names, stats, coords, evalues, scores):
+    lib = load()
+    hit_off = np.ascontiguousarray(hit_off, dtype=np.int64)
+    qn = (C.c_char_p * max(len(query_names), 1))(*[n.encode() for n in query_names])
+    tn = (C.c_char_p * max(len(target_names), 1))(*[n.encode() for n in target_names])
+    stats = np.ascontiguousarray(stats, dtype=np.int32); coords = np.ascontiguousarray(coords, dtype=np.int32)
+    evalues = np.ascontiguousarray(evalues, dtype=np.float64); scores = np.ascontiguousarray(scores, dtype=np.int32)
+    rc = lib.s4g_write_blast_tab(path.encode(), 1 if with_header else 0, len(hit_off) - 1, _ptr(hit_off), C.cast(qn, _vp), C.cast(tn, _vp), _ptr(stats),
+                                 _ptr(coords), _ptr(evalues), _ptr(scores))
+    if rc != 0:
+        raise S4GError("s4g_write_blast_tab failed (%d): %s" % (rc, lib.s4g_last_error(None).decode()))

@@ -234,3 +234,108 @@ extern "C" int s4g_alignments_select(s4g_ctx* ctx, int32_t n_queries, const int3
     S4G_CUDA(ctx, cudaStreamSynchronize(st));
     return S4G_OK;
 }
+
+// ---- the --sub-results alignment table fed from the result buffers -------------------------------------------
+// outputShotgunDatabase -> outputDatabaseBlastM8/M9 (sw/post_proc.c:253-266,962-1049): per hit identities, mismatches and gap
+// openings of the alignment (counted on the GPU from the path and the residues), then one tab-separated line per hit.
+namespace {
+
+// one thread per hit: the reference's counting loop (post_proc.c:982-1003) over the path.  Its state machine is kept as
+// written: only an identical pair closes an open gap -- a mismatch between two gaps of the same sequence does not.
+__global__ void f4_stats_kernel(const uint8_t* db_codes, const int64_t* db_off, uint32_t id_base, const uint8_t* q_codes, const int64_t* q_off,
+                                int64_t n_hits, const uint32_t* hit_q, const uint32_t* hit_t, const int32_t* coords, const uint8_t* paths,
+                                const int64_t* path_off, int32_t* stats) {
+    const int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= n_hits) return;
+    const uint8_t* q = q_codes + q_off[hit_q[h]] + coords[4 * h + 0];
+    const uint8_t* t = db_codes + db_off[hit_t[h] - id_base] + coords[4 * h + 2];
+    const uint8_t* p = paths + path_off[h];
+    const int len = (int)(path_off[h + 1] - path_off[h]);
+    int identity = 0, mismatches = 0, openings = 0, open_q = 0, open_t = 0, qi = 0, ti = 0;
+    for (int k = 0; k < len; ++k) {
+        const int op = p[k];
+        if (op == 1) {
+            if (q[qi] == t[ti]) { ++identity; open_q = 0; open_t = 0; } else ++mismatches;
+            ++qi; ++ti;
+        } else if (op == 2) {                       // MOVE_LEFT: gap in the query string
+            if (!open_q) ++openings;
+            open_q = 1; open_t = 0; ++ti;
+        } else {                                    // MOVE_UP: gap in the target string
+            if (!open_t) ++openings;
+            open_q = 0; open_t = 1; ++qi;
+        }
+    }
+    stats[4 * h + 0] = identity; stats[4 * h + 1] = mismatches; stats[4 * h + 2] = openings; stats[4 * h + 3] = len;
+}
+
+}  // namespace
+
+extern "C" int s4g_alignment_stats(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_hits, const uint32_t* hit_query, const uint32_t* hit_target,
+                                   const int32_t* coords, const uint8_t* paths, const int64_t* path_offsets, int32_t* out_stats) {
+    if (!ctx || !db || !q || n_hits < 0) return S4G_ERR_ARG;
+    if (n_hits == 0) return S4G_OK;
+    if (!hit_query || !hit_target || !coords || !paths || !path_offsets || !out_stats) return S4G_ERR_ARG;
+    S4G_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    for (int64_t h = 0; h < n_hits; ++h)
+        if (hit_query[h] >= (uint32_t)q->n || hit_target[h] < db->id_base || hit_target[h] - db->id_base >= (uint64_t)db->n) {
+            s4g_set_error(ctx, "s4g_alignment_stats: hit %lld references an unknown query or target", (long long)h);
+            return S4G_ERR_ARG;
+        }
+    const int64_t n_path = path_offsets[n_hits];
+    char* buf = (char*)s4g_scratch(ctx, SLOT_AL_WORK, (size_t)n_hits * (8 + 16 + 16 + 4 + 4) + (size_t)n_path + 256);
+    if (!buf) return S4G_ERR_NOMEM;
+    int64_t* d_poff = (int64_t*)buf;
+    int32_t* d_co = (int32_t*)(d_poff + n_hits + 1);
+    int32_t* d_stats = d_co + 4 * n_hits;
+    uint32_t* d_hq = (uint32_t*)(d_stats + 4 * n_hits);
+    uint32_t* d_ht = d_hq + n_hits;
+    uint8_t* d_paths = (uint8_t*)(d_ht + n_hits);
+    S4G_CUDA(ctx, cudaMemcpyAsync(d_poff, path_offsets, 8 * (n_hits + 1), cudaMemcpyHostToDevice, st));
+    S4G_CUDA(ctx, cudaMemcpyAsync(d_co, coords, 16 * n_hits, cudaMemcpyHostToDevice, st));
+    S4G_CUDA(ctx, cudaMemcpyAsync(d_hq, hit_query, 4 * n_hits, cudaMemcpyHostToDevice, st));
+    S4G_CUDA(ctx, cudaMemcpyAsync(d_ht, hit_target, 4 * n_hits, cudaMemcpyHostToDevice, st));
+    S4G_CUDA(ctx, cudaMemcpyAsync(d_paths, paths, n_path, cudaMemcpyHostToDevice, st));
+    f4_stats_kernel<<<(unsigned)((n_hits + 127) / 128), 128, 0, st>>>(db->d_codes, db->d_off, db->id_base, q->d_codes, q->d_off, n_hits, d_hq, d_ht, d_co,
+                                                                      d_paths, d_poff, d_stats);
+    S4G_CHECK_LAUNCH(ctx);
+    S4G_CUDA(ctx, cudaMemcpyAsync(out_stats, d_stats, 16 * n_hits, cudaMemcpyDeviceToHost, st));
+    S4G_CUDA(ctx, cudaStreamSynchronize(st));
+    return S4G_OK;
+}
+
+extern "C" int s4g_write_blast_tab(const char* path, int with_header, int32_t n_queries, const int64_t* hit_offsets, const char* const* query_names,
+                                   const char* const* target_names, const int32_t* stats, const int32_t* coords, const double* evalues,
+                                   const int32_t* scores) {
+    if (n_queries < 0 || !hit_offsets) return S4G_ERR_ARG;
+    if (hit_offsets[n_queries] > 0 && (!query_names || !target_names || !stats || !coords || !evalues || !scores)) return S4G_ERR_ARG;
+    FILE* f = path ? fopen(path, "w") : stdout;
+    if (!f) { s4g_set_error(nullptr, "cannot write '%s'", path); return S4G_ERR_IO; }
+    auto short_len = [](const char* name) {          // names are cut at the first blank, at most 30 characters (post_proc.c:1008-1016)
+        const char* sp = strchr(name, ' ');
+        const long n = sp ? sp - name : 30;
+        return (int)(n < 30 ? n : 30);
+    };
+    for (int32_t i = 0; i < n_queries; ++i) {
+        if (with_header)
+            fprintf(f, "# Fields:\n"
+                       "Query id,Subject id,%% identity,alignment length,mismatches,"
+                       "gap openings,q. start,q. end,s. start,s. end,e-value,score\n");
+        for (int64_t h = hit_offsets[i]; h < hit_offsets[i + 1]; ++h) {
+            const int length = stats[4 * h + 3];
+            fprintf(f, "%.*s\t", short_len(query_names[i]), query_names[i]);
+            fprintf(f, "%.*s\t", short_len(target_names[h]), target_names[h]);
+            fprintf(f, "%.2f\t", (100.f * stats[4 * h + 0]) / length);
+            fprintf(f, "%d\t%d\t%d\t", length, stats[4 * h + 1], stats[4 * h + 2]);
+            fprintf(f, "%d\t%d\t%d\t%d\t", coords[4 * h + 0] + 1, coords[4 * h + 1] + 1, coords[4 * h + 2] + 1, coords[4 * h + 3] + 1);
+            const double value = evalues[h];
+            if (value > 10e-3 && value < 100) fprintf(f, "%.2f\t", value); else fprintf(f, "%.2e\t", value);
+            fprintf(f, "%-d ", scores[h]);
+            fprintf(f, "\n");
+        }
+    }
+    const bool ok = !ferror(f);
+    if (f != stdout) fclose(f);
+    if (!ok) { s4g_set_error(nullptr, "write to '%s' failed", path ? path : "stdout"); return S4G_ERR_IO; }
+    return S4G_OK;
+}

@@ -179,6 +179,13 @@ void alignDatabase(DbAlignment**** alignments, int** alignments_lengths, Chain**
 
     const double t_align = since();
     // ---- hand over as reference objects ----
+    // main.cpp deletes its Scorer right after this call and BEFORE it writes the --sub-results table (main.cpp:222-228), whose
+    // bm0 / light writers still reach the scorer through the DbAlignment objects (sw/post_proc.c:812-960): a use after free in
+    // the reference that its own allocation pattern happens to survive.  The result objects get a scorer of their own
+    // (same name, table and penalties) that lives as long as the session.
+    static Scorer* result_scorer = nullptr;
+    if (result_scorer) scorerDelete(result_scorer);
+    result_scorer = scorerCreate(scorerGetName(scorer), (int*)scorerGetTable(scorer), scorerGetMaxCode(scorer), gap_open, gap_extend);
     Chain** database = (Chain**)calloc((size_t)std::max<int64_t>(n_db, 1), sizeof(Chain*));
     DbAlignment*** out = (DbAlignment***)malloc(queries_length * sizeof(DbAlignment**));
     int* out_len = (int*)malloc(queries_length * sizeof(int));
@@ -205,7 +212,7 @@ void alignDatabase(DbAlignment**** alignments, int** alignments_lengths, Chain**
             char* path = (char*)malloc(plen > 0 ? plen : 1);
             memcpy(path, src, plen);
             out[i][j] = dbAlignmentCreate(queries[i], coords[4 * h + 0], coords[4 * h + 1], 0, database[t], coords[4 * h + 2],
-                                          coords[4 * h + 3], kept[i][j].idx, kept[i][j].value, kept[i][j].score, scorer, path, plen);
+                                          coords[4 * h + 3], kept[i][j].idx, kept[i][j].value, kept[i][j].score, result_scorer, path, plen);
         }
         indices[i].clear();   // the reference consumes the candidate lists (database_alignment.cpp:159-161)
     }
@@ -214,6 +221,8 @@ void alignDatabase(DbAlignment**** alignments, int** alignments_lengths, Chain**
     s.hit_q.assign(pair_q.begin(), pair_q.begin() + n_hits);
     s.hit_t.assign(pair_t.begin(), pair_t.begin() + n_hits);
     s.hit_coords = coords;
+    s.hit_score.assign(pair_s.begin(), pair_s.begin() + n_hits);
+    s.hit_evalue.assign(pair_e.begin(), pair_e.begin() + n_hits);
     s.hit_off = hit_off;
     s.hit_path_off.assign(n_hits + 1, 0);
     for (int64_t x = 0; x < n_hits; ++x) { int plen = 0; path_of(x, plen); s.hit_path_off[x + 1] = s.hit_path_off[x] + plen; }

@@ -36,7 +36,8 @@ struct S4gSession {
     // (selectAlignments): valid while `hits_key` is the DbAlignment*** that call handed out
     const void* hits_key = nullptr;
     std::vector<uint32_t> hit_q, hit_t;
-    std::vector<int32_t> hit_coords;
+    std::vector<int32_t> hit_coords, hit_score;
+    std::vector<double> hit_evalue;
     std::vector<int64_t> hit_off, hit_path_off;
     std::vector<uint8_t> hit_paths;
     int shardOf(uint32_t id) const {     // shards are contiguous and ascending

@@ -127,3 +127,14 @@ def test_selection_step_on_the_gpu_and_in_reference_code_write_the_same_files():
     a = _run(["-q", sd + "/q.fa", "-d", sd + "/d.fa", "--sub-results", "--median-threshold", "3.4"])
     b = _run(["-q", sd + "/q.fa", "-d", sd + "/d.fa", "--sub-results", "--median-threshold", "3.4"], {"S4G_SELECT": "reference"})
     assert a == b and a != _expected("synth_default")
+
+
+def test_alignment_table_from_result_buffers_and_from_reference_code_are_the_same_file():
+    # alignments.txt (--sub-results) is written from the result buffers (s4g_alignment_stats on the GPU +
+    # s4g_write_blast_tab) for the tabular formats; S4G_WRITER=reference sends main.cpp's call to the reference writer.
+    sd = os.path.join(util.GOLDEN, "synth_e2e")
+    assert _run(["-q", sd + "/q.fa", "-d", sd + "/d.fa", "--sub-results"], {"S4G_WRITER": "reference"}) == _expected("synth_default")
+    for fmt in ("bm8", "bm9", "bm0", "light"):
+        a = _run(["-q", sd + "/q.fa", "-d", sd + "/d.fa", "--sub-results", "--outfmt", fmt])
+        b = _run(["-q", sd + "/q.fa", "-d", sd + "/d.fa", "--sub-results", "--outfmt", fmt], {"S4G_WRITER": "reference", "S4G_DEVICES": "0,0"})
+        assert a == b and "alignments.txt" in a, fmt

@@ -50,6 +50,23 @@ def test_oracle_reproduces_the_reference_aligned_fasta_files():
     assert 0 < kept_total <= sum(len(h) for h in hits)
 
 
+def test_alignment_table_of_the_reference_from_result_buffers(tmp_path):
+    """Row F4: the oracle's per-hit counts + the library's writer (s4g_write_blast_tab: host only, no GPU) reproduce the
+    reference CLI's alignments.txt (bm9) byte for byte from the reference's own alignments."""
+    from sift4g_b200 import capi
+    hits, qn, queries, dn, db, index = _golden_case()
+    want = json.load(open(os.path.join(util.GOLDEN, "expected_hashes.json")))["synth_default"]["alignments.txt"]
+    flat = [x for h in hits for x in h]
+    hoff = np.zeros(len(hits) + 1, dtype=np.int64); hoff[1:] = np.cumsum([len(h) for h in hits])
+    stats = np.array([O.alignment_stats(queries[q], db[index[x["name"]]], x["coords"], np.array(list(map(int, x["path"])), dtype=np.uint8))
+                      for q, h in enumerate(hits) for x in h], dtype=np.int32)
+    out = str(tmp_path / "alignments.txt")
+    capi.write_blast_tab(out, True, hoff, qn, [x["name"] for x in flat], stats, np.array([x["coords"] for x in flat], dtype=np.int32),
+                         np.array([float.fromhex(x["evalue_hex"]) for x in flat]), np.array([x["score"] for x in flat], dtype=np.int32))
+    assert hashlib.sha256(open(out, "rb").read()).hexdigest() == want
+    assert (stats[:, 0] + stats[:, 1] <= stats[:, 3]).all() and stats[:, 2].max() > 0
+
+
 def test_median_quirk_and_edge_cases_of_the_oracle():
     # one string: kept unless the threshold is not below log2(20) to begin with
     assert O.alignments_select([b"ACDE"], 4, 2.75) == 1
@@ -78,6 +95,9 @@ def test_gpu_strings_and_selection_match_the_oracle(ctx, blosum):
     for h in range(len(pq)):
         exp = O.alignment_string(db[pt[h]], len(queries[pq[h]]), coords[h], paths[poff[h]:poff[h + 1]])
         assert bytes(strings[soff[h]:soff[h + 1]]) == exp, "string of hit %d" % h
+    stats = capi.alignment_stats(ctx, D, Q, pq, pt, coords, paths, poff)
+    for h in range(len(pq)):
+        assert np.array_equal(stats[h], O.alignment_stats(queries[pq[h]], db[pt[h]], coords[h], paths[poff[h]:poff[h + 1]])), "table counts of hit %d" % h
     for thr in (2.75, 3.25, 1.0):
         sel = capi.alignments_select(ctx, np.diff(qo), hoff, strings, thr)
         for q in range(len(queries)):
