@@ -44,7 +44,7 @@ struct PfParams {
     const uint2* bitrank;
     const uint32_t* bucket_start;
     const unsigned long long* hits;
-    const unsigned long long* entry;  // per index k-mer: bit 63 set -> its only hit, else (bucket size << 32 | first entry in `hits`)
+    const unsigned long long* entry;  // per index k-mer: the queries of its <= 3 hits (bits 63..62 = count), else (bucket size << 32 | first entry in `hits`)
     const int64_t* q_hit_start;       // first index entry of every query (nq + 1): equal neighbours = a query without k-mers
     int nq;
     unsigned long long* thr;
@@ -233,8 +233,8 @@ constexpr uint32_t kLaneBucket = 24;      // index buckets up to this size are w
 //   pass A  walks the k-mer positions (4 per lane and step) and COUNTS the hits of every query in the warp's exact counters.
 //           Nothing is stored: a shared-memory atomic returns the previous count, and the one hit that takes a query's count
 //           across  cut-off x length  raises a flag.  The presence/rank probe is a random 32-byte sector access, of which an
-//           SM completes one per clock (tools/gather_microbench.cu: 290 G/s whole GPU); k-mers of the index with a single
-//           hit carry it in their bucket entry (one access instead of two).  A Bloom filter in shared memory in front of the
+//           SM completes one per clock (tools/gather_microbench.cu: 290 G/s whole GPU); k-mers of the index with up to three
+//           hits carry the hits' queries in their bucket entry (one access instead of two).  A Bloom filter in shared memory in front of the
 //           probe was built and measured: it halves the probes and makes the scan slower (the kernel is bound by issued
 //           instructions, not by the L1 wavefront rate -- profiles/r02_prefilter.md).
 //   no flag -> the sequence holds no candidate for any query: clear the counters, next sequence (practically every
@@ -313,9 +313,9 @@ __device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cn
             };
             // Only ~1 position in 6 of a 1 000-query batch meets a k-mer of the index, so the lanes do not chase their own
             // positions any further than the presence bit: the index ranks of the k-mers found are queued in the warp's ring and
-            // taken out 32 at a time -- entry load and counting run with full warps.  An entry is either the k-mer's only hit
-            // (counted at once) or a bucket; buckets are queued once more and walked 32 at a time, one lane each (the buckets of
-            // a batch of a few thousand queries are small), the rare large ones by the whole warp.
+            // taken out 32 at a time -- entry load and counting run with full warps.  An entry either holds the queries of the
+            // k-mer's (up to three) hits, counted at once, or names a bucket; buckets are queued once more and walked 32 at a
+            // time, one lane each (the buckets of a batch of a few thousand queries are small), the rare large ones by the warp.
             uint32_t r_head = 0, r_n = 0, m_head = 0, m_n = 0;        // both rings: first item, items queued (warp-uniform)
             auto flush_buckets = [&](uint32_t n) {                  // n <= 32
                 unsigned long long e = 0ull;
@@ -345,9 +345,12 @@ __device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cn
                 unsigned long long e = 0ull;
                 if ((uint32_t)lane < n) e = __ldg(P.entry + ring_r[(r_head + lane) & (kRankRing - 1u)]);
                 r_head += n; r_n -= n;
-                const bool single = e >> 63;
-                if (single) { count_hit((uint32_t)(e >> 32) & 0x7fffffffu); ++nh; }
-                const bool bucket = e != 0ull && !single;
+                const uint32_t inl = (uint32_t)(e >> 62);            // hits whose queries ride in the entry
+                if (inl >= 1u) count_hit((uint32_t)e & 0xfffffu);
+                if (inl >= 2u) count_hit((uint32_t)(e >> 20) & 0xfffffu);
+                if (inl == 3u) count_hit((uint32_t)(e >> 40) & 0xfffffu);
+                nh += inl;
+                const bool bucket = e != 0ull && inl == 0u;
                 const unsigned m = __ballot_sync(FULL, bucket);
                 if (m) {
                     if (bucket) ring_m[(m_head + m_n + __popc(m & lt_mask)) & (kBucketRing - 1u)] = e;
@@ -657,13 +660,19 @@ __global__ void ix_bucket_kernel(const uint32_t* sorted_keys, int64_t n, const u
     }
 }
 
-// bucket entries of the scan's pass A: a k-mer with a single hit carries it (bit 63 set; query ids stay below 2^20),
-// the others their bucket (size << 32 | first entry)
+// bucket entries of the scan's pass A, which only needs the QUERY of every hit: a k-mer with up to three hits carries their
+// queries in its entry (bits 63..62 = number of hits, three 20-bit query ids below: query ids stay under 2^20), the others
+// their bucket (size << 32 | first entry in `hits`; sizes stay under 2^30)
 __global__ void ix_entry_kernel(const uint32_t* bucket_start, const unsigned long long* hits, uint32_t n_distinct, unsigned long long* entry) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_distinct) return;
     const uint32_t b = bucket_start[r], c = bucket_start[r + 1] - b;
-    entry[r] = c == 1 ? ((1ull << 63) | hits[b]) : (((unsigned long long)c << 32) | b);
+    unsigned long long e = ((unsigned long long)c << 32) | b;
+    if (c <= 3) {
+        e = (unsigned long long)c << 62;
+        for (uint32_t i = 0; i < c; ++i) e |= (hits[b + i] >> 32) << (20 * i);
+    }
+    entry[r] = e;
 }
 
 // ---- candidate buffers -------------------------------------------------------------------------------------
