@@ -338,7 +338,7 @@ def _collect(r, nq):
     return cands, hits
 
 
-def parity_digest(ctx, mat, dist=None, log=None):
+def parity_digest(ctx, mat, dist=None, log=None, mode="exchange"):
     """-> {"digest": sha256 of the order-normalised results of PARITY_CASES through the (sharded) device pipeline,
            "sharded_equals_single": bool (rank 0 re-runs every case on one unsharded database), "cases": n}"""
     import hashlib
@@ -352,17 +352,39 @@ def parity_digest(ctx, mat, dist=None, log=None):
         qc, qo = synth.pack(queries); dc, do = synth.pack(db)
         lens = np.diff(do)
         lo, hi = n_db * rank // world, n_db * (rank + 1) // world
-        D = ctx.database(dc[do[lo]:do[hi]], do[lo:hi + 1] - do[lo], id_base=lo)
-        pipe = pipeline.DevicePipeline(ctx, D, qc, qo, mat, lens[lo:hi], int(do[-1]), max_candidates=N, max_alignments=M, dist=dist)
-        mine = _collect(pipe.step(), nq)
-        pipe.close(); D.close()
-        parts = [mine]
-        if dist is not None:
+        if mode == "striped" and dist is not None:
+            # NVLink-striped database: this rank contributes the residues of [lo, hi), sees the whole database and runs ITS
+            # slice of the queries against all of it -- nothing is merged, the ranks' results are just put side by side
+            import torch
+            from sift4g_b200 import stripes
+            S = stripes.StripedDatabase(ctx, torch.from_numpy(dc[do[lo]:do[hi]].copy()).cuda(), do, lo, hi, dist=dist)
+            qa, qb = nq * rank // world, nq * (rank + 1) // world
+            mine = ([], [])
+            if qb > qa:
+                pipe = pipeline.DevicePipeline(ctx, S.db, qc[qo[qa]:qo[qb]], qo[qa:qb + 1] - qo[qa], mat, lens, int(do[-1]), max_candidates=N, max_alignments=M)
+                c, h = _collect(pipe.step(), qb - qa)
+                mine = (c, [(x[0] + qa,) + x[1:] for x in h])
+                pipe.close()
+            torch.cuda.synchronize()
+            S.close()
             parts = [None] * world
             dist.all_gather_object(parts, mine)
+            if rank == 0:
+                cands = [np.sort(c) for p in parts for c in p[0]]
+                hits = sorted(h for p in parts for h in p[1])
+        else:
+            D = ctx.database(dc[do[lo]:do[hi]], do[lo:hi + 1] - do[lo], id_base=lo)
+            pipe = pipeline.DevicePipeline(ctx, D, qc, qo, mat, lens[lo:hi], int(do[-1]), max_candidates=N, max_alignments=M, dist=dist)
+            mine = _collect(pipe.step(), nq)
+            pipe.close(); D.close()
+            parts = [mine]
+            if dist is not None:
+                parts = [None] * world
+                dist.all_gather_object(parts, mine)
+            if rank == 0:
+                cands = [np.sort(np.concatenate([p[0][q] for p in parts])) for q in range(nq)]
+                hits = sorted(h for p in parts for h in p[1])
         if rank == 0:
-            cands = [np.sort(np.concatenate([p[0][q] for p in parts])) for q in range(nq)]
-            hits = sorted(h for p in parts for h in p[1])
             for q in range(nq):
                 sha.update(cands[q].astype("<u4").tobytes())
             for h in hits:
@@ -378,7 +400,8 @@ def parity_digest(ctx, mat, dist=None, log=None):
                     log("parity case seed %d: %d queries, %d candidates, %d hits over %d shards: %s" % (
                         seed, nq, sum(len(c) for c in c1), len(h1), world, "equal to one GPU" if ok else "DIFFERENT from one GPU"))
     return {"digest": sha.hexdigest() if rank == 0 else None, "sharded_equals_single": bool(same), "cases": len(PARITY_CASES),
-            "what": "sha256 over candidate id sets, kept hits (query, E as hex double, score, target, cells) and path bytes of %d fixed small workloads run through the %d-shard pipeline in the warm-up; the same at every N" % (len(PARITY_CASES), world)}
+            "what": "sha256 over candidate id sets, kept hits (query, E as hex double, score, target, cells) and path bytes of %d fixed small workloads run through the %d-GPU pipeline (%s) in the warm-up; the same at every N" % (
+                len(PARITY_CASES), world, "database striped over the GPUs' HBM, queries split" if (mode == "striped" and world > 1) else "database sharded, candidate/hit exchange" if world > 1 else "one resident database")}
 
 
 def workload_config(args, world):
@@ -393,9 +416,20 @@ def workload_config(args, world):
     name = "configs[1]" if n_db == 10_000_000 and args.query_shape == "uniform" else ("configs[2]-shaped" if n_db >= 40_000_000 else "custom")
     return {"workload": "%s: %d queries (%s) vs %d-sequence / %.2f B-residue synthetic database, whole hot path per step (prefilter k=5, top %d; SW BLOSUM62 10/1; E<=1e-4, top 400; traceback)" % (
                 name, n_queries, qdesc, n_db, total_res / 1e9, args.max_candidates),
-            "sharding": "database split in %d contiguous shards, one resident per GPU; %d queries per step (%s scaling: %s)" % (
+            "sharding": ("database striped over the HBM of %d GPUs (one resident stripe each, all stripes mapped into every GPU's address space, peers read over NVLink); "
+                         "every GPU runs the whole path for its own slice of the queries, no merge; %d queries per step (%s scaling: %s)" if multi_gpu_mode(args, world) == "striped" else
+                         "database split in %d contiguous shards, one resident per GPU, candidate lists and hits exchanged over NCCL; %d queries per step (%s scaling: %s)") % (
                 world, n_queries, args.scaling, "%d queries per GPU and step" % args.queries if args.scaling == "weak" else "same batch at every N"),
-            "l2": "inputs (%.2f GB database shard per GPU) exceed the 126 MB L2; no explicit flush" % (total_res / world / 1e9)}
+            "l2": "inputs (%.2f GB database %s per GPU) exceed the 126 MB L2; no explicit flush" % (total_res / world / 1e9, "stripe" if multi_gpu_mode(args, world) == "striped" else "shard")}
+
+
+def multi_gpu_mode(args, world):
+    """striped: NVLink-striped database, queries split over the ranks (default for weak scaling: per-GPU work is exactly the
+    one-GPU step).  exchange: one database shard per rank scanned for ALL queries, candidate cut-offs and hits exchanged
+    over NCCL (default for strong scaling: the prefilter's cost follows the residues scanned, not the queries)."""
+    if world == 1:
+        return "single"
+    return args.multi_gpu or ("striped" if args.scaling == "weak" else "exchange")
 
 
 def _claim_stdout():
@@ -421,6 +455,7 @@ def main():
     ap.add_argument("--max-candidates", type=int, default=5000)
     ap.add_argument("--ref-queries", type=int, default=256, help="queries of the bounded sample the reference CPU build is timed on")
     ap.add_argument("--ref-db-seqs", type=int, default=1_000_000)
+    ap.add_argument("--multi-gpu", default=None, choices=["striped", "exchange"], help="N > 1: NVLink-striped database + split queries, or sharded database + NCCL exchange (default: striped for weak, exchange for strong scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the result digest of the fixed verification workload in the warm-up")
@@ -455,9 +490,26 @@ def main():
     codes, loc_off, lens, total_res = build_db_device(torch, dev, n_db, lo, hi, q_codes, q_off)
     torch.cuda.synchronize()
     gen_s = time.time() - t0
-    db = ctx.database(codes, loc_off, id_base=lo, where=capi.S4G_DEVICE)
-    del codes
-    pipe = pipeline.DevicePipeline(ctx, db, q_codes, q_off, mat, lens, total_res, max_candidates=args.max_candidates, dist=dist if use_dist else None)
+    mode = multi_gpu_mode(args, world)
+    striped = None
+    if mode == "striped":
+        from sift4g_b200 import stripes
+        all_lens = db_lengths(n_db)
+        all_off = np.zeros(n_db + 1, dtype=np.int64)
+        np.cumsum(all_lens, out=all_off[1:])
+        striped = stripes.StripedDatabase(ctx, codes, all_off, lo, hi, dist=dist)
+        db = striped.db
+        del codes
+        # this rank's queries: an equal slice of the batch
+        qa, qb = n_queries * rank // world, n_queries * (rank + 1) // world
+        my_q_codes, my_q_off = q_codes[q_off[qa]:q_off[qb]], q_off[qa:qb + 1] - q_off[qa]
+        lens = all_lens
+        pipe = pipeline.DevicePipeline(ctx, db, my_q_codes, my_q_off, mat, all_lens, total_res, max_candidates=args.max_candidates)
+    else:
+        db = ctx.database(codes, loc_off, id_base=lo, where=capi.S4G_DEVICE)
+        del codes
+        my_q_codes, my_q_off = q_codes, q_off
+        pipe = pipeline.DevicePipeline(ctx, db, q_codes, q_off, mat, lens, total_res, max_candidates=args.max_candidates, dist=dist if use_dist else None)
 
     peak = ctx.dpx_peak(300)                  # sustained VIADDMNMX.S16x2 lane-ops/s on this device
     roof_gcups = peak * 2 / 6 / 1e9
@@ -470,7 +522,7 @@ def main():
     for _ in range(args.warmup):
         r = pipe.step()
     barrier()
-    parity = parity_digest(ctx, mat, dist if use_dist else None, log=lambda m: print(m, file=sys.stderr)) if not args.no_parity else None
+    parity = parity_digest(ctx, mat, dist if use_dist else None, log=lambda m: print(m, file=sys.stderr), mode=mode) if not args.no_parity else None
     if parity is not None and not parity["sharded_equals_single"]:
         raise SystemExit("bench: the sharded pipeline does not reproduce the single-GPU results (see stderr)")
     ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
@@ -509,7 +561,7 @@ def main():
     # e2e through the host-buffer API
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(torch, ctx, db, pipe, q_codes, q_off, mat, lens, total_res, args, use_dist, dist, dev, n_queries)
+        e2e = run_e2e(torch, ctx, db, pipe, my_q_codes, my_q_off, mat, lens, total_res, args, use_dist, dist, dev, n_queries, mode)
 
     base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -533,7 +585,7 @@ def main():
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this command (profiles/r01i_sw_digest.md; re-captured as two half-batch launches, 0.728 GB each, in profiles/r01t_sw_digest.md)",
                          "kernel_ms": round(sw_kernel_ms, 3),
                          "peak_source": "measured live on this GPU (no DPX figure in MEASURED_PEAKS.json): %.4e VIADDMNMX.S16x2 lane-ops/s sustained over 300 ms x 2 cells per op / 6 instructions per cell (BASELINE.md)" % peak},
-            "roofline_prefilter": {"bound": "hbm", "achieved": round(((hi - lo) / n_db * total_res + 8 * (hi - lo)) / (split["prefilter"] * 1e-3) / 1e9, 2) if split["prefilter"] else None,
+            "roofline_prefilter": {"bound": "hbm", "achieved": round(((total_res + 8 * n_db) if mode == "striped" else ((hi - lo) / n_db * total_res + 8 * (hi - lo))) / (split["prefilter"] * 1e-3) / 1e9, 2) if split["prefilter"] else None,
                                    "peak": hbm_peak(), "unit": "GB/s", "note": "database bytes (1 B/residue + 8 B/sequence) / prefilter stage time"},
         }
         if line["roofline_prefilter"]["achieved"]:
@@ -546,7 +598,10 @@ def main():
             line["cpu_baseline"] = base
         print(json.dumps(line), file=out, flush=True)
     pipe.close()
-    db.close()
+    if striped is not None:
+        striped.close()
+    else:
+        db.close()
     if use_dist:
         dist.barrier()
         dist.destroy_process_group()
@@ -586,7 +641,7 @@ def stage_split(torch, ctx, pipe, reps=3):
     return out
 
 
-def run_e2e(torch, ctx, db, pipe, q_codes, q_off, mat, lens, total_res, args, use_dist, dist, dev, n_queries):
+def run_e2e(torch, ctx, db, pipe, q_codes, q_off, mat, lens, total_res, args, use_dist, dist, dev, n_queries, mode="single"):
     """Same step end to end with HOST buffers, host<->device copies inside the timed region.
     One GPU: the product boundary itself -- the query batch is uploaded (s4g_queries_create) and ONE C-ABI call, s4g_search,
     returns candidate lists, kept hits with E-values and alignments in host memory (pipeline.search_host; no torch, no
@@ -594,20 +649,30 @@ def run_e2e(torch, ctx, db, pipe, q_codes, q_off, mat, lens, total_res, args, us
     queries uploaded and every result copied back each step (DevicePipeline.step(e2e=True))."""
     from sift4g_b200 import pipeline
     n = max(1, min(args.steps, 3))
-    if not use_dist:
+    if not use_dist or mode == "striped":
+        # q_codes / q_off: this rank's queries (the whole batch on one GPU)
         ctx.sync()
         run = lambda: pipeline.search_host(ctx, db, q_codes, q_off, mat, max_candidates=args.max_candidates, want_candidates=True, align=True)
         out = run()
+        if use_dist:
+            dist.barrier()
         t0 = time.time()
         for _ in range(n):
             out = run()
             checksum = int(out.path_off[-1]) + int(out.hit_off[-1]) + int(out.cand_off[-1])       # results are on the host
         dt = (time.time() - t0) / n
         ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
-        return {"value": round(out.sw_cells / dt / 1e9, 2), "unit": "GCUPS", "ms_per_step": round(dt * 1e3, 3), "h2d_bytes_per_step": int(out.h2d_bytes),
-                "d2h_bytes_per_step": int(out.d2h_bytes), "queries_per_sec": round(n_queries / dt, 2),
-                "stages_ms": {k: round(float(v), 3) for k, v in out.stage_ms.items()}, "kept_hits": int(out.n_hits), "result_checksum": checksum,
-                "timed": "host wall clock around s4g_queries_create + s4g_search (C ABI, host buffers): queries H2D; candidate lists, kept hits, E-values, alignment cells and paths D2H every step"}
+        cells, h2d, d2h, hits = float(out.sw_cells), float(out.h2d_bytes), float(out.d2h_bytes), float(out.n_hits)
+        if use_dist:
+            t = torch.tensor([dt, cells, h2d, d2h, hits, float(checksum)], dtype=torch.float64, device=dev)
+            tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            ts = t.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+            dt, cells, h2d, d2h, hits, checksum = float(tm[0]), float(ts[1]), float(ts[2]), float(ts[3]), float(ts[4]), int(ts[5])
+        return {"value": round(cells / dt / 1e9, 2), "unit": "GCUPS", "ms_per_step": round(dt * 1e3, 3), "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "queries_per_sec": round(n_queries / dt, 2),
+                "stages_ms": {k: round(float(v), 3) for k, v in out.stage_ms.items()}, "kept_hits": int(hits), "result_checksum": checksum,
+                "timed": "host wall clock around s4g_queries_create + s4g_search (C ABI, host buffers): queries H2D; candidate lists, kept hits, E-values, alignment cells and paths D2H every step"
+                         + ("; every rank for its own queries against the striped database, max over ranks (stages_ms: rank 0)" if use_dist else "")}
     pipe.step(e2e=True)
     dist.barrier()
     torch.cuda.synchronize()

@@ -54,6 +54,8 @@ extern "C" {
 typedef struct s4g_ctx s4g_ctx;
 typedef struct s4g_db s4g_db;
 typedef struct s4g_queries s4g_queries;
+typedef struct s4g_stripe s4g_stripe;
+typedef struct s4g_view s4g_view;
 
 /* ---- context ---------------------------------------------------------------------------- */
 int s4g_version(void);
@@ -109,6 +111,35 @@ uint64_t s4g_db_total_residues(const s4g_db* db);
 const int64_t* s4g_db_host_offsets(const s4g_db* db);
 const uint8_t* s4g_db_host_codes(const s4g_db* db);      /* NULL for device-created shards */
 const char* s4g_db_name(const s4g_db* db, int64_t local_index); /* NULL unless opened from a file */
+
+/* ---- NVLink-striped database (multi-GPU without a merge) ---------------------------------- */
+/* Replaces the reference's per-card split of the DATABASE with a host merge (sw/database.c:497-532: one host thread per
+ * card scores a slice of the sequences, results joined afterwards; the `cards` argument of alignDatabase,
+ * sift4g/src/database_alignment.hpp:18-23).  Here every GPU keeps one stripe of the residue array resident (1/N of the
+ * bytes, multiples of s4g_stripe_granularity), maps all N stripes into one contiguous virtual range and runs the whole hot
+ * path for ITS OWN queries against the full database, reading the other GPUs' pages over NVLink: no candidate list or hit
+ * ever has to be merged.  Ids of a view database are global FASTA indices (id_base 0).
+ *   s4g_stripe_create     physical memory on ctx's device, shareable with other processes
+ *   s4g_stripe_export_fd  POSIX file descriptor of the stripe (send it to the peers with SCM_RIGHTS; close it afterwards)
+ *   s4g_view_open         stripe i is local[i] when non-NULL (same process: the CLI's one-thread-per-GPU host), else it is
+ *                         imported from fds[i]; bytes[i] as created.  The view is readable and writable from ctx's device.
+ *   s4g_view_write/_fill  device-side copy of device memory / constant fill at byte `at` of the view (stores to a peer's
+ *                         pages travel over NVLink); enqueued on ctx's stream.
+ *   s4g_db_create_view    database over the view's bytes [0, offsets[n_seqs]) (+ 256 readable pad bytes, written here):
+ *                         the codes are NOT copied; close the database before the view. */
+uint64_t s4g_stripe_granularity(s4g_ctx* ctx);
+int s4g_stripe_create(s4g_ctx* ctx, uint64_t bytes, s4g_stripe** out);
+uint64_t s4g_stripe_bytes(const s4g_stripe* stripe);
+int s4g_stripe_export_fd(s4g_stripe* stripe, int* out_fd);
+void s4g_stripe_free(s4g_stripe* stripe);
+int s4g_view_open(s4g_ctx* ctx, int n_stripes, s4g_stripe* const* local /*may be NULL*/, const int* fds /*may be NULL*/,
+                  const uint64_t* bytes, s4g_view** out);
+void* s4g_view_ptr(const s4g_view* view);
+uint64_t s4g_view_bytes(const s4g_view* view);
+int s4g_view_write(s4g_view* view, uint64_t at, const uint8_t* src /*[dev]*/, uint64_t bytes);
+int s4g_view_fill(s4g_view* view, uint64_t at, int value, uint64_t bytes);
+void s4g_view_close(s4g_view* view);
+int s4g_db_create_view(s4g_ctx* ctx, s4g_view* view, const int64_t* offsets, int64_t n_seqs, int where, s4g_db** out);
 
 /* ---- query batch -------------------------------------------------------------------------- */
 int s4g_queries_create(s4g_ctx* ctx, const uint8_t* codes, const int64_t* offsets, int32_t n_queries,

@@ -43,6 +43,18 @@ SIGNATURES = {
     "s4g_db_host_offsets": (_i64p, [_vp]),
     "s4g_db_host_codes": (_u8p, [_vp]),
     "s4g_db_name": (C.c_char_p, [_vp, C.c_int64]),
+    "s4g_stripe_granularity": (C.c_uint64, [_vp]),
+    "s4g_stripe_create": (C.c_int, [_vp, C.c_uint64, C.POINTER(_vp)]),
+    "s4g_stripe_bytes": (C.c_uint64, [_vp]),
+    "s4g_stripe_export_fd": (C.c_int, [_vp, C.POINTER(C.c_int)]),
+    "s4g_stripe_free": (None, [_vp]),
+    "s4g_view_open": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.POINTER(_vp)]),
+    "s4g_view_ptr": (_vp, [_vp]),
+    "s4g_view_bytes": (C.c_uint64, [_vp]),
+    "s4g_view_write": (C.c_int, [_vp, C.c_uint64, _vp, C.c_uint64]),
+    "s4g_view_fill": (C.c_int, [_vp, C.c_uint64, C.c_int, C.c_uint64]),
+    "s4g_view_close": (None, [_vp]),
+    "s4g_db_create_view": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, C.POINTER(_vp)]),
     "s4g_queries_create": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int, C.POINTER(_vp)]),
     "s4g_queries_free": (None, [_vp]),
     "s4g_prefilter": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int]),
@@ -220,6 +232,71 @@ class Context:
 
     def queries(self, codes, offsets, where=S4G_HOST):
         return Queries(self, codes, offsets, where)
+
+
+class Stripe:
+    """One GPU's resident part of an NVLink-striped database (s4g_stripe_*)."""
+
+    def __init__(self, ctx, nbytes):
+        self.ctx = ctx
+        h = _vp()
+        ctx.check(ctx.lib.s4g_stripe_create(ctx.h, nbytes, C.byref(h)))
+        self.h = h
+        self.nbytes = int(nbytes)
+
+    def export_fd(self):
+        fd = C.c_int(-1)
+        self.ctx.check(self.ctx.lib.s4g_stripe_export_fd(self.h, C.byref(fd)))
+        return fd.value
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.s4g_stripe_free(self.h)
+            self.h = None
+
+
+class View:
+    """All stripes of a striped database mapped into one virtual range of ctx's device (s4g_view_*).
+    stripes[i] is a Stripe of this process or an int file descriptor received from the owning process."""
+
+    def __init__(self, ctx, stripes, nbytes):
+        self.ctx = ctx
+        n = len(stripes)
+        loc = (_vp * n)(*[s.h if isinstance(s, Stripe) else None for s in stripes])
+        fds = (C.c_int * n)(*[-1 if isinstance(s, Stripe) else int(s) for s in stripes])
+        by = (C.c_uint64 * n)(*[int(b) for b in nbytes])
+        h = _vp()
+        ctx.check(ctx.lib.s4g_view_open(ctx.h, n, loc, fds, by, C.byref(h)))
+        self.h = h
+        self.nbytes = int(ctx.lib.s4g_view_bytes(h))
+
+    @property
+    def ptr(self):
+        return int(self.ctx.lib.s4g_view_ptr(self.h))
+
+    def write(self, at, src, nbytes):
+        """copy `nbytes` of device memory `src` (tensor / pointer) to byte `at` of the view"""
+        self.ctx.check(self.ctx.lib.s4g_view_write(self.h, int(at), _ptr(src), int(nbytes)))
+
+    def fill(self, at, value, nbytes):
+        self.ctx.check(self.ctx.lib.s4g_view_fill(self.h, int(at), int(value), int(nbytes)))
+
+    def database(self, offsets, where=S4G_HOST):
+        """Database over the view's bytes (global ids, codes not copied); close it before the view."""
+        db = Database.__new__(Database)
+        db.ctx = self.ctx
+        if where == S4G_HOST:
+            offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = (len(offsets) if where == S4G_HOST else offsets.numel()) - 1
+        h = _vp()
+        self.ctx.check(self.ctx.lib.s4g_db_create_view(self.ctx.h, self.h, _ptr(offsets), n, where, C.byref(h)))
+        db.h = h
+        return db
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.s4g_view_close(self.h)
+            self.h = None
 
 
 class Database:

@@ -203,11 +203,47 @@ int s4g_db_create(s4g_ctx* ctx, const uint8_t* codes, const int64_t* offsets, in
     return S4G_OK;
 }
 
+int s4g_db_create_view(s4g_ctx* ctx, s4g_view* view, const int64_t* offsets, int64_t n_seqs, int where, s4g_db** out) {
+    if (!ctx || !view || !out || n_seqs <= 0 || !offsets) return S4G_ERR_ARG;
+    *out = nullptr;
+    S4G_CUDA(ctx, cudaSetDevice(ctx->device));
+    s4g_db* db = new s4g_db();
+    db->ctx = ctx; db->n = n_seqs; db->id_base = 0;
+    db->d_codes = (uint8_t*)s4g_view_ptr(view);
+    db->borrowed_codes = true;
+    const int rc = [&]() -> int {
+        db->h_off.resize(n_seqs + 1);
+        if (where == S4G_HOST) memcpy(db->h_off.data(), offsets, sizeof(int64_t) * (n_seqs + 1));
+        else S4G_CUDA(ctx, cudaMemcpy(db->h_off.data(), offsets, sizeof(int64_t) * (n_seqs + 1), cudaMemcpyDeviceToHost));
+        if (db->h_off[0] != 0) { s4g_set_error(ctx, "offsets[0] must be 0"); return S4G_ERR_ARG; }
+        for (int64_t i = 0; i < n_seqs; ++i) {
+            const int64_t len = db->h_off[i + 1] - db->h_off[i];
+            if (len <= 0 || len > 0x7fffff00) { s4g_set_error(ctx, "sequence %lld has invalid length %lld", (long long)i, (long long)len); return S4G_ERR_ARG; }
+            if (len > db->max_len) db->max_len = (int32_t)len;
+        }
+        db->residues = (uint64_t)db->h_off[n_seqs];
+        if (db->residues + S4G_DB_TAIL_PAD > s4g_view_bytes(view)) {
+            s4g_set_error(ctx, "s4g_db_create_view: %llu residues + %d pad bytes do not fit the view's %llu bytes", (unsigned long long)db->residues, S4G_DB_TAIL_PAD, (unsigned long long)s4g_view_bytes(view));
+            return S4G_ERR_ARG;
+        }
+        S4G_CUDA(ctx, cudaMalloc(&db->d_off, sizeof(int64_t) * (n_seqs + 1)));
+        S4G_CUDA(ctx, cudaMemcpyAsync(db->d_off, db->h_off.data(), sizeof(int64_t) * (n_seqs + 1), cudaMemcpyHostToDevice, ctx->stream));
+        // the readable pad behind the last residue (every rank of a striped database writes the same bytes)
+        int r = s4g_view_fill(view, db->residues, S4G_PAD_CODE, S4G_DB_TAIL_PAD);
+        if (r != S4G_OK) return r;
+        S4G_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return S4G_OK;
+    }();
+    if (rc != S4G_OK) { s4g_db_close(db); return rc; }
+    *out = db;
+    return S4G_OK;
+}
+
 void s4g_db_close(s4g_db* db) {
     if (!db) return;
     cudaSetDevice(db->ctx->device);
     cudaStreamSynchronize(db->ctx->stream);
-    if (db->d_codes) cudaFree(db->d_codes);
+    if (db->d_codes && !db->borrowed_codes) cudaFree(db->d_codes);
     if (db->d_off) cudaFree(db->d_off);
     if (db->d_order) cudaFree(db->d_order);
     delete db;

@@ -43,6 +43,7 @@ struct s4g_ctx {
 struct s4g_db {
     s4g_ctx* ctx = nullptr;
     uint8_t* d_codes = nullptr;     // concatenated codes, FASTA order, + S4G_DB_TAIL_PAD
+    bool borrowed_codes = false;    // d_codes points into an s4g_view (NVLink-striped database): not freed here
     int64_t* d_off = nullptr;       // n+1
     uint32_t* d_order = nullptr;    // local sequence indices by ascending length (built by the first prefilter call)
     int64_t n = 0;
