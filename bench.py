@@ -504,12 +504,36 @@ def main():
         qa, qb = n_queries * rank // world, n_queries * (rank + 1) // world
         my_q_codes, my_q_off = q_codes[q_off[qa]:q_off[qb]], q_off[qa:qb + 1] - q_off[qa]
         lens = all_lens
-        pipe = pipeline.DevicePipeline(ctx, db, my_q_codes, my_q_off, mat, all_lens, total_res, max_candidates=args.max_candidates)
     else:
         db = ctx.database(codes, loc_off, id_base=lo, where=capi.S4G_DEVICE)
         del codes
         my_q_codes, my_q_off = q_codes, q_off
+    # One GPU and the striped form run the product call itself: s4g_search on a resident query batch, cells and paths left in
+    # HBM (`value`: inputs resident, no bulk D2H; the hit lists cross to the host because the exact selection runs there).
+    # The exchange form sequences the stages from Python around its NCCL exchanges (pipeline.DevicePipeline).
+    use_search = mode in ("single", "striped")
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)) or 1)
+    host_threads = max(1, min(16, (os.cpu_count() or 1) // max(1, local_world)))
+    pipe = None
+    if use_search:
+        ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+        Q = ctx.queries(my_q_codes, my_q_off)
+
+        class _Step:
+            def step(self):
+                o = capi.search(ctx, db, Q, mat, 5, args.max_candidates, n_threads=host_threads, want_candidates=False, device_results=True)
+                o.n_kept = o.n_hits
+                return o
+        runner = _Step()
+    else:
         pipe = pipeline.DevicePipeline(ctx, db, q_codes, q_off, mat, lens, total_res, max_candidates=args.max_candidates, dist=dist if use_dist else None)
+
+        class _Step:
+            def step(self):
+                o = pipe.step()
+                o.n_kept = len(o.pair_q)
+                return o
+        runner = _Step()
 
     peak = ctx.dpx_peak(300)                  # sustained VIADDMNMX.S16x2 lane-ops/s on this device
     roof_gcups = peak * 2 / 6 / 1e9
@@ -520,7 +544,7 @@ def main():
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        r = pipe.step()
+        r = runner.step()
     barrier()
     parity = parity_digest(ctx, mat, dist if use_dist else None, log=lambda m: print(m, file=sys.stderr), mode=mode) if not args.no_parity else None
     if parity is not None and not parity["sharded_equals_single"]:
@@ -536,7 +560,7 @@ def main():
         barrier()
         e0.record()
         for _ in range(args.steps):
-            r = pipe.step()
+            r = runner.step()
             cells_local = r.sw_cells
             sw_ms.append(r.sw_kernel_ms)
         e1.record()
@@ -544,19 +568,26 @@ def main():
     ms = e0.elapsed_time(e1)
     launches = ctx.launch_count()
     sw_kernel_ms = sw_ms[-1]                 # SW score kernel launches of the last step (one per half of the query batch), CUDA events inside the library
-    t = torch.tensor([ms, float(cells_local), float(sw_kernel_ms), float(r.n_pairs), float(len(r.pair_q))], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, float(cells_local), float(sw_kernel_ms), float(r.n_pairs), float(r.n_kept)], dtype=torch.float64, device=dev)
     if use_dist:
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         ms, cells, sw_kernel_ms_max = float(tmax[0]), float(tsum[1]), float(tmax[2])
         pairs, hits = float(tsum[3]), float(tsum[4])
     else:
-        cells, sw_kernel_ms_max, pairs, hits = float(cells_local), float(sw_kernel_ms), float(r.n_pairs), float(len(r.pair_q))
+        cells, sw_kernel_ms_max, pairs, hits = float(cells_local), float(sw_kernel_ms), float(r.n_pairs), float(r.n_kept)
     ms_per_step = ms / args.steps
     gcups = cells / (ms_per_step * 1e-3) / 1e9
 
     # stage split (one extra, untimed step with synchronisation between stages; rank-local)
-    split = stage_split(torch, ctx, pipe)
+    if use_search:
+        # the call's own stage clocks (host clock at the stream synchronisations the path has anyway), last timed step of this rank
+        sm = r.stage_ms
+        split = {"prefilter": round(float(sm["prefilter"]), 3), "score_kernel": round(float(r.sw_kernel_ms), 3),
+                 "score_select_other": round(float(sm["score"]) - float(r.sw_kernel_ms), 3), "align": round(float(sm["align"]), 3),
+                 "select_host_beside_align": round(float(sm["select"]), 3)}
+    else:
+        split = stage_split(torch, ctx, pipe)
 
     # e2e through the host-buffer API
     e2e = None
@@ -597,7 +628,10 @@ def main():
         if base is not None:
             line["cpu_baseline"] = base
         print(json.dumps(line), file=out, flush=True)
-    pipe.close()
+    if pipe is not None:
+        pipe.close()
+    else:
+        Q.close()
     if striped is not None:
         striped.close()
     else:
@@ -652,7 +686,9 @@ def run_e2e(torch, ctx, db, pipe, q_codes, q_off, mat, lens, total_res, args, us
     if not use_dist or mode == "striped":
         # q_codes / q_off: this rank's queries (the whole batch on one GPU)
         ctx.sync()
-        run = lambda: pipeline.search_host(ctx, db, q_codes, q_off, mat, max_candidates=args.max_candidates, want_candidates=True, align=True)
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+        run = lambda: pipeline.search_host(ctx, db, q_codes, q_off, mat, max_candidates=args.max_candidates, want_candidates=True, align=True,
+                                           n_threads=max(1, min(16, (os.cpu_count() or 1) // max(1, local_world))))
         out = run()
         if use_dist:
             dist.barrier()

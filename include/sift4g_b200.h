@@ -291,6 +291,8 @@ typedef struct s4g_search_params {
     int n_threads;                              /* host threads of the selection; <= 0: all cores (capped) */
     int want_candidates;                        /* != 0: copy the candidate lists to the host as well */
     int want_alignments;                        /* != 0: trace the kept hits back (stage 3) */
+    int device_results;                         /* != 0: coords / paths / path_offsets of the result are DEVICE pointers (valid until the
+                                                   next call on the context) and are not copied to the host; the hit lists still are */
 } s4g_search_params;
 typedef struct s4g_search_result {
     int32_t n_queries;

@@ -89,7 +89,7 @@ class SearchParams(C.Structure):
     """s4g_search_params"""
     _fields_ = [("kmer_length", C.c_int), ("max_candidates", C.c_int), ("matrix", _vp), ("matrix_name", C.c_char_p),
                 ("gap_open", C.c_int), ("gap_extend", C.c_int), ("max_evalue", C.c_double), ("max_alignments", C.c_int),
-                ("n_threads", C.c_int), ("want_candidates", C.c_int), ("want_alignments", C.c_int)]
+                ("n_threads", C.c_int), ("want_candidates", C.c_int), ("want_alignments", C.c_int), ("device_results", C.c_int)]
 
 
 class SearchResult(C.Structure):
@@ -505,8 +505,9 @@ def score_screen(ctx, db, q, cand_ids, cand_offsets, matrix, gap_open=10, gap_ex
 class SearchOutput:
     """numpy views of an s4g_search_result (library-owned pinned memory: copy what must outlive the next call)"""
 
-    def __init__(self, r):
+    def __init__(self, r, device_results=False):
         nq = r.n_queries
+        self.device_results = device_results
         self.n_queries, self.n_pairs, self.n_survivors, self.n_hits = nq, int(r.n_pairs), int(r.n_survivors), int(r.n_hits)
         self.sw_cells, self.db_residues = int(r.sw_cells), int(r.db_residues)
         self.cand_off = _view(r.cand_offsets, nq + 1, np.int64) if r.cand_offsets else None
@@ -516,23 +517,27 @@ class SearchOutput:
         self.pair_score = _view(r.hit_score, self.n_hits, np.int32)
         self.evalue = _view(r.hit_evalue, self.n_hits, np.float64)
         self.hit_off = _view(r.hit_offsets, nq + 1, np.int64)
-        self.coords = _view(r.coords, 4 * self.n_hits, np.int32).reshape(-1, 4) if r.coords else None
-        self.path_off = _view(r.path_offsets, self.n_hits + 1, np.int64) if r.path_offsets else None
-        self.paths = _view(r.paths, int(self.path_off[-1]) if self.path_off is not None and self.n_hits else 0, np.uint8) if r.paths else None
+        if device_results:          # device pointers (int), valid until the next call on the context
+            self.coords, self.path_off, self.paths = r.coords, r.path_offsets, r.paths
+        else:
+            self.coords = _view(r.coords, 4 * self.n_hits, np.int32).reshape(-1, 4) if r.coords else None
+            self.path_off = _view(r.path_offsets, self.n_hits + 1, np.int64) if r.path_offsets else None
+            self.paths = _view(r.paths, int(self.path_off[-1]) if self.path_off is not None and self.n_hits else 0, np.uint8) if r.paths else None
         self.stage_ms = {"prefilter": r.ms_prefilter, "score": r.ms_score, "select": r.ms_select, "align": r.ms_align}
         self.sw_kernel_ms = r.sw_kernel_ms
         self.h2d_bytes, self.d2h_bytes = int(r.h2d_bytes), int(r.d2h_bytes)
 
 
 def search(ctx, db, q, matrix, k=5, max_candidates=5000, gap_open=10, gap_extend=1, max_evalue=1e-4, max_alignments=400, n_threads=0,
-           want_candidates=True, want_alignments=True, matrix_name=b"BLOSUM_62"):
-    """s4g_search: the whole hot path for one resident shard, host buffers out."""
+           want_candidates=True, want_alignments=True, matrix_name=b"BLOSUM_62", device_results=False):
+    """s4g_search: the whole hot path for one resident shard (or striped view), host buffers out; device_results=True leaves
+    cells and paths in HBM (the hit lists always come to the host: the selection runs there)."""
     matrix = np.ascontiguousarray(matrix, dtype=np.int32)
     prm = SearchParams(k, max_candidates, matrix.ctypes.data, matrix_name, gap_open, gap_extend, max_evalue, max_alignments, n_threads,
-                       1 if want_candidates else 0, 1 if want_alignments else 0)
+                       1 if want_candidates else 0, 1 if want_alignments else 0, 1 if device_results else 0)
     res = SearchResult()
     ctx.check(ctx.lib.s4g_search(ctx.h, db.h, q.h, C.addressof(prm), C.addressof(res)))
-    return SearchOutput(res)
+    return SearchOutput(res, device_results)
 
 
 def alignment_strings(ctx, db, q, pair_q, pair_t, coords, paths, path_off):

@@ -211,6 +211,7 @@ int s4g_db_create_view(s4g_ctx* ctx, s4g_view* view, const int64_t* offsets, int
     db->ctx = ctx; db->n = n_seqs; db->id_base = 0;
     db->d_codes = (uint8_t*)s4g_view_ptr(view);
     db->borrowed_codes = true;
+    { uint64_t a = 0, b = 0; s4g_view_local_range(view, &a, &b); db->local_lo = (int64_t)a; db->local_hi = (int64_t)b; }
     const int rc = [&]() -> int {
         db->h_off.resize(n_seqs + 1);
         if (where == S4G_HOST) memcpy(db->h_off.data(), offsets, sizeof(int64_t) * (n_seqs + 1));

@@ -23,7 +23,7 @@ struct s4g_ctx {
     cudaEvent_t ev_sw0 = nullptr, ev_sw1 = nullptr;
     bool sw_timed = false;
     // grow-only scratch arena, one buffer per slot (device memory)
-    static const int kSlots = 48;
+    static const int kSlots = 64;
     void* slot_ptr[kSlots] = {nullptr};
     size_t slot_bytes[kSlots] = {0};
     // pinned host staging, grow-only
@@ -44,6 +44,7 @@ struct s4g_db {
     s4g_ctx* ctx = nullptr;
     uint8_t* d_codes = nullptr;     // concatenated codes, FASTA order, + S4G_DB_TAIL_PAD
     bool borrowed_codes = false;    // d_codes points into an s4g_view (NVLink-striped database): not freed here
+    int64_t local_lo = 0, local_hi = INT64_MAX;   // bytes of d_codes resident in THIS GPU's HBM (a view: its local stripes)
     int64_t* d_off = nullptr;       // n+1
     uint32_t* d_order = nullptr;    // local sequence indices by ascending length (built by the first prefilter call)
     int64_t n = 0;
@@ -103,8 +104,20 @@ enum {
     SLOT_PF_INDEX, SLOT_PF_BITMAP, SLOT_PF_RANK, SLOT_PF_BUCKET, SLOT_PF_HITS, SLOT_PF_CAND,
     SLOT_PF_COUNT, SLOT_PF_THR, SLOT_PF_CUB, SLOT_PF_TMP, SLOT_PF_TMP2, SLOT_PF_SPILL, SLOT_PF_GBUF, SLOT_SW_STRIP,
     SLOT_AL_WORK, SLOT_AL_DIR, SLOT_AL_MISC, SLOT_AL_OUT, SLOT_PF_ENTRY,
-    SLOT_SR_ROWS, SLOT_SR_CNT, SLOT_SR_OFF, SLOT_SR_CAND, SLOT_SR_SCORES, SLOT_SR_SURV
+    SLOT_SR_ROWS, SLOT_SR_CNT, SLOT_SR_OFF, SLOT_SR_CAND, SLOT_SR_SCORES, SLOT_SR_SURV,
+    SLOT_SR_AL_COORDS, SLOT_SR_AL_PATHS, SLOT_SR_AL_POFF, SLOT_SR_HITS, SLOT_SR_OUT_COORDS, SLOT_SR_OUT_PATHS, SLOT_SR_OUT_POFF,
+    SLOT_COUNT
 };
+static_assert(SLOT_COUNT <= s4g_ctx::kSlots, "scratch slot table too small");
+
+// resident byte range of a view (csrc/view.cu), for s4g_db_create_view
+extern "C" void s4g_view_local_range(const s4g_view* v, uint64_t* lo, uint64_t* hi);
+
+// s4g_select_hits that also reports where every kept hit sits in the candidate arrays (select.cu)
+int s4g_select_hits_indexed(s4g_ctx* ctx, int32_t nq, const int32_t* query_lens, const uint32_t* cand_ids, const int64_t* cand_offsets,
+                            const int32_t* cand_scores, const int32_t* cand_lens, const char* const* cand_names, const char* matrix_name,
+                            uint64_t db_residues, int gap_open, int gap_extend, double max_evalue, int max_alignments, int n_threads,
+                            uint32_t* out_q, uint32_t* out_t, int32_t* out_score, double* out_evalue, int64_t* out_offsets, uint32_t* out_index);
 
 // ---- stage launchers (device pointers, enqueue on ctx->stream) ----------------------------------
 int s4g_sw_score_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, const uint32_t* d_cand_ids,

@@ -35,6 +35,7 @@ constexpr unsigned long long kNoThr = ~0ull;
 
 struct PfParams {
     const uint8_t* db_codes;
+    int64_t local_lo, local_hi;       // bytes of db_codes in this GPU's HBM (an NVLink-striped view: the rest is read from peers)
     const int64_t* db_off;
     const uint32_t* order;            // scan order: local sequence indices by ascending length
     uint32_t id_base;
@@ -118,6 +119,7 @@ __device__ int lis_inplace(unsigned long long* buf, int a, int n) {
 // k-mers of one scan step of a warp: 128 positions starting at `base`, 4 consecutive positions per lane.  probe[i] says
 // whether position j0 + i takes part at all: inside the sequence and not a consecutive duplicate of the k-mer in front of it
 // (database_search.cpp:212-214).
+template <bool kStaged = false>
 __device__ __forceinline__ void step_kmers(const PfParams& P, const uint8_t* seq, int npos, int base, int lane, uint32_t& carry,
                                            uint32_t (&km)[4], bool (&probe)[4]) {
     const unsigned FULL = 0xffffffffu;
@@ -130,7 +132,9 @@ __device__ __forceinline__ void step_kmers(const PfParams& P, const uint8_t* seq
     const unsigned sh = (unsigned)(addr & 3u) * 8u;
     uint32_t lo = 0, hi = 0;
     if (j0 < npos) {
-        const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+        uint32_t w0, w1, w2;
+        if (kStaged) { w0 = w[0]; w1 = w[1]; w2 = w[2]; }                  // `seq` points into the warp's staging slot (shared memory)
+        else { w0 = __ldg(w); w1 = __ldg(w + 1); w2 = __ldg(w + 2); }
         lo = __funnelshift_r(w0, w1, sh);
         hi = __funnelshift_r(w1, w2, sh);
     }
@@ -244,6 +248,28 @@ constexpr uint32_t kLaneBucket = 24;      // index buckets up to this size are w
 //           (query, emission order) and each query's run is reduced by the in-place LIS.
 // Shared memory: per warp  scap x 8 B (sort buffer; the step tables of pass B alias it) + cnt_words x 4 B counters;
 // per CTA  the 2-byte cut-off table.
+// Residue staging (kStage): every warp keeps a ring of kStageSlots segments of up to kStageSeg k-mer positions in shared memory,
+// filled by TMA bulk copies (cp.async.bulk, one mbarrier per slot) that run up to kStageSlots - 1 segments ahead of the walk --
+// across the sequences of a batch and into the next batch.  The walk then reads residues with LDS instead of three LDG per lane
+// and step, and the copies hide the latency of the residue stream: ~0.35 us from the local HBM, ~1.7 us from a peer's HBM over
+// NVLink (tools/peer_read_microbench.cu), where prefetch.global.L2 is no option.  Segment boundaries are multiples of the
+// 128-position step, so the walk is step for step the unstaged one.
+#ifndef S4G_STAGE_SEG
+#define S4G_STAGE_SEG 256
+#endif
+#ifndef S4G_STAGE_SLOTS
+#define S4G_STAGE_SLOTS 2
+#endif
+constexpr int kStageSeg = S4G_STAGE_SEG;             // k-mer positions per segment (a multiple of the 128-position step)
+constexpr int kStageSlot = 16 + kStageSeg + 16;      // bytes: alignment head + residues + k-1 tail and the lanes' 8-byte windows
+constexpr int kStageSlots = S4G_STAGE_SLOTS;         // every KB of shared memory is a KB less L1 for the index probes: keep it small
+constexpr int kStageWarpBytes = kStageSlots * (kStageSlot + 16 + 8);     // + descriptor + mbarrier per slot
+
+struct StageDesc { long long a; uint32_t s; int32_t len; };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <bool kStage>
 __device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cnt_words) {
     extern __shared__ unsigned long long sbuf[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -251,6 +277,15 @@ __device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cn
     uint32_t* cnt_all = reinterpret_cast<uint32_t*>(sbuf + (size_t)nwarps * scap);
     uint32_t* cnt = cnt_all + (size_t)warp * cnt_words;
     unsigned short* qthr = reinterpret_cast<unsigned short*>(cnt_all + (size_t)nwarps * cnt_words);
+    // staging area behind the cut-off table (16-byte aligned): per warp kStageSlots x (slot | descriptor) + mbarriers
+    unsigned char* stage_base = reinterpret_cast<unsigned char*>(sbuf) + (((size_t)nwarps * scap * 8 + (size_t)nwarps * cnt_words * 4 + (((size_t)P.nq + 7) & ~(size_t)7) * 2 + 15) & ~(size_t)15);
+    unsigned char* st_slots = stage_base + (size_t)warp * kStageWarpBytes;
+    StageDesc* st_desc = reinterpret_cast<StageDesc*>(st_slots + kStageSlots * kStageSlot);
+    unsigned long long* st_bar = reinterpret_cast<unsigned long long*>(st_desc + kStageSlots);
+    if (kStage && lane == 0) {
+        for (int i = 0; i < kStageSlots; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(st_bar + i)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     uint32_t* off_s = reinterpret_cast<uint32_t*>(buf);      // pass B only (step tables); its survivors go to the global scratch
     uint32_t* hb_s = off_s + 128;
     uint32_t* ring_r = reinterpret_cast<uint32_t*>(buf);     // pass A only: queue of index ranks (31 left over + 128 of a step)
@@ -269,31 +304,90 @@ __device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cn
         for (int q = lane; q < P.nq; q += 32) if (P.q_hit_start[q + 1] > P.q_hit_start[q]) m = min(m, (uint32_t)qthr[q]);   // queries shorter than k never get one
         thr_min = __uint_as_float(__reduce_min_sync(FULL, m) << 16);
     }
-    while (true) {
-        long long s0 = 0;
-        if (lane == 0) s0 = (long long)atomicAdd(P.counters + 0, (unsigned long long)kSeqBatch);
-        s0 = __shfl_sync(FULL, s0, 0) + P.seq_begin;
-        if (s0 >= P.seq_end) break;
-        // the batch: positions s0 .. s0+kSeqBatch-1 of the scan order (lane bi holds sequence bi: index, begin, end), and an
-        // L2 prefetch of their residues
-        long long my_a = 0, my_e = 0;
-        uint32_t my_idx = 0;
-        if (lane < kSeqBatch && s0 + lane < P.seq_end) {
-            my_idx = __ldg(P.order + s0 + lane);
-            my_a = P.db_off[my_idx];
-            my_e = P.db_off[my_idx + 1];
-        }
+    // Sequences are claimed in batches of kSeqBatch positions of the scan order (lane bi holds sequence bi of the batch: index,
+    // begin, end) with an L2 prefetch of their residues -- resident ones only: prefetch.global.L2 on a peer's page costs ~60x
+    // the load it is meant to hide (tools/peer_read_microbench.cu: 121 ms vs 1.9 ms for the same walk).
+    long long my_a = 0, my_e = 0;
+    uint32_t my_idx = 0;
+    int b_i = 0, b_n = 0;                                   // next sequence of the batch, sequences in the batch
+    auto next_sequence = [&](long long& s, int64_t& a, int& len) -> bool {
+        while (true) {
+            if (b_i >= b_n) {
+                long long s0 = 0;
+                if (lane == 0) s0 = (long long)atomicAdd(P.counters + 0, (unsigned long long)kSeqBatch);
+                s0 = __shfl_sync(FULL, s0, 0) + P.seq_begin;
+                if (s0 >= P.seq_end) return false;
+                my_a = 0; my_e = 0; my_idx = 0;
+                if (lane < kSeqBatch && s0 + lane < P.seq_end) {
+                    my_idx = __ldg(P.order + s0 + lane);
+                    my_a = P.db_off[my_idx];
+                    my_e = P.db_off[my_idx + 1];
+                }
 #pragma unroll
-        for (int bi = 0; bi < kSeqBatch; ++bi) {
-            const long long b0 = __shfl_sync(FULL, my_a, bi), b1 = __shfl_sync(FULL, my_e, bi);
-            for (long long a = b0 + 128ll * lane; a < b1; a += 128 * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.db_codes + a));
+                for (int bi = 0; bi < kSeqBatch; ++bi) {
+                    const long long b0 = __shfl_sync(FULL, my_a, bi), b1 = __shfl_sync(FULL, my_e, bi);
+                    if (b0 >= P.local_lo && b1 <= P.local_hi)
+                        for (long long x = b0 + 128ll * lane; x < b1; x += 128 * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.db_codes + x));
+                }
+                b_i = 0;
+                b_n = (int)min((long long)kSeqBatch, P.seq_end - s0);
+            }
+            s = (long long)__shfl_sync(FULL, my_idx, b_i);
+            a = __shfl_sync(FULL, my_a, b_i);
+            len = (int)(__shfl_sync(FULL, my_e, b_i) - a);
+            ++b_i;
+            if (len >= k) return true;
         }
-        for (int bi = 0; bi < kSeqBatch && s0 + bi < P.seq_end; ++bi) {
-            const long long s = (long long)__shfl_sync(FULL, my_idx, bi);
-            const int64_t a = __shfl_sync(FULL, my_a, bi);
-            const int len = (int)(__shfl_sync(FULL, my_e, bi) - a);
-            if (len < k) continue;
+    };
+    // staging: the producer walks the same sequence stream ahead of the consumer, one segment per slot
+    uint32_t st_prod = 0, st_cons = 0;                      // segments issued / consumed
+    long long p_s = 0; int64_t p_a = 0; int p_len = 0, p_pos = -1;   // sequence being cut into segments (p_pos < 0: fetch the next one)
+    bool p_end = false;
+    auto produce_ahead = [&]() {
+        while (st_prod - st_cons < (uint32_t)kStageSlots && !p_end) {
+            if (p_pos < 0) {
+                if (!next_sequence(p_s, p_a, p_len)) { p_end = true; break; }
+                p_pos = 0;
+            }
+            const int p_npos = p_len - k + 1;
+            const int seg_n = min(kStageSeg, p_npos - p_pos);
+            const uint32_t slot = st_prod % kStageSlots;
+            if (lane == 0) {
+                const uint8_t* src = P.db_codes + p_a + p_pos;
+                const uint32_t head = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u);
+                const uint32_t bytes = (head + (uint32_t)seg_n + 12u + 15u) & ~15u;          // <= kStageSlot; the buffer's tail pad keeps it readable
+                st_desc[slot].a = p_a; st_desc[slot].s = (uint32_t)p_s; st_desc[slot].len = p_len;
+                const uint32_t bar = smem_u32(st_bar + slot);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");               // the slot's last reads are done before the copy lands
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_u32(st_slots + slot * kStageSlot)), "l"(src - head), "r"(bytes), "r"(bar) : "memory");
+            }
+            ++st_prod;
+            p_pos += kStageSeg;
+            if (p_pos >= p_npos) p_pos = -1;
+        }
+        __syncwarp();
+    };
+    auto stage_wait = [&](uint32_t seg) {
+        const uint32_t bar = smem_u32(st_bar + seg % kStageSlots), parity = (seg / kStageSlots) & 1u;
+        uint32_t done = 0;
+        while (!done) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.b32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    };
+    __syncthreads();                                        // mbarriers initialised
+    {
+        while (true) {
+            long long s; int64_t a; int len;
+            if (kStage) {
+                produce_ahead();
+                if (st_cons == st_prod) break;
+                const StageDesc d = st_desc[st_cons % kStageSlots];
+                s = d.s; a = d.a; len = d.len;
+            } else {
+                if (!next_sequence(s, a, len)) break;
+            }
             const uint8_t* seq = P.db_codes + a;
+            const uint8_t* seg_seq = seq;                    // staged: the current segment's bytes, addressed by sequence position
             const int npos = len - k + 1;
             const float flen = (float)len * 0.99999f;      // margin >> float rounding: dropping stays exact
             // ---- pass A: count; `crossed` = one of this lane's hits took a query across its cut-off.
@@ -364,7 +458,16 @@ __device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cn
                 if (!drain) {
                     uint32_t km[4];
                     bool probe[4];
-                    step_kmers(P, seq, npos, base, lane, carry, km, probe);
+                    if (kStage) {
+                        if ((base % kStageSeg) == 0) {               // next segment of this sequence: release the old slot, refill ahead
+                            if (base > 0) { ++st_cons; produce_ahead(); }
+                            stage_wait(st_cons);
+                            seg_seq = st_slots + (st_cons % kStageSlots) * kStageSlot + (reinterpret_cast<uintptr_t>(seq + base) & 15u) - base;
+                        }
+                        step_kmers<true>(P, seg_seq, npos, base, lane, carry, km, probe);
+                    } else {
+                        step_kmers(P, seq, npos, base, lane, carry, km, probe);
+                    }
                     uint2 br[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) br[i] = probe[i] ? __ldg(P.bitrank + (km[i] >> 5)) : make_uint2(0u, 0u);
@@ -384,6 +487,7 @@ __device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cn
                     break;
                 }
             }
+            if (kStage) { __syncwarp(); ++st_cons; }          // the sequence's last segment is consumed
             const uint32_t T = __reduce_add_sync(FULL, nh);
             if (T == 0) continue;
             const bool any_crossed = __any_sync(FULL, crossed);
@@ -547,9 +651,9 @@ __device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cn
 }
 
 // Builds of the scan by CTA size (the register budget follows the resident warps).
-template <int kThreads>
+template <int kThreads, bool kStage>
 __global__ void __launch_bounds__(kThreads, 1) pf_scan_kernel(PfParams P, int scap, int cnt_words) {
-    pf_scan_body(P, scap, cnt_words);
+    pf_scan_body<kStage>(P, scap, cnt_words);
 }
 
 // deferred path, step 1: re-walk the sequence and write its hits into the pool
@@ -1055,6 +1159,16 @@ static int prefilter_group(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int 
     const size_t per_warp_smem = scan_warp_smem(nq), qthr_bytes = scan_qthr_smem(nq);
     int scan_warps = (int)std::min<size_t>(32, (kScanSmemCap - qthr_bytes) / per_warp_smem);
     if (const char* e = getenv("S4G_PF_WARPS")) scan_warps = std::max(1, std::min(scan_warps, atoi(e)));
+    // TMA residue staging (pf_scan_body<true>): 0.6 KB per warp.  For an NVLink-striped view (the copies hide the peer latency).
+    // A resident database is scanned without: measured at configs[1], staging costs 27.8 -> 30.8 ms there (and 41.9 ms with a
+    // 2.3 KB ring: the shared memory comes out of the L1 that serves the index probes) -- profiles/r02_stage_tma.md.
+    // S4G_PF_STAGE=0/1 overrides.
+    const size_t stage_pad = 16;
+    int stage_warps = (int)std::min<size_t>(32, (kScanSmemCap - qthr_bytes - stage_pad) / (per_warp_smem + kStageWarpBytes));
+    if (const char* e = getenv("S4G_PF_WARPS")) stage_warps = std::max(1, std::min(stage_warps, atoi(e)));
+    bool stage = stage_warps >= 1 && db->borrowed_codes;
+    if (const char* e = getenv("S4G_PF_STAGE")) stage = atoi(e) != 0 && stage_warps >= 1;
+    if (stage) scan_warps = stage_warps;
     unsigned long long* d_entry = (unsigned long long*)s4g_scratch(ctx, SLOT_PF_ENTRY, sizeof(unsigned long long) * ((size_t)n_distinct + 1));
     if (!d_entry) return S4G_ERR_NOMEM;
     if (n_distinct > 0) {
@@ -1114,7 +1228,7 @@ static int prefilter_group(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int 
     S4G_CHECK_LAUNCH(ctx);
 
     PfParams P;
-    P.db_codes = db->d_codes; P.db_off = db->d_off; P.order = db->d_order; P.id_base = db->id_base;
+    P.db_codes = db->d_codes; P.local_lo = db->local_lo; P.local_hi = db->local_hi; P.db_off = db->d_off; P.order = db->d_order; P.id_base = db->id_base;
     P.k = k; P.mask = mask; P.bitrank = d_bitrank; P.bucket_start = d_bucket; P.hits = d_vals2; P.nq = nq;
     P.thr = d_thr; P.count = d_count; P.cand = d_cand; P.cap = cap; P.counters = d_counters;
     P.def_seq = d_def_seq; P.def_off = d_def_off; P.max_deferred = max_deferred;
@@ -1122,15 +1236,16 @@ static int prefilter_group(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int 
 
     P.entry = d_entry; P.q_hit_start = d_start;
     // one CTA per SM: its warps share the cut-off table and the filter; the build follows the CTA size (register budget)
-    const size_t scan_smem = per_warp_smem * scan_warps + qthr_bytes;
+    const size_t scan_smem = per_warp_smem * scan_warps + qthr_bytes + (stage ? stage_pad + (size_t)kStageWarpBytes * scan_warps : 0);
     void (*scan_kernel)(PfParams, int, int) = nullptr;
-    scan_kernel = scan_warps > 24 ? pf_scan_kernel<1024> : (scan_warps > 16 ? pf_scan_kernel<768> : (scan_warps > 8 ? pf_scan_kernel<512> : pf_scan_kernel<256>));
+    if (stage) scan_kernel = scan_warps > 24 ? pf_scan_kernel<1024, true> : (scan_warps > 16 ? pf_scan_kernel<768, true> : (scan_warps > 8 ? pf_scan_kernel<512, true> : pf_scan_kernel<256, true>));
+    else scan_kernel = scan_warps > 24 ? pf_scan_kernel<1024, false> : (scan_warps > 16 ? pf_scan_kernel<768, false> : (scan_warps > 8 ? pf_scan_kernel<512, false> : pf_scan_kernel<256, false>));
     S4G_CUDA(ctx, cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
     const int grid = ctx->sm_count;
     P.gbuf = (unsigned long long*)s4g_scratch(ctx, SLOT_PF_GBUF, sizeof(unsigned long long) * (size_t)grid * scan_warps * kGCap);
     if (!P.gbuf) return S4G_ERR_NOMEM;
-    if (ctx->trace) fprintf(stderr, "[s4g trace] scan: %d queries, %u index k-mers (%lld hits), %d warps per SM, counters %d B per warp, %zu B of shared memory\n",
-                            nq, n_distinct, (long long)n_hits, scan_warps, cnt_words * 4, scan_smem);
+    if (ctx->trace) fprintf(stderr, "[s4g trace] scan: %d queries, %u index k-mers (%lld hits), %d warps per SM, counters %d B per warp, %zu B of shared memory, residues %s\n",
+                            nq, n_distinct, (long long)n_hits, scan_warps, cnt_words * 4, scan_smem, stage ? "staged by TMA bulk copies" : "loaded by the lanes");
 
     s4g_trace_mark(ctx, "setup");
     int64_t this_chunk = chunk < 16384 ? chunk : 16384;

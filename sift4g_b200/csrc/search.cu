@@ -14,12 +14,14 @@
 #include <cstring>
 #include <thread>
 
+#include <cub/cub.cuh>
+
 #include "common.cuh"
 
 namespace {
 
 enum { PIN_SURV_Q = 0, PIN_SURV_ID, PIN_SURV_SC, PIN_SURV_TL, PIN_MISC, PIN_CAND_IDS, PIN_CAND_OFF, PIN_HIT_Q, PIN_HIT_T, PIN_HIT_S,
-       PIN_HIT_E, PIN_HIT_OFF, PIN_COORDS, PIN_PATHS, PIN_PATH_OFF, PIN_COUNTS };
+       PIN_HIT_E, PIN_HIT_OFF, PIN_COORDS, PIN_PATHS, PIN_PATH_OFF, PIN_COUNTS, PIN_HIT_IDX };
 
 double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
@@ -43,6 +45,25 @@ __global__ void sr_cells_kernel(const uint32_t* cand_ids, const int64_t* cand_of
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
     if ((threadIdx.x & 31) == 0 && v) atomicAdd(acc, v);
+}
+
+// kept hit h sits at position idx[h] of the survivor arrays: its coords, and the length of its path (slot n: 0, for the scan)
+__global__ void sr_gather_coords_kernel(const uint32_t* idx, int64_t n, const int32_t* coords, const int64_t* path_off, int32_t* out_coords, int64_t* out_len) {
+    const int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h > n) return;
+    if (h == n) { out_len[h] = 0; return; }
+    const uint32_t i = idx[h];
+    reinterpret_cast<int4*>(out_coords)[h] = reinterpret_cast<const int4*>(coords)[i];
+    out_len[h] = path_off[i + 1] - path_off[i];
+}
+
+__global__ void sr_gather_paths_kernel(const uint32_t* idx, const uint8_t* paths, const int64_t* path_off, const int64_t* out_off, uint8_t* out) {
+    const int64_t h = blockIdx.x;
+    const uint32_t i = idx[h];
+    const uint8_t* src = paths + path_off[i];
+    uint8_t* dst = out + out_off[h];
+    const int64_t len = out_off[h + 1] - out_off[h];
+    for (int64_t x = threadIdx.x; x < len; x += blockDim.x) dst[x] = src[x];
 }
 
 // scores + screen of device-resident candidate lists; survivors to the context's pinned buffers
@@ -171,18 +192,29 @@ extern "C" int s4g_search(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, const s4g_se
     out->d2h_bytes += 16 * sv.n + 16;
     double t2 = now_ms();
     out->ms_score = (float)(t2 - t1);
-    // ---- exact selection on the host (reference arithmetic and order)
+    // ---- exact selection on the host (reference arithmetic and order) and stage 3.
+    // The survivors of the device screen are, up to the screen's 1e-6 margin and the top-max_alignments cut, the hits that
+    // will be kept -- so when at least 90 % of them are sure to stay (sum_q min(survivors_q, max_alignments)), their
+    // traceback starts right away from the device-resident survivor arrays while the host threads compute the exact
+    // E-values and the order; the kept hits are then gathered out of the survivors' results (coords, paths) on the device.
+    // Otherwise (few hits kept per query out of many survivors) the hits are selected first and only they are traced back.
     const size_t hit_cap = (size_t)nq * (size_t)prm->max_alignments;       // s4g_select_hits works in per-query blocks of max_alignments
     uint32_t* h_hq = (uint32_t*)s4g_pinned(ctx, PIN_HIT_Q, 4 * hit_cap), *h_ht = (uint32_t*)s4g_pinned(ctx, PIN_HIT_T, 4 * hit_cap);
     int32_t* h_hs = (int32_t*)s4g_pinned(ctx, PIN_HIT_S, 4 * hit_cap);
     double* h_he = (double*)s4g_pinned(ctx, PIN_HIT_E, 8 * hit_cap);
     int64_t* h_hoff = (int64_t*)s4g_pinned(ctx, PIN_HIT_OFF, 8 * ((size_t)nq + 1));
-    if (!h_hq || !h_ht || !h_hs || !h_he || !h_hoff) return S4G_ERR_NOMEM;
+    uint32_t* h_idx = (uint32_t*)s4g_pinned(ctx, PIN_HIT_IDX, 4 * hit_cap);
+    if (!h_hq || !h_ht || !h_hs || !h_he || !h_hoff || !h_idx) return S4G_ERR_NOMEM;
     std::vector<int64_t> s_off((size_t)nq + 1, 0);
+    int64_t sure = 0;
     {
         // survivors come in candidate order: grouped by ascending query
         int64_t i = 0;
-        for (int qq = 0; qq < nq; ++qq) { while (i < sv.n && sv.query[i] == (uint32_t)qq) ++i; s_off[qq + 1] = i; }
+        for (int qq = 0; qq < nq; ++qq) {
+            while (i < sv.n && sv.query[i] == (uint32_t)qq) ++i;
+            s_off[qq + 1] = i;
+            sure += std::min<int64_t>(i - s_off[qq], prm->max_alignments);
+        }
     }
     std::vector<int32_t> q_lens(nq);
     for (int i = 0; i < nq; ++i) q_lens[i] = (int32_t)(q->h_off[i + 1] - q->h_off[i]);
@@ -191,31 +223,111 @@ extern "C" int s4g_search(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, const s4g_se
         names.resize((size_t)sv.n);
         for (int64_t i = 0; i < sv.n; ++i) names[i] = db->names[sv.id[i] - db->id_base].c_str();
     }
-    rc = s4g_select_hits(ctx, nq, q_lens.data(), sv.id, s_off.data(), sv.score, sv.tlen, names.empty() ? nullptr : names.data(), prm->matrix_name,
-                         db_residues, prm->gap_open, prm->gap_extend, prm->max_evalue, prm->max_alignments, prm->n_threads, h_hq, h_ht, h_hs, h_he, h_hoff);
-    if (rc != S4G_OK) return rc;
-    const int64_t n_hits = h_hoff[nq];
-    out->n_hits = n_hits;
-    out->hit_query = h_hq; out->hit_target = h_ht; out->hit_score = h_hs; out->hit_evalue = h_he; out->hit_offsets = h_hoff;
+    int rc_sel = S4G_OK;
+    double sel_ms = 0.0;
+    auto select = [&]() {
+        const double a = now_ms();
+        rc_sel = s4g_select_hits_indexed(ctx, nq, q_lens.data(), sv.id, s_off.data(), sv.score, sv.tlen, names.empty() ? nullptr : names.data(), prm->matrix_name,
+                                         db_residues, prm->gap_open, prm->gap_extend, prm->max_evalue, prm->max_alignments, prm->n_threads, h_hq, h_ht, h_hs, h_he,
+                                         h_hoff, h_idx);
+        sel_ms = now_ms() - a;
+    };
+    const char* no_spec = getenv("S4G_NO_SPECULATE");
+    const bool speculate = prm->want_alignments && sv.n > 0 && sure * 10 >= sv.n * 9 && !(no_spec && no_spec[0] && no_spec[0] != '0');
+    // device-resident survivor arrays (score_screen_device left them in SLOT_SR_SURV: query | id | score | tlen, n_pairs each)
+    const uint32_t* d_sq = (const uint32_t*)ctx->slot_ptr[SLOT_SR_SURV];
+    const uint32_t* d_sid = d_sq ? d_sq + n_pairs : nullptr;
+    const int32_t* d_ssc = d_sq ? (const int32_t*)(d_sq + 2 * n_pairs) : nullptr;
+    std::thread sel_thread;
+    if (speculate) sel_thread = std::thread(select);
+    else select();
+    struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{sel_thread};
+    if (!speculate && rc_sel != S4G_OK) return rc_sel;
     double t3 = now_ms();
-    out->ms_select = (float)(t3 - t2);
+    if (!speculate) out->ms_select = (float)(t3 - t2);
+    int64_t n_hits = speculate ? 0 : h_hoff[nq];
     // ---- stage 3
     if (prm->want_alignments) {
         // path bytes of a hit <= its query + target lengths; the survivors' target residues bound those of the kept hits (a
         // subset) without a random gather from the shard's offset table
+        const int64_t n_al = speculate ? sv.n : n_hits;
         int64_t cap = 16;
-        for (int64_t h = 0; h < n_hits; ++h) cap += q_lens[h_hq[h]];
         for (int64_t i = 0; i < sv.n; ++i) cap += sv.tlen[i];
-        int32_t* h_co = (int32_t*)s4g_pinned(ctx, PIN_COORDS, 16 * (size_t)n_hits);
-        uint8_t* h_pa = (uint8_t*)s4g_pinned(ctx, PIN_PATHS, (size_t)cap);
-        int64_t* h_po = (int64_t*)s4g_pinned(ctx, PIN_PATH_OFF, 8 * ((size_t)n_hits + 1));
-        if (!h_co || !h_pa || !h_po) return S4G_ERR_NOMEM;
-        rc = s4g_sw_align(ctx, db, q, n_hits, h_hq, h_ht, h_hs, prm->matrix, prm->gap_open, prm->gap_extend, h_co, h_pa, cap, h_po, S4G_HOST);
-        if (rc != S4G_OK) return rc;
-        out->coords = h_co; out->paths = h_pa; out->path_offsets = h_po;
-        out->h2d_bytes += 12 * n_hits;
-        out->d2h_bytes += 16 * n_hits + h_po[n_hits] + 8 * (n_hits + 1);
+        if (speculate) for (int64_t i = 0; i < sv.n; ++i) cap += q_lens[sv.query[i]];
+        else for (int64_t h = 0; h < n_hits; ++h) cap += q_lens[h_hq[h]];
+        int32_t* d_co = (int32_t*)s4g_scratch(ctx, SLOT_SR_AL_COORDS, 16 * (size_t)n_al + 16);
+        uint8_t* d_pa = (uint8_t*)s4g_scratch(ctx, SLOT_SR_AL_PATHS, (size_t)cap + 64);
+        int64_t* d_po = (int64_t*)s4g_scratch(ctx, SLOT_SR_AL_POFF, 8 * ((size_t)n_al + 1));
+        uint32_t* d_hits = (uint32_t*)s4g_scratch(ctx, SLOT_SR_HITS, 4 * 4 * std::max<size_t>(hit_cap, 1) + 64);
+        if (!d_co || !d_pa || !d_po || !d_hits) return S4G_ERR_NOMEM;
+        const uint32_t *d_aq = d_sq, *d_at = d_sid;
+        const int32_t* d_as = d_ssc;
+        if (!speculate) {
+            if (n_hits) {
+                S4G_CUDA(ctx, cudaMemcpyAsync(d_hits, h_hq, 4 * n_hits, cudaMemcpyHostToDevice, st));
+                S4G_CUDA(ctx, cudaMemcpyAsync(d_hits + hit_cap, h_ht, 4 * n_hits, cudaMemcpyHostToDevice, st));
+                S4G_CUDA(ctx, cudaMemcpyAsync(d_hits + 2 * hit_cap, h_hs, 4 * n_hits, cudaMemcpyHostToDevice, st));
+            }
+            d_aq = d_hits; d_at = d_hits + hit_cap; d_as = (const int32_t*)(d_hits + 2 * hit_cap);
+            out->h2d_bytes += 12 * n_hits;
+        }
+        rc = s4g_sw_align(ctx, db, q, n_al, d_aq, d_at, d_as, prm->matrix, prm->gap_open, prm->gap_extend, d_co, d_pa, cap, d_po, S4G_DEVICE);
+        const int32_t* d_rco = d_co; const uint8_t* d_rpa = d_pa; const int64_t* d_rpo = d_po;
+        int64_t n_path = -1;
+        if (speculate) {
+            sel_thread.join();
+            out->ms_select = (float)sel_ms;                     // ran beside the traceback
+            if (rc_sel != S4G_OK) return rc_sel;
+            if (rc != S4G_OK) return rc;
+            n_hits = h_hoff[nq];
+            // gather the kept hits (positions h_idx in the survivor arrays) out of the survivors' results
+            int32_t* d_co2 = (int32_t*)s4g_scratch(ctx, SLOT_SR_OUT_COORDS, 16 * (size_t)n_hits + 16);
+            int64_t* d_po2 = (int64_t*)s4g_scratch(ctx, SLOT_SR_OUT_POFF, 8 * 2 * ((size_t)n_hits + 1));
+            if (!d_co2 || !d_po2) return S4G_ERR_NOMEM;
+            uint32_t* d_idx = d_hits + 3 * hit_cap;
+            if (n_hits) S4G_CUDA(ctx, cudaMemcpyAsync(d_idx, h_idx, 4 * n_hits, cudaMemcpyHostToDevice, st));
+            out->h2d_bytes += 4 * n_hits;
+            int64_t* d_len = d_po2 + (n_hits + 1);
+            sr_gather_coords_kernel<<<(unsigned)((n_hits + 1 + 255) / 256), 256, 0, st>>>(d_idx, n_hits, d_co, d_po, d_co2, d_len);
+            S4G_CHECK_LAUNCH(ctx);
+            size_t tmp = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_len, d_po2, (int)(n_hits + 1), st);
+            void* d_tmp = s4g_scratch(ctx, SLOT_SW_CUB, tmp);
+            if (!d_tmp) return S4G_ERR_NOMEM;
+            S4G_CUDA(ctx, cub::DeviceScan::ExclusiveSum(d_tmp, tmp, d_len, d_po2, (int)(n_hits + 1), st));
+            ctx->launches += 1;
+            uint8_t* d_pa2 = (uint8_t*)s4g_scratch(ctx, SLOT_SR_OUT_PATHS, (size_t)cap + 64);     // a subset of the survivors' paths
+            if (!d_pa2) return S4G_ERR_NOMEM;
+            if (n_hits) {
+                sr_gather_paths_kernel<<<(unsigned)n_hits, 64, 0, st>>>(d_idx, d_pa, d_po, d_po2, d_pa2);
+                S4G_CHECK_LAUNCH(ctx);
+            }
+            d_rco = d_co2; d_rpa = d_pa2; d_rpo = d_po2;
+        } else if (rc != S4G_OK) {
+            return rc;
+        }
+        out->n_hits = n_hits;
+        if (prm->device_results) {
+            S4G_CUDA(ctx, cudaStreamSynchronize(st));
+            out->coords = d_rco; out->paths = d_rpa; out->path_offsets = d_rpo;
+        } else {
+            int32_t* h_co = (int32_t*)s4g_pinned(ctx, PIN_COORDS, 16 * (size_t)n_hits);
+            int64_t* h_po = (int64_t*)s4g_pinned(ctx, PIN_PATH_OFF, 8 * ((size_t)n_hits + 1));
+            if (!h_co || !h_po) return S4G_ERR_NOMEM;
+            if (n_hits) S4G_CUDA(ctx, cudaMemcpyAsync(h_co, d_rco, 16 * n_hits, cudaMemcpyDeviceToHost, st));
+            S4G_CUDA(ctx, cudaMemcpyAsync(h_po, d_rpo, 8 * (n_hits + 1), cudaMemcpyDeviceToHost, st));
+            S4G_CUDA(ctx, cudaStreamSynchronize(st));
+            n_path = h_po[n_hits];
+            uint8_t* h_pa = (uint8_t*)s4g_pinned(ctx, PIN_PATHS, (size_t)n_path + 16);
+            if (!h_pa) return S4G_ERR_NOMEM;
+            if (n_path) S4G_CUDA(ctx, cudaMemcpyAsync(h_pa, d_rpa, (size_t)n_path, cudaMemcpyDeviceToHost, st));
+            S4G_CUDA(ctx, cudaStreamSynchronize(st));
+            out->coords = h_co; out->paths = h_pa; out->path_offsets = h_po;
+            out->d2h_bytes += 16 * n_hits + n_path + 8 * (n_hits + 1);
+        }
     }
+    out->n_hits = n_hits;
+    out->hit_query = h_hq; out->hit_target = h_ht; out->hit_score = h_hs; out->hit_evalue = h_he; out->hit_offsets = h_hoff;
     out->ms_align = (float)(now_ms() - t3);
     return S4G_OK;
 }

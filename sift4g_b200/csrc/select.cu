@@ -165,6 +165,16 @@ extern "C" int s4g_select_hits(s4g_ctx* ctx, int32_t nq, const int32_t* query_le
                                const char* const* cand_names, const char* matrix_name, uint64_t db_residues, int gap_open,
                                int gap_extend, double max_evalue, int max_alignments, int n_threads, uint32_t* out_q,
                                uint32_t* out_t, int32_t* out_score, double* out_evalue, int64_t* out_offsets) {
+    return s4g_select_hits_indexed(ctx, nq, query_lens, cand_ids, cand_offsets, cand_scores, cand_lens, cand_names, matrix_name, db_residues, gap_open,
+                                   gap_extend, max_evalue, max_alignments, n_threads, out_q, out_t, out_score, out_evalue, out_offsets, nullptr);
+}
+
+// s4g_select_hits + (optional) the position of every kept hit in the candidate arrays (out_index, capacity like out_q)
+int s4g_select_hits_indexed(s4g_ctx* ctx, int32_t nq, const int32_t* query_lens, const uint32_t* cand_ids,
+                            const int64_t* cand_offsets, const int32_t* cand_scores, const int32_t* cand_lens,
+                            const char* const* cand_names, const char* matrix_name, uint64_t db_residues, int gap_open,
+                            int gap_extend, double max_evalue, int max_alignments, int n_threads, uint32_t* out_q,
+                            uint32_t* out_t, int32_t* out_score, double* out_evalue, int64_t* out_offsets, uint32_t* out_index) {
     if (nq < 0 || !query_lens || !cand_offsets || !out_offsets || max_alignments < 0) return S4G_ERR_ARG;
     if (!matrix_supported(matrix_name)) { s4g_set_error(ctx, "s4g_select_hits: %s selects the DNA E-value formula, which this path does not provide", matrix_name); return S4G_ERR_ARG; }
     if (cand_offsets[nq] > 0 && (!cand_ids || !cand_scores || !cand_lens || !out_q || !out_t || !out_score || !out_evalue)) return S4G_ERR_ARG;
@@ -215,6 +225,7 @@ extern "C" int s4g_select_hits(s4g_ctx* ctx, int32_t nq, const int32_t* query_le
             uint32_t* oq = out_q + (size_t)q * max_alignments; uint32_t* ot = out_t + (size_t)q * max_alignments;
             int32_t* os = out_score + (size_t)q * max_alignments; double* oe = out_evalue + (size_t)q * max_alignments;
             for (int j = 0; j < k; ++j) { oq[j] = (uint32_t)q; ot[j] = cand_ids[rows[j].i]; os[j] = rows[j].score; oe[j] = rows[j].value; }
+            if (out_index) for (int j = 0; j < k; ++j) out_index[(size_t)q * max_alignments + j] = (uint32_t)rows[j].i;
             kept[q] = k;
         }
     };
@@ -228,7 +239,10 @@ extern "C" int s4g_select_hits(s4g_ctx* ctx, int32_t nq, const int32_t* query_le
     for (int q = 0; q < nq; ++q) {
         const size_t src = (size_t)q * max_alignments;
         if ((size_t)w != src)
-            for (int j = 0; j < kept[q]; ++j) { out_q[w + j] = out_q[src + j]; out_t[w + j] = out_t[src + j]; out_score[w + j] = out_score[src + j]; out_evalue[w + j] = out_evalue[src + j]; }
+            for (int j = 0; j < kept[q]; ++j) {
+                out_q[w + j] = out_q[src + j]; out_t[w + j] = out_t[src + j]; out_score[w + j] = out_score[src + j]; out_evalue[w + j] = out_evalue[src + j];
+                if (out_index) out_index[w + j] = out_index[src + j];
+            }
         w += kept[q];
         out_offsets[q + 1] = w;
     }

@@ -29,6 +29,7 @@ struct s4g_view {
     uint64_t bytes = 0;
     std::vector<CUmemGenericAllocationHandle> imported;      // released on close (local stripes stay with their owner)
     std::vector<std::pair<uint64_t, uint64_t>> mapped;       // (offset, bytes) of every mapping
+    uint64_t local_lo = 0, local_hi = 0;                     // byte range of the stripes handed in as local handles (resident on ctx's device)
 };
 
 namespace {
@@ -208,6 +209,10 @@ int s4g_view_open(s4g_ctx* ctx, int n_stripes, s4g_stripe* const* local, const i
             CUmemGenericAllocationHandle h;
             if (local && local[i]) {
                 h = local[i]->handle;
+                if (local[i]->ctx->device == ctx->device) {         // contiguous local stripes form one resident range
+                    if (v->local_hi == v->local_lo) { v->local_lo = at; v->local_hi = at + bytes[i]; }
+                    else if (v->local_hi == at) v->local_hi = at + bytes[i];
+                }
             } else {
                 S4G_CU(ctx, drv().MemImportFromShareableHandle(&h, (void*)(uintptr_t)fds[i], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
                 v->imported.push_back(h);
@@ -230,6 +235,7 @@ int s4g_view_open(s4g_ctx* ctx, int n_stripes, s4g_stripe* const* local, const i
 
 void* s4g_view_ptr(const s4g_view* v) { return v ? (void*)(uintptr_t)v->base : nullptr; }
 uint64_t s4g_view_bytes(const s4g_view* v) { return v ? v->bytes : 0; }
+void s4g_view_local_range(const s4g_view* v, uint64_t* lo, uint64_t* hi) { *lo = v ? v->local_lo : 0; *hi = v ? v->local_hi : 0; }
 
 int s4g_view_write(s4g_view* v, uint64_t at, const uint8_t* d_src, uint64_t bytes) {
     if (!v || (bytes > 0 && !d_src) || at > v->bytes || bytes > v->bytes - at) return S4G_ERR_ARG;
