@@ -19,6 +19,7 @@
 // shared-memory rows go to the host-sequenced rounds (al_band_warp_kernel; al_band_kernel, one thread per hit, for
 // gap_extend > gap_open, where the scan does not apply).  Score > 32767 or gap penalties beyond 8 bits: al_swalign_kernel.
 #include <algorithm>
+#include <cstring>
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -240,6 +241,7 @@ __global__ void __launch_bounds__(kSwWarps * 32) al_sweep32_kernel(AlParams P, i
             }
         } else {
             if (takes_swalign(P, score)) continue;
+            if (P.coords[4 * w + 0] >= 0) continue;              // the packed reverse sweep has settled this hit
             const int q_end = P.coords[4 * w + 1], t_end = P.coords[4 * w + 3];
             unsigned long long b = ~0ull;
             if (q_end >= 0 && t_end >= 0) b = sweep32(S, smat, q + q_end, -1, q_end + 1, t + t_end, -1, t_end + 1, score, P.go, P.ge, bH, bF, lane);
@@ -885,9 +887,20 @@ extern "C" int s4g_sw_align(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_
         }
     }
     s4g_trace_mark(ctx, "ends");
-    // 2: begin cells -- reverse 32-bit sweep from the end cell, stopped at the first column that holds the score
-    al_sweep32_kernel<<<sw_blocks, kSwWarps * 32, sw_smem, st>>>(P, 0, 0, d_counters + 0);
-    S4G_CHECK_LAUNCH(ctx);
+    // 2: begin cells -- reverse sweep from the end cell, stopped at the first column that holds the score: packed, two hits per
+    // warp (align_rev.cu); the 32-bit sweep takes what is left (end rows beyond 1024; S4G_BEGINS=sweep32 forces it for all)
+    {
+        const char* e = getenv("S4G_BEGINS");
+        const bool packed = !(e && strcmp(e, "sweep32") == 0);
+        if (packed) {
+            int rc = s4g_sw_reverse_begins_device(ctx, db, q, n_pairs, d_pq, d_pt, d_ps, d_mat8, gap_open, gap_extend, swalign_all ? 1 : 0, d_coords, d_counters + 1);
+            if (rc != S4G_OK) return rc;
+        }
+        if (!packed || q->max_len > 1024) {
+            al_sweep32_kernel<<<sw_blocks, kSwWarps * 32, sw_smem, st>>>(P, 0, 0, d_counters + 0);
+            S4G_CHECK_LAUNCH(ctx);
+        }
+    }
     s4g_trace_mark(ctx, "begins");
     // slots for the reversed paths (device scan; the host only needs an upper bound to size the buffer)
     al_slot_sizes_kernel<<<(unsigned)((n_pairs + 1 + 255) / 256), 256, 0, st>>>(P, d_sizes);

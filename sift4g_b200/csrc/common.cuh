@@ -127,6 +127,9 @@ int s4g_sw_score_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, const uint32_t
 int s4g_sw_forward_ends_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n, const uint32_t* d_pair_q, const uint32_t* d_pair_t,
                                const int32_t* d_pair_score, const int8_t* d_mat8, int gap_open, int gap_extend, int32_t* d_coords,
                                unsigned long long* d_flags);
+int s4g_sw_reverse_begins_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n, const uint32_t* d_pair_q, const uint32_t* d_pair_t,
+                                 const int32_t* d_pair_score, const int8_t* d_mat8, int gap_open, int gap_extend, int swalign_all,
+                                 int32_t* d_coords, unsigned long long* d_flags);
 int s4g_sw_long_query_rows();      // queries longer than this many residues are not handled by the packed kernels
 
 int s4g_prefilter_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int max_candidates,
