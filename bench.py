@@ -537,6 +537,7 @@ def main():
 
     peak = ctx.dpx_peak(300)                  # sustained VIADDMNMX.S16x2 lane-ops/s on this device
     roof_gcups = peak * 2 / 6 / 1e9
+    gather_peak = ctx.gather_peak(100)        # random 8-byte lookups/s into an L2-resident table: the prefilter's request-rate ceiling
 
     def barrier():
         if use_dist:
@@ -578,6 +579,21 @@ def main():
         cells, sw_kernel_ms_max, pairs, hits = float(cells_local), float(sw_kernel_ms), float(r.n_pairs), float(r.n_kept)
     ms_per_step = ms / args.steps
     gcups = cells / (ms_per_step * 1e-3) / 1e9
+    # traceback phases of the last timed step on this rank (CUDA events inside the library) against the same DPX roofline
+    roofline_align = None
+    try:
+        al_ms, al_cells = ctx.last_align_profile()
+        roofline_align = {"bound": "int_dpx", "unit": "GCUPS", "what": "stage 3 of the last timed step (rank 0): DP cells each phase has to cover / its device time; "
+                          "ends = al_forward_packed_kernel (s16x2, columns up to the end cell), begins = al_reverse_packed_kernel (s16x2, reversed prefixes up to the "
+                          "begin column), paths = al_band_persistent_kernel (32-bit banded_sw with direction bytes and traceback; cells of the first band SSW tries, "
+                          "doublings not counted; peak = half the s16x2 figure)", "phases": {}}
+        for name in ("ends", "begins", "paths"):
+            pk = roof_gcups if name != "paths" else roof_gcups / 2
+            ach = al_cells[name] / (al_ms[name] * 1e-3) / 1e9 if al_ms[name] > 0 else None
+            roofline_align["phases"][name] = {"ms": round(al_ms[name], 3), "cells": al_cells[name], "achieved": round(ach, 2) if ach else None,
+                                              "peak": round(pk, 2), "frac": round(ach / pk, 4) if ach else None}
+    except capi.S4GError:
+        pass
 
     # stage split (one extra, untimed step with synchronisation between stages; rank-local)
     if use_search:
@@ -619,6 +635,17 @@ def main():
             "roofline_prefilter": {"bound": "hbm", "achieved": round(((total_res + 8 * n_db) if mode == "striped" else ((hi - lo) / n_db * total_res + 8 * (hi - lo))) / (split["prefilter"] * 1e-3) / 1e9, 2) if split["prefilter"] else None,
                                    "peak": hbm_peak(), "unit": "GB/s", "note": "database bytes (1 B/residue + 8 B/sequence) / prefilter stage time"},
         }
+        if split.get("prefilter"):
+            # the scan issues one presence/rank probe per k-mer position (k = 5): its algorithmic request count against the
+            # measured random-lookup rate; the HBM figure above is kept because north_star asks for it
+            scanned = float(total_res if mode == "striped" else (hi - lo) / n_db * total_res)
+            ach = scanned / (split["prefilter"] * 1e-3)
+            line["roofline_prefilter_l2"] = {"bound": "l2_request_rate", "unit": "G lookups/s", "achieved": round(ach / 1e9, 2), "peak": round(gather_peak / 1e9, 2),
+                                             "frac": round(ach / gather_peak, 4),
+                                             "note": "k-mer positions scanned per second (one random 8-byte probe of the 8 MB presence/rank table each; entry and hit loads not "
+                                                     "counted) / random-lookup rate measured live on this GPU (s4g_measure_gather_peak, 100 ms); ncu: profiles/r02i_pf_scan_digest.md"}
+        if roofline_align is not None:
+            line["roofline_align"] = roofline_align
         if line["roofline_prefilter"]["achieved"]:
             line["roofline_prefilter"]["frac"] = round(line["roofline_prefilter"]["achieved"] / line["roofline_prefilter"]["peak"], 4)
         if parity is not None:

@@ -353,7 +353,16 @@ int s4g_measure_dpx_peak(s4g_ctx* ctx, int millis, double* lane_ops_per_s);
 /* device time (ms) spent in the dominant kernel of the most recent s4g_sw_score call, measured with
  * CUDA events on the context's stream (valid after s4g_sync), and the number of DP cells it covered
  * including padding (algorithmic cells are computed by the caller from lengths). */
+/* Sustained rate of random 8-byte lookups into an L2-resident 8 MiB table on this device (lookups/s): the request-rate
+ * ceiling of the prefilter scan, which probes its presence/rank table once per k-mer position (profiles/r02_prefilter.md). */
+int s4g_measure_gather_peak(s4g_ctx* ctx, int millis, double* lookups_per_s);
 int s4g_last_sw_kernel_ms(s4g_ctx* ctx, float* ms);
+/* Traceback phases of the last s4g_sw_align / s4g_search on the context (CUDA events on its stream): ms3 = {end cells, begin
+ * cells, paths}; cells3 = the DP cells each phase has to cover: end cells sum qlen x (t_end + 1) (columns up to the first one
+ * that holds the score), begin cells sum (q_end + 1) x (t_end - t_begin + 1), paths sum (q_end - q_begin + 1) x
+ * (2 (|dt - dq| + 1) + 1) (the first band SSW tries, ssw.c:549-727).  For the roofline of stage 3 (traceback
+ * cells <= 2 qlen tlen + band x qspan per kept hit). */
+int s4g_last_align_profile(s4g_ctx* ctx, float* ms3, uint64_t* cells3);
 
 #ifdef __cplusplus
 }

@@ -74,7 +74,9 @@ SIGNATURES = {
     "s4g_alignment_stats": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "s4g_write_blast_tab": (C.c_int, [C.c_char_p, C.c_int, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "s4g_measure_dpx_peak": (C.c_int, [_vp, C.c_int, _f64p]),
+    "s4g_measure_gather_peak": (C.c_int, [_vp, C.c_int, _f64p]),
     "s4g_last_sw_kernel_ms": (C.c_int, [_vp, _f32p]),
+    "s4g_last_align_profile": (C.c_int, [_vp, _f32p, C.POINTER(C.c_uint64)]),
 }
 
 
@@ -198,10 +200,23 @@ class Context:
         self.check(self.lib.s4g_measure_dpx_peak(self.h, millis, C.byref(v)))
         return v.value
 
+    def gather_peak(self, millis=50):
+        v = C.c_double(0)
+        self.check(self.lib.s4g_measure_gather_peak(self.h, millis, C.byref(v)))
+        return v.value
+
     def last_sw_kernel_ms(self):
         v = C.c_float(0)
         self.check(self.lib.s4g_last_sw_kernel_ms(self.h, C.byref(v)))
         return v.value
+
+    def last_align_profile(self):
+        """-> ({"ends": ms, "begins": ms, "paths": ms}, {"ends": cells, ...}) of the last traceback on this context"""
+        ms = (C.c_float * 3)()
+        cells = (C.c_uint64 * 3)()
+        self.check(self.lib.s4g_last_align_profile(self.h, ms, cells))
+        names = ("ends", "begins", "paths")
+        return {n: float(ms[i]) for i, n in enumerate(names)}, {n: int(cells[i]) for i, n in enumerate(names)}
 
     def close(self):
         if self.h:

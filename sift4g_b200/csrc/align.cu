@@ -772,6 +772,26 @@ __global__ void al_len64_kernel(const int32_t* path_len, int64_t n, int64_t* len
     len64[i] = (i < n && path_len[i] > 0) ? path_len[i] : 0;
 }
 
+// DP cells each traceback phase has to cover (statistic for the stage's roofline; see s4g_last_align_profile)
+__global__ void al_cells_kernel(AlParams P, unsigned long long* acc) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long e = 0, b = 0, p = 0;
+    if (i < P.n_pairs) {
+        const int q0 = P.coords[4 * i], q1 = P.coords[4 * i + 1], t0 = P.coords[4 * i + 2], t1 = P.coords[4 * i + 3];
+        const uint32_t qi = P.pair_q[i];
+        const unsigned long long qlen = (unsigned long long)(P.q_off[qi + 1] - P.q_off[qi]);
+        if (q1 >= 0 && t1 >= 0) e = qlen * (unsigned long long)(t1 + 1);
+        if (q0 >= 0 && t0 >= 0 && q1 >= q0 && t1 >= t0) {
+            b = (unsigned long long)(q1 + 1) * (unsigned long long)(t1 - t0 + 1);
+            const int dq = q1 - q0 + 1, dt = t1 - t0 + 1;
+            p = (unsigned long long)dq * (unsigned long long)(2 * (abs(dt - dq) + 1) + 1);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { e += __shfl_down_sync(0xffffffffu, e, o); b += __shfl_down_sync(0xffffffffu, b, o); p += __shfl_down_sync(0xffffffffu, p, o); }
+    if ((threadIdx.x & 31) == 0) { if (e) atomicAdd(acc, e); if (b) atomicAdd(acc + 1, b); if (p) atomicAdd(acc + 2, p); }
+}
+
 // forward-order copy of each reversed path into the packed output
 __global__ void al_pack_paths_kernel(const uint8_t* rev, const int64_t* slot_off, const int32_t* path_len, const int64_t* out_off,
                                      int64_t n, uint8_t* out, int64_t cap) {
@@ -875,6 +895,7 @@ extern "C" int s4g_sw_align(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_
     for (int64_t i = 0; i < n_pairs; ++i) n_swa += (swalign_all || h_s[i] > 32767) ? 1 : 0;
 
     s4g_trace_start(ctx);
+    S4G_CUDA(ctx, cudaEventRecord(ctx->ev_al[0], st));
     // 1: end cells -- packed s16x2 sweep, two hits of a query per warp; 32-bit sweep for queries beyond its reach
     {
         if (!swalign_all) {
@@ -886,6 +907,7 @@ extern "C" int s4g_sw_align(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_
             S4G_CHECK_LAUNCH(ctx);
         }
     }
+    S4G_CUDA(ctx, cudaEventRecord(ctx->ev_al[1], st));
     s4g_trace_mark(ctx, "ends");
     // 2: begin cells -- reverse sweep from the end cell, stopped at the first column that holds the score: packed, two hits per
     // warp (align_rev.cu); the 32-bit sweep takes what is left (end rows beyond 1024; S4G_BEGINS=sweep32 forces it for all)
@@ -901,6 +923,7 @@ extern "C" int s4g_sw_align(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_
             S4G_CHECK_LAUNCH(ctx);
         }
     }
+    S4G_CUDA(ctx, cudaEventRecord(ctx->ev_al[2], st));
     s4g_trace_mark(ctx, "begins");
     // slots for the reversed paths (device scan; the host only needs an upper bound to size the buffer)
     al_slot_sizes_kernel<<<(unsigned)((n_pairs + 1 + 255) / 256), 256, 0, st>>>(P, d_sizes);
@@ -1084,6 +1107,10 @@ extern "C" int s4g_sw_align(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_
             S4G_CUDA(ctx, cudaStreamSynchronize(st));
         }
     }
+    S4G_CUDA(ctx, cudaEventRecord(ctx->ev_al[3], st));
+    ctx->al_timed = true;
+    al_cells_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, st>>>(P, d_counters + 5);
+    S4G_CHECK_LAUNCH(ctx);
     s4g_trace_mark(ctx, "band_rounds");
     // pack: path offsets = exclusive scan of the lengths, then forward-order copy
     al_len64_kernel<<<(unsigned)((n_pairs + 1 + 255) / 256), 256, 0, st>>>(d_path_len, n_pairs, d_len64);
@@ -1098,6 +1125,7 @@ extern "C" int s4g_sw_align(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_
     }
     int64_t h_total = 0;
     S4G_CUDA(ctx, cudaMemcpyAsync(&h_total, d_out_off + n_pairs, 8, cudaMemcpyDeviceToHost, st));
+    S4G_CUDA(ctx, cudaMemcpyAsync(ctx->al_cells, d_counters + 5, 24, cudaMemcpyDeviceToHost, st));
     S4G_CUDA(ctx, cudaStreamSynchronize(st));
     if (h_total > path_capacity) { s4g_set_error(ctx, "s4g_sw_align: paths need %lld bytes, capacity %lld", (long long)h_total, (long long)path_capacity); return S4G_ERR_CAPACITY; }
     uint8_t* d_paths = where == S4G_DEVICE ? out_paths : (uint8_t*)s4g_scratch(ctx, SLOT_IO_D, (size_t)h_total + 64);

@@ -120,6 +120,7 @@ int s4g_init(int device, s4g_ctx** out) {
         S4G_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         S4G_CUDA(ctx, cudaEventCreate(&ctx->ev_sw0));
         S4G_CUDA(ctx, cudaEventCreate(&ctx->ev_sw1));
+        for (int i = 0; i < 4; ++i) S4G_CUDA(ctx, cudaEventCreate(&ctx->ev_al[i]));
         return S4G_OK;
     }();
     if (rc != S4G_OK) { s4g_shutdown(ctx); return rc; }
@@ -141,6 +142,7 @@ void s4g_shutdown(s4g_ctx* ctx) {
     for (int i = 0; i < s4g_ctx::kPins; ++i) if (ctx->pin_ptr[i]) cudaFreeHost(ctx->pin_ptr[i]);
     if (ctx->ev_sw0) cudaEventDestroy(ctx->ev_sw0);
     if (ctx->ev_sw1) cudaEventDestroy(ctx->ev_sw1);
+    for (int i = 0; i < 4; ++i) if (ctx->ev_al[i]) cudaEventDestroy(ctx->ev_al[i]);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -350,6 +352,14 @@ int s4g_prefilter(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int max_candi
     if (out_scores) S4G_CUDA(ctx, cudaMemcpyAsync(out_scores, d_sc, sizeof(float) * cells, cudaMemcpyDeviceToHost, ctx->stream));
     S4G_CUDA(ctx, cudaMemcpyAsync(out_counts, d_cnt, sizeof(uint32_t) * q->n, cudaMemcpyDeviceToHost, ctx->stream));
     S4G_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return S4G_OK;
+}
+
+int s4g_last_align_profile(s4g_ctx* ctx, float* ms3, uint64_t* cells3) {
+    if (!ctx || !ms3 || !cells3) return S4G_ERR_ARG;
+    if (!ctx->al_timed) { s4g_set_error(ctx, "no s4g_sw_align call has been timed yet"); return S4G_ERR_ARG; }
+    S4G_CUDA(ctx, cudaEventSynchronize(ctx->ev_al[3]));
+    for (int i = 0; i < 3; ++i) { S4G_CUDA(ctx, cudaEventElapsedTime(ms3 + i, ctx->ev_al[i], ctx->ev_al[i + 1])); cells3[i] = ctx->al_cells[i]; }
     return S4G_OK;
 }
 

@@ -22,6 +22,10 @@ struct s4g_ctx {
     int64_t launches = 0;
     cudaEvent_t ev_sw0 = nullptr, ev_sw1 = nullptr;
     bool sw_timed = false;
+    // traceback phases of the last s4g_sw_align: events around end cells / begin cells / paths, algorithmic cells of each
+    cudaEvent_t ev_al[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool al_timed = false;
+    unsigned long long al_cells[3] = {0, 0, 0};
     // grow-only scratch arena, one buffer per slot (device memory)
     static const int kSlots = 64;
     void* slot_ptr[kSlots] = {nullptr};

@@ -64,3 +64,57 @@ extern "C" int s4g_measure_dpx_peak(s4g_ctx* ctx, int millis, double* lane_ops_p
     *lane_ops_per_s = best;
     return S4G_OK;
 }
+
+// Measurement helper: rate of random 8-byte lookups into an L2-resident table -- what bounds the prefilter scan, which probes
+// the 8 MB presence/rank table once per k-mer position.  An SM completes one random 32-byte sector request per clock
+// whatever the load flavour (tools/gather_microbench.cu: 290-320 G lookups/s on a B200), far below L2 bandwidth.
+namespace {
+__device__ __forceinline__ uint32_t gp_mix(uint32_t x) { x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16; return x; }
+__global__ void __launch_bounds__(1024, 1) gather_peak_kernel(const uint2* tab, uint32_t mask, int rounds, unsigned* out) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t acc = 0, seed = gp_mix(tid * 0x9E3779B1u + 12345u);
+    for (int r = 0; r < rounds; ++r) {
+        uint32_t idx[4];
+        uint2 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { seed = seed * 1664525u + 1013904223u; idx[i] = gp_mix(seed + i); }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = __ldg(tab + (idx[i] & mask));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc += v[i].x ^ v[i].y;
+    }
+    if (acc == 0x12345678u) out[0] = acc;
+}
+}  // namespace
+
+extern "C" int s4g_measure_gather_peak(s4g_ctx* ctx, int millis, double* lookups_per_s) {
+    if (!ctx || !lookups_per_s) return S4G_ERR_ARG;
+    S4G_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t entries = (size_t)1 << 20;                       // 8 MiB: the size of the scan's presence/rank table
+    uint2* d_tab = (uint2*)s4g_scratch(ctx, SLOT_IO_E, sizeof(uint2) * entries + 64);
+    if (!d_tab) return S4G_ERR_NOMEM;
+    S4G_CUDA(ctx, cudaMemsetAsync(d_tab, 0x5a, sizeof(uint2) * entries, ctx->stream));
+    unsigned* d_out = (unsigned*)(d_tab + entries);
+    cudaEvent_t e0, e1;
+    S4G_CUDA(ctx, cudaEventCreate(&e0));
+    S4G_CUDA(ctx, cudaEventCreate(&e1));
+    const int blocks = ctx->sm_count, threads = 1024, rounds = 2048;
+    gather_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(d_tab, (uint32_t)entries - 1, rounds, d_out);
+    S4G_CHECK_LAUNCH(ctx);
+    if (millis < 1) millis = 1;
+    int launches = 0;
+    float ms = 0.f;
+    S4G_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+    while (true) {
+        for (int r = 0; r < 4; ++r) { gather_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(d_tab, (uint32_t)entries - 1, rounds, d_out); ++launches; }
+        ctx->launches += 4;
+        S4G_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+        S4G_CUDA(ctx, cudaEventSynchronize(e1));
+        S4G_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        if (ms >= millis || launches > 100000) break;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *lookups_per_s = (double)launches * blocks * threads * (double)rounds * 4.0 / (ms * 1e-3);
+    return S4G_OK;
+}

@@ -587,7 +587,7 @@ __device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cn
             }
             __syncwarp();
             for (int i = 4 * lane; i < cnt_words; i += 128) *reinterpret_cast<uint4*>(cnt + i) = make_uint4(0u, 0u, 0u, 0u);
-            if (!defer && wb != buf && nsurv <= (uint32_t)scap) {       // few survivors: sort them in shared memory
+            if (!defer && wb != buf && nsurv <= (1u << (31 - __clz(scap)))) {       // few survivors: sort them in shared memory (the bitonic sort pads to a power of two)
                 for (int i = lane; i < (int)nsurv; i += 32) buf[i] = wb[i];
                 wb = buf;
             }
@@ -1029,7 +1029,7 @@ static int build_scan_order(s4g_ctx* ctx, s4g_db* db) {
 // leaves kMinScanWarps warps per SM beside the 2-byte cut-off table (larger batches are scanned in groups of queries: the
 // candidate lists of different queries are independent, the database streams once per group).
 constexpr size_t kScanSmemCap = 227 * 1024;
-constexpr int kScanSortCap = 256;          // 8-byte entries of a warp's buffer: hit queue of pass A (twice as many 32-bit items), sort buffer of pass B
+constexpr int kScanSortCap = 192;          // 8-byte entries of a warp's buffer: the two queues of pass A (1 KB of ranks + 512 B of buckets), step tables / sort buffer of pass B; every KB here is a KB less L1 for the index probes
 constexpr int kMinScanWarps = 4;
 static int scan_cnt_words(int nq) { return ((nq + 1) / 2 + 127) / 128 * 128; }
 static int scan_sort_cap(int) { return kScanSortCap; }
