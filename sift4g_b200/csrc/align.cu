@@ -947,7 +947,8 @@ extern "C" int s4g_sw_align(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_
     struct Pending { uint32_t pair; int32_t w, readLen, refLen; };
     std::vector<Pending> pending;
     std::vector<int32_t> h_coords;
-    const bool warp_rule = gap_extend <= gap_open;     // the max-plus scan of the warp kernels needs ge <= go
+    bool warp_rule = gap_extend <= gap_open;           // the max-plus scan of the warp kernels needs ge <= go
+    { const char* e = getenv("S4G_BAND"); if (e && strcmp(e, "thread") == 0) warp_rule = false; }     // experiment: one thread per hit for every band
     unsigned long long h_flags[4] = {0, 0, 0, 0};
     if (warp_rule) {
         const int w_max = 256;
