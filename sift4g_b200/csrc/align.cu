@@ -532,6 +532,8 @@ struct PersistParams {
     unsigned long long* cursor;  // [0] work cursor, [1] overflow count, [2] error flags
     uint2* overflow;             // (pair, w)
     const uint32_t* order;       // processing order (largest hits first), or nullptr
+    const uint2* in_list;        // (pair, half band width to start with) handed over by the group kernels, or nullptr = every hit from its first band
+    const unsigned long long* in_count;
 };
 
 __global__ void __launch_bounds__(kBandWarps * 32) al_band_persistent_kernel(AlParams P, PersistParams B) {
@@ -553,15 +555,15 @@ __global__ void __launch_bounds__(kBandWarps * 32) al_band_persistent_kernel(AlP
         unsigned long long wi = 0;
         if (lane == 0) wi = atomicAdd(B.cursor, 1ull);
         wi = __shfl_sync(FULL, wi, 0);
-        if ((long long)wi >= P.n_pairs) break;
-        const uint32_t p = B.order ? B.order[wi] : (uint32_t)wi;
+        if ((long long)wi >= (B.in_list ? (long long)*B.in_count : P.n_pairs)) break;
+        const uint32_t p = B.in_list ? B.in_list[wi].x : (B.order ? B.order[wi] : (uint32_t)wi);
         const int q0 = P.coords[4 * p + 0], q1 = P.coords[4 * p + 1], t0 = P.coords[4 * p + 2], t1 = P.coords[4 * p + 3];
         if (q0 < 0 || t0 < 0) continue;                      // reported by the sweeps
         const uint8_t* read = P.q_codes + P.q_off[P.pair_q[p]] + q0;
         const uint8_t* ref = P.db_codes + P.db_off[P.pair_t[p] - P.id_base] + t0;
         const int readLen = q1 - q0 + 1, refLen = t1 - t0 + 1;
         const int score = P.pair_score[p];
-        int w = abs(refLen - readLen) + 1;
+        int w = B.in_list ? (int)B.in_list[wi].y : abs(refLen - readLen) + 1;
         for (int round = 0; ; ++round) {
             if (round > 40) { if (lane == 0) atomicOr(B.cursor + 2, 2ull); break; }
             if (w > B.w_max || (int64_t)(2 * w + 1) * readLen > B.dir_per_warp) {
@@ -578,6 +580,196 @@ __global__ void __launch_bounds__(kBandWarps * 32) al_band_persistent_kernel(AlP
             }
             w *= 2;
             __syncwarp();
+        }
+        __syncwarp();
+    }
+}
+
+// ---- narrow bands: several hits per warp -------------------------------------------------------------------------
+// The bands of near-diagonal alignments are a few cells wide (configs[1]: 2 w + 1 ~ 10 on average), and a band row costs the
+// warp kernel above ~90 instructions however narrow it is -- it is bound by issue slots (ncu: 89 % issue active), with most
+// lanes idle.  Here G = 8 or 16 lanes own a hit (half band width w <= (G - 1) / 2, so a row is at most one cell per lane) and
+// 32 / G hits share the warp's instruction stream: same integers, same direction bytes, same traceback rules as band_fill /
+// band_trace (ssw.c:549-727), shuffles confined to the group.  A hit whose band doubles beyond the group's width is handed
+// on as (pair, w) -- to the next wider group kernel, finally to al_band_persistent_kernel, which continues at that width.
+struct GroupParams {
+    const uint2* in_list;              // (pair, w) to start from, or nullptr = every hit from its first band
+    const unsigned long long* in_count;
+    unsigned long long* cursor;
+    uint2* out_list;
+    unsigned long long* out_count;
+    unsigned long long* err;           // bit 2: the traceback left the band or its slot
+    uint8_t* dir;
+    int64_t dir_per_group;
+    uint8_t* rev_paths;
+    const int64_t* slot_off;
+    int32_t* path_len;
+};
+
+template <int G>
+__global__ void __launch_bounds__(kBandWarps * 32) al_band_group_kernel(AlParams P, GroupParams B) {
+    constexpr int kGroups = 32 / G, kWMax = (G - 1) / 2, kStride = 2 * kWMax + 5;
+    __shared__ int8_t smatT[32 * 32];
+    __shared__ int32_t rows[kBandWarps * kGroups * 3 * kStride];
+    for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) {
+        const int ql = i >> 5, tl = i & 31;
+        smatT[i] = tl <= S4G_PAD_CODE ? P.mat8[tl * 32 + ql] : 0;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gl = lane & (G - 1), grp = lane / G, gbase = lane & ~(G - 1);
+    const unsigned FULL = 0xffffffffu;
+    const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << gbase;
+    int32_t* bufA = rows + (size_t)(warp * kGroups + grp) * 3 * kStride;
+    int32_t* bufB = bufA + kStride;
+    int32_t* E = bufB + kStride;
+    uint8_t* dir = B.dir + (size_t)((blockIdx.x * kBandWarps + warp) * kGroups + grp) * B.dir_per_group;
+    const long long n_work = B.in_list ? (long long)*B.in_count : P.n_pairs;
+    const int go = P.go, ge = P.ge;
+    const int f0 = max(-go, -ge);
+    // the group's hit (the same values in all its lanes)
+    bool has = false, exhausted = false;
+    uint32_t p = 0;
+    int w = 0, readLen = 0, refLen = 0, score = 0;
+    const uint8_t *read = nullptr, *ref = nullptr;
+    while (true) {
+        // ---- (1) idle groups take the next hit they can hold
+        while (!has && !exhausted) {
+            unsigned long long wi = 0;
+            if (gl == 0) wi = atomicAdd(B.cursor, 1ull);
+            wi = __shfl_sync(gmask, wi, gbase);
+            if ((long long)wi >= n_work) { exhausted = true; break; }
+            p = B.in_list ? B.in_list[wi].x : (uint32_t)wi;
+            const int q0 = P.coords[4 * p + 0], q1 = P.coords[4 * p + 1], t0 = P.coords[4 * p + 2], t1 = P.coords[4 * p + 3];
+            if (q0 < 0 || t0 < 0) continue;                      // swAlign-rule hits, hits reported by the sweeps
+            readLen = q1 - q0 + 1; refLen = t1 - t0 + 1;
+            w = B.in_list ? (int)B.in_list[wi].y : abs(refLen - readLen) + 1;
+            if (w > kWMax || (int64_t)(2 * w + 1) * readLen > B.dir_per_group) {
+                if (gl == 0) B.out_list[atomicAdd(B.out_count, 1ull)] = make_uint2(p, (uint32_t)w);
+                continue;
+            }
+            read = P.q_codes + P.q_off[P.pair_q[p]] + q0;
+            ref = P.db_codes + P.db_off[P.pair_t[p] - P.id_base] + t0;
+            score = P.pair_score[p];
+            has = true;
+        }
+        __syncwarp();
+        if (!__any_sync(FULL, has)) break;
+        // ---- (2) one banded_sw attempt of every group that holds a hit, rows in lockstep
+        const int rows_max = __reduce_max_sync(FULL, has ? readLen : 0);
+        const int width = 2 * w + 3, width_d = 2 * w + 1;
+        int32_t* prevH = bufA;
+        int32_t* curH = bufB;
+        for (int j = gl; j < kStride; j += G) { bufA[j] = 0; bufB[j] = 0; E[j] = 0; }
+        __syncwarp();
+        int best = 0;
+        for (int i = 0; i < rows_max; ++i) {
+            const bool rowact = has && i < readLen;
+            const int beg = i - w > 0 ? i - w : 0;
+            const int end = i + w < refLen - 1 ? i + w : refLen - 1;
+            const int edge = end + 1 < width - 1 ? end + 1 : width - 1;
+            const int xp = (i - 1 - w > 0) ? i - 1 - w : 0;
+            if (gl == 0 && rowact) { prevH[0] = 0; E[0] = 0; prevH[edge] = 0; E[edge] = 0; curH[0] = 0; }
+            __syncwarp();
+            const int j = beg + gl;
+            const bool act = rowact && j <= end;
+            const int t = j - beg, u = t + 1, up = j - xp + 1;
+            int ph = 0, pe = 0, pd = 0, sc = 0;
+            if (act) { ph = prevH[up]; pe = E[up]; pd = prevH[up - 1]; sc = smatT[(int)read[i] * 32 + ref[j]]; }
+            const int open_e = i == 0 ? -go : ph - go;
+            const int ext_e = i == 0 ? -ge : pe - ge;
+            const int e = open_e > ext_e ? open_e : ext_e;
+            const unsigned de = open_e > ext_e ? 1u : 0u;
+            const int e1 = e > 0 ? e : 0;
+            const int dsc = pd + sc;
+            const int g = e1 > dsc ? e1 : dsc;
+            const int a = act ? g - go + t * ge : kNegBig;
+            int incl = a;
+#pragma unroll
+            for (int o = 1; o < G; o <<= 1) { const int y = __shfl_up_sync(FULL, incl, o, G); if (gl >= o) incl = max(incl, y); }
+            int excl = __shfl_up_sync(FULL, incl, 1, G);
+            if (gl == 0) excl = kNegBig;
+            const int f = t == 0 ? f0 : max(f0 - t * ge, excl - (t - 1) * ge);
+            const int hc = g > f ? g : f;
+            int hc_left = __shfl_up_sync(FULL, hc, 1, G), f_left = __shfl_up_sync(FULL, f, 1, G);
+            if (gl == 0) { hc_left = 0; f_left = 0; }
+            const unsigned df = (hc_left - go) > (f_left - ge) ? 1u : 0u;
+            const int f1 = f > 0 ? f : 0;
+            const int gap = e1 > f1 ? e1 : f1;
+            const unsigned sel = gap <= dsc ? 0u : (e1 > f1 ? 1u : 2u);
+            __syncwarp();
+            if (act) {
+                E[u] = e;
+                curH[u] = hc;
+                dir[(size_t)width_d * i + t] = (uint8_t)(de | (df << 1) | (sel << 2));
+                best = max(best, hc);
+            }
+            __syncwarp();
+            int32_t* tmp = prevH; prevH = curH; curH = tmp;
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(FULL, best, o));
+        // ---- (3) groups whose band reached the score trace back; the others double their band (or hand the hit on)
+        bool tracing = has && best >= score;
+        if (has && !tracing) {
+            w *= 2;
+            if (w > kWMax || (int64_t)(2 * w + 1) * readLen > B.dir_per_group) {
+                if (gl == 0) B.out_list[atomicAdd(B.out_count, 1ull)] = make_uint2(p, (uint32_t)w);
+                has = false;
+            }
+        }
+        __threadfence_block();
+        __syncwarp();
+        if (__any_sync(FULL, tracing)) {
+            uint8_t* out = B.rev_paths + (tracing ? B.slot_off[p] : 0);
+            const int cap = tracing ? (int)(B.slot_off[p + 1] - B.slot_off[p]) : 0;
+            int i = readLen - 1, j = refLen - 1, state = 2, n = 0;
+            bool fail = false;
+            while (true) {
+                const bool tr = tracing && !fail && i > 0;
+                if (!__any_sync(FULL, tr)) break;
+                const int ii = i - gl, jj = j - gl;
+                unsigned d = 0xffu;
+                if (tr && ii > 0 && jj >= 0) {
+                    const int x = ii - w > 0 ? ii - w : 0;
+                    const int hi = ii + w < refLen - 1 ? ii + w : refLen - 1;
+                    if (jj >= x && jj <= hi) d = __ldcg(dir + (size_t)width_d * ii + (jj - x));
+                }
+                const unsigned d0 = __shfl_sync(FULL, d, gbase);
+                const unsigned ndw = __ballot_sync(FULL, !(d != 0xffu && (d >> 2) == 0u));
+                if (!tr) continue;
+                if (d0 == 0xffu) { fail = true; continue; }
+                if (state == 2 && (d0 >> 2) == 0u) {
+                    const unsigned nd = (ndw & gmask) >> gbase;
+                    int run = nd ? __ffs(nd) - 1 : G;
+                    if (run > i) run = i;
+                    if (n + run >= cap) { fail = true; continue; }
+                    if (gl < run) out[n + gl] = 1;
+                    n += run; i -= run; j -= run;
+                    continue;
+                }
+                unsigned code;
+                if (state == 0) code = (d0 & 1u) ? 3u : 2u;
+                else if (state == 1) code = (d0 & 2u) ? 5u : 4u;
+                else { const unsigned sl = d0 >> 2; code = sl == 1 ? ((d0 & 1u) ? 3u : 2u) : ((d0 & 2u) ? 5u : 4u); }
+                if (n + 1 >= cap) { fail = true; continue; }
+                uint8_t op;
+                switch (code) {
+                    case 2: --i; state = 0; op = 3; break;
+                    case 3: --i; state = 2; op = 3; break;
+                    case 4: --j; state = 1; op = 2; break;
+                    default: --j; state = 2; op = 2; break;
+                }
+                if (gl == 0) out[n] = op;
+                ++n;
+            }
+            if (tracing) {
+                if (gl == 0) {
+                    if (fail) atomicOr(B.err, 4ull);
+                    else { out[n] = 1; B.path_len[p] = n + 1; }          // the remaining cell is closed as one more match
+                }
+                has = false;
+            }
         }
         __syncwarp();
     }
@@ -965,7 +1157,36 @@ extern "C" int s4g_sw_align(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_
         S4G_CUDA(ctx, cudaMemsetAsync(d_pw, 0, 64, st));
         PersistParams B;
         B.w_max = w_max; B.dir_per_warp = dir_per_warp; B.dir = d_dirp; B.rev_paths = d_rev; B.slot_off = d_slot_off; B.path_len = d_path_len;
-        B.cursor = (unsigned long long*)d_pw; B.overflow = (uint2*)(d_pw + 64); B.order = nullptr;
+        B.cursor = (unsigned long long*)d_pw; B.overflow = (uint2*)(d_pw + 64); B.order = nullptr; B.in_list = nullptr; B.in_count = nullptr;
+        // narrow bands first, several hits per warp: 8 lanes per hit (w <= 3), then 16 (w <= 7); what outgrows them is handed on as
+        // (pair, w) and the warp-per-hit kernel continues at that width.  S4G_BAND_GROUPS=0 / 8 / 16 selects the stages (default both).
+        {
+            const char* e = getenv("S4G_BAND_GROUPS");
+            const int stages = e ? atoi(e) : 24;                 // bit 3: the 8-lane stage, bit 4: the 16-lane stage
+            char* d_gl = (char*)s4g_scratch(ctx, SLOT_AL_GROUPS, 128 + 2 * sizeof(uint2) * (size_t)n_pairs);
+            if (!d_gl) return S4G_ERR_NOMEM;
+            S4G_CUDA(ctx, cudaMemsetAsync(d_gl, 0, 128, st));
+            unsigned long long* g_cnt = (unsigned long long*)d_gl;      // [0] cursor8 [1] count A [2] cursor16 [3] count B
+            uint2* listA = (uint2*)(d_gl + 128);
+            uint2* listB = listA + n_pairs;
+            GroupParams G;
+            G.err = (unsigned long long*)d_pw + 2; G.dir = d_dirp; G.rev_paths = d_rev; G.slot_off = d_slot_off; G.path_len = d_path_len;
+            const uint2* cur_list = nullptr;
+            const unsigned long long* cur_count = nullptr;
+            if (stages & 8) {
+                G.in_list = nullptr; G.in_count = nullptr; G.cursor = g_cnt + 0; G.out_list = listA; G.out_count = g_cnt + 1; G.dir_per_group = dir_per_warp / 4;
+                al_band_group_kernel<8><<<grid, kBandWarps * 32, 0, st>>>(P, G);
+                S4G_CHECK_LAUNCH(ctx);
+                cur_list = listA; cur_count = g_cnt + 1;
+            }
+            if (stages & 16) {
+                G.in_list = cur_list; G.in_count = cur_count; G.cursor = g_cnt + 2; G.out_list = listB; G.out_count = g_cnt + 3; G.dir_per_group = dir_per_warp / 2;
+                al_band_group_kernel<16><<<grid, kBandWarps * 32, 0, st>>>(P, G);
+                S4G_CHECK_LAUNCH(ctx);
+                cur_list = listB; cur_count = g_cnt + 3;
+            }
+            B.in_list = cur_list; B.in_count = cur_count;
+        }
         al_band_persistent_kernel<<<grid, kBandWarps * 32, p_smem, st>>>(P, B);
         S4G_CHECK_LAUNCH(ctx);
         S4G_CUDA(ctx, cudaMemcpyAsync(h_flags, d_pw, 32, cudaMemcpyDeviceToHost, st));
@@ -977,7 +1198,12 @@ extern "C" int s4g_sw_align(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_
     if (h_flags[2] & 2ull) { s4g_set_error(ctx, "s4g_sw_align: band doubling did not converge"); return S4G_ERR_INTERNAL; }
     if (h_flags[2] & 4ull) { s4g_set_error(ctx, "s4g_sw_align: traceback left the band (the reference's behaviour is undefined there)"); return S4G_ERR_INTERNAL; }
     s4g_trace_mark(ctx, "band_persistent");
-    if (ctx->trace) fprintf(stderr, "[s4g trace] align: %lld hits, %llu handed back to the host-sequenced band rounds\n", (long long)n_pairs, h_flags[1]);
+    if (ctx->trace) {
+        unsigned long long g[4] = {0, 0, 0, 0};
+        if (ctx->slot_ptr[SLOT_AL_GROUPS] && warp_rule) cudaMemcpy(g, ctx->slot_ptr[SLOT_AL_GROUPS], 32, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[s4g trace] align: %lld hits, %llu handed from the 8-lane to the 16-lane band kernel, %llu on to the warp kernel, %llu handed back to the host-sequenced band rounds\n",
+                (long long)n_pairs, g[1], g[3], h_flags[1]);
+    }
     const bool need_host_rounds = !warp_rule || h_flags[1] > 0;
     if (need_host_rounds || where == S4G_HOST) {
         h_coords.resize(4 * n_pairs);

@@ -37,7 +37,7 @@ constexpr int kTilePairs = 64;            // pairs per (query, tile)
 constexpr int kRing = 64;                 // ring refill granularity (columns), >= 32
 constexpr int kMaxK = 32;                 // rows per lane in the packed kernel -> queries up to 1024
 constexpr int kGenK = 8;                  // rows per lane in the 32-bit kernel (256 rows per pass)
-constexpr int kStripCols = 4096;          // longest target the striped kernel takes (longer ones: 32-bit kernel)
+constexpr int kStripColsMin = 4096;       // boundary rows of the striped kernel: at least this many columns per target, grown to the shard's longest sequence
 
 __device__ __forceinline__ unsigned prmt(unsigned a, unsigned b, unsigned sel) {
     unsigned d;
@@ -68,7 +68,8 @@ struct ScoreParams {
     const int32_t* pair_score;
     // striped kernel (queries longer than 32 * kMaxK rows)
     const int64_t* long_tile_start;   // nq+1: exclusive scan of its tiles per query
-    unsigned* strip_bound;            // per CTA: kTilePairs x 2 x kStripCols packed boundary rows (H, F)
+    unsigned* strip_bound;            // per CTA: kTilePairs x 2 x strip_cols packed boundary rows (H, F)
+    int32_t strip_cols;               // columns per boundary row (targets beyond it take the 32-bit kernel)
 };
 
 // ------------------------------------------------------------------------------------------------------
@@ -602,7 +603,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) sw_score_striped_kernel(ScoreP
     const long long total = P.long_tile_start[P.nq];
     const unsigned negQ = ((unsigned)(-P.gap_open) & 0xffffu) * 0x10001u;
     const unsigned negR = ((unsigned)(-P.gap_extend) & 0xffffu) * 0x10001u;
-    unsigned* cta_bound = P.strip_bound + (size_t)blockIdx.x * kTilePairs * 2 * kStripCols;
+    unsigned* cta_bound = P.strip_bound + (size_t)blockIdx.x * kTilePairs * 2 * P.strip_cols;
     while (true) {
         __syncthreads();
         if (threadIdx.x == 0) s_tile = (long long)atomicAdd(&P.counters[4], 1ull);
@@ -632,12 +633,12 @@ __global__ void __launch_bounds__(kWarps * 32, 2) sw_score_striped_kernel(ScoreP
                 const int64_t a1 = P.db_off[P.cand_ids[c1] - P.id_base], b1 = P.db_off[P.cand_ids[c1] - P.id_base + 1];
                 const int64_t a2 = P.db_off[P.cand_ids[c2] - P.id_base], b2 = P.db_off[P.cand_ids[c2] - P.id_base + 1];
                 const int len1 = (int)(b1 - a1), len2 = has2 ? (int)(b2 - a2) : 0;
-                if (len1 > kStripCols || len2 > kStripCols) {           // too long for the boundary buffer: 32-bit kernel
+                if (len1 > P.strip_cols || len2 > P.strip_cols) {       // too long for the boundary buffer: 32-bit kernel
                     if (lane == 0) s_best[p - pb] = 0x7fff7fffu;
                     continue;
                 }
-                unsigned* bH = cta_bound + (size_t)(p - pb) * 2 * kStripCols;
-                const unsigned best = sweep_stripe(prof + lane, S, P.db_codes + a1, len1, P.db_codes + a2, len2, negQ, negR, bH, bH + kStripCols,
+                unsigned* bH = cta_bound + (size_t)(p - pb) * 2 * P.strip_cols;
+                const unsigned best = sweep_stripe(prof + lane, S, P.db_codes + a1, len1, P.db_codes + a2, len2, negQ, negR, bH, bH + P.strip_cols,
                                                    pass == 0, pass == npass - 1, lane);
                 if (lane == 0) s_best[p - pb] = __vmaxs2(s_best[p - pb], best);
             }
@@ -844,7 +845,7 @@ int s4g_sw_score_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, const uint32_t
     P.cand_ids = d_cand_ids; P.cand_off = d_cand_off;
     P.sorted_idx = d_vals2; P.tile_start = d_tile_start; P.mat8 = d_mat8; P.out = d_out;
     P.counters = d_counters; P.overflow = d_ovf; P.bound = d_bound; P.bound_stride = bound_stride;
-    P.long_tile_start = d_long_start; P.strip_bound = nullptr; P.pair_score = nullptr;
+    P.long_tile_start = d_long_start; P.strip_bound = nullptr; P.strip_cols = 0; P.pair_score = nullptr;
     P.gap_open = gap_open; P.gap_extend = gap_extend; P.ovf_limit = 32767 - max_s;
 
     // 1. sort candidates of each query by target length (longest first)
@@ -894,7 +895,12 @@ int s4g_sw_score_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, const uint32_t
         S4G_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw_score_striped_kernel, kWarps * 32, smem));
         if (per_sm < 1) per_sm = 1;
         const int grid = ctx->sm_count * per_sm;
-        unsigned* d_strip = (unsigned*)s4g_scratch(ctx, SLOT_SW_STRIP, sizeof(unsigned) * (size_t)grid * kTilePairs * 2 * kStripCols);
+        // boundary rows sized for the longest sequence of the shard (a titin-like query meets titin-like targets), within 16 GiB
+        const size_t per_col = sizeof(unsigned) * (size_t)grid * kTilePairs * 2;
+        int64_t strip_cols = std::max<int64_t>(kStripColsMin, ((int64_t)db->max_len + 63) / 64 * 64);
+        strip_cols = std::min<int64_t>(strip_cols, (int64_t)(((size_t)16 << 30) / per_col) / 64 * 64);
+        unsigned* d_strip = (unsigned*)s4g_scratch(ctx, SLOT_SW_STRIP, per_col * (size_t)strip_cols);
+        P.strip_cols = (int32_t)strip_cols;
         if (!d_strip) return S4G_ERR_NOMEM;
         P.strip_bound = d_strip;
         sw_score_striped_kernel<<<grid, kWarps * 32, smem, st>>>(P);
