@@ -998,10 +998,105 @@ __global__ void al_pack_paths_kernel(const uint8_t* rev, const int64_t* slot_off
 
 }  // namespace
 
+static int sw_align_impl(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_pairs, const uint32_t* pair_q,
+                         const uint32_t* pair_t, const int32_t* pair_score, const int32_t* matrix, int gap_open,
+                         int gap_extend, int32_t* out_coords, uint8_t* out_paths, int64_t path_capacity,
+                         int64_t* out_path_offsets, int where);
+
+namespace {
+// NVLink-striped database: the targets of the hits are copied once into a resident buffer (coalesced peer reads at link
+// bandwidth), so that the three traceback phases -- ring refills, band rows, direction walks: latency-sensitive gathers that
+// touch every target several times -- run on local memory.  Hit h's target becomes sequence h of a temporary database.
+__global__ void al_gather_lens_kernel(const uint32_t* pair_t, int64_t n, const int64_t* db_off, uint32_t id_base, int64_t* lens) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    int64_t l = 0;
+    if (i < n) { const uint32_t t = pair_t[i] - id_base; l = db_off[t + 1] - db_off[t]; }
+    lens[i] = l;
+}
+__global__ void al_gather_codes_kernel(const uint32_t* pair_t, int64_t n, const uint8_t* db_codes, const int64_t* db_off, uint32_t id_base,
+                                       const int64_t* out_off, uint8_t* out, uint32_t* iota) {
+    const int64_t h = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (h >= n) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t t = pair_t[h] - id_base;
+    const uint8_t* src = db_codes + db_off[t];
+    uint8_t* dst = out + out_off[h];
+    const int64_t len = out_off[h + 1] - out_off[h];
+    // 4-byte body on the source's alignment (the destination is written byte-wise: it is local)
+    int64_t head = (int64_t)((4 - (reinterpret_cast<uintptr_t>(src) & 3u)) & 3u);
+    if (head > len) head = len;
+    if (lane < head) dst[lane] = src[lane];
+    const int64_t nw = (len - head) / 4;
+    const uint32_t* s4 = reinterpret_cast<const uint32_t*>(src + head);
+    for (int64_t w = lane; w < nw; w += 32) {
+        const uint32_t v = s4[w];
+        uint8_t* d = dst + head + 4 * w;
+        d[0] = (uint8_t)v; d[1] = (uint8_t)(v >> 8); d[2] = (uint8_t)(v >> 16); d[3] = (uint8_t)(v >> 24);
+    }
+    const int64_t done = head + 4 * nw;
+    if (lane < len - done) dst[done + lane] = src[done + lane];
+    if (lane == 0) iota[h] = (uint32_t)h;
+}
+}  // namespace
+
 extern "C" int s4g_sw_align(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_pairs, const uint32_t* pair_q,
                             const uint32_t* pair_t, const int32_t* pair_score, const int32_t* matrix, int gap_open,
                             int gap_extend, int32_t* out_coords, uint8_t* out_paths, int64_t path_capacity,
                             int64_t* out_path_offsets, int where) {
+    const char* e = getenv("S4G_ALIGN_GATHER");
+    const bool gather = db && db->borrowed_codes && n_pairs > 0 && n_pairs < ((int64_t)1 << 31) && pair_t && !(e && e[0] == '0');
+    if (!ctx || !gather) return sw_align_impl(ctx, db, q, n_pairs, pair_q, pair_t, pair_score, matrix, gap_open, gap_extend, out_coords, out_paths, path_capacity, out_path_offsets, where);
+    S4G_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint32_t* d_pt = pair_t;
+    char* g = (char*)s4g_scratch(ctx, SLOT_AL_GATHER_IDX, 2 * sizeof(int64_t) * (size_t)(n_pairs + 1) + 2 * sizeof(uint32_t) * (size_t)n_pairs + 64);
+    if (!g) return S4G_ERR_NOMEM;
+    int64_t* d_lens = (int64_t*)g;
+    int64_t* d_goff = d_lens + (n_pairs + 1);
+    uint32_t* d_iota = (uint32_t*)(d_goff + (n_pairs + 1));
+    uint32_t* d_pt_up = d_iota + n_pairs;
+    if (where == S4G_HOST) {
+        for (int64_t i = 0; i < n_pairs; ++i)
+            if (pair_t[i] < db->id_base || pair_t[i] - db->id_base >= (uint64_t)db->n) { s4g_set_error(ctx, "pair %lld references an unknown target", (long long)i); return S4G_ERR_ARG; }
+        S4G_CUDA(ctx, cudaMemcpyAsync(d_pt_up, pair_t, 4 * n_pairs, cudaMemcpyHostToDevice, st));
+        d_pt = d_pt_up;
+    }
+    al_gather_lens_kernel<<<(unsigned)((n_pairs + 1 + 255) / 256), 256, 0, st>>>(d_pt, n_pairs, db->d_off, db->id_base, d_lens);
+    S4G_CHECK_LAUNCH(ctx);
+    {
+        size_t tmp = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_lens, d_goff, (int)(n_pairs + 1), st);
+        void* d_tmp = s4g_scratch(ctx, SLOT_SW_CUB, tmp);
+        if (!d_tmp) return S4G_ERR_NOMEM;
+        S4G_CUDA(ctx, cub::DeviceScan::ExclusiveSum(d_tmp, tmp, d_lens, d_goff, (int)(n_pairs + 1), st));
+        ctx->launches += 1;
+    }
+    s4g_db tdb;
+    tdb.ctx = ctx; tdb.n = n_pairs; tdb.id_base = 0; tdb.max_len = db->max_len; tdb.d_off = d_goff;
+    tdb.h_off.resize(n_pairs + 1);
+    S4G_CUDA(ctx, cudaMemcpyAsync(tdb.h_off.data(), d_goff, sizeof(int64_t) * (n_pairs + 1), cudaMemcpyDeviceToHost, st));
+    S4G_CUDA(ctx, cudaStreamSynchronize(st));
+    if (where == S4G_DEVICE && tdb.h_off[n_pairs] < 0) return S4G_ERR_ARG;
+    tdb.residues = (uint64_t)tdb.h_off[n_pairs];
+    uint8_t* d_gcodes = (uint8_t*)s4g_scratch(ctx, SLOT_AL_GATHER, tdb.residues + S4G_DB_TAIL_PAD);
+    if (!d_gcodes) return S4G_ERR_NOMEM;
+    tdb.d_codes = d_gcodes;
+    al_gather_codes_kernel<<<(unsigned)((n_pairs + 7) / 8), 256, 0, st>>>(d_pt, n_pairs, db->d_codes, db->d_off, db->id_base, d_goff, d_gcodes, d_iota);
+    S4G_CHECK_LAUNCH(ctx);
+    S4G_CUDA(ctx, cudaMemsetAsync(d_gcodes + tdb.residues, S4G_PAD_CODE, S4G_DB_TAIL_PAD, st));
+    std::vector<uint32_t> h_iota;
+    const uint32_t* t_arg = d_iota;
+    if (where == S4G_HOST) { h_iota.resize(n_pairs); for (int64_t i = 0; i < n_pairs; ++i) h_iota[i] = (uint32_t)i; t_arg = h_iota.data(); }
+    const int rc = sw_align_impl(ctx, &tdb, q, n_pairs, pair_q, t_arg, pair_score, matrix, gap_open, gap_extend, out_coords, out_paths, path_capacity, out_path_offsets, where);
+    tdb.d_codes = nullptr; tdb.d_off = nullptr;           // scratch of the context, not the temporary's
+    return rc;
+}
+
+static int sw_align_impl(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_pairs, const uint32_t* pair_q,
+                         const uint32_t* pair_t, const int32_t* pair_score, const int32_t* matrix, int gap_open,
+                         int gap_extend, int32_t* out_coords, uint8_t* out_paths, int64_t path_capacity,
+                         int64_t* out_path_offsets, int where) {
     if (!ctx || !db || !q || n_pairs < 0 || !matrix || !out_path_offsets) return S4G_ERR_ARG;
     if (n_pairs > 0 && (!pair_q || !pair_t || !pair_score || !out_coords || !out_paths)) return S4G_ERR_ARG;
     if (n_pairs >= ((int64_t)1 << 31)) { s4g_set_error(ctx, "s4g_sw_align: %lld hits in one call (limit 2^31 - 1); split the batch", (long long)n_pairs); return S4G_ERR_CAPACITY; }

@@ -109,7 +109,7 @@ enum {
     SLOT_PF_COUNT, SLOT_PF_THR, SLOT_PF_CUB, SLOT_PF_TMP, SLOT_PF_TMP2, SLOT_PF_SPILL, SLOT_PF_GBUF, SLOT_SW_STRIP,
     SLOT_AL_WORK, SLOT_AL_DIR, SLOT_AL_MISC, SLOT_AL_OUT, SLOT_PF_ENTRY,
     SLOT_SR_ROWS, SLOT_SR_CNT, SLOT_SR_OFF, SLOT_SR_CAND, SLOT_SR_SCORES, SLOT_SR_SURV,
-    SLOT_SR_AL_COORDS, SLOT_SR_AL_PATHS, SLOT_SR_AL_POFF, SLOT_SR_HITS, SLOT_SR_OUT_COORDS, SLOT_SR_OUT_PATHS, SLOT_SR_OUT_POFF, SLOT_AL_GROUPS,
+    SLOT_SR_AL_COORDS, SLOT_SR_AL_PATHS, SLOT_SR_AL_POFF, SLOT_SR_HITS, SLOT_SR_OUT_COORDS, SLOT_SR_OUT_PATHS, SLOT_SR_OUT_POFF, SLOT_AL_GROUPS, SLOT_AL_GATHER, SLOT_AL_GATHER_IDX,
     SLOT_COUNT
 };
 static_assert(SLOT_COUNT <= s4g_ctx::kSlots, "scratch slot table too small");
