@@ -110,10 +110,11 @@ def load():
     """Load the shared library (raises if it has not been built: no fallback)."""
     global _LIB
     if _LIB is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("S4G_LIB_PATH", LIB_PATH)       # experiments: another build of the same library
+        if not os.path.exists(path):
             raise RuntimeError("sift4g_b200: %s is missing -- run `python -c 'import __graft_entry__ as g; g.build()'` "
-                               "(there is no CPU fallback)" % LIB_PATH)
-        lib = C.CDLL(LIB_PATH)
+                               "(there is no CPU fallback)" % path)
+        lib = C.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)          # AttributeError if the symbol is not exported
             fn.restype = res
