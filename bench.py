@@ -4,10 +4,11 @@
 A step = one pass of the whole hot path (k-mer prefilter -> Smith-Waterman scores -> E-value selection ->
 traceback of kept hits) over one batch of synthetic queries against a synthetic, HBM-resident database of
 BASELINE.json configs[1]'s shape: 1,000 queries (len 100-1,000) vs 10 M sequences / ~3.5 B residues.
-At N GPUs the database is sharded (one resident shard per rank) and the query batch grows with N (1,000 x N queries per
-step): every GPU then scans 1/N of the database for N times the queries and scores/aligns 1/N of every candidate list,
-i.e. per-GPU work is fixed -- "scaling": "weak" (towards configs[2]'s 20,000-query batch).  --scaling strong keeps the
-1,000-query batch and only shards the database.
+At N GPUs (weak scaling, the default: 1,000 queries per GPU and step) the database is STRIPED over the GPUs' HBM -- one
+resident stripe each, all stripes mapped into every GPU's address space (CUDA VMM, peers read over NVLink) -- and every rank
+runs the whole path for its own 1,000 queries against all of it: per-GPU work is exactly the one-GPU step and nothing is
+merged.  --multi-gpu exchange selects the other form (one database shard per rank scanned for all queries, candidate cut-offs
+and hits exchanged over NCCL), which is the default for --scaling strong (the same 1,000-query batch at every N).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
@@ -497,7 +498,20 @@ def main():
         all_lens = db_lengths(n_db)
         all_off = np.zeros(n_db + 1, dtype=np.int64)
         np.cumsum(all_lens, out=all_off[1:])
-        striped = stripes.StripedDatabase(ctx, codes, all_off, lo, hi, dist=dist)
+        try:
+            striped = stripes.StripedDatabase(ctx, codes, all_off, lo, hi, dist=dist)
+            ok = 1
+        except Exception as exc:            # no peer mapping on this box (no NVLink / no VMM export): the exchange form needs neither
+            print("bench: striped database unavailable (%s); falling back to --multi-gpu exchange" % exc, file=sys.stderr)
+            ok = 0
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            if striped is not None:
+                striped.close()
+                striped = None
+            args.multi_gpu = mode = "exchange"
+    if mode == "striped":
         db = striped.db
         del codes
         # this rank's queries: an equal slice of the batch
