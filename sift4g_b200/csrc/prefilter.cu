@@ -133,7 +133,12 @@ __device__ __forceinline__ void step_kmers(const PfParams& P, const uint8_t* seq
     uint32_t lo = 0, hi = 0;
     if (j0 < npos) {
         uint32_t w0, w1, w2;
-        if (kStaged) { w0 = w[0]; w1 = w[1]; w2 = w[2]; }                  // `seq` points into the warp's staging slot (shared memory)
+        if (kStaged) {                                                     // `seq` points into the warp's staging slot: LDS, not generic loads
+            const uint32_t sa = (uint32_t)__cvta_generic_to_shared(w);
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(sa));
+            asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(sa));
+            asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w2) : "r"(sa));
+        }
         else { w0 = __ldg(w); w1 = __ldg(w + 1); w2 = __ldg(w + 2); }
         lo = __funnelshift_r(w0, w1, sh);
         hi = __funnelshift_r(w1, w2, sh);
@@ -358,7 +363,8 @@ __device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cn
                 const uint32_t bytes = (head + (uint32_t)seg_n + 12u + 15u) & ~15u;          // <= kStageSlot; the buffer's tail pad keeps it readable
                 st_desc[slot].a = p_a; st_desc[slot].s = (uint32_t)p_s; st_desc[slot].len = p_len;
                 const uint32_t bar = smem_u32(st_bar + slot);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");               // the slot's last reads are done before the copy lands
+                // (no proxy fence: the slot was only READ through the generic proxy, and those loads have delivered their data --
+                // the k-mers of the segment are computed -- before the warp gets here)
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                              ::"r"(smem_u32(st_slots + slot * kStageSlot)), "l"(src - head), "r"(bytes), "r"(bar) : "memory");
