@@ -535,18 +535,14 @@ def main():
 
         class _Step:
             def step(self):
-                o = capi.search(ctx, db, Q, mat, 5, args.max_candidates, n_threads=host_threads, want_candidates=False, device_results=True)
-                o.n_kept = o.n_hits
-                return o
+                return capi.search(ctx, db, Q, mat, 5, args.max_candidates, n_threads=host_threads, want_candidates=False, device_results=True)
         runner = _Step()
     else:
         pipe = pipeline.DevicePipeline(ctx, db, q_codes, q_off, mat, lens, total_res, max_candidates=args.max_candidates, dist=dist if use_dist else None)
 
         class _Step:
             def step(self):
-                o = pipe.step()
-                o.n_kept = len(o.pair_q)
-                return o
+                return pipe.step()
         runner = _Step()
 
     peak = ctx.dpx_peak(300)                  # sustained VIADDMNMX.S16x2 lane-ops/s on this device
@@ -583,14 +579,14 @@ def main():
     ms = e0.elapsed_time(e1)
     launches = ctx.launch_count()
     sw_kernel_ms = sw_ms[-1]                 # SW score kernel launches of the last step (one per half of the query batch), CUDA events inside the library
-    t = torch.tensor([ms, float(cells_local), float(sw_kernel_ms), float(r.n_pairs), float(r.n_kept)], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, float(cells_local), float(sw_kernel_ms), float(r.n_pairs), float(len(r.pair_q))], dtype=torch.float64, device=dev)
     if use_dist:
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         ms, cells, sw_kernel_ms_max = float(tmax[0]), float(tsum[1]), float(tmax[2])
         pairs, hits = float(tsum[3]), float(tsum[4])
     else:
-        cells, sw_kernel_ms_max, pairs, hits = float(cells_local), float(sw_kernel_ms), float(r.n_pairs), float(r.n_kept)
+        cells, sw_kernel_ms_max, pairs, hits = float(cells_local), float(sw_kernel_ms), float(r.n_pairs), float(len(r.pair_q))
     ms_per_step = ms / args.steps
     gcups = cells / (ms_per_step * 1e-3) / 1e9
     # traceback phases of the last timed step on this rank (CUDA events inside the library) against the same DPX roofline
