@@ -26,6 +26,7 @@
 // Work decomposition: candidates of each query are sorted by length (device radix sort) and paired
 // neighbour-wise; a persistent grid of CTAs pulls (query, block of pairs) tiles from an atomic counter,
 // builds the query profile once per tile and lets its warps pull pairs from the tile.
+#include <cstring>
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -517,6 +518,9 @@ struct StripSmem {
     unsigned *outH, *outF;            // [128] boundary produced by lane 31
 };
 constexpr int kStripWarpBytes = 4 * kRing * 2 + 2 * kRing * 4 + 4 * kRing * 4;
+// streaming form (stream_stripe): rings of 2 * kRing stream columns for the target offsets (2 x u16), the incoming boundary (H, F),
+// the outgoing boundary (H, F) and its destination (u32), plus the pairs in flight
+constexpr int kStreamStripWarpBytes = 2 * (2 * kRing) * 2 + 5 * (2 * kRing) * 4 + kDescRing * 4;
 
 __device__ __forceinline__ unsigned sweep_stripe(const unsigned* __restrict__ prof_lane, const StripSmem& S, const uint8_t* __restrict__ t1,
                                                  int len1, const uint8_t* __restrict__ t2, int len2, unsigned negQ, unsigned negR,
@@ -598,6 +602,168 @@ __device__ __forceinline__ unsigned sweep_stripe(const unsigned* __restrict__ pr
     return best;
 }
 
+// Streaming form of a stripe sweep: the pairs a warp takes from the tile are laid end to end as one stream of target columns
+// (see stream_pairs_packed), so the 31-step fill/drain of the wavefront is paid once per warp, tile and stripe instead of once
+// per pair and stripe -- the candidates of a titin-like query are ~100-residue targets, where the drain is a quarter of all
+// steps.  Per stream column the rings carry the two profile offsets, the boundary values coming in from the previous stripe
+// (lane 0) and, for what lane 31 produces, the place in the CTA's boundary buffer they go to.
+struct StreamStripSmem {
+    unsigned short *ring1, *ring2;    // [2 kRing]
+    unsigned *inH, *inF;              // [2 kRing]
+    unsigned *outH, *outF, *oaddr;    // [2 kRing]
+    unsigned* desc;                   // [kDescRing] tile-relative pair index of the pairs in flight
+};
+
+__device__ __forceinline__ void stream_stripe(const ScoreParams& P, const unsigned* __restrict__ prof_lane, const StreamStripSmem& S, int* s_next,
+                                              unsigned* s_best, unsigned* cta_bound, int64_t cbeg, int64_t cend, int pb, int pe, unsigned negQ,
+                                              unsigned negR, bool first, bool last, int lane) {
+    constexpr int K = kMaxK, KW = K / 4;
+    constexpr unsigned kRowBytes = KW * 128;
+    constexpr unsigned kPadOff = S4G_PAD_CODE * kRowBytes;
+    constexpr unsigned kFlag = 0x8000u;
+    constexpr int kRingMask = 2 * kRing - 1;
+    constexpr int kOpen = 0x7fffffff;
+    constexpr unsigned kNoAddr = 0xffffffffu;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned strip_cols = (unsigned)P.strip_cols;
+
+    unsigned H[K], E[K];
+#pragma unroll
+    for (int r = 0; r < K; ++r) { H[r] = 0; E[r] = 0; }
+    unsigned best = 0, h_last = 0, f_out = 0, diag_in = 0, b_out = 0;
+    int n31 = 0;
+    const uint8_t *t1 = nullptr, *t2 = nullptr;
+    int len1 = 0, len2 = 0, L = 0, pos = 0, n_pulled = 0, end_col = kOpen, cur_pair = 0;
+    for (int c = lane; c < kRing; c += 32) { S.ring1[kRing + c] = kPadOff; S.ring2[kRing + c] = kPadOff; S.inH[kRing + c] = 0u; S.inF[kRing + c] = 0u; S.oaddr[kRing + c] = kNoAddr; }
+    const char* prof_bytes = reinterpret_cast<const char*>(prof_lane);
+    int flushed = 0;
+    auto flush_out = [&](int upto) {          // boundary values of the stream columns lane 31 has finished -> the pairs' boundary rows
+        if (last) return;
+        for (int c = flushed + lane; c < upto; c += 32) {
+            const unsigned a = S.oaddr[c & kRingMask];
+            if (a != kNoAddr) { cta_bound[a] = S.outH[c & kRingMask]; cta_bound[a + strip_cols] = S.outF[c & kRingMask]; }
+        }
+        if (upto > flushed) flushed = upto;
+    };
+
+    for (int s0 = 0;; s0 += kRing) {
+        flush_out(s0 - 31);
+        __syncwarp();
+        // ---- stage stream columns s0 .. s0+kRing-1
+        int col = s0;
+        while (col < s0 + kRing) {
+            if (pos >= L && end_col == kOpen) {
+                int p = 0;
+                if (lane == 0) p = atomicAdd(s_next, 1);
+                p = __shfl_sync(FULL, p, 0);
+                if (p < pe) {
+                    const int64_t i1 = cbeg + 2 * (int64_t)p, i2 = i1 + 1;
+                    const uint32_t c1 = P.sorted_idx[i1];
+                    const bool has2 = i2 < cend;
+                    const uint32_t c2 = has2 ? P.sorted_idx[i2] : c1;
+                    const uint32_t g1 = P.cand_ids[c1] - P.id_base, g2 = P.cand_ids[c2] - P.id_base;
+                    const int64_t a1 = P.db_off[g1], b1 = P.db_off[g1 + 1];
+                    const int64_t a2 = P.db_off[g2], b2 = P.db_off[g2 + 1];
+                    len1 = (int)(b1 - a1); len2 = has2 ? (int)(b2 - a2) : 0;
+                    if (len1 > P.strip_cols || len2 > P.strip_cols) {       // too long for the boundary buffer: 32-bit kernel
+                        if (lane == 0) s_best[p - pb] = 0x7fff7fffu;
+                        pos = 0; L = 0;
+                        continue;
+                    }
+                    t1 = P.db_codes + a1; t2 = P.db_codes + a2;
+                    L = len1 > len2 ? len1 : len2;
+                    if (L < kMinCols) L = kMinCols;
+                    pos = 0;
+                    cur_pair = p - pb;
+                    if (lane == 0) S.desc[n_pulled & (kDescRing - 1)] = (unsigned)cur_pair;
+                    ++n_pulled;
+                } else {
+                    end_col = col;
+                }
+            }
+            if (end_col != kOpen) {
+                for (int c = col + lane; c < s0 + kRing; c += 32) {
+                    S.ring1[c & kRingMask] = (unsigned short)(c == end_col ? (kPadOff | kFlag) : kPadOff);
+                    S.ring2[c & kRingMask] = (unsigned short)kPadOff;
+                    S.inH[c & kRingMask] = 0u; S.inF[c & kRingMask] = 0u; S.oaddr[c & kRingMask] = kNoAddr;
+                }
+                break;
+            }
+            const int n = min(L - pos, s0 + kRing - col);
+            const unsigned row = (unsigned)cur_pair * 2u * strip_cols;
+            const int maxlen = len1 > len2 ? len1 : len2;
+            for (int i = lane; i < n; i += 32) {
+                const int j = pos + i;
+                unsigned o1 = j < len1 ? (unsigned)t1[j] * kRowBytes : kPadOff;
+                const unsigned o2 = j < len2 ? (unsigned)t2[j] * kRowBytes : kPadOff;
+                if (j == 0) o1 |= kFlag;
+                const int x = (col + i) & kRingMask;
+                S.ring1[x] = (unsigned short)o1;
+                S.ring2[x] = (unsigned short)o2;
+                const bool real = j < maxlen;
+                S.inH[x] = (!first && real) ? cta_bound[row + j] : 0u;
+                S.inF[x] = (!first && real) ? cta_bound[row + strip_cols + j] : 0u;
+                S.oaddr[x] = real ? row + (unsigned)j : kNoAddr;
+            }
+            col += n; pos += n;
+        }
+        if (n_pulled == 0) return;
+        __syncwarp();
+        const int send = end_col == kOpen ? kRing : min(kRing, end_col + 32 - s0);
+#pragma unroll 1
+        for (int ss = 0; ss < send; ++ss) {
+            const int j = (s0 + ss - lane) & kRingMask;
+            int o1 = (short)S.ring1[j];
+            const unsigned o2 = S.ring2[j];
+            unsigned h_up = __shfl_up_sync(FULL, h_last, 1);
+            unsigned f = __shfl_up_sync(FULL, f_out, 1);
+            unsigned b_in = __shfl_up_sync(FULL, b_out, 1);
+            if (lane == 0) { h_up = S.inH[j]; f = S.inF[j]; b_in = 0; }
+            if (o1 < 0) {                                            // first column of a pair (or the sentinel)
+                o1 &= 0x7fff;
+                b_out = __vmaxs2(best, b_in);
+                if (lane == 31) {
+                    if (n31 > 0) { const unsigned d = S.desc[(n31 - 1) & (kDescRing - 1)]; s_best[d] = __vmaxs2(s_best[d], b_out); }
+                    ++n31;
+                }
+                best = 0; diag_in = 0;
+#pragma unroll
+                for (int r = 0; r < K; ++r) { H[r] = 0; E[r] = 0; }
+            }
+            unsigned w1[KW], w2[KW];
+#pragma unroll
+            for (int m = 0; m < KW; ++m) {
+                w1[m] = *reinterpret_cast<const unsigned*>(prof_bytes + o1 + m * 128);
+                w2[m] = *reinterpret_cast<const unsigned*>(prof_bytes + o2 + m * 128);
+            }
+            unsigned t = __vadd2(diag_in, prmt(w1[0], w2[0], 0xC480u)), t_prev = 0;
+            diag_in = h_up;
+#pragma unroll
+            for (int r = 0; r < K; ++r) {                            // cell update: see score_pair_packed
+                unsigned t_next = 0;
+                if (r + 1 < K) {
+                    const unsigned sel = ((r + 1) & 3) == 0 ? 0xC480u : ((r + 1) & 3) == 1 ? 0xD591u : ((r + 1) & 3) == 2 ? 0xE6A2u : 0xF7B3u;
+                    t_next = __vadd2(H[r], prmt(w1[(r + 1) >> 2], w2[(r + 1) >> 2], sel));
+                }
+                const unsigned h = __vimax3_s16x2_relu(t, E[r], f);
+                H[r] = h;
+                const unsigned hq = __vadd2(h, negQ);
+                E[r] = __viaddmax_s16x2(E[r], negR, hq);
+                f = __viaddmax_s16x2(f, negR, hq);
+                if (r & 1) best = __vimax3_s16x2(best, t_prev, t);
+                t_prev = t;
+                t = t_next;
+            }
+            h_last = H[K - 1];
+            f_out = f;
+            if (lane == 31 && !last) { S.outH[j] = h_last; S.outF[j] = f_out; }
+        }
+        __syncwarp();
+        if (end_col != kOpen && s0 + kRing >= end_col + 32) { flush_out(end_col); break; }
+    }
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(kWarps * 32, 2) sw_score_striped_kernel(ScoreParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned* prof = reinterpret_cast<unsigned*>(smem);
@@ -659,6 +825,72 @@ __global__ void __launch_bounds__(kWarps * 32, 2) sw_score_striped_kernel(ScoreP
                                                    pass == 0, pass == npass - 1, lane);
                 if (lane == 0) s_best[p - pb] = __vmaxs2(s_best[p - pb], best);
             }
+        }
+        __syncthreads();
+        for (int p = pb + threadIdx.x; p < pe; p += blockDim.x) {
+            const int64_t i1 = cbeg + 2 * (int64_t)p, i2 = i1 + 1;
+            const uint32_t c1 = P.sorted_idx[i1];
+            const unsigned best = s_best[p - pb];
+            const int s1 = (int)(best & 0xffffu), s2 = (int)(best >> 16);
+            if (s1 > P.ovf_limit) P.overflow[atomicAdd(&P.counters[1], 1ull)] = c1; else P.out[c1] = s1;
+            if (i2 < cend) {
+                const uint32_t c2 = P.sorted_idx[i2];
+                if (s2 > P.ovf_limit) P.overflow[atomicAdd(&P.counters[1], 1ull)] = c2; else P.out[c2] = s2;
+            }
+        }
+    }
+}
+
+// striped kernel, streaming form (the default; S4G_STRIPED=pairs selects the pair-by-pair kernel above)
+__global__ void __launch_bounds__(kWarps * 32, 2) sw_score_striped_stream_kernel(ScoreParams P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned* prof = reinterpret_cast<unsigned*>(smem);
+    int8_t* smat = reinterpret_cast<int8_t*>(smem + (S4G_PAD_CODE + 1) * 8 * 32 * 4);
+    unsigned char* wbase = reinterpret_cast<unsigned char*>(smat + (S4G_PAD_CODE + 1) * 32);
+    __shared__ long long s_tile;
+    __shared__ int s_next;
+    __shared__ unsigned s_best[kTilePairs];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    StreamStripSmem S;
+    {
+        unsigned char* wb = wbase + warp * kStreamStripWarpBytes;
+        S.ring1 = reinterpret_cast<unsigned short*>(wb);
+        S.ring2 = S.ring1 + 2 * kRing;
+        S.inH = reinterpret_cast<unsigned*>(S.ring2 + 2 * kRing);
+        S.inF = S.inH + 2 * kRing;
+        S.outH = S.inF + 2 * kRing;
+        S.outF = S.outH + 2 * kRing;
+        S.oaddr = S.outF + 2 * kRing;
+        S.desc = S.oaddr + 2 * kRing;
+    }
+    for (int i = threadIdx.x; i < (S4G_PAD_CODE + 1) * 32; i += blockDim.x) smat[i] = P.mat8[i];
+    const long long total = P.long_tile_start[P.nq];
+    const unsigned negQ = ((unsigned)(-P.gap_open) & 0xffffu) * 0x10001u;
+    const unsigned negR = ((unsigned)(-P.gap_extend) & 0xffffu) * 0x10001u;
+    unsigned* cta_bound = P.strip_bound + (size_t)blockIdx.x * kTilePairs * 2 * P.strip_cols;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = (long long)atomicAdd(&P.counters[4], 1ull);
+        __syncthreads();
+        const long long tile = s_tile;
+        if (tile >= total) break;
+        int lo = 0, hi = P.nq;
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (P.long_tile_start[mid] <= tile) lo = mid; else hi = mid; }
+        const int q = lo;
+        const int64_t qo = P.q_off[q];
+        const int qlen = (int)(P.q_off[q + 1] - qo);
+        const int64_t cbeg = P.cand_off[q], cend = P.cand_off[q + 1];
+        const int n_pairs = (int)((cend - cbeg + 1) >> 1);
+        const int pb = (int)(tile - P.long_tile_start[q]) * kTilePairs;
+        const int pe = pb + kTilePairs < n_pairs ? pb + kTilePairs : n_pairs;
+        const int npass = (qlen + 32 * kMaxK - 1) / (32 * kMaxK);
+        for (int i = threadIdx.x; i < kTilePairs; i += blockDim.x) s_best[i] = 0;
+        for (int pass = 0; pass < npass; ++pass) {
+            __syncthreads();
+            build_profile<kMaxK>(prof, smat, P.q_codes + qo + (int64_t)pass * 32 * kMaxK, qlen - pass * 32 * kMaxK);
+            if (threadIdx.x == 0) s_next = pb;
+            __syncthreads();
+            stream_stripe(P, prof + lane, S, &s_next, s_best, cta_bound, cbeg, cend, pb, pe, negQ, negR, pass == 0, pass == npass - 1, lane);
         }
         __syncthreads();
         for (int p = pb + threadIdx.x; p < pe; p += blockDim.x) {
@@ -906,10 +1138,13 @@ int s4g_sw_score_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, const uint32_t
     }
     // 4. long queries: striped kernel (stripes of 1024 rows, boundary rows through a per-CTA buffer)
     if (q->max_len > 32 * kMaxK) {
-        const size_t smem = (S4G_PAD_CODE + 1) * 8 * 32 * 4 + (S4G_PAD_CODE + 1) * 32 + kWarps * kStripWarpBytes;
-        S4G_CUDA(ctx, cudaFuncSetAttribute(sw_score_striped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const char* sv = getenv("S4G_STRIPED");
+        const bool stream = !(sv && strcmp(sv, "pairs") == 0);
+        void (*strip_kernel)(ScoreParams) = stream ? sw_score_striped_stream_kernel : sw_score_striped_kernel;
+        const size_t smem = (S4G_PAD_CODE + 1) * 8 * 32 * 4 + (S4G_PAD_CODE + 1) * 32 + kWarps * (stream ? kStreamStripWarpBytes : kStripWarpBytes);
+        S4G_CUDA(ctx, cudaFuncSetAttribute(strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
-        S4G_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw_score_striped_kernel, kWarps * 32, smem));
+        S4G_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, strip_kernel, kWarps * 32, smem));
         if (per_sm < 1) per_sm = 1;
         const int grid = ctx->sm_count * per_sm;
         // boundary rows sized for the longest sequence of the shard (a titin-like query meets titin-like targets), within 16 GiB
@@ -920,7 +1155,7 @@ int s4g_sw_score_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, const uint32_t
         P.strip_cols = (int32_t)strip_cols;
         if (!d_strip) return S4G_ERR_NOMEM;
         P.strip_bound = d_strip;
-        sw_score_striped_kernel<<<grid, kWarps * 32, smem, st>>>(P);
+        strip_kernel<<<grid, kWarps * 32, smem, st>>>(P);
         S4G_CHECK_LAUNCH(ctx);
     }
     S4G_CUDA(ctx, cudaEventRecord(ctx->ev_sw1, st));      // s4g_last_sw_kernel_ms: packed + striped kernels
