@@ -221,6 +221,7 @@ __global__ void __launch_bounds__(kSwWarps * 32) al_sweep32_kernel(AlParams P, i
         if (mode == 1) {
             const bool swa = takes_swalign(P, score);
             if (qlen <= long_rows && !swa) continue;
+            if (!swa && P.coords[4 * w + 1] >= 0) continue;      // settled by the striped end-cell sweep (sw_score.cu)
             if (swa) {
                 // swAlign's end cell: the first cell in query-major order that reaches the maximum (cpu_module.c:1320-1325)
                 // = the SSW rule on the transposed problem (rows = target, columns = query)

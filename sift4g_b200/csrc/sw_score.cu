@@ -908,6 +908,214 @@ __global__ void __launch_bounds__(kWarps * 32, 2) sw_score_striped_stream_kernel
 }
 
 // ------------------------------------------------------------------------------------------------------
+// End cells of the kept hits of LONG queries (stage 3, step 1): the striped sweep with the end-cell rule of
+// score_pair_packed<K, true>.  SSW's end cell is the first column, then the first row in it, whose H equals the score
+// (ssw.c:283-308,491-512).  Stripes are swept top down; a stripe that finds the score in column c leaves only the columns
+// before c to the stripes below it (a cell further down in the same column has a larger row), so the column range -- and the
+// boundary rows handed on -- shrink from stripe to stripe.  Two hits of a query per warp, 16-bit; hits under the swAlign rules
+// (score > 32767) are left to al_sweep32_kernel.
+__device__ __forceinline__ void track_stripe(const unsigned* __restrict__ prof_lane, const StripSmem& S, const uint8_t* __restrict__ t1, int len1,
+                                             const uint8_t* __restrict__ t2, int len2, unsigned score2, int rows_valid, unsigned negQ, unsigned negR,
+                                             unsigned* bH, unsigned* bF, bool first, bool last, int lane, unsigned* found1, unsigned* found2) {
+    constexpr int K = kMaxK, KW = K / 4;
+    constexpr unsigned kRowBytes = KW * 128;
+    constexpr unsigned kPadOff = S4G_PAD_CODE * kRowBytes;
+    constexpr int kRingMask = 2 * kRing - 1;
+    const unsigned FULL = 0xffffffffu;
+    unsigned H[K], E[K];
+#pragma unroll
+    for (int r = 0; r < K; ++r) { H[r] = 0; E[r] = 0; }
+    unsigned best = 0, h_last = 0, f_out = 0, diag_in = 0;
+    unsigned fnd1 = kNotFound, fnd2 = kNotFound;
+    const int maxlen = len1 > len2 ? len1 : len2;
+    const int nsteps = maxlen + 31;
+    for (int c = lane; c < kRing; c += 32) { S.ring1[kRing + c] = kPadOff; S.ring2[kRing + c] = kPadOff; }
+    const char* prof_bytes = reinterpret_cast<const char*>(prof_lane);
+    int flushed = 0, done_cols = 0;
+    for (int s0 = 0; s0 < nsteps; s0 += kRing) {
+        if (!last) {
+            const int upto = min(maxlen, s0 - 31);
+            for (int c = flushed + lane; c < upto; c += 32) { bH[c] = S.outH[c & kRingMask]; bF[c] = S.outF[c & kRingMask]; }
+            if (upto > flushed) flushed = upto;
+        }
+        if (s0 > 0) {
+            unsigned m1 = fnd1, m2 = fnd2;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { m1 = min(m1, __shfl_xor_sync(FULL, m1, o)); m2 = min(m2, __shfl_xor_sync(FULL, m2, o)); }
+            const bool d1 = (m1 != kNotFound && (int)(m1 >> 10) + 32 <= s0) || len1 + 31 <= s0;
+            const bool d2 = (m2 != kNotFound && (int)(m2 >> 10) + 32 <= s0) || len2 + 31 <= s0;
+            if (d1 && d2) break;
+        }
+        {
+            const int base = s0 & kRingMask;
+#pragma unroll
+            for (int c = 0; c < kRing; c += 32) {
+                const int j = s0 + c + lane;
+                S.ring1[base + c + lane] = (unsigned short)(j < len1 ? (unsigned)t1[j] * kRowBytes : kPadOff);
+                S.ring2[base + c + lane] = (unsigned short)(j < len2 ? (unsigned)t2[j] * kRowBytes : kPadOff);
+                if (!first) { S.inH[c + lane] = j < maxlen ? bH[j] : 0u; S.inF[c + lane] = j < maxlen ? bF[j] : 0u; }
+            }
+        }
+        __syncwarp();
+        const int send = (nsteps - s0) < kRing ? (nsteps - s0) : kRing;
+#pragma unroll 1
+        for (int ss = 0; ss < send; ++ss) {
+            const int j = s0 + ss - lane;
+            const unsigned o1 = S.ring1[j & kRingMask];
+            const unsigned o2 = S.ring2[j & kRingMask];
+            unsigned w1[KW], w2[KW];
+#pragma unroll
+            for (int m = 0; m < KW; ++m) {
+                w1[m] = *reinterpret_cast<const unsigned*>(prof_bytes + o1 + m * 128);
+                w2[m] = *reinterpret_cast<const unsigned*>(prof_bytes + o2 + m * 128);
+            }
+            unsigned h_up = __shfl_up_sync(FULL, h_last, 1);
+            unsigned f = __shfl_up_sync(FULL, f_out, 1);
+            if (lane == 0) { h_up = first ? 0u : S.inH[ss]; f = first ? 0u : S.inF[ss]; }
+            unsigned t = __vadd2(diag_in, prmt(w1[0], w2[0], 0xC480u)), t_prev = 0;
+            diag_in = h_up;
+            best = 0;
+#pragma unroll
+            for (int r = 0; r < K; ++r) {
+                unsigned t_next = 0;
+                if (r + 1 < K) {
+                    const unsigned sel = ((r + 1) & 3) == 0 ? 0xC480u : ((r + 1) & 3) == 1 ? 0xD591u : ((r + 1) & 3) == 2 ? 0xE6A2u : 0xF7B3u;
+                    t_next = __vadd2(H[r], prmt(w1[(r + 1) >> 2], w2[(r + 1) >> 2], sel));
+                }
+                const unsigned h = __vimax3_s16x2_relu(t, E[r], f);
+                H[r] = h;
+                const unsigned hq = __vadd2(h, negQ);
+                E[r] = __viaddmax_s16x2(E[r], negR, hq);
+                f = __viaddmax_s16x2(f, negR, hq);
+                if (r & 1) best = __vimax3_s16x2(best, t_prev, t);
+                t_prev = t;
+                t = t_next;
+            }
+            h_last = H[K - 1];
+            f_out = f;
+            if (lane == 31 && !last && j >= 0 && j < maxlen) { S.outH[j & kRingMask] = h_last; S.outF[j & kRingMask] = f_out; }
+            // the score is reached by a diagonal step (also across a stripe boundary: row 0 forms Hdiag + S from the boundary row), so
+            // the column maximum of Hdiag + S gates the search for the row
+            const unsigned eq = __vcmpeq2(best, score2);
+            if (eq && j >= 0) {
+                if ((eq & 0xffffu) && j < len1) {
+                    int rr = -1;
+#pragma unroll
+                    for (int r = K - 1; r >= 0; --r) if ((H[r] & 0xffffu) == (score2 & 0xffffu) && lane * K + r < rows_valid) rr = r;
+                    if (rr >= 0) fnd1 = min(fnd1, ((unsigned)j << 10) | (unsigned)(lane * K + rr));
+                }
+                if ((eq >> 16) && j < len2) {
+                    int rr = -1;
+#pragma unroll
+                    for (int r = K - 1; r >= 0; --r) if ((H[r] >> 16) == (score2 >> 16) && lane * K + r < rows_valid) rr = r;
+                    if (rr >= 0) fnd2 = min(fnd2, ((unsigned)j << 10) | (unsigned)(lane * K + rr));
+                }
+            }
+        }
+        done_cols = s0 + send - 31;
+        __syncwarp();
+    }
+    if (!last) { const int upto = min(maxlen, done_cols); for (int c = flushed + lane; c < upto; c += 32) { bH[c] = S.outH[c & kRingMask]; bF[c] = S.outF[c & kRingMask]; } }
+    __syncwarp();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { fnd1 = min(fnd1, __shfl_xor_sync(FULL, fnd1, o)); fnd2 = min(fnd2, __shfl_xor_sync(FULL, fnd2, o)); }
+    *found1 = fnd1; *found2 = fnd2;
+}
+
+__global__ void __launch_bounds__(kWarps * 32, 2) al_forward_striped_kernel(ScoreParams P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned* prof = reinterpret_cast<unsigned*>(smem);
+    int8_t* smat = reinterpret_cast<int8_t*>(smem + (S4G_PAD_CODE + 1) * 8 * 32 * 4);
+    unsigned char* wbase = reinterpret_cast<unsigned char*>(smat + (S4G_PAD_CODE + 1) * 32);
+    __shared__ long long s_tile;
+    __shared__ int s_lim[kTilePairs][2];            // columns of each hit that can still hold the end cell
+    __shared__ int s_col[kTilePairs][2], s_row[kTilePairs][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    StripSmem S;
+    {
+        unsigned char* wb = wbase + warp * kStripWarpBytes;
+        S.ring1 = reinterpret_cast<unsigned short*>(wb);
+        S.ring2 = S.ring1 + 2 * kRing;
+        S.inH = reinterpret_cast<unsigned*>(S.ring2 + 2 * kRing);
+        S.inF = S.inH + kRing;
+        S.outH = S.inF + kRing;
+        S.outF = S.outH + 2 * kRing;
+    }
+    for (int i = threadIdx.x; i < (S4G_PAD_CODE + 1) * 32; i += blockDim.x) smat[i] = P.mat8[i];
+    const long long total = P.long_tile_start[P.nq];
+    const unsigned negQ = ((unsigned)(-P.gap_open) & 0xffffu) * 0x10001u;
+    const unsigned negR = ((unsigned)(-P.gap_extend) & 0xffffu) * 0x10001u;
+    unsigned* cta_bound = P.strip_bound + (size_t)blockIdx.x * kTilePairs * 2 * P.strip_cols;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = (long long)atomicAdd(&P.counters[4], 1ull);
+        __syncthreads();
+        const long long tile = s_tile;
+        if (tile >= total) break;
+        int lo = 0, hi = P.nq;
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (P.long_tile_start[mid] <= tile) lo = mid; else hi = mid; }
+        const int q = lo;
+        const int64_t qo = P.q_off[q];
+        const int qlen = (int)(P.q_off[q + 1] - qo);
+        const int64_t cbeg = P.cand_off[q], cend = P.cand_off[q + 1];
+        const int n_pairs = (int)((cend - cbeg + 1) >> 1);
+        const int pb = (int)(tile - P.long_tile_start[q]) * kTilePairs;
+        const int pe = pb + kTilePairs < n_pairs ? pb + kTilePairs : n_pairs;
+        const int npass = (qlen + 32 * kMaxK - 1) / (32 * kMaxK);
+        for (int x = threadIdx.x; x < 2 * (pe - pb); x += blockDim.x) {
+            const int p = pb + (x >> 1), h = x & 1;
+            const int64_t i = cbeg + 2 * (int64_t)p + h;
+            int lim = 0;
+            if (i < cend) {
+                const uint32_t c = P.sorted_idx[i];
+                const uint32_t g = P.cand_ids[c] - P.id_base;
+                const int len = (int)(P.db_off[g + 1] - P.db_off[g]);
+                const int sc = P.pair_score[c];
+                if (sc > 0 && sc <= 32767 && len <= P.strip_cols) lim = len;          // others: al_sweep32_kernel
+            }
+            s_lim[x >> 1][h] = lim; s_col[x >> 1][h] = -1; s_row[x >> 1][h] = -1;
+        }
+        for (int pass = 0; pass < npass; ++pass) {
+            __syncthreads();
+            build_profile<kMaxK>(prof, smat, P.q_codes + qo + (int64_t)pass * 32 * kMaxK, qlen - pass * 32 * kMaxK);
+            __syncthreads();
+            for (int p = pb + warp; p < pe; p += kWarps) {
+                const int l1 = s_lim[p - pb][0], l2 = s_lim[p - pb][1];
+                if (l1 == 0 && l2 == 0) continue;
+                const int64_t i1 = cbeg + 2 * (int64_t)p, i2 = i1 + 1;
+                const uint32_t c1 = P.sorted_idx[i1];
+                const uint32_t c2 = i2 < cend ? P.sorted_idx[i2] : c1;
+                const int64_t a1 = P.db_off[P.cand_ids[c1] - P.id_base], a2 = P.db_off[P.cand_ids[c2] - P.id_base];
+                const unsigned sc2 = (l1 > 0 ? ((unsigned)P.pair_score[c1] & 0xffffu) : 0x7fffu) | ((l2 > 0 ? (unsigned)P.pair_score[c2] : 0x7fffu) << 16);
+                unsigned* bH = cta_bound + (size_t)(p - pb) * 2 * P.strip_cols;
+                unsigned f1, f2;
+                track_stripe(prof + lane, S, P.db_codes + a1, l1, P.db_codes + a2, l2, sc2, min(32 * kMaxK, qlen - pass * 32 * kMaxK), negQ, negR, bH,
+                             bH + P.strip_cols, pass == 0, pass == npass - 1, lane, &f1, &f2);
+                if (lane == 0) {
+                    if (f1 != kNotFound) { s_col[p - pb][0] = (int)(f1 >> 10); s_row[p - pb][0] = pass * 32 * kMaxK + (int)(f1 & 1023u); s_lim[p - pb][0] = (int)(f1 >> 10); }
+                    if (f2 != kNotFound) { s_col[p - pb][1] = (int)(f2 >> 10); s_row[p - pb][1] = pass * 32 * kMaxK + (int)(f2 & 1023u); s_lim[p - pb][1] = (int)(f2 >> 10); }
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        for (int x = threadIdx.x; x < 2 * (pe - pb); x += blockDim.x) {
+            const int p = pb + (x >> 1), h = x & 1;
+            const int64_t i = cbeg + 2 * (int64_t)p + h;
+            if (i >= cend) continue;
+            const uint32_t c = P.sorted_idx[i];
+            const uint32_t g = P.cand_ids[c] - P.id_base;
+            const int len = (int)(P.db_off[g + 1] - P.db_off[g]);
+            const int sc = P.pair_score[c];
+            if (!(sc > 0 && sc <= 32767 && len <= P.strip_cols)) continue;
+            if (s_col[x >> 1][h] < 0) { atomicOr(&P.counters[3], 1ull); continue; }
+            P.out[4 * (int64_t)c + 1] = s_row[x >> 1][h];
+            P.out[4 * (int64_t)c + 3] = s_col[x >> 1][h];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // exact 32-bit kernel: one warp per (query, target), any query length (256-row passes, the boundary row
 // H/F travels through a per-warp global scratch that stays in L2).  Used for 16-bit overflow re-runs and
 // for queries longer than 32*kMaxK rows.
@@ -1227,6 +1435,31 @@ int s4g_sw_forward_ends_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t
     if (per_sm < 1) per_sm = 1;
     al_forward_packed_kernel<<<ctx->sm_count * per_sm, kWarps * 32, smem, st>>>(P);
     S4G_CHECK_LAUNCH(ctx);
+    // long queries: striped end-cell sweep (S4G_ENDS=sweep32 leaves them to align.cu's 32-bit kernel)
+    const char* ev = getenv("S4G_ENDS");
+    if (q->max_len > 32 * kMaxK && !(ev && strcmp(ev, "sweep32") == 0)) {
+        int64_t* d_long_start = d_tiles + 3 * (nq + 1);
+        size_t tmp_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_long_cnt, d_long_start, nq + 1, st);
+        void* d_tmp = s4g_scratch(ctx, SLOT_SW_CUB, tmp_bytes);
+        if (!d_tmp) return S4G_ERR_NOMEM;
+        S4G_CUDA(ctx, cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_long_cnt, d_long_start, nq + 1, st));
+        ctx->launches += 1;
+        const size_t ssmem = (S4G_PAD_CODE + 1) * 8 * 32 * 4 + (S4G_PAD_CODE + 1) * 32 + kWarps * kStripWarpBytes;
+        S4G_CUDA(ctx, cudaFuncSetAttribute(al_forward_striped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
+        int sper = 0;
+        S4G_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sper, al_forward_striped_kernel, kWarps * 32, ssmem));
+        if (sper < 1) sper = 1;
+        const int grid = ctx->sm_count * sper;
+        const size_t per_col = sizeof(unsigned) * (size_t)grid * kTilePairs * 2;
+        int64_t strip_cols = std::max<int64_t>(kStripColsMin, ((int64_t)db->max_len + 63) / 64 * 64);
+        strip_cols = std::min<int64_t>(strip_cols, (int64_t)(((size_t)16 << 30) / per_col) / 64 * 64);
+        unsigned* d_strip = (unsigned*)s4g_scratch(ctx, SLOT_SW_STRIP, per_col * (size_t)strip_cols);
+        if (!d_strip) return S4G_ERR_NOMEM;
+        P.long_tile_start = d_long_start; P.strip_bound = d_strip; P.strip_cols = (int32_t)strip_cols;
+        al_forward_striped_kernel<<<grid, kWarps * 32, ssmem, st>>>(P);
+        S4G_CHECK_LAUNCH(ctx);
+    }
     // fold the error flag into the caller's flag word
     S4G_CUDA(ctx, cudaMemcpyAsync(d_flags, d_counters + 3, 8, cudaMemcpyDeviceToDevice, st));
     return S4G_OK;
