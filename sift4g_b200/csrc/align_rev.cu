@@ -24,7 +24,7 @@
 namespace {
 
 constexpr int kWarps = 8;
-constexpr int kRing = 64;
+constexpr int kRing = 32;                         // columns per refill = granularity of the early stop (the wavefront needs 2 x 32 ring entries)
 constexpr int kTileHits = 128;
 constexpr unsigned kNotFound = 0xffffffffu;
 constexpr int kBlocks = 33;                       // 32 lanes + one all-pad block for lanes shifted beyond the query start
