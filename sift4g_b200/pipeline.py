@@ -147,7 +147,13 @@ class DevicePipeline:
         # one half running beside the GPU work of the other.  Two launches per stage cost ~10 ms of GPU time at configs[1]
         # (tails, per-call sorts; 133.3 vs 136.5 ms per step on one GPU), so halves only pay where the ranks of a box leave
         # each other so few host cores that the selection takes longer than that (8 ranks on 16 cores: ~12 ms, 154 -> 151 ms).
-        self.parts = 2 if self.host_threads <= 2 else 1
+        self.parts = int(os.environ.get("S4G_PARTS", "0")) or (2 if self.host_threads <= 2 else 1)
+        if self.world > 1:
+            # the number of halves decides how many hit-merge collectives a rank issues per step: every rank must use the same
+            # one, whatever its own core count or environment says (the smallest wins)
+            t = torch.tensor([self.parts], dtype=torch.int32, device=self.dev if dist.get_backend() == "nccl" else "cpu")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            self.parts = int(t.item())
         ctx.set_stream(torch.cuda.current_stream(self.dev).cuda_stream)
 
     def close(self):
@@ -219,7 +225,7 @@ class DevicePipeline:
         # E-values, a few ms on a few cores) the GPU scores or aligns the other half
         r.n_pairs = n_pairs
         r.cand_ids, r.cand_off, r.scores = cand_ids, cand_off, scores     # device tensors (all candidates)
-        n_parts = int(os.environ.get("S4G_PARTS", "0")) or self.parts
+        n_parts = self.parts
         overlap = n_parts > 1 and nq >= 2 and stages is None and os.environ.get("S4G_NO_OVERLAP", "") in ("", "0")
         mid = nq // 2 if (nq >= 2 and n_parts > 1) else nq
         p_mid = int(cand_off[mid].item()) if 0 < mid < nq else n_pairs
