@@ -230,3 +230,29 @@ def test_packed_database_opens_like_the_fasta(ctx, tmp_path):
     D = ctx.database_from_file(src)          # s4g_db_open on a FASTA falls through to the FASTA reader
     assert D.n_seqs == D.total_seqs > 0
     D.close()
+
+
+def test_one_call_search_without_hits_and_with_lonely_queries(ctx, blosum):
+    """s4g_search edge cases: a batch none of whose queries has a hit (no survivors of the screen: nothing to trace back), and a
+    batch where only one query has homologs (the others contribute empty hit lists)."""
+    rng = np.random.default_rng(77)
+    db = [synth.random_codes(rng, int(l), 0.001) for l in rng.integers(40, 400, size=1500)]
+    queries = [synth.random_codes(rng, int(l), 0.001) for l in (120, 333, 64)]
+    qc, qo = synth.pack(queries); dc, do = synth.pack(db)
+    D = ctx.database(dc, do)
+    out = pipeline.search_host(ctx, D, qc, qo, blosum, max_candidates=100, max_alignments=10)
+    assert out.n_hits == 0 and out.n_pairs == 300 and int(out.hit_off[-1]) == 0 and int(out.path_off[-1]) == 0
+    D.close()
+    # plant homologs of query 1 only
+    db2 = list(db)
+    for i in range(6):
+        db2[100 + 7 * i] = synth.mutate(rng, queries[1], identity=0.8)
+    dc2, do2 = synth.pack(db2)
+    D2 = ctx.database(dc2, do2)
+    out = pipeline.search_host(ctx, D2, qc, qo, blosum, max_candidates=100, max_alignments=10)
+    assert out.n_hits == 6 and list(np.diff(out.hit_off)) == [0, 6, 0]
+    assert sorted(out.pair_t.tolist()) == [100 + 7 * i for i in range(6)]
+    for h in range(6):
+        coords, path = O.align(queries[1], db2[int(out.pair_t[h])], int(out.pair_score[h]), blosum)
+        assert np.array_equal(coords, out.coords[h]) and np.array_equal(path, out.paths[out.path_off[h]:out.path_off[h + 1]])
+    D2.close()
