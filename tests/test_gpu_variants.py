@@ -25,16 +25,18 @@ def test_older_kernel_forms_agree_with_the_current_ones(ctx, blosum):
     rng = np.random.default_rng(5)
     queries, db = synth.make_dataset(91, 40, 60000, q_len=(60, 1000), homologs=(20, 60), rare_fraction=0.003)
     # a few long queries with long, partly very similar homologs (stripes, boundary rows, end rows beyond 1024, score > 32767)
-    for L in (1500, 2600, 5200):
+    for L in (1500, 2600, 9000):
         q = synth.random_codes(rng, L, 0.001)
         queries.append(q)
         for ident in (0.5, 0.8, 0.97):
-            a = int(rng.integers(0, L // 3)); b = int(rng.integers(2 * L // 3, L))
+            a = int(rng.integers(0, L // 10)); b = int(rng.integers(9 * L // 10, L))
             db[int(rng.integers(0, len(db)))] = np.concatenate([synth.random_codes(rng, 40, 0.001), synth.mutate(rng, q[a:b], identity=ident), synth.random_codes(rng, 25, 0.001)])
     qc, qo = synth.pack(queries); dc, do = synth.pack(db)
     D = ctx.database(dc, do)
     want = _run(ctx, D, qc, qo, blosum, 800, 100)
-    assert len(want[1]) > 1500 and (want[3] > 32767).any() and (want[5][:, 1] >= 1024).any()
+    assert len(want[1]) > 800, len(want[1])
+    assert (want[3] > 32767).any(), int(want[3].max())
+    assert (want[5][:, 1] >= 1024).any()
     for name, value in SWITCHES:
         old = os.environ.get(name)
         os.environ[name] = value
