@@ -19,6 +19,7 @@ ap.add_argument("--db-seqs", type=int, default=10_000_000)
 ap.add_argument("--max-candidates", type=int, default=5000)
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--stage", default="all")
+ap.add_argument("--query-shape", default="uniform", choices=["uniform", "human"])
 args = ap.parse_args()
 
 import torch  # noqa: E402
@@ -28,7 +29,7 @@ dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)
 ctx = capi.Context(0)
 mat = np.array(bench.BLOSUM62_A_TO_Z, dtype=np.int32)
-q_codes, q_off = bench.make_queries(args.queries)
+q_codes, q_off = bench.make_queries(args.queries, shape=args.query_shape)
 codes, loc_off, lens, total_res = bench.build_db_device(torch, dev, args.db_seqs, 0, args.db_seqs, q_codes, q_off)
 db = ctx.database(codes, loc_off, id_base=0, where=capi.S4G_DEVICE)
 del codes
