@@ -1246,6 +1246,7 @@ static int prefilter_group(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int 
     void (*scan_kernel)(PfParams, int, int) = nullptr;
     if (stage) scan_kernel = scan_warps > 24 ? pf_scan_kernel<1024, true> : (scan_warps > 16 ? pf_scan_kernel<768, true> : (scan_warps > 8 ? pf_scan_kernel<512, true> : pf_scan_kernel<256, true>));
     else scan_kernel = scan_warps > 24 ? pf_scan_kernel<1024, false> : (scan_warps > 16 ? pf_scan_kernel<768, false> : (scan_warps > 8 ? pf_scan_kernel<512, false> : pf_scan_kernel<256, false>));
+    if (const char* e = getenv("S4G_PF_BUILD")) { if (atoi(e) == 1024) scan_kernel = stage ? pf_scan_kernel<1024, true> : pf_scan_kernel<1024, false>; }   // experiment: 64-register build at any CTA size
     S4G_CUDA(ctx, cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
     const int grid = ctx->sm_count;
     P.gbuf = (unsigned long long*)s4g_scratch(ctx, SLOT_PF_GBUF, sizeof(unsigned long long) * (size_t)grid * scan_warps * kGCap);

@@ -356,6 +356,163 @@ __device__ __forceinline__ void stream_pairs_packed(const ScoreParams& P, const 
     }
 }
 
+// Two columns per step (round 2, the shipped score path): a lane takes the columns 2(step - lane) and 2(step - lane) + 1 of the
+// stream through its K rows in one pass.  Per row the first column's H is a temporary (it is the diagonal input of the next row's
+// second cell), only the second column's H and the E entering the next step are carried over the loop: ptxas no longer parks the
+// new H in a temporary and moves it back (one IMAD.MOV per cell in the one-column loop: it forms Hdiag + S in place in H's register
+// at the top of the step), and shuffles, ring reads and loop control are paid once per two columns.  SASS of the step loop:
+// K = 17: 8.4 issue slots per cell against 10.3, K = 32: 7.7 against 9.1; the ALU pipe (4.5 ops per cell) is the only bound left.
+// Pairs are padded to an even number of columns (boundaries sit on even stream columns: the flag rides the first column).
+constexpr int kDescRing2 = 32;            // pairs in flight: 64 staged columns + 62 columns back to lane 31, 8 columns per pair at least
+
+template <int K>
+__device__ __forceinline__ void stream_pairs_packed2(const ScoreParams& P, const unsigned* __restrict__ prof_lane, unsigned short* ring1,
+                                                     unsigned short* ring2, uint2* desc, int* s_next, int64_t cbeg, int64_t cend,
+                                                     int pair_end, unsigned negQ, unsigned negR, int lane) {
+    constexpr int KW = (K + 3) / 4;
+    constexpr unsigned kRowBytes = KW * 128;
+    constexpr unsigned kPadOff = S4G_PAD_CODE * kRowBytes;
+    constexpr unsigned kFlag = 0x8000u;
+    constexpr int kRingMask = 2 * kRing - 1;
+    constexpr int kSteps = kRing / 2;     // steps per refill
+    constexpr int kOpen = 0x7fffffff;
+    const unsigned FULL = 0xffffffffu;
+    static_assert(kPadOff < kFlag, "profile offsets must leave bit 15 free");
+    static_assert(kMinCols % 2 == 0 && kRing % 2 == 0, "even columns");
+
+    unsigned H[K], E[K];
+#pragma unroll
+    for (int r = 0; r < K; ++r) { H[r] = 0; E[r] = 0; }
+    unsigned best = 0, hA_last = 0, hB_last = 0, fA_out = 0, fB_out = 0, diag_in = 0, b_out = 0;
+    int n31 = 0;                          // boundaries this lane has crossed (used by lane 31)
+
+    // fill state (warp uniform): current pair and the next column of it to be staged
+    const uint8_t *t1 = nullptr, *t2 = nullptr;
+    int len1 = 0, len2 = 0, L = 0, pos = 0, n_pulled = 0, end_col = kOpen;
+
+    for (int c = lane; c < kRing; c += 32) { ring1[kRing + c] = kPadOff; ring2[kRing + c] = kPadOff; }
+    const char* prof_bytes = reinterpret_cast<const char*>(prof_lane);
+    const unsigned* ring1w = reinterpret_cast<const unsigned*>(ring1);
+    const unsigned* ring2w = reinterpret_cast<const unsigned*>(ring2);
+
+    for (int s0 = 0;; s0 += kRing) {
+        // ---- stage stream columns s0 .. s0+kRing-1
+        int col = s0;
+        while (col < s0 + kRing) {
+            if (pos >= L && end_col == kOpen) {
+                int p = 0;
+                if (lane == 0) p = atomicAdd(s_next, 1);
+                p = __shfl_sync(FULL, p, 0);
+                if (p < pair_end) {
+                    const int64_t i1 = cbeg + 2 * (int64_t)p, i2 = i1 + 1;
+                    const uint32_t c1 = P.sorted_idx[i1];
+                    const bool has2 = i2 < cend;
+                    const uint32_t c2 = has2 ? P.sorted_idx[i2] : c1;
+                    const uint32_t g1 = P.cand_ids[c1] - P.id_base, g2 = P.cand_ids[c2] - P.id_base;
+                    const int64_t a1 = P.db_off[g1], b1 = P.db_off[g1 + 1];
+                    const int64_t a2 = P.db_off[g2], b2 = P.db_off[g2 + 1];
+                    t1 = P.db_codes + a1; len1 = (int)(b1 - a1);
+                    t2 = P.db_codes + a2; len2 = has2 ? (int)(b2 - a2) : 0;
+                    L = len1 > len2 ? len1 : len2;
+                    L = (L + 1) & ~1;                                // pad columns change no maximum
+                    if (L < kMinCols) L = kMinCols;
+                    pos = 0;
+                    if (lane == 0) desc[n_pulled & (kDescRing2 - 1)] = make_uint2(c1, has2 ? c2 : kNoTarget);
+                    ++n_pulled;
+                } else {
+                    end_col = col;                                   // the sentinel boundary sits here (an even column)
+                }
+            }
+            if (end_col != kOpen) {
+                for (int c = col + lane; c < s0 + kRing; c += 32) {
+                    ring1[c & kRingMask] = (unsigned short)(c == end_col ? (kPadOff | kFlag) : kPadOff);
+                    ring2[c & kRingMask] = (unsigned short)kPadOff;
+                }
+                break;
+            }
+            const int n = min(L - pos, s0 + kRing - col);
+            for (int i = lane; i < n; i += 32) {
+                const int j = pos + i;
+                unsigned o1 = j < len1 ? (unsigned)t1[j] * kRowBytes : kPadOff;
+                const unsigned o2 = j < len2 ? (unsigned)t2[j] * kRowBytes : kPadOff;
+                if (j == 0) o1 |= kFlag;
+                ring1[(col + i) & kRingMask] = (unsigned short)o1;
+                ring2[(col + i) & kRingMask] = (unsigned short)o2;
+            }
+            col += n; pos += n;
+        }
+        if (n_pulled == 0) return;                                   // the tile was empty for this warp
+        __syncwarp();
+        // lane 31 crosses the sentinel at step end_col / 2 + 31
+        const int S0 = s0 >> 1;
+        const int send = end_col == kOpen ? kSteps : min(kSteps, (end_col >> 1) + 32 - S0);
+#pragma unroll 1
+        for (int ss = 0; ss < send; ++ss) {
+            const int j = (S0 + ss - lane) & (kRing - 1);            // column pair of this lane in the ring of kRing pairs
+            const unsigned p1 = ring1w[j], p2 = ring2w[j];
+            unsigned o1a = p1 & 0xffffu;
+            const unsigned o1b = p1 >> 16, o2a = p2 & 0xffffu, o2b = p2 >> 16;
+            unsigned hA_up = __shfl_up_sync(FULL, hA_last, 1);
+            unsigned hB_up = __shfl_up_sync(FULL, hB_last, 1);
+            unsigned fA = __shfl_up_sync(FULL, fA_out, 1);
+            unsigned fB = __shfl_up_sync(FULL, fB_out, 1);
+            unsigned b_in = __shfl_up_sync(FULL, b_out, 1);
+            if (lane == 0) { hA_up = 0; hB_up = 0; fA = 0; fB = 0; b_in = 0; }
+            if (o1a & kFlag) {                                       // first column of a pair (or the sentinel)
+                o1a &= 0x7fffu;
+                b_out = __vmaxs2(best, b_in);
+                if (lane == 31) {
+                    if (n31 > 0) {
+                        const uint2 d = desc[(n31 - 1) & (kDescRing2 - 1)];
+                        const int s1 = (int)(b_out & 0xffffu), s2 = (int)(b_out >> 16);
+                        if (s1 > P.ovf_limit) P.overflow[atomicAdd(&P.counters[1], 1ull)] = d.x; else P.out[d.x] = s1;
+                        if (d.y != kNoTarget) { if (s2 > P.ovf_limit) P.overflow[atomicAdd(&P.counters[1], 1ull)] = d.y; else P.out[d.y] = s2; }
+                    }
+                    ++n31;
+                }
+                best = 0; diag_in = 0;
+#pragma unroll
+                for (int r = 0; r < K; ++r) { H[r] = 0; E[r] = 0; }
+            }
+            unsigned wa1[KW], wa2[KW], wb1[KW], wb2[KW];
+#pragma unroll
+            for (int m = 0; m < KW; ++m) {
+                wa1[m] = *reinterpret_cast<const unsigned*>(prof_bytes + o1a + m * 128);
+                wa2[m] = *reinterpret_cast<const unsigned*>(prof_bytes + o2a + m * 128);
+                wb1[m] = *reinterpret_cast<const unsigned*>(prof_bytes + o1b + m * 128);
+                wb2[m] = *reinterpret_cast<const unsigned*>(prof_bytes + o2b + m * 128);
+            }
+            // cell A = (row, first column), cell B = (row, second column); recurrences as in score_pair_packed
+            unsigned tA = __vadd2(diag_in, prmt(wa1[0], wa2[0], 0xC480u));       // H(row above, column before A) + S
+            unsigned tB = __vadd2(hA_up, prmt(wb1[0], wb2[0], 0xC480u));         // H(row above, A) + S
+            diag_in = hB_up;
+#pragma unroll
+            for (int r = 0; r < K; ++r) {
+                unsigned tA_next = 0, tB_next = 0;
+                const unsigned sel = ((r + 1) & 3) == 0 ? 0xC480u : ((r + 1) & 3) == 1 ? 0xD591u : ((r + 1) & 3) == 2 ? 0xE6A2u : 0xF7B3u;
+                if (r + 1 < K) tA_next = __vadd2(H[r], prmt(wa1[(r + 1) >> 2], wa2[(r + 1) >> 2], sel));
+                const unsigned hA = __vimax3_s16x2_relu(tA, E[r], fA);
+                const unsigned hqA = __vadd2(hA, negQ);
+                const unsigned eB = __viaddmax_s16x2(E[r], negR, hqA);           // E of column B
+                fA = __viaddmax_s16x2(fA, negR, hqA);
+                if (r + 1 < K) tB_next = __vadd2(hA, prmt(wb1[(r + 1) >> 2], wb2[(r + 1) >> 2], sel));
+                const unsigned hB = __vimax3_s16x2_relu(tB, eB, fB);
+                H[r] = hB;
+                const unsigned hqB = __vadd2(hB, negQ);
+                E[r] = __viaddmax_s16x2(eB, negR, hqB);                          // E of the next step's column A
+                fB = __viaddmax_s16x2(fB, negR, hqB);
+                best = __vimax3_s16x2(best, tA, tB);
+                if (r == K - 1) hA_last = hA;
+                tA = tA_next; tB = tB_next;
+            }
+            hB_last = H[K - 1];
+            fA_out = fA; fB_out = fB;
+        }
+        __syncwarp();
+        if (end_col != kOpen && S0 + kSteps >= (end_col >> 1) + 32) break;
+    }
+}
+
 // Build the int8 profile of one query into shared memory: prof[letter][m][lane] words, byte b of word
 // (m, lane) = S[q[lane*K + 4m + b]][letter]; rows beyond the query read 0; pad letter row reads mat8 row 26.
 template <int K>
@@ -376,7 +533,7 @@ __device__ void build_profile(unsigned* prof, const int8_t* smat, const uint8_t*
     }
 }
 
-template <int K, bool TRACK>
+template <int K, int MODE>
 __device__ void run_tile(const ScoreParams& P, unsigned* prof, const int8_t* smat, unsigned short* rings,
                          int* s_next, int q, int pair_begin, int pair_end) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -390,7 +547,14 @@ __device__ void run_tile(const ScoreParams& P, unsigned* prof, const int8_t* sma
     unsigned short* ring2 = ring1 + 2 * kRing;
     const unsigned negQ = ((unsigned)(-P.gap_open) & 0xffffu) * 0x10001u;
     const unsigned negR = ((unsigned)(-P.gap_extend) & 0xffffu) * 0x10001u;
-    if (!TRACK) {
+    constexpr bool TRACK = MODE == 1;
+    if (MODE == 2) {
+        uint2* desc = reinterpret_cast<uint2*>(rings + kWarps * (4 * kRing)) + warp * kDescRing2;
+        stream_pairs_packed2<K>(P, prof + lane, ring1, ring2, desc, s_next, cbeg, cend, pair_end, negQ, negR, lane);
+        __syncthreads();
+        return;
+    }
+    if (MODE == 0) {
         uint2* desc = reinterpret_cast<uint2*>(rings + kWarps * (4 * kRing)) + warp * kDescRing;
         stream_pairs_packed<K>(P, prof + lane, ring1, ring2, desc, s_next, cbeg, cend, pair_end, negQ, negR, lane);
         __syncthreads();
@@ -436,8 +600,9 @@ __device__ void run_tile(const ScoreParams& P, unsigned* prof, const int8_t* sma
     __syncthreads();
 }
 
-template <bool TRACK>
+template <int MODE>
 __device__ __forceinline__ void packed_kernel_body(const ScoreParams& P) {
+    constexpr bool TRACK = MODE == 1;
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned* prof = reinterpret_cast<unsigned*>(smem);                                   // 27*8*32 words max
     int8_t* smat = reinterpret_cast<int8_t*>(smem + (S4G_PAD_CODE + 1) * 8 * 32 * 4);      // 27*32
@@ -466,45 +631,47 @@ __device__ __forceinline__ void packed_kernel_body(const ScoreParams& P) {
         // the average configs[1] query by 32 rows, 5.8 percent of the cells)
         const int K = (qlen + 31) >> 5;
         switch (K) {
-            case 0: case 1: case 2: run_tile<2, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 3: run_tile<3, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 4: run_tile<4, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 5: run_tile<5, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 6: run_tile<6, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 7: run_tile<7, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 8: run_tile<8, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 9: run_tile<9, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 10: run_tile<10, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 11: run_tile<11, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 12: run_tile<12, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 13: run_tile<13, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 14: run_tile<14, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 15: run_tile<15, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 16: run_tile<16, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 17: run_tile<17, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 18: run_tile<18, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 19: run_tile<19, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 20: run_tile<20, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 21: run_tile<21, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 22: run_tile<22, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 23: run_tile<23, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 24: run_tile<24, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 25: run_tile<25, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 26: run_tile<26, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 27: run_tile<27, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 28: run_tile<28, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 29: run_tile<29, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 30: run_tile<30, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            case 31: run_tile<31, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
-            default: run_tile<32, TRACK>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 0: case 1: case 2: run_tile<2, MODE>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 3: run_tile<3, MODE>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 4: run_tile<4, MODE>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 5: run_tile<5, MODE>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 6: run_tile<6, MODE>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 7: run_tile<7, MODE>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 8: run_tile<8, MODE>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 9: run_tile<9, MODE>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 10: run_tile<10, MODE>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 11: run_tile<11, MODE>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 12: run_tile<12, MODE>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 13: run_tile<13, MODE>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 14: run_tile<14, MODE>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 15: run_tile<15, MODE>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 16: run_tile<16, MODE>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 17: run_tile<17, MODE>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 18: run_tile<18, MODE>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 19: run_tile<19, MODE>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 20: run_tile<20, MODE>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 21: run_tile<21, MODE>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 22: run_tile<22, MODE>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 23: run_tile<23, MODE>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 24: run_tile<24, MODE>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 25: run_tile<25, MODE>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 26: run_tile<26, MODE>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 27: run_tile<27, MODE>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 28: run_tile<28, MODE>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 29: run_tile<29, MODE>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 30: run_tile<30, MODE>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            case 31: run_tile<31, MODE>(P, prof, smat, rings, &s_next, q, pb, pe); break;
+            default: run_tile<32, MODE>(P, prof, smat, rings, &s_next, q, pb, pe); break;
         }
     }
 }
 
-__global__ void __launch_bounds__(kWarps * 32, 2) sw_score_packed_kernel(ScoreParams P) { packed_kernel_body<false>(P); }
+__global__ void __launch_bounds__(kWarps * 32, 2) sw_score_packed_kernel(ScoreParams P) { packed_kernel_body<0>(P); }
+// the same with two stream columns per step (stream_pairs_packed2): the shipped form
+__global__ void __launch_bounds__(kWarps * 32, 2) sw_score_packed2_kernel(ScoreParams P) { packed_kernel_body<2>(P); }
 
 // End cells of the kept hits with the same systolic sweep (stage 3, step 1).
-__global__ void __launch_bounds__(kWarps * 32, 2) al_forward_packed_kernel(ScoreParams P) { packed_kernel_body<true>(P); }
+__global__ void __launch_bounds__(kWarps * 32, 2) al_forward_packed_kernel(ScoreParams P) { packed_kernel_body<1>(P); }
 
 // ------------------------------------------------------------------------------------------------------
 // striped kernel for long queries (intra-sequence): the query is cut into stripes of 32 * kMaxK = 1024 rows; a stripe
@@ -1334,14 +1501,19 @@ int s4g_sw_score_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, const uint32_t
     }
     // 3. packed kernel (persistent grid)
     {
+        // two stream columns per step (S4G_SCORE=1col: the one-column loop, kept for comparison)
+        const char* sc = getenv("S4G_SCORE");
+        const bool two = !(sc && strcmp(sc, "1col") == 0);
+        void (*score_kernel)(ScoreParams) = two ? sw_score_packed2_kernel : sw_score_packed_kernel;
         const size_t smem = (S4G_PAD_CODE + 1) * 8 * 32 * 4 + (S4G_PAD_CODE + 1) * 32 + kWarps * 4 * kRing * sizeof(unsigned short) +
-                            kWarps * kDescRing * sizeof(uint2);
-        S4G_CUDA(ctx, cudaFuncSetAttribute(sw_score_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                            kWarps * (two ? kDescRing2 : kDescRing) * sizeof(uint2);
+        S4G_CUDA(ctx, cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
-        S4G_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw_score_packed_kernel, kWarps * 32, smem));
+        S4G_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_kernel, kWarps * 32, smem));
         if (per_sm < 1) per_sm = 1;
+        if (const char* e = getenv("S4G_SW_CTAS")) per_sm = std::max(1, std::min(per_sm, atoi(e)));   // tools/corun_experiment.py
         S4G_CUDA(ctx, cudaEventRecord(ctx->ev_sw0, st));
-        sw_score_packed_kernel<<<ctx->sm_count * per_sm, kWarps * 32, smem, st>>>(P);
+        score_kernel<<<ctx->sm_count * per_sm, kWarps * 32, smem, st>>>(P);
         S4G_CHECK_LAUNCH(ctx);
     }
     // 4. long queries: striped kernel (stripes of 1024 rows, boundary rows through a per-CTA buffer)
