@@ -5,6 +5,7 @@
 #include <cstring>
 #include <cctype>
 
+#include <algorithm>
 #include "common.cuh"
 
 static thread_local std::string g_tls_error;
@@ -286,7 +287,11 @@ int s4g_queries_create(s4g_ctx* ctx, const uint8_t* codes, const int64_t* offset
     if (where == S4G_HOST) memcpy(q->h_codes.data(), codes, total);
     else cudaMemcpy(q->h_codes.data(), codes, total, cudaMemcpyDeviceToHost);
     for (int64_t i = 0; i < total; ++i) if (q->h_codes[i] >= S4G_NLET) { s4g_set_error(ctx, "query code %d out of range", q->h_codes[i]); delete q; return S4G_ERR_ARG; }
-    if (cudaMalloc(&q->d_codes, total + S4G_DB_TAIL_PAD) != cudaSuccess || cudaMalloc(&q->d_off, sizeof(int64_t) * (nq + 1)) != cudaSuccess) {
+    std::vector<int32_t> order(nq);
+    for (int32_t i = 0; i < nq; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return q->h_off[a + 1] - q->h_off[a] > q->h_off[b + 1] - q->h_off[b]; });
+    if (cudaMalloc(&q->d_codes, total + S4G_DB_TAIL_PAD) != cudaSuccess || cudaMalloc(&q->d_off, sizeof(int64_t) * (nq + 1)) != cudaSuccess ||
+        cudaMalloc(&q->d_len_order, sizeof(int32_t) * nq) != cudaSuccess) {
         s4g_set_error(ctx, "cudaMalloc failed for the query batch");
         s4g_queries_free(q);
         return S4G_ERR_NOMEM;
@@ -294,6 +299,7 @@ int s4g_queries_create(s4g_ctx* ctx, const uint8_t* codes, const int64_t* offset
     cudaMemcpyAsync(q->d_codes, q->h_codes.data(), total, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemsetAsync(q->d_codes + total, S4G_PAD_CODE, S4G_DB_TAIL_PAD, ctx->stream);
     cudaMemcpyAsync(q->d_off, q->h_off.data(), sizeof(int64_t) * (nq + 1), cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(q->d_len_order, order.data(), sizeof(int32_t) * nq, cudaMemcpyHostToDevice, ctx->stream);
     S4G_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *out = q;
     return S4G_OK;
@@ -305,6 +311,7 @@ void s4g_queries_free(s4g_queries* q) {
     cudaStreamSynchronize(q->ctx->stream);
     if (q->d_codes) cudaFree(q->d_codes);
     if (q->d_off) cudaFree(q->d_off);
+    if (q->d_len_order) cudaFree(q->d_len_order);
     delete q;
 }
 

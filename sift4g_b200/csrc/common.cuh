@@ -66,6 +66,7 @@ struct s4g_queries {
     s4g_ctx* ctx = nullptr;
     uint8_t* d_codes = nullptr;
     int64_t* d_off = nullptr;
+    int32_t* d_len_order = nullptr; // query indices by descending length (tile order of the score kernels: neighbouring tiles share a row class)
     int32_t n = 0;
     int32_t max_len = 0;
     std::vector<int64_t> h_off;

@@ -56,7 +56,9 @@ struct ScoreParams {
     const uint32_t* cand_ids;       // original order
     const int64_t* cand_off;        // nq+1
     const uint32_t* sorted_idx;     // positions into cand_ids, grouped by query, longest target first
-    const int64_t* tile_start;      // nq+1: exclusive scan of packed-kernel tiles per query
+    const int64_t* tile_start;      // nq+1: exclusive scan of packed-kernel tiles per query, queries taken in q_order
+    const int32_t* q_order;         // queries by descending length (nullptr: as given): co-resident CTAs run the same row class
+                                    // (one step loop in the instruction cache) and the long tiles go first
     const int8_t* mat8;             // 27 x 32 int8 (row = target letter incl. pad, col = query letter)
     int32_t* out;                   // scores, original order
     unsigned long long* counters;   // [0] tile counter, [1] overflow count, [2] generic work counter
@@ -620,12 +622,12 @@ __device__ __forceinline__ void packed_kernel_body(const ScoreParams& P) {
         // query of this tile: last q with tile_start[q] <= tile
         int lo = 0, hi = P.nq;
         while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (P.tile_start[mid] <= tile) lo = mid; else hi = mid; }
-        const int q = lo;
+        const int q = P.q_order ? P.q_order[lo] : lo;
         const int qlen = (int)(P.q_off[q + 1] - P.q_off[q]);
         const long long n_c = P.cand_off[q + 1] - P.cand_off[q];
         const int n_pairs = (int)((n_c + 1) >> 1);
         constexpr int TP = TRACK ? kTilePairs : kStreamTilePairs;
-        const int pb = (int)(tile - P.tile_start[q]) * TP;
+        const int pb = (int)(tile - P.tile_start[lo]) * TP;
         const int pe = pb + TP < n_pairs ? pb + TP : n_pairs;
         // rows per lane: exactly ceil(qlen / 32) (every class from 2 to 32 has its own instantiation: an even-only dispatch pads
         // the average configs[1] query by 32 rows, 5.8 percent of the cells)
@@ -1387,17 +1389,19 @@ __global__ void make_keys_kernel(ScoreParams P, int64_t n_pairs, unsigned long l
 
 // tiles per query for the packed kernel (0 for long queries) and for the striped kernel (0 for short ones)
 __global__ void count_tiles_kernel(ScoreParams P, int64_t* tiles, int64_t* long_cands, int packed_tile_pairs) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q > P.nq) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > P.nq) return;
     int64_t t = 0, l = 0;
-    if (q < P.nq) {
+    if (i < P.nq) {
+        const int q = P.q_order ? P.q_order[i] : i;                      // packed tiles: position i of the tile table is query q
         const int64_t n_c = P.cand_off[q + 1] - P.cand_off[q];
         const int qlen = (int)(P.q_off[q + 1] - P.q_off[q]);
         if (qlen <= 32 * kMaxK) t = ((n_c + 1) / 2 + packed_tile_pairs - 1) / packed_tile_pairs;
-        else l = ((n_c + 1) / 2 + kTilePairs - 1) / kTilePairs;      // tiles of the striped kernel
+        const int64_t n_l = P.cand_off[i + 1] - P.cand_off[i];           // striped tiles stay in query order
+        if ((int)(P.q_off[i + 1] - P.q_off[i]) > 32 * kMaxK) l = ((n_l + 1) / 2 + kTilePairs - 1) / kTilePairs;
     }
-    tiles[q] = t;
-    long_cands[q] = l;
+    tiles[i] = t;
+    long_cands[i] = l;
 }
 
 
@@ -1468,6 +1472,7 @@ int s4g_sw_score_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, const uint32_t
     P.q_codes = q->d_codes; P.q_off = q->d_off; P.nq = nq;
     P.cand_ids = d_cand_ids; P.cand_off = d_cand_off;
     P.sorted_idx = d_vals2; P.tile_start = d_tile_start; P.mat8 = d_mat8; P.out = d_out;
+    { const char* e = getenv("S4G_TILE_ORDER"); P.q_order = (e && strcmp(e, "query") == 0) ? nullptr : q->d_len_order; }
     P.counters = d_counters; P.overflow = d_ovf; P.bound = d_bound; P.bound_stride = bound_stride;
     P.long_tile_start = d_long_start; P.strip_bound = nullptr; P.strip_cols = 0; P.pair_score = nullptr;
     P.gap_open = gap_open; P.gap_extend = gap_extend; P.ovf_limit = 32767 - max_s;
@@ -1574,6 +1579,7 @@ int s4g_sw_forward_ends_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t
     P.q_codes = q->d_codes; P.q_off = q->d_off; P.nq = nq;
     P.cand_ids = d_pair_t; P.cand_off = d_qstart;
     P.sorted_idx = d_vals2; P.tile_start = d_tile_start; P.mat8 = d_mat8; P.out = d_coords;
+    { const char* e = getenv("S4G_TILE_ORDER"); P.q_order = (e && strcmp(e, "query") == 0) ? nullptr : q->d_len_order; }
     P.counters = d_counters; P.gap_open = gap_open; P.gap_extend = gap_extend; P.pair_score = d_pair_score;
 
     hit_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, d_pair_q, n, d_keys, d_vals);
