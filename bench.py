@@ -636,10 +636,12 @@ def main():
             "stages_ms": split,
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
-            "roofline": {"bound": "int_dpx", "kernel": "sw_score_packed_kernel", "achieved": round(kern_gcups, 2) if kern_gcups else None, "peak": round(roof_gcups, 2),
+            "roofline": {"bound": "int_dpx", "kernel": "sw_score_packed2_kernel", "achieved": round(kern_gcups, 2) if kern_gcups else None, "peak": round(roof_gcups, 2),
                          "unit": "GCUPS", "frac": round(kern_gcups / roof_gcups, 4) if kern_gcups else None,
                          "traffic": NCU_TRAFFIC_C2 if (world == 1 and n_queries == 1000 and n_db == 10_000_000 and args.max_candidates == 5000) else None,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this command (profiles/r01i_sw_digest.md; re-captured as two half-batch launches, 0.728 GB each, in profiles/r01t_sw_digest.md)",
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch of this workload, ncu --set full capture (profiles/r04h_kernels_digest.md)",
+                         "frac_of_kernel_floor": round(kern_gcups / (roof_gcups * 6 / 4.5), 4) if kern_gcups else None,
+                         "kernel_floor": "the kernel's own count: 4.5 ALU-pipe instructions per 2 cells (VIADD.16x2 issues on the FMA pipe), against BASELINE.md's 6",
                          "kernel_ms": round(sw_kernel_ms, 3),
                          "peak_source": "measured live on this GPU (no DPX figure in MEASURED_PEAKS.json): %.4e VIADDMNMX.S16x2 lane-ops/s sustained over 300 ms x 2 cells per op / 6 instructions per cell (BASELINE.md)" % peak},
             "roofline_prefilter": {"bound": "hbm", "achieved": round(((total_res + 8 * n_db) if mode == "striped" else ((hi - lo) / n_db * total_res + 8 * (hi - lo))) / (split["prefilter"] * 1e-3) / 1e9, 2) if split["prefilter"] else None,
@@ -678,10 +680,10 @@ def main():
         dist.destroy_process_group()
 
 
-# DRAM bytes of one sw_score_packed_kernel launch at the default C2 workload (1.404 GB read + 28.3 MB written), from the
-# ncu --set full capture summarised in profiles/r01i_sw_digest.md.  The kernel is integer-issue bound; its algorithmic
+# DRAM bytes of one sw_score_packed2_kernel launch at the default C2 workload (1.391 GB read + 24.5 MB written), from the
+# ncu --set full capture summarised in profiles/r04h_kernels_digest.md.  The kernel is integer-issue bound; its algorithmic
 # DRAM traffic is the candidates' residues (5 M targets, ~107 residues each, fetched in 32-byte sectors).
-NCU_TRAFFIC_C2 = 1404079000 + 28333056
+NCU_TRAFFIC_C2 = 1390900000 + 24490496
 
 
 def hbm_peak():
