@@ -60,6 +60,8 @@ struct PfParams {
     uint32_t* pool_vals;              // query position
     unsigned long long pool_cap;
     unsigned long long* gbuf;         // per-warp global scratch (kGCap entries) for sequences with many surviving hits
+    int trace;                        // S4G_TRACE: counters[5] / [6] count the flagged sequences re-walked / replayed from the rank queue
+    int no_replay;                    // S4G_PF_REPLAY=0: every flagged sequence is re-walked (the form before r04, for comparison)
 };
 
 __device__ __forceinline__ unsigned long long cand_key(float score, uint32_t id) {
@@ -295,6 +297,7 @@ __device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cn
     uint32_t* hb_s = off_s + 128;
     uint32_t* ring_r = reinterpret_cast<uint32_t*>(buf);     // pass A only: queue of index ranks (31 left over + 128 of a step)
     unsigned long long* ring_m = buf + kRankRing / 2;        // pass A only: queue of buckets (31 left over + 32 of a take)
+    unsigned short* ring_p = reinterpret_cast<unsigned short*>(ring_m + kBucketRing);   // sequence position of every queued rank (the replay of pass B)
     const uint32_t lt_mask = (1u << lane) - 1u;
     constexpr int kHitUnroll = 2;
     const unsigned FULL = 0xffffffffu;
@@ -402,6 +405,7 @@ __device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cn
             const uint32_t need_min = max(1u, (uint32_t)ceilf(thr_min * flen));
             uint32_t nh = 0, carry = 0xffffffffu;            // nh: hits counted by this lane
             bool crossed = false;
+            bool wide_bucket = false;                        // a bucket beyond 63 hits: the replay's order field cannot number its hits
             auto count_hit = [&](uint32_t q) {
                 const uint32_t old = atomicAdd(cnt + (q >> 1), (q & 1u) ? 0x10000u : 1u);
                 const uint32_t oc = (q & 1u) ? (old >> 16) : (old & 0xffffu);
@@ -451,6 +455,7 @@ __device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cn
                 if (inl == 3u) count_hit((uint32_t)(e >> 40) & 0xfffffu);
                 nh += inl;
                 const bool bucket = e != 0ull && inl == 0u;
+                wide_bucket |= bucket && (uint32_t)(e >> 32) > 63u;
                 const unsigned m = __ballot_sync(FULL, bucket);
                 if (m) {
                     if (bucket) ring_m[(m_head + m_n + __popc(m & lt_mask)) & (kBucketRing - 1u)] = e;
@@ -482,7 +487,11 @@ __device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cn
                         const uint32_t bit = km[i] & 31u;
                         const bool has = (br[i].x >> bit) & 1u;      // br is zero where the position does not take part
                         const unsigned m = __ballot_sync(FULL, has);
-                        if (has) ring_r[(r_head + r_n + __popc(m & lt_mask)) & (kRankRing - 1u)] = br[i].y + __popc(br[i].x & ((1u << bit) - 1u));
+                        if (has) {
+                            const uint32_t slot = (r_head + r_n + __popc(m & lt_mask)) & (kRankRing - 1u);
+                            ring_r[slot] = br[i].y + __popc(br[i].x & ((1u << bit) - 1u));
+                            ring_p[slot] = (unsigned short)(base + 4 * lane + i);
+                        }
                         r_n += __popc(m);
                     }
                     __syncwarp();
@@ -520,9 +529,48 @@ __device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cn
                     }
                     direct = __reduce_add_sync(FULL, m2) <= (uint32_t)kGCap;
                 }
+                // The k-mers found in pass A are still in the rank queue when the sequence queued at most kRankRing of them (r_head counts
+                // from 0 per sequence, nothing was overwritten): the survivors are then collected by REPLAYING the queue -- entry load,
+                // counter test, and the query positions of the few hits that stay (counters >= 2) -- instead of walking the residues and
+                // probing the index a second time.  Short sequences reach a cut-off with one or two hits (1 / len, 2 / len), so on a
+                // length-sorted scan the first third of the database is flagged almost sequence by sequence.  Order field of a hit =
+                // (position << 6 | index in its bucket): the emission order of the walk.
+                const uint32_t F = r_head;
+                const bool replay = !P.no_replay && F <= kRankRing && len < 65536 && !__any_sync(FULL, wide_bucket);
+                if (P.trace && lane == 0) atomicAdd(P.counters + (replay ? 6 : 5), 1ull);
+                for (uint32_t r0 = 0; replay && r0 < F && !defer; r0 += 32) {
+                    const uint32_t idx = r0 + lane;
+                    unsigned long long e = 0ull;
+                    uint32_t rank = 0, pos = 0;
+                    if (idx < F) { rank = ring_r[idx]; pos = ring_p[idx]; e = __ldg(P.entry + rank); }
+                    const uint32_t inl = (uint32_t)(e >> 62);
+                    const uint32_t c = inl ? inl : (uint32_t)(e >> 32), st = (uint32_t)e;       // hits of this lane's k-mer (a bucket: first entry st)
+                    const uint32_t cmax = __reduce_max_sync(FULL, c);
+                    for (uint32_t j = 0; j < cmax && !defer; ++j) {
+                        unsigned long long ee = 0;
+                        bool keep = false;
+                        if (j < c) {
+                            unsigned long long h = 0ull;
+                            uint32_t q;
+                            if (inl) q = (uint32_t)(e >> (20u * j)) & 0xfffffu;
+                            else { h = __ldg(P.hits + st + j); q = (uint32_t)(h >> 32); }
+                            const uint32_t cq = count_of(cnt, q);
+                            keep = may_pass(qthr, cq, q, flen);
+                            if (direct && keep && cq == 1) { emit(P, q, 1, len, id); keep = false; }
+                            if (keep) {
+                                if (inl) h = __ldg(P.hits + __ldg(P.bucket_start + rank) + j);
+                                ee = ((unsigned long long)q << 44) | ((unsigned long long)((pos << 6) | j) << 22) | (h & 0x3fffffu);
+                            }
+                        }
+                        const uint32_t bal = __ballot_sync(FULL, keep);
+                        if (nsurv + __popc(bal) > (uint32_t)kGCap) { defer = true; continue; }
+                        if (keep) wb[nsurv + __popc(bal & lt_mask)] = ee;
+                        nsurv += __popc(bal);
+                    }
+                }
                 uint32_t ordbase = 0;
                 carry = 0xffffffffu;
-                for (int base = 0; base < npos && !defer; base += 128) {
+                for (int base = 0; !replay && base < npos && !defer; base += 128) {
                     uint32_t hb[4], hc[4];
                     scan_step(P, seq, npos, base, lane, carry, hb, hc);
                     const uint32_t c = hc[0] + hc[1] + hc[2] + hc[3];
@@ -1035,7 +1083,7 @@ static int build_scan_order(s4g_ctx* ctx, s4g_db* db) {
 // leaves kMinScanWarps warps per SM beside the 2-byte cut-off table (larger batches are scanned in groups of queries: the
 // candidate lists of different queries are independent, the database streams once per group).
 constexpr size_t kScanSmemCap = 227 * 1024;
-constexpr int kScanSortCap = 192;          // 8-byte entries of a warp's buffer: the two queues of pass A (1 KB of ranks + 512 B of buckets), step tables / sort buffer of pass B; every KB here is a KB less L1 for the index probes
+constexpr int kScanSortCap = 256;          // 8-byte entries of a warp's buffer: the queues of pass A (1 KB of ranks + 512 B of buckets + 512 B of positions), step tables / sort buffer of pass B; every KB here is a KB less L1 for the index probes
 constexpr int kMinScanWarps = 4;
 static int scan_cnt_words(int nq) { return ((nq + 1) / 2 + 127) / 128 * 128; }
 static int scan_sort_cap(int) { return kScanSortCap; }
@@ -1241,6 +1289,8 @@ static int prefilter_group(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int 
     P.pool_keys = nullptr; P.pool_vals = nullptr; P.pool_cap = pool_cap;
 
     P.entry = d_entry; P.q_hit_start = d_start;
+    P.trace = ctx->trace ? 1 : 0;
+    { const char* e = getenv("S4G_PF_REPLAY"); P.no_replay = (e && e[0] == '0') ? 1 : 0; }
     // one CTA per SM: its warps share the cut-off table and the filter; the build follows the CTA size (register budget)
     const size_t scan_smem = per_warp_smem * scan_warps + qthr_bytes + (stage ? stage_pad + (size_t)kStageWarpBytes * scan_warps : 0);
     void (*scan_kernel)(PfParams, int, int) = nullptr;
@@ -1261,19 +1311,19 @@ static int prefilter_group(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int 
     for (int64_t s0 = 0; s0 < db->n && n_hits > 0; ) {
         P.seq_begin = s0;
         P.seq_end = s0 + this_chunk < db->n ? s0 + this_chunk : db->n;
-        S4G_CUDA(ctx, cudaMemsetAsync(d_counters, 0, 32, st));
+        S4G_CUDA(ctx, cudaMemsetAsync(d_counters, 0, 64, st));
         S4G_CUDA(ctx, cudaMemcpyAsync(d_count_saved, d_count, sizeof(uint32_t) * nq, cudaMemcpyDeviceToDevice, st));
         // the pool is only allocated once a chunk needs it (first pass counts; see below)
         P.pool_keys = (unsigned long long*)ctx->slot_ptr[SLOT_PF_HITS];
         const auto t_chunk = std::chrono::steady_clock::now();
         scan_kernel<<<grid, scan_warps * 32, scan_smem, st>>>(P, scap, cnt_words);
         S4G_CHECK_LAUNCH(ctx);
-        unsigned long long h_c[4];
-        S4G_CUDA(ctx, cudaMemcpyAsync(h_c, d_counters, 32, cudaMemcpyDeviceToHost, st));
+        unsigned long long h_c[8];
+        S4G_CUDA(ctx, cudaMemcpyAsync(h_c, d_counters, 64, cudaMemcpyDeviceToHost, st));
         S4G_CUDA(ctx, cudaStreamSynchronize(st));
         s4g_trace_mark(ctx, "scan");
-        if (ctx->trace) fprintf(stderr, "[s4g trace] chunk [%lld,%lld): scan %.3f ms, deferred %llu sequences, %llu hits\n", (long long)P.seq_begin, (long long)P.seq_end,
-                                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_chunk).count(), h_c[1], h_c[2]);
+        if (ctx->trace) fprintf(stderr, "[s4g trace] chunk [%lld,%lld): scan %.3f ms, deferred %llu sequences, %llu hits; %llu flagged sequences re-walked, %llu replayed from the rank queue\n", (long long)P.seq_begin, (long long)P.seq_end,
+                                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_chunk).count(), h_c[1], h_c[2], h_c[5], h_c[6]);
         if (h_c[3] & 1ull) { s4g_set_error(ctx, "prefilter: candidate buffer overflow (internal)"); return S4G_ERR_INTERNAL; }
         if (h_c[3] & 2ull) {
             if (P.seq_end - P.seq_begin <= 256) { s4g_set_error(ctx, "prefilter: more than %u deferred sequences or %llu deferred hits in a chunk of %lld sequences", max_deferred, pool_cap, (long long)(P.seq_end - P.seq_begin)); return S4G_ERR_CAPACITY; }
