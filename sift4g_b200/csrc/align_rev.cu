@@ -50,6 +50,8 @@ struct RevParams {
     const int8_t* mat8;
     int32_t go, ge;
     int32_t* coords;
+    const int32_t* q_rank;                // position of a query in the descending-length order: the key's query field (long queries' tiles first)
+    const int32_t* q_order;               // and back
     const unsigned long long* keys;       // sorted
     const uint32_t* vals;                 // hit index of every sorted key
     const unsigned long long* n_valid;    // sorted keys that are real work (the rest carry ~0)
@@ -198,14 +200,14 @@ __device__ __forceinline__ void reverse_pair_packed(const unsigned* prof, int R,
     *found1 = fnd1; *found2 = fnd2;
 }
 
-// sort key of a hit: query (bits 63..35) | K class - 1 (34..32) | ~columns (31..0); hits this kernel does not take: ~0
+// sort key of a hit: query, as its position in the descending-length order (bits 63..35; the long queries' tiles go first) | K class - 1 (34..32) | ~columns (31..0); hits this kernel does not take: ~0
 __device__ __forceinline__ int key_kclass(unsigned long long key) { return (int)((key >> 32) & 7u) + 1; }     // rows per lane / 4
 
 template <int K>
 __device__ void run_group(const RevParams& P, unsigned* prof, const int8_t* smat, unsigned short* rings, int* s_next, const unsigned long long* s_keys,
                           const uint32_t* s_vals, int g0, int g1) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t q = (uint32_t)(s_keys[g0] >> 35);
+    const uint32_t q = (uint32_t)P.q_order[(uint32_t)(s_keys[g0] >> 35)];
     const int64_t qo = P.q_off[q];
     const int qlen = (int)(P.q_off[q + 1] - qo);
     const int R = min(32 * K, qlen) - 1;
@@ -297,7 +299,7 @@ __global__ void rev_keys_kernel(RevParams P, int64_t n, int swalign_all, unsigne
     unsigned long long key = ~0ull;
     if (!swalign_all && score <= 32767 && score > 0 && q_end >= 0 && t_end >= 0 && q_end < 1024) {
         const unsigned kc = (unsigned)(q_end / 128);                   // rows per lane = 4 (kc + 1) covers q_end + 1 rows
-        key = ((unsigned long long)P.pair_q[i] << 35) | ((unsigned long long)kc << 32) | (unsigned long long)(0xffffffffu - (unsigned)(t_end + 1));
+        key = ((unsigned long long)(uint32_t)P.q_rank[P.pair_q[i]] << 35) | ((unsigned long long)kc << 32) | (unsigned long long)(0xffffffffu - (unsigned)(t_end + 1));
         atomicAdd(n_valid, 1ull);
     }
     keys[i] = key;
@@ -325,6 +327,7 @@ int s4g_sw_reverse_begins_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64
     P.q_codes = q->d_codes; P.q_off = q->d_off;
     P.pair_q = d_pair_q; P.pair_t = d_pair_t; P.pair_score = d_pair_score; P.mat8 = d_mat8;
     P.go = gap_open; P.ge = gap_extend; P.coords = d_coords;
+    P.q_rank = q->d_len_rank; P.q_order = q->d_len_order;
     P.keys = d_keys2; P.vals = d_vals2; P.n_valid = d_counters + 1; P.counters = d_counters; P.flags = d_flags;
     rev_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, n, swalign_all, d_keys, d_vals, d_counters + 1);
     S4G_CHECK_LAUNCH(ctx);

@@ -291,7 +291,7 @@ int s4g_queries_create(s4g_ctx* ctx, const uint8_t* codes, const int64_t* offset
     for (int32_t i = 0; i < nq; ++i) order[i] = i;
     std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return q->h_off[a + 1] - q->h_off[a] > q->h_off[b + 1] - q->h_off[b]; });
     if (cudaMalloc(&q->d_codes, total + S4G_DB_TAIL_PAD) != cudaSuccess || cudaMalloc(&q->d_off, sizeof(int64_t) * (nq + 1)) != cudaSuccess ||
-        cudaMalloc(&q->d_len_order, sizeof(int32_t) * nq) != cudaSuccess) {
+        cudaMalloc(&q->d_len_order, sizeof(int32_t) * nq) != cudaSuccess || cudaMalloc(&q->d_len_rank, sizeof(int32_t) * nq) != cudaSuccess) {
         s4g_set_error(ctx, "cudaMalloc failed for the query batch");
         s4g_queries_free(q);
         return S4G_ERR_NOMEM;
@@ -300,6 +300,9 @@ int s4g_queries_create(s4g_ctx* ctx, const uint8_t* codes, const int64_t* offset
     cudaMemsetAsync(q->d_codes + total, S4G_PAD_CODE, S4G_DB_TAIL_PAD, ctx->stream);
     cudaMemcpyAsync(q->d_off, q->h_off.data(), sizeof(int64_t) * (nq + 1), cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(q->d_len_order, order.data(), sizeof(int32_t) * nq, cudaMemcpyHostToDevice, ctx->stream);
+    std::vector<int32_t> rank(nq);
+    for (int32_t i = 0; i < nq; ++i) rank[order[i]] = i;
+    cudaMemcpyAsync(q->d_len_rank, rank.data(), sizeof(int32_t) * nq, cudaMemcpyHostToDevice, ctx->stream);
     S4G_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *out = q;
     return S4G_OK;
@@ -312,6 +315,7 @@ void s4g_queries_free(s4g_queries* q) {
     if (q->d_codes) cudaFree(q->d_codes);
     if (q->d_off) cudaFree(q->d_off);
     if (q->d_len_order) cudaFree(q->d_len_order);
+    if (q->d_len_rank) cudaFree(q->d_len_rank);
     delete q;
 }
 

@@ -67,6 +67,7 @@ struct s4g_queries {
     uint8_t* d_codes = nullptr;
     int64_t* d_off = nullptr;
     int32_t* d_len_order = nullptr; // query indices by descending length (tile order of the score kernels: neighbouring tiles share a row class)
+    int32_t* d_len_rank = nullptr;  // inverse: position of every query in d_len_order
     int32_t n = 0;
     int32_t max_len = 0;
     std::vector<int64_t> h_off;
@@ -111,6 +112,7 @@ enum {
     SLOT_AL_WORK, SLOT_AL_DIR, SLOT_AL_MISC, SLOT_AL_OUT, SLOT_PF_ENTRY,
     SLOT_SR_ROWS, SLOT_SR_CNT, SLOT_SR_OFF, SLOT_SR_CAND, SLOT_SR_SCORES, SLOT_SR_SURV,
     SLOT_SR_AL_COORDS, SLOT_SR_AL_PATHS, SLOT_SR_AL_POFF, SLOT_SR_HITS, SLOT_SR_OUT_COORDS, SLOT_SR_OUT_PATHS, SLOT_SR_OUT_POFF, SLOT_AL_GROUPS, SLOT_AL_GATHER, SLOT_AL_GATHER_IDX,
+    SLOT_AL_LPT_KEYS, SLOT_AL_LPT_KEYS2, SLOT_AL_LPT_LIST,
     SLOT_COUNT
 };
 static_assert(SLOT_COUNT <= s4g_ctx::kSlots, "scratch slot table too small");
