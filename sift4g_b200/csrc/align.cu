@@ -586,22 +586,6 @@ __global__ void __launch_bounds__(kBandWarps * 32) al_band_persistent_kernel(AlP
     }
 }
 
-// Sort key of a handed-over hit for the warp kernel: rows x band cells of its next attempt, largest first (the kernel's items cost
-// from a few hundred to several hundred thousand cells; taken in arrival order a handful of late large ones kept a quarter of the
-// SM cycles idle -- sm__cycles_active / elapsed 0.76, profiles/r04h_kernels_digest.md).
-__global__ void al_band_lpt_keys_kernel(AlParams P, const uint2* list, const unsigned long long* count, int64_t cap, uint32_t* keys) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= cap) return;
-    uint32_t key = 0;
-    if ((unsigned long long)i < *count) {
-        const uint32_t p = list[i].x, w = list[i].y;
-        const long long rows = (long long)P.coords[4 * p + 1] - P.coords[4 * p + 0] + 1;
-        const long long cells = rows > 0 ? rows * (2ll * w + 1) : 0;
-        key = (uint32_t)(cells < 0xffffffffll ? cells : 0xffffffffll);
-    }
-    keys[i] = key;
-}
-
 // ---- narrow bands: several hits per warp -------------------------------------------------------------------------
 // The bands of near-diagonal alignments are a few cells wide (configs[1]: 2 w + 1 ~ 10 on average), and a band row costs the
 // warp kernel above ~90 instructions however narrow it is -- it is bound by issue slots (ncu: 89 % issue active), with most
@@ -1298,23 +1282,6 @@ static int sw_align_impl(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t n_pai
                 cur_list = listB; cur_count = g_cnt + 3;
             }
             B.in_list = cur_list; B.in_count = cur_count;
-            // largest first (S4G_BAND_LPT=0: arrival order)
-            const char* el = getenv("S4G_BAND_LPT");
-            if (cur_list && !(el && el[0] == '0')) {
-                uint32_t* d_k = (uint32_t*)s4g_scratch(ctx, SLOT_AL_LPT_KEYS, sizeof(uint32_t) * (size_t)n_pairs);
-                uint32_t* d_k2 = (uint32_t*)s4g_scratch(ctx, SLOT_AL_LPT_KEYS2, sizeof(uint32_t) * (size_t)n_pairs);
-                unsigned long long* d_l2 = (unsigned long long*)s4g_scratch(ctx, SLOT_AL_LPT_LIST, sizeof(unsigned long long) * (size_t)n_pairs);
-                if (!d_k || !d_k2 || !d_l2) return S4G_ERR_NOMEM;
-                al_band_lpt_keys_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, st>>>(P, cur_list, cur_count, n_pairs, d_k);
-                S4G_CHECK_LAUNCH(ctx);
-                size_t tmp = 0;
-                cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp, d_k, d_k2, (const unsigned long long*)cur_list, d_l2, (int)n_pairs, 0, 32, st);
-                void* d_tmp = s4g_scratch(ctx, SLOT_SW_CUB, tmp);
-                if (!d_tmp) return S4G_ERR_NOMEM;
-                S4G_CUDA(ctx, cub::DeviceRadixSort::SortPairsDescending(d_tmp, tmp, d_k, d_k2, (const unsigned long long*)cur_list, d_l2, (int)n_pairs, 0, 32, st));
-                ctx->launches += 4;
-                B.in_list = (const uint2*)d_l2;
-            }
         }
         al_band_persistent_kernel<<<grid, kBandWarps * 32, p_smem, st>>>(P, B);
         S4G_CHECK_LAUNCH(ctx);
