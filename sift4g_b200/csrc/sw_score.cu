@@ -222,7 +222,14 @@ __device__ __forceinline__ unsigned score_pair_packed(const unsigned* __restrict
 // column and 31 pad columns flush the wavefront.
 constexpr int kDescRing = 16;             // output positions of the pairs in flight
 constexpr int kMinCols = 8;               // pairs are padded to this many columns (bounds the pairs in flight)
-constexpr int kStreamTilePairs = 256;     // pairs per (query, tile) of the streaming score kernel
+#ifndef S4G_STREAM_TILE
+#define S4G_STREAM_TILE 256
+#endif
+#ifndef S4G_TRACK_TILE
+#define S4G_TRACK_TILE 64
+#endif
+constexpr int kStreamTilePairs = S4G_STREAM_TILE;     // pairs per (query, tile) of the streaming score kernel
+constexpr int kTrackTilePairs = S4G_TRACK_TILE;       // pairs per (query, tile) of the end-cell kernel
 constexpr unsigned kNoTarget = 0xffffffffu;
 
 template <int K>
@@ -626,7 +633,7 @@ __device__ __forceinline__ void packed_kernel_body(const ScoreParams& P) {
         const int qlen = (int)(P.q_off[q + 1] - P.q_off[q]);
         const long long n_c = P.cand_off[q + 1] - P.cand_off[q];
         const int n_pairs = (int)((n_c + 1) >> 1);
-        constexpr int TP = TRACK ? kTilePairs : kStreamTilePairs;
+        constexpr int TP = TRACK ? kTrackTilePairs : kStreamTilePairs;
         const int pb = (int)(tile - P.tile_start[lo]) * TP;
         const int pe = pb + TP < n_pairs ? pb + TP : n_pairs;
         // rows per lane: exactly ceil(qlen / 32) (every class from 2 to 32 has its own instantiation: an even-only dispatch pads
@@ -1596,7 +1603,7 @@ int s4g_sw_forward_ends_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int64_t
     }
     hit_qstart_kernel<<<(nq + 1 + 255) / 256, 256, 0, st>>>(d_keys2, n, nq, d_qstart);
     S4G_CHECK_LAUNCH(ctx);
-    count_tiles_kernel<<<(nq + 1 + 255) / 256, 256, 0, st>>>(P, d_tile_cnt, d_long_cnt, kTilePairs);
+    count_tiles_kernel<<<(nq + 1 + 255) / 256, 256, 0, st>>>(P, d_tile_cnt, d_long_cnt, kTrackTilePairs);
     S4G_CHECK_LAUNCH(ctx);
     {
         size_t tmp_bytes = 0;
