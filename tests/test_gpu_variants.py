@@ -1,7 +1,8 @@
 """GPU: every kernel that has an older, independently written form still in the library gives that form's results bit for bit on a
 workload large enough to meet all their code paths (begin cells: packed reverse sweep vs the 32-bit sweep; paths: 8/16-lane group
 kernels vs one warp per hit; long queries: streaming stripes vs pair by pair, striped end cells vs the 32-bit sweep; no speculative
-traceback).  The forms are selected per call through the environment switches the kernels document."""
+traceback; score kernel with one stream column per step vs two; tiles in query order vs by descending query length; flagged sequences
+of the prefilter re-walked vs replayed from the rank queue).  The forms are selected per call through the environment switches the kernels document."""
 import os
 
 import numpy as np
@@ -12,7 +13,7 @@ from sift4g_b200 import pipeline, synth
 pytestmark = pytest.mark.gpu
 
 SWITCHES = [("S4G_BEGINS", "sweep32"), ("S4G_BAND_GROUPS", "0"), ("S4G_BAND_GROUPS", "16"), ("S4G_STRIPED", "pairs"), ("S4G_ENDS", "sweep32"),
-            ("S4G_NO_SPECULATE", "1")]
+            ("S4G_NO_SPECULATE", "1"), ("S4G_SCORE", "1col"), ("S4G_TILE_ORDER", "query"), ("S4G_PF_REPLAY", "0")]
 
 
 def _run(ctx, D, qc, qo, blosum, N, M):
