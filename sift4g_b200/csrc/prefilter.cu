@@ -490,7 +490,7 @@ __device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cn
                         if (has) {
                             const uint32_t slot = (r_head + r_n + __popc(m & lt_mask)) & (kRankRing - 1u);
                             ring_r[slot] = br[i].y + __popc(br[i].x & ((1u << bit) - 1u));
-                            ring_p[slot] = (unsigned short)(base + 4 * lane + i);
+                            if (!P.no_replay) ring_p[slot] = (unsigned short)(base + 4 * lane + i);
                         }
                         r_n += __popc(m);
                     }
@@ -1083,9 +1083,10 @@ static int build_scan_order(s4g_ctx* ctx, s4g_db* db) {
 // leaves kMinScanWarps warps per SM beside the 2-byte cut-off table (larger batches are scanned in groups of queries: the
 // candidate lists of different queries are independent, the database streams once per group).
 constexpr size_t kScanSmemCap = 227 * 1024;
-constexpr int kScanSortCap = 256;          // 8-byte entries of a warp's buffer: the queues of pass A (1 KB of ranks + 512 B of buckets + 512 B of positions), step tables / sort buffer of pass B; every KB here is a KB less L1 for the index probes
+constexpr int kScanSortCap = 192;          // 8-byte entries of a warp's buffer: the queues of pass A (1 KB of ranks + 512 B of buckets; + 512 B of positions = kScanReplayCap when flagged sequences are replayed), step tables / sort buffer of pass B; every KB here is a KB less L1 for the index probes
 constexpr int kMinScanWarps = 4;
 static int scan_cnt_words(int nq) { return ((nq + 1) / 2 + 127) / 128 * 128; }
+constexpr int kScanReplayCap = 256;
 static int scan_sort_cap(int) { return kScanSortCap; }
 static size_t scan_warp_smem(int nq) { return sizeof(uint32_t) * (size_t)scan_cnt_words(nq) + sizeof(unsigned long long) * scan_sort_cap(nq); }
 static size_t scan_qthr_smem(int nq) { return sizeof(unsigned short) * (size_t)((nq + 7) & ~7); }
@@ -1209,8 +1210,20 @@ static int prefilter_group(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int 
     }
     // ---- scan configuration: warps per SM from the exact counters (2 B per query and warp) ----
     const int cnt_words = scan_cnt_words(nq);
-    const int scap = scan_sort_cap(nq);
-    const size_t per_warp_smem = scan_warp_smem(nq), qthr_bytes = scan_qthr_smem(nq);
+    // Flagged sequences are replayed from the rank queue (pass B without a second walk) where that pays: the index holds a minority
+    // of the k-mer space in small buckets -- a replay round takes 32 found k-mers, a re-walk step 128 positions, so the replay wins
+    // while fewer than ~1 position in 4 hits the index (configs[1]: 1 in 7; measured at configs[2]'s groups of 4 000 human-sized
+    // queries, 1 in 2: replay 262 ms against 254 ms; configs[3]: every position hits) -- and where the 512 B of positions per warp cost no
+    // resident warp.  S4G_PF_REPLAY=0/1 overrides the density rule.
+    bool replay = n_hits <= 2 * (int64_t)n_distinct && n_distinct <= (1u << 20);
+    { const char* e = getenv("S4G_PF_REPLAY"); if (e) replay = e[0] != '0'; }
+    const size_t qthr_bytes = scan_qthr_smem(nq);
+    {
+        const size_t base_w = scan_warp_smem(nq), replay_w = base_w + sizeof(unsigned long long) * (kScanReplayCap - kScanSortCap);
+        if (std::min<size_t>(32, (kScanSmemCap - qthr_bytes) / replay_w) < std::min<size_t>(32, (kScanSmemCap - qthr_bytes) / base_w)) replay = false;
+    }
+    const int scap = replay ? kScanReplayCap : scan_sort_cap(nq);
+    const size_t per_warp_smem = scan_warp_smem(nq) + sizeof(unsigned long long) * (scap - scan_sort_cap(nq));
     int scan_warps = (int)std::min<size_t>(32, (kScanSmemCap - qthr_bytes) / per_warp_smem);
     if (const char* e = getenv("S4G_PF_WARPS")) scan_warps = std::max(1, std::min(scan_warps, atoi(e)));
     // TMA residue staging (pf_scan_body<true>): 0.6 KB per warp.  For an NVLink-striped view (the copies hide the peer latency).
@@ -1290,7 +1303,7 @@ static int prefilter_group(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, int k, int 
 
     P.entry = d_entry; P.q_hit_start = d_start;
     P.trace = ctx->trace ? 1 : 0;
-    { const char* e = getenv("S4G_PF_REPLAY"); P.no_replay = (e && e[0] == '0') ? 1 : 0; }
+    P.no_replay = replay ? 0 : 1;
     // one CTA per SM: its warps share the cut-off table and the filter; the build follows the CTA size (register budget)
     const size_t scan_smem = per_warp_smem * scan_warps + qthr_bytes + (stage ? stage_pad + (size_t)kStageWarpBytes * scan_warps : 0);
     void (*scan_kernel)(PfParams, int, int) = nullptr;

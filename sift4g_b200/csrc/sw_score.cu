@@ -696,7 +696,7 @@ struct StripSmem {
 constexpr int kStripWarpBytes = 4 * kRing * 2 + 2 * kRing * 4 + 4 * kRing * 4;
 // streaming form (stream_stripe): rings of 2 * kRing stream columns for the target offsets (2 x u16), the incoming boundary (H, F),
 // the outgoing boundary (H, F) and its destination (u32), plus the pairs in flight
-constexpr int kStreamStripWarpBytes = 2 * (2 * kRing) * 2 + 5 * (2 * kRing) * 4 + kDescRing * 4;
+constexpr int kStreamStripWarpBytes = 2 * (2 * kRing) * 2 + 5 * (2 * kRing) * 4 + 32 * 4;      // 32 = kDescRing2 descriptors (the one-column form uses 16)
 
 __device__ __forceinline__ unsigned sweep_stripe(const unsigned* __restrict__ prof_lane, const StripSmem& S, const uint8_t* __restrict__ t1,
                                                  int len1, const uint8_t* __restrict__ t2, int len2, unsigned negQ, unsigned negR,
@@ -940,6 +940,177 @@ __device__ __forceinline__ void stream_stripe(const ScoreParams& P, const unsign
     __syncwarp();
 }
 
+// The same with two stream columns per step (see stream_pairs_packed2: no register moves, shuffles and ring reads once per two
+// columns): lane 0 takes the boundary values of both columns from the in-rings (one 8-byte read each), lane 31 leaves both in the
+// out-rings; lane 31 runs 62 columns behind lane 0, so finished columns are flushed up to s0 - 62 and 32 pairs can be in flight.
+__device__ __forceinline__ void stream_stripe2(const ScoreParams& P, const unsigned* __restrict__ prof_lane, const StreamStripSmem& S, int* s_next,
+                                              unsigned* s_best, unsigned* cta_bound, int64_t cbeg, int64_t cend, int pb, int pe, unsigned negQ,
+                                              unsigned negR, bool first, bool last, int lane) {
+    constexpr int K = kMaxK, KW = K / 4;
+    constexpr unsigned kRowBytes = KW * 128;
+    constexpr unsigned kPadOff = S4G_PAD_CODE * kRowBytes;
+    constexpr unsigned kFlag = 0x8000u;
+    constexpr int kRingMask = 2 * kRing - 1;
+    constexpr int kSteps = kRing / 2;     // steps per refill (two stream columns per step)
+    constexpr int kOpen = 0x7fffffff;
+    constexpr unsigned kNoAddr = 0xffffffffu;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned strip_cols = (unsigned)P.strip_cols;
+
+    unsigned H[K], E[K];
+#pragma unroll
+    for (int r = 0; r < K; ++r) { H[r] = 0; E[r] = 0; }
+    unsigned best = 0, hA_last = 0, hB_last = 0, fA_out = 0, fB_out = 0, diag_in = 0, b_out = 0;
+    int n31 = 0;
+    const uint8_t *t1 = nullptr, *t2 = nullptr;
+    int len1 = 0, len2 = 0, L = 0, pos = 0, n_pulled = 0, end_col = kOpen, cur_pair = 0;
+    for (int c = lane; c < kRing; c += 32) { S.ring1[kRing + c] = kPadOff; S.ring2[kRing + c] = kPadOff; S.inH[kRing + c] = 0u; S.inF[kRing + c] = 0u; S.oaddr[kRing + c] = kNoAddr; }
+    const char* prof_bytes = reinterpret_cast<const char*>(prof_lane);
+    int flushed = 0;
+    auto flush_out = [&](int upto) {          // boundary values of the stream columns lane 31 has finished -> the pairs' boundary rows
+        if (last) return;
+        for (int c = flushed + lane; c < upto; c += 32) {
+            const unsigned a = S.oaddr[c & kRingMask];
+            if (a != kNoAddr) { cta_bound[a] = S.outH[c & kRingMask]; cta_bound[a + strip_cols] = S.outF[c & kRingMask]; }
+        }
+        if (upto > flushed) flushed = upto;
+    };
+
+    for (int s0 = 0;; s0 += kRing) {
+        flush_out(s0 - 62);
+        __syncwarp();
+        // ---- stage stream columns s0 .. s0+kRing-1
+        int col = s0;
+        while (col < s0 + kRing) {
+            if (pos >= L && end_col == kOpen) {
+                int p = 0;
+                if (lane == 0) p = atomicAdd(s_next, 1);
+                p = __shfl_sync(FULL, p, 0);
+                if (p < pe) {
+                    const int64_t i1 = cbeg + 2 * (int64_t)p, i2 = i1 + 1;
+                    const uint32_t c1 = P.sorted_idx[i1];
+                    const bool has2 = i2 < cend;
+                    const uint32_t c2 = has2 ? P.sorted_idx[i2] : c1;
+                    const uint32_t g1 = P.cand_ids[c1] - P.id_base, g2 = P.cand_ids[c2] - P.id_base;
+                    const int64_t a1 = P.db_off[g1], b1 = P.db_off[g1 + 1];
+                    const int64_t a2 = P.db_off[g2], b2 = P.db_off[g2 + 1];
+                    len1 = (int)(b1 - a1); len2 = has2 ? (int)(b2 - a2) : 0;
+                    if (len1 > P.strip_cols || len2 > P.strip_cols) {       // too long for the boundary buffer: 32-bit kernel
+                        if (lane == 0) s_best[p - pb] = 0x7fff7fffu;
+                        pos = 0; L = 0;
+                        continue;
+                    }
+                    t1 = P.db_codes + a1; t2 = P.db_codes + a2;
+                    L = len1 > len2 ? len1 : len2;
+                    L = (L + 1) & ~1;                                // boundaries on even stream columns; a pad column changes no maximum
+                    if (L < kMinCols) L = kMinCols;
+                    pos = 0;
+                    cur_pair = p - pb;
+                    if (lane == 0) S.desc[n_pulled & (kDescRing2 - 1)] = (unsigned)cur_pair;
+                    ++n_pulled;
+                } else {
+                    end_col = col;
+                }
+            }
+            if (end_col != kOpen) {
+                for (int c = col + lane; c < s0 + kRing; c += 32) {
+                    S.ring1[c & kRingMask] = (unsigned short)(c == end_col ? (kPadOff | kFlag) : kPadOff);
+                    S.ring2[c & kRingMask] = (unsigned short)kPadOff;
+                    S.inH[c & kRingMask] = 0u; S.inF[c & kRingMask] = 0u; S.oaddr[c & kRingMask] = kNoAddr;
+                }
+                break;
+            }
+            const int n = min(L - pos, s0 + kRing - col);
+            const unsigned row = (unsigned)cur_pair * 2u * strip_cols;
+            const int maxlen = len1 > len2 ? len1 : len2;
+            for (int i = lane; i < n; i += 32) {
+                const int j = pos + i;
+                unsigned o1 = j < len1 ? (unsigned)t1[j] * kRowBytes : kPadOff;
+                const unsigned o2 = j < len2 ? (unsigned)t2[j] * kRowBytes : kPadOff;
+                if (j == 0) o1 |= kFlag;
+                const int x = (col + i) & kRingMask;
+                S.ring1[x] = (unsigned short)o1;
+                S.ring2[x] = (unsigned short)o2;
+                const bool real = j < maxlen;
+                S.inH[x] = (!first && real) ? cta_bound[row + j] : 0u;
+                S.inF[x] = (!first && real) ? cta_bound[row + strip_cols + j] : 0u;
+                S.oaddr[x] = real ? row + (unsigned)j : kNoAddr;
+            }
+            col += n; pos += n;
+        }
+        if (n_pulled == 0) return;
+        __syncwarp();
+        const int S0 = s0 >> 1;
+        const int send = end_col == kOpen ? kSteps : min(kSteps, (end_col >> 1) + 32 - S0);
+#pragma unroll 1
+        for (int ss = 0; ss < send; ++ss) {
+            const int jp = (S0 + ss - lane) & (kRing - 1);           // column pair of this lane; its columns sit at ring slots 2 jp, 2 jp + 1
+            const unsigned p1 = reinterpret_cast<const unsigned*>(S.ring1)[jp], p2 = reinterpret_cast<const unsigned*>(S.ring2)[jp];
+            unsigned o1a = p1 & 0xffffu;
+            const unsigned o1b = p1 >> 16, o2a = p2 & 0xffffu, o2b = p2 >> 16;
+            unsigned hA_up = __shfl_up_sync(FULL, hA_last, 1);
+            unsigned hB_up = __shfl_up_sync(FULL, hB_last, 1);
+            unsigned fA = __shfl_up_sync(FULL, fA_out, 1);
+            unsigned fB = __shfl_up_sync(FULL, fB_out, 1);
+            unsigned b_in = __shfl_up_sync(FULL, b_out, 1);
+            if (lane == 0) {
+                const uint2 ih = reinterpret_cast<const uint2*>(S.inH)[jp], jf = reinterpret_cast<const uint2*>(S.inF)[jp];
+                hA_up = ih.x; hB_up = ih.y; fA = jf.x; fB = jf.y; b_in = 0;
+            }
+            if (o1a & kFlag) {                                       // first column of a pair (or the sentinel)
+                o1a &= 0x7fffu;
+                b_out = __vmaxs2(best, b_in);
+                if (lane == 31) {
+                    if (n31 > 0) { const unsigned d = S.desc[(n31 - 1) & (kDescRing2 - 1)]; s_best[d] = __vmaxs2(s_best[d], b_out); }
+                    ++n31;
+                }
+                best = 0; diag_in = 0;
+#pragma unroll
+                for (int r = 0; r < K; ++r) { H[r] = 0; E[r] = 0; }
+            }
+            unsigned wa1[KW], wa2[KW], wb1[KW], wb2[KW];
+#pragma unroll
+            for (int m = 0; m < KW; ++m) {
+                wa1[m] = *reinterpret_cast<const unsigned*>(prof_bytes + o1a + m * 128);
+                wa2[m] = *reinterpret_cast<const unsigned*>(prof_bytes + o2a + m * 128);
+                wb1[m] = *reinterpret_cast<const unsigned*>(prof_bytes + o1b + m * 128);
+                wb2[m] = *reinterpret_cast<const unsigned*>(prof_bytes + o2b + m * 128);
+            }
+            unsigned tA = __vadd2(diag_in, prmt(wa1[0], wa2[0], 0xC480u));       // cells A / B of a row: see stream_pairs_packed2
+            unsigned tB = __vadd2(hA_up, prmt(wb1[0], wb2[0], 0xC480u));
+            diag_in = hB_up;
+#pragma unroll
+            for (int r = 0; r < K; ++r) {
+                unsigned tA_next = 0, tB_next = 0;
+                const unsigned sel = ((r + 1) & 3) == 0 ? 0xC480u : ((r + 1) & 3) == 1 ? 0xD591u : ((r + 1) & 3) == 2 ? 0xE6A2u : 0xF7B3u;
+                if (r + 1 < K) tA_next = __vadd2(H[r], prmt(wa1[(r + 1) >> 2], wa2[(r + 1) >> 2], sel));
+                const unsigned hA = __vimax3_s16x2_relu(tA, E[r], fA);
+                const unsigned hqA = __vadd2(hA, negQ);
+                const unsigned eB = __viaddmax_s16x2(E[r], negR, hqA);
+                fA = __viaddmax_s16x2(fA, negR, hqA);
+                if (r + 1 < K) tB_next = __vadd2(hA, prmt(wb1[(r + 1) >> 2], wb2[(r + 1) >> 2], sel));
+                const unsigned hB = __vimax3_s16x2_relu(tB, eB, fB);
+                H[r] = hB;
+                const unsigned hqB = __vadd2(hB, negQ);
+                E[r] = __viaddmax_s16x2(eB, negR, hqB);
+                fB = __viaddmax_s16x2(fB, negR, hqB);
+                best = __vimax3_s16x2(best, tA, tB);
+                if (r == K - 1) hA_last = hA;
+                tA = tA_next; tB = tB_next;
+            }
+            hB_last = H[K - 1];
+            fA_out = fA; fB_out = fB;
+            if (lane == 31 && !last) {
+                reinterpret_cast<uint2*>(S.outH)[jp] = make_uint2(hA_last, hB_last);
+                reinterpret_cast<uint2*>(S.outF)[jp] = make_uint2(fA_out, fB_out);
+            }
+        }
+        __syncwarp();
+        if (end_col != kOpen && S0 + kSteps >= (end_col >> 1) + 32) { flush_out(end_col); break; }
+    }
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(kWarps * 32, 2) sw_score_striped_kernel(ScoreParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned* prof = reinterpret_cast<unsigned*>(smem);
@@ -1017,8 +1188,10 @@ __global__ void __launch_bounds__(kWarps * 32, 2) sw_score_striped_kernel(ScoreP
     }
 }
 
-// striped kernel, streaming form (the default; S4G_STRIPED=pairs selects the pair-by-pair kernel above)
-__global__ void __launch_bounds__(kWarps * 32, 2) sw_score_striped_stream_kernel(ScoreParams P) {
+// striped kernel, streaming form (TWO: two stream columns per step, the default; S4G_STRIPED=stream1 selects one column per step,
+// S4G_STRIPED=pairs the pair-by-pair kernel above)
+template <bool TWO>
+__device__ __forceinline__ void striped_stream_body(const ScoreParams& P) {
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned* prof = reinterpret_cast<unsigned*>(smem);
     int8_t* smat = reinterpret_cast<int8_t*>(smem + (S4G_PAD_CODE + 1) * 8 * 32 * 4);
@@ -1066,7 +1239,8 @@ __global__ void __launch_bounds__(kWarps * 32, 2) sw_score_striped_stream_kernel
             build_profile<kMaxK>(prof, smat, P.q_codes + qo + (int64_t)pass * 32 * kMaxK, qlen - pass * 32 * kMaxK);
             if (threadIdx.x == 0) s_next = pb;
             __syncthreads();
-            stream_stripe(P, prof + lane, S, &s_next, s_best, cta_bound, cbeg, cend, pb, pe, negQ, negR, pass == 0, pass == npass - 1, lane);
+            if (TWO) stream_stripe2(P, prof + lane, S, &s_next, s_best, cta_bound, cbeg, cend, pb, pe, negQ, negR, pass == 0, pass == npass - 1, lane);
+            else stream_stripe(P, prof + lane, S, &s_next, s_best, cta_bound, cbeg, cend, pb, pe, negQ, negR, pass == 0, pass == npass - 1, lane);
         }
         __syncthreads();
         for (int p = pb + threadIdx.x; p < pe; p += blockDim.x) {
@@ -1082,6 +1256,9 @@ __global__ void __launch_bounds__(kWarps * 32, 2) sw_score_striped_stream_kernel
         }
     }
 }
+
+__global__ void __launch_bounds__(kWarps * 32, 2) sw_score_striped_stream_kernel(ScoreParams P) { striped_stream_body<false>(P); }
+__global__ void __launch_bounds__(kWarps * 32, 2) sw_score_striped_stream2_kernel(ScoreParams P) { striped_stream_body<true>(P); }
 
 // ------------------------------------------------------------------------------------------------------
 // End cells of the kept hits of LONG queries (stage 3, step 1): the striped sweep with the end-cell rule of
@@ -1532,7 +1709,8 @@ int s4g_sw_score_device(s4g_ctx* ctx, s4g_db* db, s4g_queries* q, const uint32_t
     if (q->max_len > 32 * kMaxK) {
         const char* sv = getenv("S4G_STRIPED");
         const bool stream = !(sv && strcmp(sv, "pairs") == 0);
-        void (*strip_kernel)(ScoreParams) = stream ? sw_score_striped_stream_kernel : sw_score_striped_kernel;
+        const bool stream1 = sv && strcmp(sv, "stream1") == 0;
+        void (*strip_kernel)(ScoreParams) = stream ? (stream1 ? sw_score_striped_stream_kernel : sw_score_striped_stream2_kernel) : sw_score_striped_kernel;
         const size_t smem = (S4G_PAD_CODE + 1) * 8 * 32 * 4 + (S4G_PAD_CODE + 1) * 32 + kWarps * (stream ? kStreamStripWarpBytes : kStripWarpBytes);
         S4G_CUDA(ctx, cudaFuncSetAttribute(strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;

@@ -12,7 +12,7 @@ from sift4g_b200 import pipeline, synth
 
 pytestmark = pytest.mark.gpu
 
-SWITCHES = [("S4G_BEGINS", "sweep32"), ("S4G_BAND_GROUPS", "0"), ("S4G_BAND_GROUPS", "16"), ("S4G_STRIPED", "pairs"), ("S4G_ENDS", "sweep32"),
+SWITCHES = [("S4G_BEGINS", "sweep32"), ("S4G_BAND_GROUPS", "0"), ("S4G_BAND_GROUPS", "16"), ("S4G_STRIPED", "pairs"), ("S4G_STRIPED", "stream1"), ("S4G_ENDS", "sweep32"),
             ("S4G_NO_SPECULATE", "1"), ("S4G_SCORE", "1col"), ("S4G_TILE_ORDER", "query"), ("S4G_PF_REPLAY", "0")]
 
 
