@@ -639,7 +639,7 @@ def main():
             "roofline": {"bound": "int_dpx", "kernel": "sw_score_packed2_kernel", "achieved": round(kern_gcups, 2) if kern_gcups else None, "peak": round(roof_gcups, 2),
                          "unit": "GCUPS", "frac": round(kern_gcups / roof_gcups, 4) if kern_gcups else None,
                          "traffic": NCU_TRAFFIC_C2 if (world == 1 and n_queries == 1000 and n_db == 10_000_000 and args.max_candidates == 5000) else None,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch of this workload, ncu --set full capture (profiles/r04h_kernels_digest.md)",
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch of this workload, ncu --set full capture (profiles/r04r_kernels_digest.md)",
                          "frac_of_kernel_floor": round(kern_gcups / (roof_gcups * 6 / 4.5), 4) if kern_gcups else None,
                          "kernel_floor": "the kernel's own count: 4.5 ALU-pipe instructions per 2 cells (VIADD.16x2 issues on the FMA pipe), against BASELINE.md's 6",
                          "kernel_ms": round(sw_kernel_ms, 3),
@@ -655,7 +655,7 @@ def main():
             line["roofline_prefilter_l2"] = {"bound": "l2_request_rate", "unit": "G lookups/s", "achieved": round(ach / 1e9, 2), "peak": round(gather_peak / 1e9, 2),
                                              "frac": round(ach / gather_peak, 4),
                                              "note": "k-mer positions scanned per second (one random 8-byte probe of the 8 MB presence/rank table each; entry and hit loads not "
-                                                     "counted) / random-lookup rate measured live on this GPU (s4g_measure_gather_peak, 100 ms); ncu: profiles/r02i_pf_scan_digest.md"}
+                                                     "counted) / random-lookup rate measured live on this GPU (s4g_measure_gather_peak, 100 ms); ncu: profiles/r04r_kernels_digest.md (one row per chunk), profiles/r02i_pf_scan_digest.md"}
         if roofline_align is not None:
             line["roofline_align"] = roofline_align
         if line["roofline_prefilter"]["achieved"]:
@@ -681,7 +681,7 @@ def main():
 
 
 # DRAM bytes of one sw_score_packed2_kernel launch at the default C2 workload (1.391 GB read + 24.5 MB written), from the
-# ncu --set full capture summarised in profiles/r04h_kernels_digest.md.  The kernel is integer-issue bound; its algorithmic
+# ncu --set full capture summarised in profiles/r04r_kernels_digest.md.  The kernel is integer-issue bound; its algorithmic
 # DRAM traffic is the candidates' residues (5 M targets, ~107 residues each, fetched in 32-byte sectors).
 NCU_TRAFFIC_C2 = 1390900000 + 24490496
 
