@@ -25,7 +25,16 @@
 //
 // Work decomposition: candidates of each query are sorted by length (device radix sort) and paired
 // neighbour-wise; a persistent grid of CTAs pulls (query, block of pairs) tiles from an atomic counter,
-// builds the query profile once per tile and lets its warps pull pairs from the tile.
+// builds the query profile once per tile and lets its warps pull pairs from the tile.  The tile table runs
+// over the queries in DESCENDING LENGTH (ScoreParams::q_order): the two CTAs of an SM then execute the same
+// row-class instantiation (one 6-9 KB step loop in the 32 KB instruction cache instead of two) and the
+// expensive tiles go first.
+//
+// The shipped score kernel (sw_score_packed2_kernel / stream_pairs_packed2) takes TWO stream columns per
+// step: a lane works on columns 2(step - lane) and 2(step - lane) + 1; the first column's H is a temporary
+// (the diagonal input of the next row's second cell), which removes the one register move per cell ptxas
+// puts into the one-column loop, and halves shuffles, ring reads and loop control per column.  The
+// one-column forms (stream_pairs_packed, score_pair_packed) stay for the end-cell mode and as A/B arms.
 #include <cstring>
 #include <cub/cub.cuh>
 
