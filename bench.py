@@ -656,6 +656,13 @@ def main():
                                              "frac": round(ach / gather_peak, 4),
                                              "note": "k-mer positions scanned per second (one random 8-byte probe of the 8 MB presence/rank table each; entry and hit loads not "
                                                      "counted) / random-lookup rate measured live on this GPU (s4g_measure_gather_peak, 100 ms); ncu: profiles/r04r_kernels_digest.md (one row per chunk), profiles/r02i_pf_scan_digest.md"}
+            if world == 1 and n_queries == 1000 and n_db == 10_000_000 and args.max_candidates == 5000 and args.query_shape == "uniform":
+                # all L2 sectors of the scan kernels of one step (probes + entries + hits + residues), from the ncu capture of this
+                # workload, over the measured prefilter stage time: what the request-rate ceiling is actually spent on
+                line["roofline_prefilter_l2"]["l2_sectors_per_step"] = NCU_PF_SECTORS_C2
+                line["roofline_prefilter_l2"]["sectors_frac"] = round(NCU_PF_SECTORS_C2 / (split["prefilter"] * 1e-3) / gather_peak, 4)
+                line["roofline_prefilter_l2"]["sectors_source"] = ("lts__t_sectors.sum over the 15 pf_scan_kernel launches of a step (profiles/r04r_kernels_digest.md: chunks of "
+                                                                   "sequences >= 235 aa run at 0.67-0.87 of the ceiling, the short-sequence chunks at 0.15-0.39)")
         if roofline_align is not None:
             line["roofline_align"] = roofline_align
         if line["roofline_prefilter"]["achieved"]:
@@ -684,6 +691,8 @@ def main():
 # ncu --set full capture summarised in profiles/r04r_kernels_digest.md.  The kernel is integer-issue bound; its algorithmic
 # DRAM traffic is the candidates' residues (5 M targets, ~107 residues each, fetched in 32-byte sectors).
 NCU_TRAFFIC_C2 = 1390900000 + 24490496
+# L2 sectors of the 15 pf_scan_kernel launches of one step at the same workload (profiles/r04r_kernels_digest.md)
+NCU_PF_SECTORS_C2 = 4766630000
 
 
 def hbm_peak():
