@@ -641,7 +641,19 @@ __device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cn
             }
             __syncwarp();
             for (int i = 4 * lane; i < cnt_words; i += 128) *reinterpret_cast<uint4*>(cnt + i) = make_uint4(0u, 0u, 0u, 0u);
-            if (!defer && wb != buf && nsurv <= (1u << (31 - __clz(scap)))) {       // few survivors: sort them in shared memory (the bitonic sort pads to a power of two)
+            // Up to 32 survivors (the usual flagged sequence: a handful of hits of one or two queries): rank sort in registers -- the keys are
+            // distinct (the order field numbers the hits), a survivor's place is the number of smaller keys -- written straight into the
+            // shared buffer.  The bitonic network below costs 15 shared-memory passes however few entries there are: 17 % of the
+            // stall samples of a short-sequence chunk (profiles/r04u_pf_short_chunk_lines.txt).
+            bool sorted_small = false;
+            if (!defer && wb != buf && nsurv > 0u && nsurv <= 32u) {
+                const unsigned long long e = (uint32_t)lane < nsurv ? wb[lane] : ~0ull;
+                uint32_t rank = 0;
+                for (uint32_t x = 0; x < nsurv; ++x) rank += __shfl_sync(FULL, e, x) < e ? 1u : 0u;
+                if ((uint32_t)lane < nsurv) buf[rank] = e;
+                wb = buf;
+                sorted_small = true;
+            } else if (!defer && wb != buf && nsurv <= (1u << (31 - __clz(scap)))) {       // few survivors: sort them in shared memory (the bitonic sort pads to a power of two)
                 for (int i = lane; i < (int)nsurv; i += 32) buf[i] = wb[i];
                 wb = buf;
             }
@@ -660,9 +672,9 @@ __device__ __forceinline__ void pf_scan_body(const PfParams& P, int scap, int cn
             // bitonic sort of wb[0..P2) by (query, emission order)
             int P2 = 32;
             while (P2 < S) P2 <<= 1;
-            for (int i = S + lane; i < P2; i += 32) wb[i] = ~0ull;
+            if (!sorted_small) for (int i = S + lane; i < P2; i += 32) wb[i] = ~0ull;
             __syncwarp();
-            for (int size = 2; size <= P2; size <<= 1) {
+            for (int size = 2; !sorted_small && size <= P2; size <<= 1) {
                 for (int stride = size >> 1, lg = 31 - __clz(size >> 1); stride > 0; stride >>= 1, --lg) {
                     for (int t = lane; t < (P2 >> 1); t += 32) {
                         const int lo = ((t >> lg) << (lg + 1)) | (t & (stride - 1));
