@@ -1,3 +1,15 @@
+// The bare step loop of the packed score kernel (csrc/sw_score.cu) without pair boundaries, staging or tiles: what the loop alone
+// sustains, and how many issue slots a cell costs in SASS, for the forms that were tried (profiles/r04d_loop_microbench.jsonl,
+// profiles/r04h_kernels_digest.md).
+//   -DVARIANT=0  one stream column per step (stream_pairs_packed): ptxas parks the new H in a temporary and moves it back, one
+//                IMAD.MOV per cell
+//   -DVARIANT=1  the same with H - Q carried instead of H (profile bytes hold S + Q): fewer registers, the moves stay
+//   -DVARIANT=2  running maximum taken from the previous column's H: ptxas folds the add into VIADDMNMX (5.5 ALU ops per cell) -- worse
+//   -DVARIANT=3  two stream columns per step (stream_pairs_packed2, the shipped form): no moves
+//   -DNOFLAG     without the pair-boundary block
+// Build and run (B200):  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -DVARIANT=3 -DNOFLAG -o sw_loop_microbench_2col
+//                        tools/sw_loop_microbench.cu && ./sw_loop_microbench_2col        (one JSON line per row class and CTAs per SM)
+// SASS counts:           nvcc ... -cubin, cuobjdump -sass, count the instructions of the loop that holds the VIADDMNMX.
 #include <cstdint>
 #include <cuda_runtime.h>
 __device__ __forceinline__ unsigned prmt(unsigned a, unsigned b, unsigned sel) {
